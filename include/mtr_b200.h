@@ -1,0 +1,157 @@
+/*
+ * include/mtr_b200.h -- C ABI of the B200-native mTR hot path (libmtr_b200.so).
+ *
+ * Plain C: pointers, sizes and PODs only; no torch / C++ types.  Every entry point returns 0 on success
+ * or a negative MTR_E* code (mtr_last_error() gives the text); nothing here falls back to the CPU -- if no
+ * CUDA device is usable mtr_cuda_init fails and so does everything after it.
+ *
+ * Two layers:
+ *   (1) the kernel-level ABI (mtr_cuda_*, mtr_reads_*, mtr_wdp_*, mtr_di_*): batched device work, used by
+ *       the host pipeline below, by tests/ and by bench.py;
+ *   (2) the reference's own entry points for this path, kept verbatim so that mTR's main.c links against
+ *       this library unchanged: handle_one_file / handle_one_read and the globals main.c sets and prints
+ *       (/root/reference/mTR.h:61-62,126-127,142-143; main.c:53-56,93-121).
+ *
+ * Each declaration cites the reference interface it replaces (file:line under /root/reference).
+ */
+#ifndef MTR_B200_H
+#define MTR_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ errors */
+enum {
+    MTR_OK = 0,
+    MTR_ENODEV = -1,     /* no usable CUDA device / CUDA runtime error at init */
+    MTR_ECUDA = -2,      /* a CUDA call failed; see mtr_last_error */
+    MTR_EINVAL = -3,     /* bad argument (unit length outside 1..499, rows < 0, ...) */
+    MTR_ENOMEM = -4,     /* device or host allocation failed */
+    MTR_ERANGE = -5      /* a job exceeds the reference's own caps (WrapDPsize, MAX_INPUT_LENGTH) */
+};
+
+typedef struct mtr_ctx mtr_ctx;          /* one per GPU; not thread-safe, one caller thread per ctx */
+
+/* Replaces malloc_global_variables / free_global_variables (handle_one_file.c:71-167): all device and
+ * pinned-host buffers live in the context and grow on demand. */
+int  mtr_cuda_init(int device, mtr_ctx **out);
+void mtr_cuda_shutdown(mtr_ctx *ctx);
+const char *mtr_last_error(const mtr_ctx *ctx);   /* ctx may be NULL: error of the last failed init */
+int  mtr_device_count(void);
+
+/* ------------------------------------------------------------------ reads (orgInputString, mTR.h:65) */
+/* A batch of reads, 2-bit packed (A,C,G,T = 0..3; base b of a read is bits [2*(b%16), 2*(b%16)+2) of word
+ * b/16, counted from that read's first word).  word_off[r] is the index of read r's first word in `packed`
+ * (word_off[n_reads] = total words); each read's words must cover len[r] + 2 bases: positions len[r] and
+ * len[r]+1 hold the two "stale" bases the reference reads past the end of the read (SURVEY.md 4.3 H4,
+ * wrap_around_DP.c:243-245,264).  The batch stays resident until the next upload. */
+int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int64_t *word_off, const int32_t *len,
+                     int n_reads);
+
+/* ------------------------------------------------------------------ K3: wrap-around DP */
+/* One job = one call of wrap_around_DP_sub (wrap_around_DP.c:222-354), of the DP inside
+ * revise_representative_unit_sub (consensus.c:851-962, mode CONSENSUS) or of pretty_print_alignment
+ * (wrap_around_DP.c:57-186, mode PATH); with n_param == 2 it is one call of wrap_around_DP
+ * (wrap_around_DP.c:357-429): the same window and unit under two penalty sets.
+ *
+ * Rows i = 1..rows are the read bases x_i = read[first + i]  (so first = query_start for
+ * wrap_around_DP_sub, whose window is orgInputString[query_start+1 .. query_end+1], and first = rep_start-1
+ * for pretty_print_alignment); columns j = 1..ulen are units[unit_off + j - 1] (one byte per base, 0..3). */
+enum { MTR_TB_COUNTS = 0, MTR_TB_CONSENSUS = 1, MTR_TB_PATH = 2 };
+
+typedef struct {
+    int32_t read;          /* index into the resident read batch */
+    int32_t first;         /* see above; may be -1 (then row 1 is base 0) */
+    int32_t rows;          /* rep_len = query_end - query_start + 1 */
+    int32_t unit_off;      /* offset of the unit in the `units` byte array */
+    int32_t ulen;          /* 1..499 (MAX_PERIOD-1, mTR.h:34) */
+    int8_t  gain[2], mis[2], indel[2];   /* MATCH_GAIN, MISMATCH_PENALTY, INDEL_PENALTY per penalty set */
+    uint8_t n_param;       /* 1 or 2 */
+    uint8_t mode;          /* MTR_TB_*; CONSENSUS and PATH need n_param == 1 */
+    int64_t aux_off;       /* CONSENSUS: offset (in int32) of this job's (ulen+1)*9 histogram block in aux;
+                              PATH: offset (in bytes) of this job's path block in aux; else ignored */
+    int64_t aux_cap;       /* PATH: capacity in bytes of the path block */
+} mtr_wdp_job;
+
+/* The fields wrap_around_DP_sub derives its record from (wrap_around_DP.c:337-350):
+ * rep_start = query_start + end_i + 1, rep_end = query_start + max_i, repeat_len = max_i - end_i,
+ * Num_freq_unit = n_scanned / ulen. */
+typedef struct {
+    int32_t best;          /* max_wrd: maximum cell value (0 => max_i = max_j = 0, empty traceback) */
+    int32_t max_i, max_j;  /* first row-major argmax */
+    int32_t end_i, end_j;  /* where the traceback stopped */
+    int32_t n_match, n_mismatch, n_ins, n_del, n_scanned;
+    int32_t path_len;      /* number of traceback steps (PATH: bytes written, clipped to aux_cap) */
+    int32_t flags;         /* bit 0: path clipped */
+} mtr_wdp_result;
+
+/* CONSENSUS aux block layout per job: int32 consensus[(ulen+1)][5] then int32 missing[(ulen+1)][4]
+ * (the two histograms of consensus.c:919-962, row j = unit position, 1-origin).
+ * PATH aux block: one byte per traceback step, in traceback order (from the alignment's end):
+ * 0 match, 1 mismatch, 2 deletion (unit base, no read base), 3 insertion (read base, no unit base). */
+
+/* Synchronous: H2D(jobs, units) -> fill kernels -> traceback kernel -> D2H(results[, aux]).
+ * results has n_jobs * 2 entries: results[2*j + p] for penalty set p (p = 1 unused when n_param == 1).
+ * aux / aux_bytes may be NULL / 0 when no job asks for CONSENSUS or PATH output. */
+int mtr_wdp_run(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
+                mtr_wdp_result *results, void *aux, int64_t aux_bytes);
+
+/* The same in three phases, for pipelining and for timing the kernels with the operands resident in HBM:
+ * upload (H2D + job classification), launch (kernels only; may be repeated), download (D2H). */
+int mtr_wdp_upload(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
+                   int64_t aux_bytes);
+int mtr_wdp_launch(mtr_ctx *ctx);
+int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes);
+
+/* ------------------------------------------------------------------ K1/K2: directional index */
+/* Replaces fill_directional_index_with_end (fill_directional_index.c:549-602) for every read of the
+ * resident batch: k-mer coding with the MT19937 flanks (:137-169), the sliding three-window distance
+ * (Manhattan :171-295, or Pearson :298-450 when manhattan == 0), the local max/min merge (:467-503), the
+ * unshift (:587-597) and remove_redundant_ranges (:505-546).
+ *
+ * stale / stale_off: per read, the values the reference would find in inputString_w_rand beyond the area it
+ * re-initialises for this read (index >= len + 4r); stale_off[r]..stale_off[r+1] delimit
+ * read r's uint16 values, missing values read as 0 (fresh process).  May be NULL (all zero).
+ *
+ * Output, per read r, for positions [0, len[r]): di (fp64), end, w -- exactly the reference's
+ * directional_index / directional_index_end / directional_index_w after the call; pos_off[r] is the offset
+ * of read r in the three arrays (pos_off[n] = total). */
+int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
+               const int64_t *pos_off, double *di, int32_t *end, int32_t *w);
+
+/* ------------------------------------------------------------------ counters for the roofline */
+typedef struct {
+    double   wdp_fill_ms, wdp_tb_ms, di_ms;      /* CUDA-event time of the last launch of each stage */
+    int64_t  wdp_cells;                          /* sum over jobs and penalty sets of rows * ulen */
+    int64_t  wdp_slot_cells;                     /* cells actually computed incl. padding lanes */
+    int64_t  wdp_dir_bytes;                      /* direction bytes written by the last launch */
+    int64_t  di_position_passes;                 /* sum over passes of (L + r - w - k + 1) */
+    int64_t  di_bytes_in, di_bytes_out;
+    int32_t  launches;                           /* kernels launched by the last call */
+    int32_t  n_sm;
+} mtr_stats;
+int mtr_get_stats(const mtr_ctx *ctx, mtr_stats *out);
+
+/* ------------------------------------------------------------------ the reference's entry points */
+/* mTR.h:126  handle_one_file(char *inputFile, int print_alignment): parses the FASTA, runs the pipeline on
+ * the GPUs named by MTR_GPUS (default: device 0), prints the records to stdout in input order; returns the
+ * number of reads.  Reads the globals below, like the reference. */
+int  handle_one_file(char *inputFile, int print_alignment);
+/* mTR.h:127  handle_one_read: the read is orgInputString[0..inputLen) (int per base), as in the reference
+ * (handle_one_file.c:284-286).  Here it enqueues a copy; mtr_flush() completes and prints everything
+ * enqueued so far, in order. */
+void handle_one_read(char *readID, int inputLen, int read_cnt, int print_alignment);
+void mtr_flush(void);
+
+extern int   Manhattan_Distance;      /* mTR.h:61, set by main.c:56,77 */
+extern float min_match_ratio;         /* mTR.h:62, set by main.c:54,68 */
+extern int  *orgInputString;          /* mTR.h:65 */
+extern float time_all, time_memory, time_range, time_period, time_initialize_input_string,
+             time_wrap_around_DP, time_count_table, time_chaining;      /* mTR.h:142 */
+extern int   query_counter;           /* mTR.h:143 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,156 @@
+// ctx.cu -- context, resident read batch and the kernel-level C ABI of libmtr_b200.so.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "mtr_internal.h"
+
+static std::string g_init_error;
+
+void mtr_set_error(mtr_ctx *ctx, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_init_error = buf;
+}
+
+extern "C" const char *mtr_last_error(const mtr_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_init_error.c_str();
+}
+
+extern "C" int mtr_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int mtr_cuda_init(int device, mtr_ctx **out)
+{
+    if (!out) return MTR_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        mtr_set_error(nullptr, "mtr_cuda_init: no CUDA device (%s); this library has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        cudaGetLastError();
+        return MTR_ENODEV;
+    }
+    if (device < 0 || device >= n) { mtr_set_error(nullptr, "mtr_cuda_init: device %d out of range (%d devices)", device, n); return MTR_EINVAL; }
+    mtr_ctx *ctx = new mtr_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        mtr_set_error(nullptr, "mtr_cuda_init: %s", cudaGetErrorString(e));
+        delete ctx;
+        return MTR_ENODEV;
+    }
+    if (prop.major < 10) {
+        mtr_set_error(nullptr, "mtr_cuda_init: device %d is sm_%d%d; this build contains sm_100a code only", device, prop.major, prop.minor);
+        delete ctx;
+        return MTR_ENODEV;
+    }
+    ctx->n_sm = prop.multiProcessorCount;
+    ctx->stats.n_sm = ctx->n_sm;
+    bool ok = cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; ok && k < WDP_NCLASS; k++) {
+        ok = cudaStreamCreateWithFlags(&ctx->stream[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->class_done[k], cudaEventDisableTiming) == cudaSuccess;
+    }
+    for (int k = 0; ok && k < 8; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+    if (!ok) {
+        mtr_set_error(nullptr, "mtr_cuda_init: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return MTR_ECUDA;
+    }
+    *out = ctx;
+    return MTR_OK;
+}
+
+extern "C" void mtr_cuda_shutdown(mtr_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    di_state_free(ctx);
+    WdpState &w = ctx->wdp;
+    w.d_tasks.release(); w.d_units.release(); w.d_dirs.release(); w.d_results.release(); w.d_aux.release();
+    w.d_counters.release(); w.h_tasks.release(); w.h_results.release();
+    ctx->d_packed.release(); ctx->d_word_off.release(); ctx->d_len.release();
+    for (int k = 0; k < WDP_NCLASS; k++) {
+        if (ctx->stream[k]) cudaStreamDestroy(ctx->stream[k]);
+        if (ctx->class_done[k]) cudaEventDestroy(ctx->class_done[k]);
+    }
+    for (int k = 0; k < 8; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    delete ctx;
+}
+
+extern "C" int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int64_t *word_off, const int32_t *len, int n_reads)
+{
+    if (!ctx) return MTR_EINVAL;
+    if (n_reads < 0 || (n_reads > 0 && (!packed || !word_off || !len))) { mtr_set_error(ctx, "reads_upload: null argument"); return MTR_EINVAL; }
+    for (int r = 0; r < n_reads; r++) {
+        if (len[r] < 0 || len[r] >= 1000000) { mtr_set_error(ctx, "reads_upload: read %d has length %d (MAX_INPUT_LENGTH is 1000000)", r, len[r]); return MTR_ERANGE; }
+        if (word_off[r + 1] - word_off[r] < (len[r] + 2 + 15) / 16) { mtr_set_error(ctx, "reads_upload: read %d: words do not cover len + 2 bases", r); return MTR_EINVAL; }
+    }
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nw = n_reads ? word_off[n_reads] : 0;
+    // 16 spare words so that vectorised (uint4) loads of the last read never leave the allocation
+    MTR_CUDA(ctx, ctx->d_packed.reserve((size_t)(nw + 16) * 4));
+    MTR_CUDA(ctx, ctx->d_word_off.reserve((size_t)(n_reads + 1) * 8));
+    MTR_CUDA(ctx, ctx->d_len.reserve((size_t)(n_reads + 1) * 4));
+    if (n_reads > 0) {
+        MTR_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed.p, packed, (size_t)nw * 4, cudaMemcpyHostToDevice, ctx->main_stream));
+        MTR_CUDA(ctx, cudaMemsetAsync((char *)ctx->d_packed.p + (size_t)nw * 4, 0, 64, ctx->main_stream));
+        MTR_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_off.p, word_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->main_stream));
+        MTR_CUDA(ctx, cudaMemcpyAsync(ctx->d_len.p, len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->main_stream));
+        MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+    }
+    ctx->word_off.assign(word_off, word_off + (n_reads ? n_reads + 1 : 0));
+    ctx->len.assign(len, len + n_reads);
+    ctx->n_reads = n_reads;
+    ctx->n_words = nw;
+    ctx->wdp.uploaded = false;
+    return MTR_OK;
+}
+
+extern "C" int mtr_wdp_upload(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len, int64_t aux_bytes)
+{
+    if (!ctx) return MTR_EINVAL;
+    return wdp_upload_impl(ctx, jobs, n_jobs, units, units_len, aux_bytes);
+}
+
+extern "C" int mtr_wdp_launch(mtr_ctx *ctx)
+{
+    if (!ctx) return MTR_EINVAL;
+    return wdp_launch_impl(ctx);
+}
+
+extern "C" int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes)
+{
+    if (!ctx) return MTR_EINVAL;
+    return wdp_download_impl(ctx, results, aux, aux_bytes);
+}
+
+extern "C" int mtr_wdp_run(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
+                           mtr_wdp_result *results, void *aux, int64_t aux_bytes)
+{
+    if (!ctx) return MTR_EINVAL;
+    int rc = wdp_upload_impl(ctx, jobs, n_jobs, units, units_len, aux_bytes);
+    if (rc) return rc;
+    rc = wdp_launch_impl(ctx);
+    if (rc) return rc;
+    return wdp_download_impl(ctx, results, aux, aux_bytes);
+}
+
+extern "C" int mtr_get_stats(const mtr_ctx *ctx, mtr_stats *out)
+{
+    if (!ctx || !out) return MTR_EINVAL;
+    *out = ctx->stats;
+    return MTR_OK;
+}

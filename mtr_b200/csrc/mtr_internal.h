@@ -1,0 +1,106 @@
+// mtr_internal.h -- shared declarations of libmtr_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/mtr_b200.h"
+
+// ---------------------------------------------------------------- error plumbing
+void mtr_set_error(mtr_ctx *ctx, const char *fmt, ...);
+#define MTR_CUDA(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            mtr_set_error((ctx), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+                          cudaGetErrorString(e_));                                              \
+            return MTR_ECUDA;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------- growable device / pinned buffers
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = bytes + bytes / 4 + 4096;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = bytes + bytes / 4 + 4096;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ---------------------------------------------------------------- wrap-around DP (wdp.cu)
+// One fill task = one (job, penalty set) pair, or -- in the paired int16x2 kernels -- one job with both sets.
+struct WdpTask {
+    long long base0;      // x_i = base (base0 + i) of the packed read buffer
+    long long dir_off;    // byte offset of this task's direction matrix (second set: + dir_bytes)
+    long long dir_bytes;  // bytes of one direction matrix = rows * dir_stride
+    long long aux_off;    // CONSENSUS: int32 offset, PATH: byte offset
+    long long aux_cap;
+    int rows, ulen, unit_off;
+    int dir_stride;       // bytes per row of the direction matrix (= slots / 4)
+    int result_idx;       // results[result_idx (+1 for the second set of a paired task)]
+    short gain[2], mis[2], indel[2];
+    unsigned char n_param, mode;
+    unsigned char pad_[2];
+};
+
+constexpr int WDP_NCLASS = 12;
+struct WdpClass { int G, C, paired; };          // lanes per job, cells per lane, int16x2 pairing
+
+struct WdpState {
+    DevBuf d_tasks, d_units, d_dirs, d_results, d_aux, d_counters;
+    PinBuf h_tasks, h_results;
+    std::vector<WdpTask> tasks;                 // sorted by class, then by rows descending
+    int class_begin[WDP_NCLASS + 1] = {0};
+    int n_jobs = 0, n_results = 0;
+    long long dir_total = 0, aux_bytes = 0;
+    long long cells = 0, slot_cells = 0;
+    bool uploaded = false;
+};
+
+// ---------------------------------------------------------------- context
+struct mtr_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream[WDP_NCLASS] = {};
+    cudaStream_t main_stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t class_done[WDP_NCLASS] = {};
+    std::string err;
+    // resident reads
+    DevBuf d_packed, d_word_off, d_len;
+    std::vector<int64_t> word_off;
+    std::vector<int32_t> len;
+    int n_reads = 0;
+    int64_t n_words = 0;
+    WdpState wdp;
+    struct DiState *di = nullptr;
+    mtr_stats stats = {};
+};
+
+int  wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
+                     int64_t aux_bytes);
+int  wdp_launch_impl(mtr_ctx *ctx);
+int  wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes);
+void di_state_free(mtr_ctx *ctx);

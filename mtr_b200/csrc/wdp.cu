@@ -1,0 +1,426 @@
+// wdp.cu -- K3: batched wrap-around DP (fill + argmax + direction bits) and traceback for sm_100a.
+//
+// Replaces wrap_around_DP_sub (/root/reference/wrap_around_DP.c:222-354), the DP nest inside
+// revise_representative_unit_sub (consensus.c:875-962) and pretty_print_alignment (wrap_around_DP.c:68-186).
+//
+// The recurrence (wrap_around_DP.c:258-285):
+//     x_i == u_j :  W[i][j] = W[i-1][j-1] + G                                  (unconditionally)
+//     else       :  W[i][j] = max(0, W[i-1][j-1]-MM, W[i-1][j]-IN, (j>1) W[i][j-1]-IN)
+//     W[i][0] := W[i][U]  (wrap)  => cell (i,1) depends on (i-1,U): rows are strictly sequential.
+// There is no valid anti-diagonal wavefront; the parallelism inside one DP is along a
+// row.  A group of G lanes owns one job; lane l holds C consecutive columns in registers.  Each row:
+//   phase A   per cell, the left-independent candidate  a = max(0, diag-MM, up-IN)  (or diag+G on a match)
+//   phase B   the left chain  W[j] = max(a_j, W[j-1]-IN)  inside the lane, speculating that nothing
+//             crosses the lane boundary; the last cell of every lane is handed to its right neighbour by
+//             one shuffle and the chain is redone only while some lane's first cell really changes
+//             (monotone fixpoint, at most G rounds, usually none or one)
+//   epilogue  W[i][U] is shuffled to lane 0 (wrap), direction codes are packed and stored, argmax updated.
+//
+// Scores are kept multiplied by 4 with the low two bits free, so that the candidate that wins the max
+// carries its own traceback code: diag-MM is tagged 3, left-IN 2, up-IN 1, the zero floor 0.  A tie between
+// candidates is then resolved by the max itself in the reference's traceback priority (mismatch before
+// deletion before insertion, wrap_around_DP.c:306-323) and the 2-bit direction code is just (r & 3):
+// no compares.  Match cells need no code: the traceback tests x_i == u_j first (:306), and a match cell
+// always equals diag+G.  The j == 1 "deletion" test of the traceback reads W[i][0], the wrap copy of the
+// same row (:302,314); that code is patched in lane 0 at row end, when W[i][U] is known.
+//
+// Direction matrix in HBM: 2 bits per slot, row-major, row stride = G*C/4 bytes, written with one
+// coalesced 1/2/4-byte store per lane per row.  The traceback kernel walks it with one thread per task,
+// tracking the running score exactly as the reference does (max_wrd), so no "stop" code is needed.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include "mtr_internal.h"
+
+// ---------------------------------------------------------------- job classes
+// U <= G*C.  Small C for tiny units (many tiny jobs per warp), C = 16 for long units.
+static const WdpClass kClasses[WDP_NCLASS] = {
+    {4, 4, 0},  {4, 8, 0},  {8, 8, 0},  {8, 16, 0}, {16, 16, 0}, {32, 16, 0},
+    {4, 4, 1},  {4, 8, 1},  {8, 8, 1},  {8, 16, 1}, {16, 16, 1}, {32, 16, 1},
+};
+
+static int class_of(int ulen, int paired)
+{
+    for (int k = 0; k < 6; k++)
+        if (ulen <= kClasses[k].G * kClasses[k].C) return k + (paired ? 6 : 0);
+    return -1;
+}
+
+#define NEG_INF (-(1 << 28))
+
+__device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, long long b)
+{
+    return (int)((packed[b >> 4] >> ((int)(b & 15) * 2)) & 3u);
+}
+
+// ---------------------------------------------------------------- fill kernel, int32 scores
+template <int G, int C>
+__global__ void __launch_bounds__(128)
+wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
+             const uint8_t *__restrict__ units, uint8_t *__restrict__ dirs,
+             mtr_wdp_result *__restrict__ results, int *__restrict__ counter)
+{
+    constexpr int JPW = 32 / G;                    // jobs per warp
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;                       // lane within its group
+    const int grp = lane / G;
+    const int nslots = (ntasks + JPW - 1) / JPW;
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(counter, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= nslots) break;
+        const int tidx = slot * JPW + grp;
+        const bool have = tidx < ntasks;
+        const WdpTask *tp = tasks + (have ? tidx : 0);
+        const int rows = have ? tp->rows : 0;
+        const int ulen = tp->ulen;
+        const long long base0 = tp->base0;
+        const int g4 = 4 * tp->gain[0];
+        const int cD = -4 * tp->mis[0] + 3;        // diagonal (mismatch) candidate, tag 3
+        const int cL = -4 * tp->indel[0] + 2;      // left (deletion) candidate, tag 2
+        const int cU = -4 * tp->indel[0] + 1;      // up (insertion) candidate, tag 1
+        const int in4 = 4 * tp->indel[0];
+        uint8_t *drow = dirs + tp->dir_off + (size_t)gl * (C / 4);
+        const int dstride = tp->dir_stride;
+
+        // per-lane match masks: bit c of eq[b] <=> unit base of my c-th column == b
+        unsigned eq01 = 0, eq23 = 0;
+        const int lu = (ulen - 1) / C, cu = (ulen - 1) % C;
+        int sel[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = gl * C + c;
+            if (j < ulen) {
+                const int b = units[tp->unit_off + j];
+                const unsigned bit = 1u << (c + ((b & 1) ? 16 : 0));
+                if (b & 2) eq23 |= bit; else eq01 |= bit;
+            }
+            sel[c] = (gl == lu && c == cu) ? -1 : 0;
+        }
+
+        int Wp[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) Wp[c] = 0;
+        int dgin = 0;
+        int best_v = 0, best_i = 0, best_c = 0;
+
+        int maxrows = rows;
+#pragma unroll
+        for (int off = 16; off >= G; off >>= 1) maxrows = max(maxrows, __shfl_xor_sync(FULL, maxrows, off));
+
+        unsigned xw = 0;
+        for (int i = 1; i <= maxrows; i++) {
+            const bool act = i <= rows;
+            const long long bi = base0 + i;
+            if (act && (i == 1 || (bi & 15) == 0)) xw = packed[bi >> 4];
+            const int xi = (int)((xw >> ((int)(bi & 15) * 2)) & 3u);
+            const unsigned m = ((xi & 2) ? eq23 : eq01) >> ((xi & 1) * 16);
+
+            // phase A: left-independent candidates
+            int A[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const int dg = (c == 0) ? dgin : Wp[c - 1];
+                const int a = __viaddmax_s32_relu(dg, cD, Wp[c] + cU);
+                A[c] = (m & (1u << c)) ? dg + g4 : a;
+            }
+            // phase B: left chain with speculative lane-boundary carries
+            int r[C], v[C];
+            int carry = NEG_INF, cn;
+            for (;;) {
+                int left = carry;
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    int t = __viaddmax_s32(left, cL, A[c]);
+                    t = (m & (1u << c)) ? A[c] : t;
+                    r[c] = t;
+                    v[c] = t & ~3;
+                    left = v[c];
+                }
+                cn = __shfl_up_sync(FULL, v[C - 1], 1, G);
+                if (gl == 0) cn = NEG_INF;
+                const bool need = (cn != carry) && !(m & 1u) && (cn + cL > r[0]);
+                if (!__any_sync(FULL, need)) break;
+                carry = cn;
+            }
+            // W[i][U] -> everybody (lane 0 needs it as next row's diagonal and for the j == 1 quirk)
+            int mine = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) mine |= v[c] & sel[c];
+            const int wU = __shfl_sync(FULL, mine, lu, G);
+
+            unsigned bits = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) bits |= (unsigned)(r[c] & 3) << (2 * c);
+            // traceback at j == 1 tests "deletion" against W[i][0] == W[i][U] before insertion
+            if (gl == 0 && (bits & 3u) == 1u && v[0] == wU - in4) bits ^= 3u;
+
+            if (act) {
+                uint8_t *p = drow + (size_t)(i - 1) * dstride;
+                if (C == 4) *p = (uint8_t)bits;
+                else if (C == 8) *(uint16_t *)p = (uint16_t)bits;
+                else *(uint32_t *)p = bits;
+            }
+
+            int key = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) key = max(key, (v[c] << 2) | (15 - c));
+            if (act && (key >> 4) > best_v) { best_v = key >> 4; best_i = i; best_c = 15 - (key & 15); }
+
+#pragma unroll
+            for (int c = 0; c < C; c++) Wp[c] = v[c];
+            dgin = (gl == 0) ? wU : cn;
+        }
+
+        // first row-major argmax over the group: larger value, then smaller row, then smaller column
+        int best_j = gl * C + best_c + 1;
+#pragma unroll
+        for (int off = G / 2; off >= 1; off >>= 1) {
+            const int ov = __shfl_xor_sync(FULL, best_v, off);
+            const int oi = __shfl_xor_sync(FULL, best_i, off);
+            const int oj = __shfl_xor_sync(FULL, best_j, off);
+            const bool take = (ov > best_v) || (ov == best_v && (oi < best_i || (oi == best_i && oj < best_j)));
+            if (take) { best_v = ov; best_i = oi; best_j = oj; }
+        }
+        if (have && gl == 0) {
+            mtr_wdp_result *res = results + tp->result_idx;
+            res->best = best_v;
+            res->max_i = best_v > 0 ? best_i : 0;
+            res->max_j = best_v > 0 ? best_j : 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- traceback (one thread per task)
+// wrap_around_DP.c:288-333 (counts), consensus.c:919-962 (histograms), wrap_around_DP.c:123-186 (path).
+__global__ void __launch_bounds__(128)
+wdp_traceback(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
+              const uint8_t *__restrict__ units, const uint8_t *__restrict__ dirs,
+              mtr_wdp_result *__restrict__ results, void *__restrict__ aux)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ntasks) return;
+    const WdpTask t = tasks[idx];
+    for (int p = 0; p < (t.n_param == 2 ? 2 : 1); p++) {
+        mtr_wdp_result *res = results + t.result_idx + p;
+        const int G = t.gain[p], MM = t.mis[p], IN = t.indel[p];
+        const uint8_t *d = dirs + t.dir_off + (size_t)p * t.dir_bytes;
+        int i = res->max_i, j = res->max_j, run = res->best;
+        if (j == 0) j = t.ulen;                             // wrap_around_DP.c:296
+        int nm = 0, nx = 0, ni = 0, nd = 0, steps = 0, flags = 0;
+        int *cons = nullptr, *miss = nullptr;
+        uint8_t *path = nullptr;
+        if (t.mode == MTR_TB_CONSENSUS) {
+            cons = (int *)aux + t.aux_off;
+            miss = cons + (size_t)(t.ulen + 1) * 5;
+        } else if (t.mode == MTR_TB_PATH) {
+            path = (uint8_t *)aux + t.aux_off;
+        }
+        while (i > 0 && run > 0) {
+            const int xi = read_base(packed, t.base0 + i);
+            const int uj = units[t.unit_off + j - 1];
+            int op;
+            if (xi == uj) {
+                op = 0;
+            } else {
+                const int code = (d[(size_t)(i - 1) * t.dir_stride + ((j - 1) >> 2)] >> (((j - 1) & 3) * 2)) & 3;
+                if (code == 0) { flags |= 2; break; }       // cannot happen: run > 0 means W[i][j] > 0
+                op = code == 3 ? 1 : (code == 2 ? 2 : 3);
+            }
+            if (path) { if (steps < t.aux_cap) path[steps] = (uint8_t)op; else flags |= 1; }
+            steps++;
+            if (op == 0)      { if (cons) cons[j * 5 + xi]++; run -= G;  i--; j--; nm++; }
+            else if (op == 1) { if (cons) cons[j * 5 + xi]++; run += MM; i--; j--; nx++; }
+            else if (op == 2) { if (cons) cons[j * 5 + 4]++;  run += IN; j--;      nd++; }
+            else              { if (miss) miss[j * 4 + xi]++; run += IN; i--;      ni++; }
+            if (j == 0) j = t.ulen;
+        }
+        res->end_i = i; res->end_j = j;
+        res->n_match = nm; res->n_mismatch = nx; res->n_ins = ni; res->n_del = nd;
+        res->n_scanned = nm + nx + nd;
+        res->path_len = steps; res->flags = flags;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+template <int G, int C>
+static void launch_fill(mtr_ctx *ctx, int k, const WdpTask *d_tasks, int ntasks, cudaStream_t s)
+{
+    const int jpw = 32 / G;
+    const int nslots = (ntasks + jpw - 1) / jpw;
+    int blocks = (nslots + 3) / 4;
+    blocks = std::min(blocks, ctx->n_sm * 8);
+    wdp_fill_i32<G, C><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p,
+                                              (const uint8_t *)ctx->wdp.d_units.p, (uint8_t *)ctx->wdp.d_dirs.p,
+                                              (mtr_wdp_result *)ctx->wdp.d_results.p,
+                                              (int *)ctx->wdp.d_counters.p + k);
+}
+
+int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
+                    int64_t aux_bytes)
+{
+    WdpState &w = ctx->wdp;
+    w.uploaded = false;
+    if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !units))) { mtr_set_error(ctx, "wdp_upload: null argument"); return MTR_EINVAL; }
+    if (n_jobs > 0 && ctx->n_reads == 0) { mtr_set_error(ctx, "wdp_upload: no resident read batch"); return MTR_EINVAL; }
+    w.tasks.clear();
+    w.tasks.reserve((size_t)n_jobs * 2);
+    w.n_jobs = n_jobs;
+    w.n_results = n_jobs * 2;
+    w.cells = 0; w.slot_cells = 0;
+    std::vector<int> cls;
+    cls.reserve((size_t)n_jobs * 2);
+    for (int jn = 0; jn < n_jobs; jn++) {
+        const mtr_wdp_job &j = jobs[jn];
+        if (j.read < 0 || j.read >= ctx->n_reads || j.ulen < 1 || j.ulen >= 500 || j.rows < 0 ||
+            (j.n_param != 1 && j.n_param != 2) || j.mode > MTR_TB_PATH || (j.mode != MTR_TB_COUNTS && j.n_param != 1) ||
+            j.unit_off < 0 || (int64_t)j.unit_off + j.ulen > units_len || j.first < -1 ||
+            (int64_t)j.first + j.rows > (int64_t)ctx->len[j.read] + 1) {
+            mtr_set_error(ctx, "wdp_upload: job %d is malformed (read %d first %d rows %d ulen %d n_param %d mode %d)",
+                          jn, j.read, j.first, j.rows, j.ulen, j.n_param, j.mode);
+            return MTR_EINVAL;
+        }
+        if ((int64_t)j.ulen * j.rows > 200000000LL) {       // WrapDPsize, mTR.h:51 / handle_one_read.c:89
+            mtr_set_error(ctx, "wdp_upload: job %d exceeds WrapDPsize", jn);
+            return MTR_ERANGE;
+        }
+        if (j.mode == MTR_TB_CONSENSUS && (j.aux_off < 0 || (j.aux_off + (int64_t)(j.ulen + 1) * 9) * 4 > aux_bytes)) {
+            mtr_set_error(ctx, "wdp_upload: job %d consensus block outside aux", jn);
+            return MTR_EINVAL;
+        }
+        if (j.mode == MTR_TB_PATH && (j.aux_off < 0 || j.aux_cap < 0 || j.aux_off + j.aux_cap > aux_bytes)) {
+            mtr_set_error(ctx, "wdp_upload: job %d path block outside aux", jn);
+            return MTR_EINVAL;
+        }
+        for (int p = 0; p < j.n_param; p++) {
+            WdpTask t;
+            memset(&t, 0, sizeof t);
+            t.base0 = ctx->word_off[j.read] * 16 + j.first;
+            t.rows = j.rows; t.ulen = j.ulen; t.unit_off = j.unit_off;
+            t.gain[0] = j.gain[p]; t.mis[0] = j.mis[p]; t.indel[0] = j.indel[p];
+            t.n_param = 1; t.mode = j.mode;
+            t.aux_off = j.aux_off; t.aux_cap = j.aux_cap;
+            t.result_idx = jn * 2 + p;
+            const int k = class_of(j.ulen, 0);
+            t.dir_stride = kClasses[k].G * kClasses[k].C / 4;
+            t.dir_bytes = (long long)t.rows * t.dir_stride;
+            cls.push_back(k);
+            w.tasks.push_back(t);
+            w.cells += (long long)j.rows * j.ulen;
+            w.slot_cells += (long long)j.rows * kClasses[k].G * kClasses[k].C;
+        }
+    }
+    // sort by (class, rows descending): similar jobs share a warp, long jobs start first
+    const int nt = (int)w.tasks.size();
+    std::vector<int> order(nt);
+    for (int i = 0; i < nt; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (cls[a] != cls[b]) return cls[a] < cls[b];
+        if (w.tasks[a].rows != w.tasks[b].rows) return w.tasks[a].rows > w.tasks[b].rows;
+        return a < b;
+    });
+    std::vector<WdpTask> sorted(nt);
+    for (int k = 0; k <= WDP_NCLASS; k++) w.class_begin[k] = 0;
+    long long off = 0;
+    for (int i = 0; i < nt; i++) {
+        sorted[i] = w.tasks[order[i]];
+        sorted[i].dir_off = off;
+        off += (sorted[i].dir_bytes * sorted[i].n_param + 15) & ~15LL;
+        w.class_begin[cls[order[i]] + 1]++;
+    }
+    for (int k = 0; k < WDP_NCLASS; k++) w.class_begin[k + 1] += w.class_begin[k];
+    w.tasks.swap(sorted);
+    w.dir_total = off;
+    w.aux_bytes = aux_bytes;
+
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    MTR_CUDA(ctx, w.d_tasks.reserve(sizeof(WdpTask) * (size_t)std::max(nt, 1)));
+    MTR_CUDA(ctx, w.d_units.reserve((size_t)std::max<int64_t>(units_len, 1)));
+    MTR_CUDA(ctx, w.d_dirs.reserve((size_t)std::max<long long>(w.dir_total, 16)));
+    MTR_CUDA(ctx, w.d_results.reserve(sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1)));
+    MTR_CUDA(ctx, w.d_aux.reserve((size_t)std::max<int64_t>(aux_bytes, 16)));
+    MTR_CUDA(ctx, w.d_counters.reserve(sizeof(int) * WDP_NCLASS));
+    if (nt > 0) {
+        MTR_CUDA(ctx, w.h_tasks.reserve(sizeof(WdpTask) * (size_t)nt));
+        memcpy(w.h_tasks.p, w.tasks.data(), sizeof(WdpTask) * (size_t)nt);
+        MTR_CUDA(ctx, cudaMemcpyAsync(w.d_tasks.p, w.h_tasks.p, sizeof(WdpTask) * (size_t)nt, cudaMemcpyHostToDevice, ctx->main_stream));
+        MTR_CUDA(ctx, cudaMemcpyAsync(w.d_units.p, units, (size_t)units_len, cudaMemcpyHostToDevice, ctx->main_stream));
+    }
+    MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+    w.uploaded = true;
+    return MTR_OK;
+}
+
+int wdp_launch_impl(mtr_ctx *ctx)
+{
+    WdpState &w = ctx->wdp;
+    if (!w.uploaded) { mtr_set_error(ctx, "wdp_launch: nothing uploaded"); return MTR_EINVAL; }
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nt = (int)w.tasks.size();
+    ctx->stats.launches = 0;
+    ctx->stats.wdp_cells = w.cells;
+    ctx->stats.wdp_slot_cells = w.slot_cells;
+    ctx->stats.wdp_dir_bytes = w.dir_total;
+    cudaStream_t ms = ctx->main_stream;
+    MTR_CUDA(ctx, cudaMemsetAsync(w.d_counters.p, 0, sizeof(int) * WDP_NCLASS, ms));
+    MTR_CUDA(ctx, cudaMemsetAsync(w.d_results.p, 0, sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1), ms));
+    if (w.aux_bytes > 0) MTR_CUDA(ctx, cudaMemsetAsync(w.d_aux.p, 0, (size_t)w.aux_bytes, ms));
+    MTR_CUDA(ctx, cudaEventRecord(ctx->ev[0], ms));
+    for (int k = 0; k < WDP_NCLASS; k++) {
+        const int n = w.class_begin[k + 1] - w.class_begin[k];
+        if (n == 0) continue;
+        cudaStream_t s = ctx->stream[k];
+        MTR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev[0], 0));
+        const WdpTask *dt = (const WdpTask *)w.d_tasks.p + w.class_begin[k];
+        switch (k) {
+        case 0: launch_fill<4, 4>(ctx, k, dt, n, s); break;
+        case 1: launch_fill<4, 8>(ctx, k, dt, n, s); break;
+        case 2: launch_fill<8, 8>(ctx, k, dt, n, s); break;
+        case 3: launch_fill<8, 16>(ctx, k, dt, n, s); break;
+        case 4: launch_fill<16, 16>(ctx, k, dt, n, s); break;
+        case 5: launch_fill<32, 16>(ctx, k, dt, n, s); break;
+        default: mtr_set_error(ctx, "wdp_launch: class %d has no kernel", k); return MTR_EINVAL;
+        }
+        MTR_CUDA(ctx, cudaGetLastError());
+        ctx->stats.launches++;
+        MTR_CUDA(ctx, cudaEventRecord(ctx->class_done[k], s));
+        MTR_CUDA(ctx, cudaStreamWaitEvent(ms, ctx->class_done[k], 0));
+    }
+    MTR_CUDA(ctx, cudaEventRecord(ctx->ev[1], ms));
+    if (nt > 0) {
+        wdp_traceback<<<(nt + 127) / 128, 128, 0, ms>>>((const WdpTask *)w.d_tasks.p, nt, (const uint32_t *)ctx->d_packed.p,
+                                                        (const uint8_t *)w.d_units.p, (const uint8_t *)w.d_dirs.p,
+                                                        (mtr_wdp_result *)w.d_results.p, w.d_aux.p);
+        MTR_CUDA(ctx, cudaGetLastError());
+        ctx->stats.launches++;
+    }
+    MTR_CUDA(ctx, cudaEventRecord(ctx->ev[2], ms));
+    MTR_CUDA(ctx, cudaStreamSynchronize(ms));
+    float f0 = 0, f1 = 0;
+    MTR_CUDA(ctx, cudaEventElapsedTime(&f0, ctx->ev[0], ctx->ev[1]));
+    MTR_CUDA(ctx, cudaEventElapsedTime(&f1, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.wdp_fill_ms = f0;
+    ctx->stats.wdp_tb_ms = f1;
+    return MTR_OK;
+}
+
+int wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes)
+{
+    WdpState &w = ctx->wdp;
+    if (!w.uploaded) { mtr_set_error(ctx, "wdp_download: nothing uploaded"); return MTR_EINVAL; }
+    if (aux_bytes > w.aux_bytes) { mtr_set_error(ctx, "wdp_download: aux_bytes larger than uploaded"); return MTR_EINVAL; }
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (w.n_results > 0) {
+        MTR_CUDA(ctx, w.h_results.reserve(sizeof(mtr_wdp_result) * (size_t)w.n_results));
+        MTR_CUDA(ctx, cudaMemcpyAsync(w.h_results.p, w.d_results.p, sizeof(mtr_wdp_result) * (size_t)w.n_results,
+                                      cudaMemcpyDeviceToHost, ctx->main_stream));
+    }
+    if (aux && aux_bytes > 0)
+        MTR_CUDA(ctx, cudaMemcpyAsync(aux, w.d_aux.p, (size_t)aux_bytes, cudaMemcpyDeviceToHost, ctx->main_stream));
+    MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+    if (w.n_results > 0) memcpy(results, w.h_results.p, sizeof(mtr_wdp_result) * (size_t)w.n_results);
+    return MTR_OK;
+}

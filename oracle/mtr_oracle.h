@@ -108,6 +108,8 @@ void mtro_get_stats(const mtro_ctx *c, mtro_stats *s);
 typedef void (*mtro_dp_hook)(void *user, int kind, const int *x, int rows, const int *u, int ulen,
                              int gain, int mis_pen, int indel_pen, const mtro_dp_result *res);
 void mtro_set_dp_hook(mtro_ctx *c, mtro_dp_hook hook, void *user);
+/* Base of the persistent read buffer (orgInputString); a hook's x pointer minus this is the job's `first`. */
+const int *mtro_org(const mtro_ctx *c);
 
 /* ---- chaining (C++ side, mtr_oracle_chain.cpp; chaining.cpp:43-363) ---- */
 typedef struct mtro_chain mtro_chain;

@@ -1,0 +1,120 @@
+"""K3 parity: CUDA wrap-around DP (through the C ABI) vs the CPU oracle, bit-exact on every field."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import wdp_cases
+from mtr_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    o = oracle_lib.Oracle()
+    yield o
+    o.close()
+
+
+def _run(ctx, reads, tails, jobs, mode=capi.TB_COUNTS, pair=False):
+    packed, woff, lens = capi.pack_reads(reads, tails)
+    ctx.upload_reads(packed, woff, lens)
+    arr, units, aux_bytes = wdp_cases.build_job_array(jobs, mode=mode, pair=pair)
+    res, aux = ctx.wdp_run(arr, units, aux_bytes)
+    return arr, res, aux
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_jobs_counts(gpu_ctx, oracle, seed):
+    rng = np.random.default_rng(seed)
+    reads, tails, jobs = wdp_cases.random_jobs(rng, n_jobs=400)
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res)
+    assert not bad, bad[:10]
+
+
+def test_random_jobs_paired(gpu_ctx, oracle):
+    rng = np.random.default_rng(11)
+    reads, tails, jobs = wdp_cases.random_jobs(rng, n_jobs=300)
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs, pair=True)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res, pair=True)
+    assert not bad, bad[:10]
+
+
+def test_consensus_and_path(gpu_ctx, oracle):
+    rng = np.random.default_rng(21)
+    reads, tails, jobs = wdp_cases.random_jobs(rng, n_jobs=150, max_ulen=300)
+    for mode in (capi.TB_CONSENSUS, capi.TB_PATH):
+        arr, res, aux = _run(gpu_ctx, reads, tails, jobs, mode=mode)
+        bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res, aux=aux, arr=arr, mode=mode)
+        assert not bad, (mode, bad[:10])
+
+
+def test_adversarial(gpu_ctx, oracle):
+    """Ties everywhere: homopolymers, unit AC, U = 1, 2, 499, the j == 1 deletion quirk, gain 5."""
+    rng = np.random.default_rng(5)
+    reads = [np.zeros(600, np.int8), np.tile(np.array([0, 1], np.int8), 400), np.tile(np.array([0, 0, 1], np.int8), 300),
+             rng.integers(0, 4, 2000).astype(np.int8), np.tile(rng.integers(0, 4, 499).astype(np.int8), 4)]
+    tails = [(0, 0), (1, 0), (3, 3), (2, 1), (0, 3)]
+    units = [np.array([0], np.uint8), np.array([0, 1], np.uint8), np.array([1, 0], np.uint8), np.array([0, 0], np.uint8),
+             np.array([0, 0, 1], np.uint8), np.array([0, 1, 0, 1], np.uint8), reads[4][:499].astype(np.uint8),
+             rng.integers(0, 4, 33).astype(np.uint8), rng.integers(0, 4, 17).astype(np.uint8), reads[3][100:165].astype(np.uint8)]
+    jobs = []
+    for r, rd in enumerate(reads):
+        for u in units:
+            for (g, mm, ind) in wdp_cases.PARAM_SETS:
+                for first, rows in ((-1, len(rd)), (0, len(rd)), (7, min(300, len(rd) - 7)), (len(rd) - 4, 5)):
+                    if len(u) > rows:
+                        continue
+                    jobs.append(dict(read=r, first=first, rows=rows, unit=u, gain=g, mis=mm, indel=ind))
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res)
+    assert not bad, bad[:10]
+
+
+def test_harvested_pipeline_jobs(gpu_ctx, oracle):
+    """Every DP the reference pipeline executes on a few synthetic reads, replayed on the GPU."""
+    reads = []
+    for ulen, copies, seed in ((5, 30, 1), (23, 12, 2), (100, 10, 3), (160, 8, 4)):
+        rd, _ = synth.rand_seq_reads(ulen, copies, 0.016, 0.09, 0.038, 150, 200, 1, seed=seed)
+        reads += rd
+    o2 = oracle_lib.Oracle()
+    hj, tails = o2.harvest_dp_jobs(reads)
+    o2.close()
+    assert len(hj) > 100
+    for kind, mode in ((0, capi.TB_COUNTS), (1, capi.TB_CONSENSUS)):
+        jobs = [j for j in hj if j["kind"] == kind]
+        arr, res, aux = _run(gpu_ctx, reads, tails, jobs, mode=mode)
+        for i, j in enumerate(jobs):           # the harvested results are the pipeline's own
+            for f in ("best", "max_i", "max_j", "end_i", "n_match", "n_mismatch", "n_ins", "n_del", "n_scanned"):
+                assert int(res[i, 0][f]) == j["result"][f], (kind, i, f, res[i, 0], j["result"])
+        bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res, aux=aux, arr=arr, mode=mode)
+        assert not bad, bad[:10]
+
+
+def test_long_job_int32_scores(gpu_ctx, oracle):
+    """Scores beyond the int16 range: 12 000 rows at gain 5, and a 40 000-row job."""
+    rd, _ = synth.rand_seq_reads(50, 800, 0.01, 0.02, 0.02, 100, 100, 1, seed=9)
+    reads, tails = [rd[0]], [(1, 2)]
+    unit = np.array(rd[0][100:150], dtype=np.uint8)
+    L = len(rd[0])
+    jobs = [dict(read=0, first=50, rows=12000, unit=unit, gain=5, mis=1, indel=1),
+            dict(read=0, first=-1, rows=L + 1, unit=unit, gain=1, mis=1, indel=3),
+            dict(read=0, first=10, rows=L - 20, unit=unit, gain=1, mis=3, indel=1)]
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res)
+    assert not bad, bad
+    assert res[0, 0]["best"] > 32767
+
+
+def test_rejects_malformed_jobs(gpu_ctx):
+    reads = [np.zeros(100, np.int8)]
+    packed, woff, lens = capi.pack_reads(reads)
+    gpu_ctx.upload_reads(packed, woff, lens)
+    for bad in (dict(ulen=0), dict(ulen=500), dict(rows=200), dict(read=3), dict(first=-2)):
+        j = dict(read=0, first=0, rows=50, unit=np.zeros(4, np.uint8), gain=1, mis=1, indel=3)
+        arr, units, _ = wdp_cases.build_job_array([j])
+        for k, v in bad.items():
+            arr[0][k] = v
+        with pytest.raises(capi.MtrError):
+            gpu_ctx.wdp_run(arr, np.zeros(600, np.uint8))
