@@ -1,9 +1,405 @@
-// di.cu -- K1/K2: directional index (placeholder until the kernels land; fails loudly, never falls back).
+// di.cu -- K1/K2: directional index of every read of the resident batch, for sm_100a.
+//
+// Replaces fill_directional_index_with_end (/root/reference/fill_directional_index.c:549-602):
+//   K1  di_codes   : 2-bit packed read + MT19937 flanks (+ stale tail) -> per-position k-mer codes for
+//                    k = 1, 3, 5  (init_inputString_surrounded_by_random_seq, :137-169)
+//   K2  di_slide   : per (read, k, w, chunk): slides two adjacent w-wide k-mer histograms and emits one
+//                    distance stream  D(q) = |H(q) - H(q+w)|_1  (Manhattan, :171-295) or the Pearson
+//                    correlation P(q) of the two histograms (:298-450).  The reference's three windows are
+//                    two consecutive samples of this stream (v1(p) = v0(p+w)):
+//                        Manhattan  tmp[p] = (D(p-w) - D(p)) / (2w)        Pearson  tmp[p] = P(p) - P(p-w)
+//                    Every operand is an exact integer, so the fp64 results are bit-identical to the CPU's.
+//   K2b di_merge   : per read, the sequential local-max / local-min merge of the passes (:467-503), the
+//                    unshift (:587-597) and remove_redundant_ranges (:505-546).
+#include <algorithm>
+#include <cstring>
 #include "mtr_internal.h"
-void di_state_free(mtr_ctx *) {}
-extern "C" int mtr_di_run(mtr_ctx *ctx, int, const uint16_t *, const int64_t *, const int64_t *, double *, int32_t *, int32_t *)
+
+#define MT_TABLE_LEN 1300000
+
+struct DiRead {
+    long long word_off;     // first word of the packed read
+    long long code_off;     // offset of this read in the S1/S3/S5 arrays
+    long long stale_off;    // offset into the stale array (uint16)
+    long long pos_off;      // offset into the di/end/w output arrays
+    long long work_off;     // offset into the merge work arrays (N entries)
+    int len, r, N, M;       // read length, flank length, N = L + 2r, M = coded positions kept
+    int nstale;
+    int pass_begin;         // first entry of this read in the pass table
+    int npass;
+};
+
+struct DiPass {
+    long long stream_off;   // offset into the distance stream (int32 or double)
+    int k, w, steps, nq;    // steps = L + r - w - k + 1, nq = steps + w samples of the stream
+};
+
+struct DiTask {             // one chunk of one pass
+    int read, pass, q0, nq;
+};
+
+struct DiState {
+    DevBuf d_mt, d_reads, d_passes, d_tasks[3], d_s1, d_s3, d_s5, d_stream, d_stale;
+    DevBuf d_di, d_end, d_w, d_work_di, d_work_end, d_work_w;
+    bool mt_ready = false;
+};
+
+void di_state_free(mtr_ctx *ctx)
+{
+    if (!ctx->di) return;
+    DiState *d = ctx->di;
+    d->d_mt.release(); d->d_reads.release(); d->d_passes.release();
+    for (int i = 0; i < 3; i++) d->d_tasks[i].release();
+    d->d_s1.release(); d->d_s3.release(); d->d_s5.release(); d->d_stream.release(); d->d_stale.release();
+    d->d_di.release(); d->d_end.release(); d->d_w.release();
+    d->d_work_di.release(); d->d_work_end.release(); d->d_work_w.release();
+    delete d;
+    ctx->di = nullptr;
+}
+
+// MT19937 with seed 0, reduced mod 4: the flank bases (MT.h:65-78,110-145; fill_directional_index.c:129-141).
+static void mt_base_table(std::vector<uint8_t> &out)
+{
+    out.resize(MT_TABLE_LEN);
+    uint32_t st[624];
+    st[0] = 0;
+    for (int i = 1; i < 624; i++) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    int pos = 624;
+    for (size_t t = 0; t < out.size(); t++) {
+        if (pos == 624) {
+            for (int i = 0; i < 624; i++) {
+                const uint32_t y = (st[i] & 0x80000000u) | (st[(i + 1) % 624] & 0x7fffffffu);
+                st[i] = st[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            pos = 0;
+        }
+        uint32_t y = st[pos++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        out[t] = (uint8_t)(y & 3u);
+    }
+}
+
+// ---------------------------------------------------------------- K1: k-mer codes
+__device__ __forceinline__ int padded_base(const DiRead &rd, const uint32_t *__restrict__ packed,
+                                           const uint8_t *__restrict__ mt, int i)
+{
+    // rand(r) | read | rand(r) | first-loop randoms, fill_directional_index.c:143-156
+    const int L = rd.len, r = rd.r;
+    const int c = min(L + 4 * r, 1000000);
+    if (i < r) return mt[c + i];
+    if (i < r + L) {
+        const int b = i - r;
+        return (int)((packed[rd.word_off + (b >> 4)] >> ((b & 15) * 2)) & 3u);
+    }
+    if (i < rd.N) return mt[c + r + (i - r - L)];
+    return mt[i];
+}
+
+__global__ void __launch_bounds__(256)
+di_codes(const DiRead *__restrict__ reads, int n_reads, const uint32_t *__restrict__ packed,
+         const uint8_t *__restrict__ mt, const uint16_t *__restrict__ stale,
+         uint8_t *__restrict__ s1, uint8_t *__restrict__ s3, uint16_t *__restrict__ s5)
+{
+    const int rdi = blockIdx.x;
+    const DiRead rd = reads[rdi];
+    const int written = min(rd.len + 4 * rd.r, 1000000);       // area re-initialised for this read (:143)
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < rd.M; i += gridDim.y * blockDim.x) {
+        int c1, c3, c5;
+        if (i >= written) {
+            // beyond the area this read re-initialises: what an earlier, longer read left there (H3)
+            const int t = i - written;
+            c5 = t < rd.nstale ? stale[rd.stale_off + t] : 0;
+            c1 = c5 & 3; c3 = c5 & 63;                         // never read by the k = 1, 3 passes
+        } else {
+            int b[5];
+#pragma unroll
+            for (int t = 0; t < 5; t++) b[t] = (i + t < written) ? padded_base(rd, packed, mt, i + t) : 0;
+            c1 = b[0];
+            c3 = (i < rd.N - 2) ? (b[0] * 16 + b[1] * 4 + b[2]) : b[0];
+            c5 = (i < rd.N - 4) ? ((((b[0] * 4 + b[1]) * 4 + b[2]) * 4 + b[3]) * 4 + b[4]) : b[0];
+        }
+        s1[rd.code_off + i] = (uint8_t)c1;
+        s3[rd.code_off + i] = (uint8_t)c3;
+        s5[rd.code_off + i] = (uint16_t)c5;
+    }
+}
+
+// ---------------------------------------------------------------- K2: sliding two-window distance stream
+// One thread per chunk; the two histograms live in shared memory, bin-major so that a warp touching the
+// same bin is conflict-free.
+template <int K, bool MANHATTAN, int T, typename CodeT>
+__global__ void __launch_bounds__(T)
+di_slide(const DiTask *__restrict__ tasks, int ntasks, const DiRead *__restrict__ reads,
+         const DiPass *__restrict__ passes, const CodeT *__restrict__ codes,
+         int *__restrict__ stream_i, double *__restrict__ stream_d)
+{
+    constexpr int BINS = K == 1 ? 4 : (K == 3 ? 64 : 1024);
+    extern __shared__ short sh[];
+    short *HA = sh + threadIdx.x;                   // HA[bin * T]
+    short *HB = sh + BINS * T + threadIdx.x;
+    const int tid = blockIdx.x * T + threadIdx.x;
+    if (tid >= ntasks) return;
+    const DiTask tk = tasks[tid];
+    const DiRead rd = reads[tk.read];
+    const DiPass ps = passes[rd.pass_begin + tk.pass];
+    const CodeT *S = codes + rd.code_off;
+    const int w = ps.w;
+    for (int b = 0; b < BINS; b++) { HA[b * T] = 0; HB[b * T] = 0; }
+    // exact integer sums
+    int D = 0;                                       // sum |HA - HB|
+    long long SA = 0, SB = 0, IP = 0;                // sum HA^2, sum HB^2, sum HA*HB
+    auto bumpA = [&](int bin, int delta) {
+        const int a = HA[bin * T], b = HB[bin * T];
+        if (MANHATTAN) D += abs(a + delta - b) - abs(a - b);
+        else { SA += 2 * a * delta + 1; IP += (long long)delta * b; }
+        HA[bin * T] = (short)(a + delta);
+    };
+    auto bumpB = [&](int bin, int delta) {
+        const int a = HA[bin * T], b = HB[bin * T];
+        if (MANHATTAN) D += abs(a - b - delta) - abs(a - b);
+        else { SB += 2 * b * delta + 1; IP += (long long)delta * a; }
+        HB[bin * T] = (short)(b + delta);
+    };
+    const int q0 = tk.q0;
+    for (int t = 0; t < w; t++) { bumpA(S[q0 + t], +1); bumpB(S[q0 + w + t], +1); }
+    const double n = (double)BINS, sw = (double)w;
+    for (int q = q0; q < q0 + tk.nq; q++) {
+        if (MANHATTAN) {
+            stream_i[ps.stream_off + q] = D;
+        } else {
+            // fill_directional_index.c:340-352 (all operands are exact integers below 2^53)
+            const double sda = sqrt((double)SA * n - sw * sw);
+            const double sdb = sqrt((double)SB * n - sw * sw);
+            double P = 0;
+            if (sda * sdb > 0) P = ((double)IP * n - sw * sw) / (sda * sdb);
+            stream_d[ps.stream_off + q] = P;
+        }
+        const int a = S[q], b = S[q + w], c = S[q + 2 * w];
+        bumpA(a, -1); bumpA(b, +1); bumpB(b, -1); bumpB(c, +1);
+    }
+}
+
+// ---------------------------------------------------------------- K2b: merge, unshift, prune (one thread per read)
+template <bool MANHATTAN>
+__device__ __forceinline__ double di_value(const DiPass &ps, const int *__restrict__ si,
+                                           const double *__restrict__ sd, int p)
+{
+    // directional_index_tmp[p]: -1 outside [w, w + steps)
+    const int i = p - ps.w;
+    if (i < 0 || i >= ps.steps) return -1.0;
+    if (MANHATTAN) {
+        const int d01 = si[ps.stream_off + i], d12 = si[ps.stream_off + i + ps.w];
+        return ((double)d01 - (double)d12) / (2 * (double)ps.w);          // :211
+    }
+    return sd[ps.stream_off + i + ps.w] - sd[ps.stream_off + i];          // P_12 - P_01, :355
+}
+
+template <bool MANHATTAN>
+__global__ void __launch_bounds__(64)
+di_merge(const DiRead *__restrict__ reads, int n_reads, const DiPass *__restrict__ passes,
+         const int *__restrict__ si, const double *__restrict__ sd,
+         double *__restrict__ wdi, int *__restrict__ wend, int *__restrict__ ww,
+         double *__restrict__ odi, int *__restrict__ oend, int *__restrict__ ow)
+{
+    const int rdi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rdi >= n_reads) return;
+    const DiRead rd = reads[rdi];
+    const int N = rd.N, L = rd.len, r = rd.r;
+    double *DI = wdi + rd.work_off;
+    int *EN = wend + rd.work_off, *WW = ww + rd.work_off;
+    for (int i = 0; i < N; i++) { DI[i] = -1; EN[i] = -1; WW[i] = -1; }
+    for (int pi = 0; pi < rd.npass; pi++) {
+        const DiPass ps = passes[rd.pass_begin + pi];
+        const int w = ps.w;
+        // put_local_maximum_into_directional_index, :467-503
+        double local_max = -1;
+        int local_max_i = -1;
+        for (int i = 0; i < N; i++) {
+            const double t = di_value<MANHATTAN>(ps, si, sd, i);
+            if (local_max < t) { local_max = t; local_max_i = i; }
+            if (local_max_i >= 0 && local_max_i + w < i && DI[local_max_i] < local_max && 0 < local_max) {
+                double local_min = 1;
+                int local_min_j = local_max_i;
+                for (int j = local_max_i; j < N; j++) {
+                    const double tj = di_value<MANHATTAN>(ps, si, sd, j);
+                    if (local_min > tj) { local_min = tj; local_min_j = j; }
+                    if (local_min_j + w < j) {
+                        DI[local_max_i] = local_max;
+                        WW[local_max_i] = w;
+                        EN[local_max_i] = local_min_j + w;
+                        i = local_min_j + w;
+                        break;
+                    }
+                }
+                local_max = -1;
+            }
+        }
+    }
+    // unshift (:587-597) into the output arrays (only [0, L) is ever read again)
+    double *O = odi + rd.pos_off;
+    int *OE = oend + rd.pos_off, *OW = ow + rd.pos_off;
+    for (int i = 0; i < L; i++) { O[i] = DI[i + r]; OE[i] = EN[i + r] - r; OW[i] = WW[i + r]; }
+    // remove_redundant_ranges (:505-546); entries at or beyond L are -1 in the reference
+    for (int i = 0; i < L; i++) {
+        const int ie = OE[i];
+        const double idi = O[i];
+        if (!(0 < idi)) continue;
+        for (int j = i + 1; j <= ie && j < L; j++) {
+            const int je = OE[j];
+            const double jdi = O[j];
+            if (!(0 < jdi)) continue;
+            const double jac = (double)(min(ie, je) - j) / (double)(max(ie, je) - i);
+            if (0.98 < jac) {
+                if (idi < jdi) { O[i] = -1; OE[i] = -1; break; }
+                O[j] = -1; OE[j] = -1;
+            } else if (ie >= je && idi > jdi) {
+                O[j] = -1; OE[j] = -1;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int wmax_for(int k, int L)       // largest w of the pass list, fill_directional_index.c:559-574
+{
+    const int cap = k == 1 ? 20 : (k == 3 ? 80 : 10240);
+    int best = 0;
+    for (int w = 5; w <= cap && w < L / 2; w *= 2) best = w;
+    return best;
+}
+
+extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
+                          const int64_t *pos_off, double *di, int32_t *end, int32_t *w_out)
 {
     if (!ctx) return MTR_EINVAL;
-    mtr_set_error(ctx, "mtr_di_run: not built yet");
-    return MTR_EINVAL;
+    if (ctx->n_reads == 0) return MTR_OK;
+    if (!pos_off || !di || !end || !w_out) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->di) ctx->di = new DiState();
+    DiState &d = *ctx->di;
+    cudaStream_t s = ctx->main_stream;
+    if (!d.mt_ready) {
+        std::vector<uint8_t> mt;
+        mt_base_table(mt);
+        MTR_CUDA(ctx, d.d_mt.reserve(mt.size()));
+        MTR_CUDA(ctx, cudaMemcpy(d.d_mt.p, mt.data(), mt.size(), cudaMemcpyHostToDevice));
+        d.mt_ready = true;
+    }
+    const int n = ctx->n_reads;
+    std::vector<DiRead> reads(n);
+    std::vector<DiPass> passes;
+    std::vector<DiTask> tasks[3];
+    long long code_total = 0, work_total = 0, stream_total = 0, pp = 0;
+    int max_M = 0;
+    for (int r = 0; r < n; r++) {
+        DiRead &rd = reads[r];
+        const int L = ctx->len[r];
+        rd.word_off = ctx->word_off[r];
+        rd.len = L;
+        rd.r = L < 1000 ? 100 : L / 10;                       // handle_one_read.c:194-202
+        rd.N = L + 2 * rd.r;
+        rd.M = L + rd.r + 2 * std::max(wmax_for(5, L), 80) + 8;
+        rd.M = std::max(rd.M, rd.N);
+        rd.code_off = code_total; code_total += (rd.M + 15) & ~15;
+        rd.work_off = work_total; work_total += rd.N;
+        rd.pos_off = pos_off[r];
+        rd.stale_off = stale_off ? stale_off[r] : 0;
+        rd.nstale = (stale && stale_off) ? (int)(stale_off[r + 1] - stale_off[r]) : 0;
+        rd.pass_begin = (int)passes.size();
+        max_M = std::max(max_M, rd.M);
+        for (int k = 1; k <= 5; k += 2) {
+            const int cap = k == 1 ? 20 : (k == 3 ? 80 : 10240);
+            for (int w = 5; w <= cap && w < L / 2; w *= 2) {
+                DiPass ps;
+                ps.k = k; ps.w = w;
+                ps.steps = L + rd.r - w - k + 1;
+                ps.nq = ps.steps + w;
+                ps.stream_off = stream_total; stream_total += ps.nq;
+                pp += ps.steps;
+                const int chunk = std::max(1024, 2 * w);
+                const int pidx = (int)passes.size() - rd.pass_begin;
+                for (int q0 = 0; q0 < ps.nq; q0 += chunk)
+                    tasks[k / 2].push_back(DiTask{r, pidx, q0, std::min(chunk, ps.nq - q0)});
+                passes.push_back(ps);
+            }
+        }
+        rd.npass = (int)passes.size() - rd.pass_begin;
+    }
+    const long long total_pos = pos_off[n];
+    const long long nstale_total = (stale && stale_off) ? stale_off[n] : 0;
+    MTR_CUDA(ctx, d.d_reads.reserve(sizeof(DiRead) * (size_t)n));
+    MTR_CUDA(ctx, d.d_passes.reserve(sizeof(DiPass) * std::max<size_t>(passes.size(), 1)));
+    MTR_CUDA(ctx, d.d_s1.reserve((size_t)code_total + 64));
+    MTR_CUDA(ctx, d.d_s3.reserve((size_t)code_total + 64));
+    MTR_CUDA(ctx, d.d_s5.reserve((size_t)code_total * 2 + 64));
+    MTR_CUDA(ctx, d.d_stream.reserve((size_t)std::max<long long>(stream_total, 1) * (manhattan ? 4 : 8)));
+    MTR_CUDA(ctx, d.d_stale.reserve((size_t)std::max<long long>(nstale_total, 1) * 2));
+    MTR_CUDA(ctx, d.d_di.reserve((size_t)std::max<long long>(total_pos, 1) * 8));
+    MTR_CUDA(ctx, d.d_end.reserve((size_t)std::max<long long>(total_pos, 1) * 4));
+    MTR_CUDA(ctx, d.d_w.reserve((size_t)std::max<long long>(total_pos, 1) * 4));
+    MTR_CUDA(ctx, d.d_work_di.reserve((size_t)work_total * 8));
+    MTR_CUDA(ctx, d.d_work_end.reserve((size_t)work_total * 4));
+    MTR_CUDA(ctx, d.d_work_w.reserve((size_t)work_total * 4));
+    MTR_CUDA(ctx, cudaMemcpyAsync(d.d_reads.p, reads.data(), sizeof(DiRead) * (size_t)n, cudaMemcpyHostToDevice, s));
+    if (!passes.empty())
+        MTR_CUDA(ctx, cudaMemcpyAsync(d.d_passes.p, passes.data(), sizeof(DiPass) * passes.size(), cudaMemcpyHostToDevice, s));
+    if (nstale_total > 0)
+        MTR_CUDA(ctx, cudaMemcpyAsync(d.d_stale.p, stale, (size_t)nstale_total * 2, cudaMemcpyHostToDevice, s));
+    for (int t = 0; t < 3; t++) {
+        MTR_CUDA(ctx, d.d_tasks[t].reserve(sizeof(DiTask) * std::max<size_t>(tasks[t].size(), 1)));
+        if (!tasks[t].empty())
+            MTR_CUDA(ctx, cudaMemcpyAsync(d.d_tasks[t].p, tasks[t].data(), sizeof(DiTask) * tasks[t].size(), cudaMemcpyHostToDevice, s));
+    }
+    MTR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+    int launches = 0;
+    {
+        dim3 grid((unsigned)n, (unsigned)std::min((max_M + 255) / 256, 64));
+        di_codes<<<grid, 256, 0, s>>>((const DiRead *)d.d_reads.p, n, (const uint32_t *)ctx->d_packed.p, (const uint8_t *)d.d_mt.p,
+                                      (const uint16_t *)d.d_stale.p, (uint8_t *)d.d_s1.p, (uint8_t *)d.d_s3.p, (uint16_t *)d.d_s5.p);
+        MTR_CUDA(ctx, cudaGetLastError());
+        launches++;
+    }
+    const DiRead *dr = (const DiRead *)d.d_reads.p;
+    const DiPass *dp = (const DiPass *)d.d_passes.p;
+    int *si = (int *)d.d_stream.p;
+    double *sd = (double *)d.d_stream.p;
+#define SLIDE(K, T, CODET, CODES, IDX)                                                                         \
+    if (!tasks[IDX].empty()) {                                                                                 \
+        const int nt = (int)tasks[IDX].size();                                                                 \
+        const size_t smem = (size_t)2 * (K == 1 ? 4 : (K == 3 ? 64 : 1024)) * T * sizeof(short);               \
+        if (manhattan) {                                                                                       \
+            MTR_CUDA(ctx, cudaFuncSetAttribute(di_slide<K, true, T, CODET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            di_slide<K, true, T, CODET><<<(nt + T - 1) / T, T, smem, s>>>((const DiTask *)d.d_tasks[IDX].p, nt, dr, dp, (const CODET *)CODES, si, sd); \
+        } else {                                                                                               \
+            MTR_CUDA(ctx, cudaFuncSetAttribute(di_slide<K, false, T, CODET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            di_slide<K, false, T, CODET><<<(nt + T - 1) / T, T, smem, s>>>((const DiTask *)d.d_tasks[IDX].p, nt, dr, dp, (const CODET *)CODES, si, sd); \
+        }                                                                                                      \
+        MTR_CUDA(ctx, cudaGetLastError());                                                                     \
+        launches++;                                                                                            \
+    }
+    SLIDE(1, 128, uint8_t, d.d_s1.p, 0)
+    SLIDE(3, 128, uint8_t, d.d_s3.p, 1)
+    SLIDE(5, 48, uint16_t, d.d_s5.p, 2)
+#undef SLIDE
+    if (manhattan)
+        di_merge<true><<<(n + 63) / 64, 64, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
+                                                   (double *)d.d_di.p, (int *)d.d_end.p, (int *)d.d_w.p);
+    else
+        di_merge<false><<<(n + 63) / 64, 64, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
+                                                    (double *)d.d_di.p, (int *)d.d_end.p, (int *)d.d_w.p);
+    MTR_CUDA(ctx, cudaGetLastError());
+    launches++;
+    MTR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(di, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(end, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(w_out, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaStreamSynchronize(s));
+    float ms = 0;
+    MTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+    ctx->stats.di_ms = ms;
+    ctx->stats.di_position_passes = pp;
+    ctx->stats.di_bytes_in = ctx->n_words * 4 + nstale_total * 2;
+    ctx->stats.di_bytes_out = total_pos * 16;
+    ctx->stats.launches = launches;
+    return MTR_OK;
 }
