@@ -73,7 +73,7 @@ def load_library() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("libmtr_b200.so is missing (%s): build it with __graft_entry__.build(); "
                            "there is no CPU fallback" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(LIB_PATH)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     lib.mtr_cuda_init.argtypes = [C.c_int, C.POINTER(vp)]
     lib.mtr_cuda_init.restype = C.c_int

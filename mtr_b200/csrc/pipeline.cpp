@@ -1,0 +1,1090 @@
+// pipeline.cpp -- host side of the drop-in: mTR's entry points (handle_one_file / handle_one_read) on top of
+// the CUDA kernels.  Replaces /root/reference/handle_one_file.c, handle_one_read.c, the control logic of
+// consensus.c (unit finder, polish, revise) and chaining.cpp; the arithmetic-heavy stages run on the GPU:
+//   fill_directional_index_with_end  -> mtr_di_run   (K1/K2, di.cu)
+//   wrap_around_DP / _sub, the DP of revise_representative_unit_sub, pretty_print_alignment -> mtr_wdp_run (K3, wdp.cu)
+//
+// The reference evaluates one candidate range of one read at a time and calls the DP synchronously.  Here every
+// read of a batch is a small state machine; one "round" advances all reads in parallel on the host cores until
+// each of them needs DP results, the DP jobs of all reads go to the GPU as one batch, and the next round consumes
+// them.  Inside one candidate the 9-11 k values, both walk directions and both penalty sets are independent, so
+// they share a round; the revise chain (consensus DP -> DP, twice) and the candidate loop itself (an accepted
+// repeat prunes later candidates, handle_one_read.c:178-188,243) stay sequential per read, exactly as in the
+// reference.  There is no CPU implementation of the DP or of the directional index in this file: without a
+// usable GPU handle_one_file fails.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "mtr_internal.h"
+
+// ================================================================ the reference's globals (mTR.h:61-96,142-143)
+extern "C" {
+int   Manhattan_Distance = 1;
+float min_match_ratio = 0.6f;
+int  *orgInputString = nullptr;
+float time_all, time_memory, time_range, time_period, time_initialize_input_string, time_wrap_around_DP,
+      time_count_table, time_chaining;
+int   query_counter;
+}
+
+namespace {
+
+constexpr int kMaxLen = 1000000;      // MAX_INPUT_LENGTH, mTR.h:31
+constexpr int kMaxPeriod = 500;       // MAX_PERIOD, mTR.h:34
+constexpr int kMaxTies = 1024;        // MAX_tiebreaks, mTR.h:46
+constexpr long long kWrapCap = 200000000LL;   // WrapDPsize, mTR.h:51
+
+struct Pow4 { int v[16]; Pow4() { v[0] = 1; for (int i = 1; i < 16; i++) v[i] = v[i - 1] * 4; } };
+const Pow4 P4;
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- the per-repeat feature record (mTR.h:99-119)
+struct Rec {
+    int inputLen = -1, rep_start = -1, rep_end = -1, repeat_len = -1, period = -1, units = -1;
+    int nm = -1, nx = -1, ni = -1, nd = -1, kmer = -1, gain = -1, mis = -1, indel = -1;
+    std::vector<uint8_t> unit;        // bases 0..3
+    std::vector<int> score;           // string_score of the walk that produced the unit
+    void clear() { *this = Rec(); }   // clear_rr, fill_directional_index.c:40-60
+    float ratio() const { return (float)nm / (nm + nx + ni + nd); }       // e.g. wrap_around_DP.c:398
+};
+
+// apply one DP result the way wrap_around_DP_sub fills its record (wrap_around_DP.c:337-350)
+void apply_dp(Rec &r, int qs, const mtr_wdp_result &d, int g, int m, int in)
+{
+    r.rep_start = qs + d.end_i + 1;
+    r.rep_end = qs + d.max_i;
+    r.repeat_len = d.max_i - d.end_i;
+    r.units = d.n_scanned / r.period;
+    r.nm = d.n_match; r.nx = d.n_mismatch; r.ni = d.n_ins; r.nd = d.n_del;
+    r.gain = g; r.mis = m; r.indel = in;
+}
+
+// ---------------------------------------------------------------- exact k-mer counts of one window
+// (init_inputString + generate_freqNode_*, consensus.c:37-253; the hash layout is unobservable)
+struct Counter {
+    std::vector<int> codes;           // codes[i - qs] for i in [qs, qe]
+    std::vector<int> direct;          // k <= 6
+    std::vector<uint32_t> hkey, hstamp;
+    std::vector<int> hval;
+    uint32_t epoch = 0;
+    uint32_t hmask = 0;
+    int k = 0;
+
+    void build(const uint8_t *org, int L, int kk, int qs, int qe)
+    {
+        k = kk;
+        const int n = qe - qs + 1;
+        codes.resize(n);
+        const int coded_end = std::min(qe, L - k + 1);        // codes for i < coded_end (:48-51)
+        int carry = 0;
+        for (int i = qs; i < qs + k - 1; i++) carry = 4 * carry + (i < L ? org[i] : 0);
+        const int mask = P4.v[k - 1];
+        for (int i = qs; i <= qe; i++) {
+            if (i < coded_end) {
+                const int c = 4 * carry + org[i + k - 1];
+                codes[i - qs] = c;
+                carry = c % mask;
+            } else {
+                // raw base left by the copy loop (:42-44); index L itself is stale in the reference (H4b): 0 here
+                codes[i - qs] = i < L ? org[i] : 0;
+            }
+        }
+        if (k <= 6) {
+            direct.assign(P4.v[k], 0);
+            for (int c : codes) direct[c]++;
+        } else {
+            uint32_t cap = 1024;
+            while (cap < 2u * (uint32_t)(n + 1)) cap <<= 1;
+            if (hkey.size() < cap) { hkey.assign(cap, 0); hval.assign(cap, 0); hstamp.assign(cap, 0); epoch = 0; }
+            hmask = cap - 1;
+            if (++epoch == 0) { std::fill(hstamp.begin(), hstamp.end(), 0u); epoch = 1; }
+            for (int c : codes) (*slot(c, true))++;
+        }
+    }
+    int *slot(int node, bool create)
+    {
+        if (k <= 6) return (node >= 0 && node < P4.v[k]) ? &direct[node] : nullptr;
+        uint32_t h = ((uint32_t)node * 2654435761u) & hmask;
+        for (;;) {
+            if (hstamp[h] != epoch) {
+                if (!create) return nullptr;
+                hstamp[h] = epoch; hkey[h] = (uint32_t)node; hval[h] = 0;
+                return &hval[h];
+            }
+            if (hkey[h] == (uint32_t)node) return &hval[h];
+            h = (h + 1) & hmask;
+        }
+    }
+    int get(int node) { int *p = slot(node, false); return p ? *p : 0; }      // freq_node, consensus.c:231-253
+    int max_freq() { int m = -1; for (int c : codes) m = std::max(m, get(c)); return m; }
+    // generate_freqNode_return_list_maxNodes (:132-229): listing a node decrements its count
+    int list_max_nodes(int *list, int cap, int maxf)
+    {
+        int n = 0;
+        for (int c : codes) {
+            int *p = slot(c, false);
+            if (p && *p == maxf) { list[n++] = c; (*p)--; if (cap <= n) break; }
+        }
+        return n;
+    }
+};
+
+// ---------------------------------------------------------------- greedy de Bruijn walk (consensus.c:269-505)
+bool walk(Counter &cnt, int qs, int qe, int start, int k, bool backward, Rec &out)
+{
+    int ustr[kMaxPeriod], uscore[kMaxPeriod];
+    int ties[kMaxTies], fresh[kMaxTies];
+    int node = start, period = 0;
+    const int limit = (qe - qs) / 5;                       // MIN_NUM_FREQ_UNIT
+    for (int l = 0; l < kMaxPeriod && l < limit; l++) {
+        if (!backward) { ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node); }
+        int m, pick = 0, nties = 1;
+        ties[0] = 0;
+        const int depth = l < 10 ? 1 : k;
+        for (m = 1; m <= depth; m++) {
+            int best = -1, nf = 0;
+            pick = 0;
+            for (int t = 0; t < nties; t++)
+                for (int b = 0; b < 4; b++) {
+                    const int digits = backward ? b * P4.v[m - 1] + ties[t] : 4 * ties[t] + b;
+                    const int cand = backward ? digits * P4.v[k - m] + node / P4.v[m]
+                                              : P4.v[m] * (node % P4.v[k - m]) + digits;
+                    const int c = cnt.get(cand);
+                    if (best < c) { best = c; pick = digits; nf = 0; fresh[nf++] = digits; }
+                    else if (best == c && nf < kMaxTies) fresh[nf++] = digits;
+                }
+            if (backward ? nf <= 1 : nf == 1) break;
+            std::copy(fresh, fresh + nf, ties);
+            nties = nf;
+        }
+        if (!backward) {
+            node = 4 * (node % P4.v[k - 1]) + pick / P4.v[m - 1];       // unresolved ties append 'A' (:336)
+        } else {
+            node = (pick % 4) * P4.v[k - 1] + node / 4;
+            ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node);
+        }
+        if (node == start) { period = l + 1; if (kMaxPeriod <= period) period = 0; break; }
+    }
+    if (period == 0) return false;
+    out.period = period;
+    out.unit.resize(period); out.score.resize(period);
+    for (int i = 0; i < period; i++) {
+        const int s = backward ? period - 1 - i : i;
+        out.unit[i] = (uint8_t)ustr[s]; out.score[i] = uscore[s];
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- polish_repeat (consensus.c:584-704)
+int align_score(Counter &cnt, int start, int k, int node, int period, const uint8_t *unit)
+{
+    int sum = 0;
+    for (int j = start; 0 <= j && start - k < j; j--) {
+        node = unit[j % period] * P4.v[k - 1] + node / 4;
+        sum += cnt.get(node);
+    }
+    return sum;
+}
+
+bool suspicious(const Rec &r, int j)
+{
+    int c = 0;
+    for (int i = 0; i < r.kmer - 1 && 0 <= j - i; i++) {
+        const int sc = (j - i) < (int)r.score.size() ? r.score[j - i] : -1;
+        if (sc < 2) c++;
+    }
+    return (r.kmer - 1) * 0.8 < (double)c;
+}
+
+void polish(Counter &cnt, const uint8_t *org, int L, Rec &r)
+{
+    const int k = r.kmer, period = r.period;
+    if (period <= k) return;
+    cnt.build(org, L, k, r.rep_start, r.rep_end);
+    const std::vector<uint8_t> unit = r.unit;
+    uint8_t revised[kMaxPeriod];
+    int jr = kMaxPeriod - 1;
+    int best = 0;
+    for (int i = 0; i < k; i++) best = unit[i] * P4.v[k - 1 - i] + best;
+    for (int j = period - 1; 0 <= j;) {
+        const int ref = unit[j] * P4.v[k - 1] + best / 4;
+        int best_freq = cnt.get(ref);
+        best = ref;
+        const int sc = j < (int)r.score.size() ? r.score[j] : -1;
+        if (sc == 1 && suspicious(r, j)) {
+            for (int l = 0; l < 4; l++) {
+                const int alt = (ref + (l - unit[j]) * P4.v[k - 1]) % P4.v[k];
+                if (best_freq < cnt.get(alt)) { best_freq = cnt.get(alt); best = alt; }
+            }
+            if (best == ref) {
+                revised[jr--] = unit[j--];
+            } else {
+                const int s_del = align_score(cnt, j, k, best, period, unit.data());
+                const int s_sub = align_score(cnt, j - 1, k, best, period, unit.data());
+                int s_ins = -1;
+                if (j >= 1 && best / P4.v[k - 1] == unit[(j - 1) % period])
+                    s_ins = align_score(cnt, j - 2, k, best, period, unit.data());
+                revised[jr--] = (uint8_t)(best / P4.v[k - 1]);
+                const int mx = std::max(std::max(s_del, s_sub), s_ins);
+                if (mx == s_del) {} else if (mx == s_sub) j -= 1; else j -= 2;
+            }
+        } else {
+            revised[jr--] = unit[j--];
+        }
+        if (jr < 0) return;                                 // "fails to revise": record unchanged
+    }
+    r.period = (kMaxPeriod - 1) - jr;
+    r.unit.assign(revised + jr + 1, revised + kMaxPeriod);
+}
+
+// ---------------------------------------------------------------- min_missing (consensus.c:714-820)
+// each row of min_missing_bases[10][10][20] starts at 1 and steps by 0 or 1: stored as 19 step bits
+const unsigned kMissingSteps[10][10] = {
+    {0x21127,0x42227,0x08447,0x1084b,0x0108b,0x08113,0x40423,0x04043,0x00205,0x00041},
+    {0x21127,0x04227,0x0844b,0x2088b,0x0210b,0x08213,0x00823,0x04085,0x00409,0x00081},
+    {0x42227,0x0444b,0x1084b,0x4108b,0x04113,0x20413,0x01023,0x10085,0x00809,0x00101},
+    {0x0422b,0x0844b,0x2088b,0x0208b,0x08213,0x20423,0x02045,0x20105,0x01009,0x00201},
+    {0x0444b,0x1084b,0x4108b,0x04113,0x10213,0x00823,0x04045,0x40205,0x02011,0x00402},
+    {0x1084b,0x2108b,0x02113,0x08213,0x20423,0x01045,0x08085,0x00409,0x08021,0x01002},
+    {0x1088b,0x41113,0x04113,0x10423,0x40825,0x02085,0x10109,0x00809,0x10021,0x04002},
+    {0x42113,0x04213,0x10423,0x40845,0x02085,0x08109,0x00409,0x02011,0x00081,0x40004},
+    {0x04225,0x10425,0x40845,0x02085,0x08109,0x40209,0x01011,0x10041,0x00202,0x00010},
+    {0x20845,0x01085,0x04089,0x08209,0x40411,0x01021,0x08041,0x00102,0x01004,0x00040},
+};
+
+int min_missing(int period, double error, int coverage)
+{
+    static const int plim[9] = {200, 150, 100, 75, 50, 30, 20, 10, 5};
+    static const double elim[9] = {0.25, 0.225, 0.2, 0.175, 0.15, 0.125, 0.1, 0.075, 0.05};
+    int i = 9, j = 9;
+    for (int t = 0; t < 9; t++) if (period > plim[t]) { i = t; break; }
+    for (int t = 0; t < 9; t++) if (error > elim[t]) { j = t; break; }
+    const int k = coverage <= 1 ? 0 : (coverage >= 20 ? 19 : coverage - 1);
+    return 1 + __builtin_popcount(kMissingSteps[i][j] & ((1u << k) - 1u));
+}
+
+// majority vote of revise_representative_unit_sub (consensus.c:964-1013) from the two histograms
+void vote_unit(Rec &r, const int *cons, const int *miss)
+{
+    const int ulen = r.period;
+    std::vector<uint8_t> revised;
+    revised.reserve(2 * ulen);
+    const int coverage = r.repeat_len / r.period;
+    for (int j = 1; j <= ulen; j++) {
+        int mv = -1, mb = -1;
+        for (int q = 0; q < 5; q++) if (mv < cons[j * 5 + q]) { mv = cons[j * 5 + q]; mb = q; }
+        if (mb < 4) revised.push_back((uint8_t)mb);
+        mv = -1; int mm = -1;
+        for (int q = 0; q < 4; q++) if (mv < miss[j * 4 + q]) { mv = miss[j * 4 + q]; mm = q; }
+        if (5 <= coverage && coverage <= 20) {
+            const double mismatch_ratio = (double)(r.nx + r.ni + r.nd) / r.repeat_len;
+            if (min_missing(r.period, mismatch_ratio, coverage) <= mv && 0 <= mm && mm <= 3) revised.push_back((uint8_t)mm);
+        }
+    }
+    r.period = (int)revised.size();
+    r.unit.swap(revised);
+}
+
+// ---------------------------------------------------------------- chaining + printing (chaining.cpp:43-363)
+struct ChainItem { Rec rec; int start, end, score; ChainItem *pred; };
+
+// Returns the records of the best chain, oldest first.  The set of alignments is taken in insertion order
+// (canonical tie-break for the reference's pointer-ordered std::set); the sweep issues the same
+// std::multimap operations in the same order as chaining.cpp:262-335, including its erase-then-increment loop.
+std::vector<const Rec *> best_chain(std::vector<ChainItem> &items)
+{
+    std::vector<const Rec *> out;
+    if (items.empty()) return out;
+    typedef std::multimap<int, ChainItem *> MM;
+    MM by_x, by_y;
+    for (ChainItem &a : items)
+        if (a.start + 10 <= a.end) {
+            by_x.insert(std::make_pair(a.start, &a));
+            by_x.insert(std::make_pair(a.end - 10, &a));
+        }
+    for (MM::iterator ev = by_x.begin(); ev != by_x.end(); ev++) {
+        ChainItem *cur = ev->second;
+        if (cur->start == ev->first) {
+            if (by_y.empty()) continue;
+            const int lim = cur->start + 10;
+            MM::iterator y = by_y.begin(), prev = y;
+            for (; y != by_y.end(); prev = y, y++)
+                if (prev->second->end <= lim && y->second->end > lim) {
+                    cur->pred = prev->second; cur->score += prev->second->score;
+                    break;
+                }
+            if (prev->second->end <= lim && y == by_y.end()) { cur->pred = prev->second; cur->score += prev->second->score; }
+        } else if (by_y.empty()) {
+            by_y.insert(std::make_pair(cur->end, cur));
+        } else {
+            bool keep = true;
+            for (MM::iterator y = by_y.begin(); y != by_y.end(); y++) {
+                if (y->second->end <= cur->end && y->second->score > cur->score) keep = false;
+                if (y->second->end > cur->end) break;
+            }
+            if (!keep) continue;
+            by_y.insert(std::make_pair(cur->end, cur));
+            for (MM::iterator y = by_y.begin(); y != by_y.end(); y++)
+                if (y->second->end >= cur->end && y->second->score < cur->score) y = by_y.erase(y);
+        }
+    }
+    for (const ChainItem *a = by_y.rbegin()->second; a; a = a->pred) out.push_back(&a->rec);
+    std::reverse(out.begin(), out.end());
+    return out;
+}
+
+void append_record(std::string &out, const std::string &id, const Rec &r)      // print_one_TR, chaining.cpp:127-143
+{
+    char head[256];
+    snprintf(head, sizeof head, "\t%d\t%d\t%d\t%d\t%d\t%d\t%d\t%f\t%d\t%d\t%d\t", r.inputLen, r.rep_start + 1, r.rep_end + 1,
+             r.repeat_len, r.period, r.units, r.nm, (float)r.nm / r.repeat_len, r.nx, r.ni, r.nd);
+    out += id; out += head;
+    for (uint8_t b : r.unit) out += "ACGT"[b];
+    out += '\n';
+}
+
+// pretty_print_alignment's output (wrap_around_DP.c:188-212) from the traceback ops of a PATH job
+void append_alignment(std::string &out, const Rec &r, const uint8_t *org, const mtr_wdp_result &d, const uint8_t *path)
+{
+    const int n = d.path_len;
+    std::string a(n, ' '), m(n, ' '), b(n, ' ');
+    int i = d.max_i, j = d.max_j;
+    if (j == 0) j = r.period;
+    const uint8_t *x = org + r.rep_start - 1;              // rows are org[rep_start .. rep_end]
+    for (int t = 0; t < n; t++) {
+        switch (path[t]) {
+        case 0: a[t] = "ACGT"[x[i]]; m[t] = '|'; b[t] = "ACGT"[r.unit[j - 1]]; i--; j--; break;
+        case 1: a[t] = "ACGT"[x[i]]; b[t] = "ACGT"[r.unit[j - 1]]; i--; j--; break;
+        case 2: a[t] = '-'; b[t] = "ACGT"[r.unit[j - 1]]; j--; break;
+        default: a[t] = "ACGT"[x[i]]; b[t] = '-'; i--; break;
+        }
+        if (j == 0) j = r.period;
+    }
+    char head[128];
+    snprintf(head, sizeof head, "\nmatch gain = %i, mismatch penalty = %i, indel penalty = %i\n\n", r.gain, r.mis, r.indel);
+    out += head;
+    for (int s = n - 1; s >= 0; s -= 50) {
+        const int e = s - 50 >= -1 ? s - 50 : -1;
+        for (int t = s; t > e; t--) out += a[t];
+        out += '\n';
+        for (int t = s; t > e; t--) out += m[t];
+        out += '\n';
+        for (int t = s; t > e; t--) out += b[t];
+        out += "\n\n";
+    }
+}
+
+// ---------------------------------------------------------------- per-read state machine
+struct JobReq {
+    int first, rows, unit_off, ulen;
+    int8_t g[2], m[2], in[2];
+    uint8_t n_param, mode;
+    long long aux_need;         // CONSENSUS: int32 count, PATH: bytes
+};
+
+struct Chain {                  // one k of one candidate: find_tandem_repeat_sub (handle_one_read.c:77-100)
+    enum Stage { SEARCH_WAIT, CONS_WAIT, DP_WAIT, DONE } stage = DONE;
+    int k = 0, pass = 0;
+    Rec rr, tmp, dir[2];
+    bool dir_found[2] = {false, false};
+    int dir_job[2] = {-1, -1};
+    bool found_last = false;
+    float ratio0 = 0;
+    int job = -1;
+};
+
+struct ReadState {
+    std::string id;
+    const uint8_t *org = nullptr;      // len + 2 bases (two stale tail bases, H4a)
+    int L = 0, index = 0;
+    std::vector<int> end, w;           // directional_index_end / _w; dead entries have end < 0
+    int cursor = 0;
+    bool in_candidate = false;
+    int qs = 0, qe = 0;
+    std::vector<Chain> chains;
+    std::vector<ChainItem> accepted;
+    std::vector<Rec> printing;         // -a: the chain waiting for its PATH jobs
+    enum Phase { RUN, PRINT_WAIT, FINISHED } phase = RUN;
+    // round I/O
+    std::vector<JobReq> jobs;
+    std::vector<uint8_t> units;
+    long long job_base = 0;            // global index of this read's first job of the previous round
+    std::vector<long long> job_aux;    // byte offset in the round's aux buffer of each job of the previous round
+    std::string out;
+    long long candidates = 0;
+};
+
+struct Worker { Counter cnt; };
+
+struct RoundResults {
+    const mtr_wdp_result *res = nullptr;   // [2 * job]
+    const uint8_t *aux = nullptr;
+};
+
+int add_job(ReadState &rs, int first, int rows, const std::vector<uint8_t> &unit, int n_param, const int (*p)[3], int mode)
+{
+    JobReq j;
+    memset(&j, 0, sizeof j);
+    j.first = first; j.rows = rows; j.unit_off = (int)rs.units.size(); j.ulen = (int)unit.size();
+    for (int s = 0; s < n_param; s++) { j.g[s] = (int8_t)p[s][0]; j.m[s] = (int8_t)p[s][1]; j.in[s] = (int8_t)p[s][2]; }
+    j.n_param = (uint8_t)n_param; j.mode = (uint8_t)mode;
+    if ((long long)(j.ulen + 1) * (rows + 1) >= kWrapCap) {
+        // wrap_around_DP.c:260-263: the reference aborts the whole run here
+        fprintf(stderr, "You need to increse the value of WrapDPsize.\n");
+        exit(EXIT_FAILURE);
+    }
+    j.aux_need = mode == MTR_TB_CONSENSUS ? (long long)(j.ulen + 1) * 9 : (mode == MTR_TB_PATH ? (long long)6 * rows + 64 : 0);
+    rs.units.insert(rs.units.end(), unit.begin(), unit.end());
+    rs.jobs.push_back(j);
+    return (int)rs.jobs.size() - 1;
+}
+
+const int kSearchParams[2][3] = {{1, 1, 3}, {1, 3, 1}};       // wrap_around_DP.c:395,405
+const int kReviseParams[2][3] = {{5, 1, 1}, {1, 1, 3}};       // consensus.c:1062,1076
+
+void emit_revise_cons(ReadState &rs, Chain &ch)
+{
+    ch.tmp = ch.rr;
+    const int *p = kReviseParams[ch.pass];
+    ch.tmp.gain = p[0]; ch.tmp.mis = p[1]; ch.tmp.indel = p[2];
+    ch.job = add_job(rs, ch.tmp.rep_start, ch.tmp.rep_end - ch.tmp.rep_start + 1, ch.tmp.unit, 1, &kReviseParams[ch.pass], MTR_TB_CONSENSUS);
+    ch.stage = Chain::CONS_WAIT;
+}
+
+// search_De_Bruijn_graph up to the point where it needs wrap_around_DP (consensus.c:507-549)
+void start_chain(ReadState &rs, Chain &ch, Worker &wk)
+{
+    ch.rr.clear();
+    ch.rr.inputLen = rs.L; ch.rr.kmer = ch.k;
+    ch.dir_found[0] = ch.dir_found[1] = false;
+    ch.found_last = false;
+    wk.cnt.build(rs.org, rs.L, ch.k, rs.qs, rs.qe);
+    const int maxf = wk.cnt.max_freq();
+    int nodes[100];
+    const int nn = wk.cnt.list_max_nodes(nodes, 100, maxf);
+    bool any = false;
+    if (5 < maxf) {
+        for (int d = 0; d < 2; d++)
+            for (int i = 0; i < nn; i++) {
+                Rec r = ch.rr;
+                const bool found = walk(wk.cnt, rs.qs, rs.qe, nodes[i], ch.k, d == 1, r);
+                ch.found_last = found;
+                if (!found) continue;
+                ch.dir[d] = r; ch.dir_found[d] = true;
+                ch.dir_job[d] = add_job(rs, rs.qs, rs.qe - rs.qs + 1, r.unit, 2, kSearchParams, MTR_TB_COUNTS);
+                any = true;
+                break;
+            }
+    }
+    if (any) { ch.stage = Chain::SEARCH_WAIT; return; }
+    ch.rr.clear();                                          // nothing found: find_tandem_repeat_sub clears (:86-88)
+    ch.stage = Chain::DONE;
+}
+
+void advance_chain(ReadState &rs, Chain &ch, Worker &wk, const RoundResults &rr)
+{
+    const mtr_wdp_result *res = rr.res + 2 * rs.job_base;
+    if (ch.stage == Chain::SEARCH_WAIT) {
+        Rec best;                                           // max_rr of search_De_Bruijn_graph, starts cleared
+        float best_ratio = -1;
+        for (int d = 0; d < 2; d++) {
+            if (!ch.dir_found[d]) continue;
+            // wrap_around_DP (wrap_around_DP.c:357-429): keep the strictly better of the two penalty sets
+            Rec pick;
+            float pick_ratio = -1;
+            for (int s = 0; s < 2; s++) {
+                Rec t = ch.dir[d];
+                apply_dp(t, rs.qs, res[2 * ch.dir_job[d] + s], kSearchParams[s][0], kSearchParams[s][1], kSearchParams[s][2]);
+                const float ratio = t.ratio();
+                if (pick_ratio < ratio) { pick = t; pick_ratio = ratio; }
+            }
+            const float ratio = pick.ratio();
+            if (best_ratio < ratio && min_match_ratio <= ratio && 5 < pick.units && 2 <= pick.period && pick.period < kMaxPeriod) {
+                best_ratio = ratio; best = pick;
+            }
+        }
+        ch.rr = best;
+        if (!ch.found_last) { ch.rr.clear(); ch.stage = Chain::DONE; return; }            // Q4
+        if ((long long)ch.rr.period * (rs.qe - rs.qs + 1) > kWrapCap) {
+            fprintf(stderr, "You need to increse the value of WrapDPsize.\n");
+            ch.rr.clear(); ch.stage = Chain::DONE; return;
+        }
+        const int coverage = ch.rr.repeat_len / ch.rr.period;
+        if (!(5 <= coverage && coverage <= 20 && 5 < ch.rr.period)) { ch.stage = Chain::DONE; return; }
+        // revise_representative_unit (consensus.c:1048-1087)
+        polish(wk.cnt, rs.org, rs.L, ch.rr);
+        ch.ratio0 = ch.rr.ratio();
+        ch.pass = 0;
+        emit_revise_cons(rs, ch);
+        return;
+    }
+    if (ch.stage == Chain::CONS_WAIT) {
+        const int *cons = (const int *)(rr.aux + rs.job_aux[ch.job]);
+        vote_unit(ch.tmp, cons, cons + (size_t)(ch.tmp.period + 1) * 5);
+        if (ch.tmp.period < kMaxPeriod) {
+            if (ch.tmp.period <= 0) {                       // the reference divides by zero here (H9)
+                fprintf(stderr, "mTR: the revised repeat unit is empty (read %s)\n", rs.id.c_str());
+                exit(EXIT_FAILURE);
+            }
+            ch.job = add_job(rs, ch.tmp.rep_start, ch.tmp.rep_end - ch.tmp.rep_start + 1, ch.tmp.unit, 1, &kReviseParams[ch.pass], MTR_TB_COUNTS);
+            ch.stage = Chain::DP_WAIT;
+            return;
+        }
+    } else if (ch.stage == Chain::DP_WAIT) {
+        const int *p = kReviseParams[ch.pass];
+        apply_dp(ch.tmp, ch.tmp.rep_start, res[2 * ch.job], p[0], p[1], p[2]);
+        if (ch.ratio0 < ch.tmp.ratio()) ch.rr = ch.tmp;     // ratio0 is never refreshed (Q10)
+    }
+    if (ch.pass == 0) { ch.pass = 1; emit_revise_cons(rs, ch); return; }
+    ch.stage = Chain::DONE;
+}
+
+void finish_read(ReadState &rs, int print_alignment)
+{
+    std::vector<const Rec *> chain = best_chain(rs.accepted);
+    if (!print_alignment) {
+        for (const Rec *r : chain) append_record(rs.out, rs.id, *r);
+        rs.phase = ReadState::FINISHED;
+        return;
+    }
+    rs.printing.clear();
+    for (const Rec *r : chain) rs.printing.push_back(*r);
+    if (rs.printing.empty()) { rs.phase = ReadState::FINISHED; return; }
+    for (const Rec &r : rs.printing) {
+        const int p[1][3] = {{r.gain, r.mis, r.indel}};
+        add_job(rs, r.rep_start - 1, r.rep_end - r.rep_start + 1, r.unit, 1, p, MTR_TB_PATH);
+    }
+    rs.phase = ReadState::PRINT_WAIT;
+}
+
+// One round of one read: consume the results of the jobs it emitted last round, then run until it needs the
+// GPU again (or is finished).  handle_one_TR's candidate loop, handle_one_read.c:227-246.
+void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alignment)
+{
+    rs.jobs.clear();
+    rs.units.clear();
+    if (rs.phase == ReadState::PRINT_WAIT) {
+        const mtr_wdp_result *res = rr.res + 2 * rs.job_base;
+        for (size_t i = 0; i < rs.printing.size(); i++) {
+            append_record(rs.out, rs.id, rs.printing[i]);
+            append_alignment(rs.out, rs.printing[i], rs.org, res[2 * i], rr.aux + rs.job_aux[i]);
+        }
+        rs.phase = ReadState::FINISHED;
+        return;
+    }
+    if (rs.in_candidate)
+        for (Chain &ch : rs.chains)
+            if (ch.stage != Chain::DONE) advance_chain(rs, ch, wk, rr);
+    for (;;) {
+        if (rs.in_candidate) {
+            for (const Chain &ch : rs.chains)
+                if (ch.stage != Chain::DONE) return;        // its jobs are queued in rs.jobs
+            // find_tandem_repeat's pick over k (handle_one_read.c:135-146), then handle_one_TR's accept (:236-243)
+            Rec pick;
+            float best_ratio = -1;
+            for (const Chain &ch : rs.chains) {
+                const float ratio = ch.rr.ratio();
+                if (best_ratio < ratio && min_match_ratio <= ratio && 5 < ch.rr.units && 2 <= ch.rr.period) {
+                    best_ratio = ratio; pick = ch.rr;
+                }
+            }
+            rs.candidates++;
+            if (pick.repeat_len > 0 && pick.rep_start + 10 < pick.rep_end) {
+                for (int i = pick.rep_start; i < pick.rep_end && i < rs.L; i++)       // :178-188
+                    if (rs.end[i] >= 0 && rs.end[i] < pick.rep_end) { rs.end[i] = -1; rs.w[i] = -1; }
+                ChainItem it;
+                it.rec = pick; it.start = pick.rep_start; it.end = pick.rep_end; it.score = pick.nm; it.pred = nullptr;
+                rs.accepted.push_back(it);
+            }
+            rs.in_candidate = false;
+        }
+        while (rs.cursor < rs.L && !(rs.end[rs.cursor] > -1 && rs.end[rs.cursor] < rs.L)) rs.cursor++;
+        if (rs.cursor >= rs.L) { finish_read(rs, print_alignment); return; }
+        rs.qs = rs.cursor; rs.qe = rs.end[rs.cursor];
+        const int cw = rs.w[rs.cursor];
+        rs.cursor++;
+        int min_k, max_k;                                   // handle_one_read.c:105-120
+        if (cw < 100) { min_k = 2; max_k = 10; } else if (cw < 1000) { min_k = 2; max_k = 12; } else { min_k = 5; max_k = 15; }
+        rs.chains.resize(max_k - min_k + 1);
+        for (int k = min_k; k <= max_k; k++) {
+            Chain &ch = rs.chains[k - min_k];
+            ch.k = k;
+            start_chain(rs, ch, wk);
+        }
+        rs.in_candidate = true;
+    }
+}
+
+// ---------------------------------------------------------------- a small persistent thread pool
+class Pool {
+public:
+    explicit Pool(int n) : n_(std::max(1, n))
+    {
+        for (int t = 1; t < n_; t++) th_.emplace_back([this, t] { loop(t); });
+    }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    void run(int count, const std::function<void(int, int)> &fn)
+    {
+        if (count <= 0) return;
+        { std::lock_guard<std::mutex> g(m_); fn_ = &fn; count_ = count; next_ = 0; busy_ = n_ - 1; gen_++; }
+        cv_.notify_all();
+        work(0);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return busy_ == 0; });
+    }
+private:
+    void work(int tid)
+    {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= count_) break;
+            (*fn_)(tid, i);
+        }
+    }
+    void loop(int tid)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work(tid);
+            { std::lock_guard<std::mutex> g(m_); busy_--; }
+            done_.notify_one();
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int count_ = 0, busy_ = 0;
+    unsigned gen_ = 0;
+    bool stop_ = false;
+};
+
+// ---------------------------------------------------------------- one GPU + its host workers
+struct ReadInput {
+    std::string id;
+    std::vector<uint8_t> bases;        // len + 2 (the two stale bases of H4a at the end)
+    std::vector<uint16_t> stale;       // inputString_w_rand beyond len + 4r (H3)
+    int len = 0;
+};
+
+[[noreturn]] void die(mtr_ctx *ctx, const char *what, int rc)
+{
+    fprintf(stderr, "mTR (B200): %s failed (%d): %s\n", what, rc, mtr_last_error(ctx));
+    exit(EXIT_FAILURE);
+}
+
+struct Engine {
+    mtr_ctx *ctx = nullptr;
+    Pool *pool = nullptr;
+    std::vector<Worker> workers;
+    double t_di = 0, t_dp = 0, t_rounds = 0;
+    long long candidates = 0, rounds = 0, jobs_total = 0;
+
+    Engine(int device, int threads)
+    {
+        const int rc = mtr_cuda_init(device, &ctx);
+        if (rc) die(nullptr, "mtr_cuda_init", rc);
+        pool = new Pool(threads);
+        workers.resize(pool->size());
+    }
+    ~Engine() { delete pool; mtr_cuda_shutdown(ctx); }
+
+    // Processes one batch; returns the text the reference would have printed for these reads, in order.
+    std::string process(std::vector<ReadInput> &in, int print_alignment)
+    {
+        const int n = (int)in.size();
+        std::string out;
+        if (n == 0) return out;
+        // ---- pack (2 bit) and upload; directional index on the GPU
+        std::vector<int64_t> word_off(n + 1, 0), stale_off(n + 1, 0), pos_off(n + 1, 0);
+        std::vector<int32_t> lens(n);
+        for (int r = 0; r < n; r++) {
+            lens[r] = in[r].len;
+            const int64_t words = (in[r].len + 2 + 15) / 16;
+            word_off[r + 1] = word_off[r] + ((words + 3) / 4) * 4;
+            stale_off[r + 1] = stale_off[r] + (int64_t)in[r].stale.size();
+            pos_off[r + 1] = pos_off[r] + in[r].len;
+        }
+        std::vector<uint32_t> packed((size_t)word_off[n], 0u);
+        std::vector<uint16_t> stale((size_t)stale_off[n]);
+        pool->run(n, [&](int, int r) {
+            uint32_t *dst = packed.data() + word_off[r];
+            const uint8_t *b = in[r].bases.data();
+            const int nb = in[r].len + 2;
+            for (int i = 0; i < nb; i++) dst[i >> 4] |= (uint32_t)b[i] << ((i & 15) * 2);
+            if (!in[r].stale.empty()) memcpy(stale.data() + stale_off[r], in[r].stale.data(), in[r].stale.size() * 2);
+        });
+        int rc = mtr_reads_upload(ctx, packed.data(), word_off.data(), lens.data(), n);
+        if (rc) die(ctx, "mtr_reads_upload", rc);
+        std::vector<double> di((size_t)pos_off[n]);
+        std::vector<int32_t> end((size_t)pos_off[n]), ww((size_t)pos_off[n]);
+        double t0 = now_s();
+        rc = mtr_di_run(ctx, Manhattan_Distance, stale.data(), stale_off.data(), pos_off.data(), di.data(), end.data(), ww.data());
+        if (rc) die(ctx, "mtr_di_run", rc);
+        t_di += now_s() - t0;
+        // ---- per-read state machines
+        std::vector<ReadState> st(n);
+        for (int r = 0; r < n; r++) {
+            ReadState &rs = st[r];
+            rs.id = in[r].id; rs.org = in[r].bases.data(); rs.L = in[r].len; rs.index = r;
+            rs.end.assign(end.begin() + pos_off[r], end.begin() + pos_off[r + 1]);
+            rs.w.assign(ww.begin() + pos_off[r], ww.begin() + pos_off[r + 1]);
+        }
+        std::vector<int> active(n);
+        for (int r = 0; r < n; r++) active[r] = r;
+        std::vector<mtr_wdp_job> jobs;
+        std::vector<uint8_t> units, aux;
+        std::vector<mtr_wdp_result> res;
+        RoundResults cur;
+        const long long dir_cap = dir_budget();
+        t0 = now_s();
+        while (!active.empty()) {
+            pool->run((int)active.size(), [&](int tid, int i) { step_read(st[active[i]], workers[tid], cur, print_alignment); });
+            jobs.clear(); units.clear();
+            long long aux_bytes = 0;
+            size_t keep = 0;
+            for (size_t a = 0; a < active.size(); a++) {
+                ReadState &rs = st[active[a]];
+                if (rs.phase == ReadState::FINISHED) continue;
+                active[keep++] = active[a];
+                rs.job_base = (long long)jobs.size();
+                rs.job_aux.assign(rs.jobs.size(), 0);
+                for (size_t j = 0; j < rs.jobs.size(); j++) {
+                    const JobReq &q = rs.jobs[j];
+                    mtr_wdp_job g;
+                    memset(&g, 0, sizeof g);
+                    g.read = rs.index; g.first = q.first; g.rows = q.rows; g.ulen = q.ulen;
+                    g.unit_off = (int32_t)(units.size() + (size_t)q.unit_off);
+                    for (int s = 0; s < 2; s++) { g.gain[s] = q.g[s]; g.mis[s] = q.m[s]; g.indel[s] = q.in[s]; }
+                    g.n_param = q.n_param; g.mode = q.mode;
+                    if (q.mode != MTR_TB_COUNTS) {
+                        aux_bytes = (aux_bytes + 15) & ~15LL;
+                        rs.job_aux[j] = aux_bytes;
+                        g.aux_off = q.mode == MTR_TB_CONSENSUS ? aux_bytes / 4 : aux_bytes;
+                        g.aux_cap = q.aux_need;
+                        aux_bytes += q.mode == MTR_TB_CONSENSUS ? q.aux_need * 4 : q.aux_need;
+                    }
+                    jobs.push_back(g);
+                }
+                units.insert(units.end(), rs.units.begin(), rs.units.end());
+            }
+            active.resize(keep);
+            if (jobs.empty()) break;
+            rounds++; jobs_total += (long long)jobs.size();
+            res.resize(jobs.size() * 2);
+            aux.assign((size_t)aux_bytes, 0);
+            run_jobs(jobs, units, res, aux, dir_cap);
+            cur.res = res.data(); cur.aux = aux.data();
+        }
+        t_rounds += now_s() - t0;
+        for (int r = 0; r < n; r++) { out += st[r].out; candidates += st[r].candidates; }
+        return out;
+    }
+
+    static long long dir_budget()
+    {
+        const char *e = getenv("MTR_DIR_BUDGET_MB");
+        return (e ? atoll(e) : 16384LL) << 20;
+    }
+
+    // Runs the round's jobs in sub-batches whose direction matrices fit the budget.
+    void run_jobs(std::vector<mtr_wdp_job> &jobs, std::vector<uint8_t> &units, std::vector<mtr_wdp_result> &res,
+                  std::vector<uint8_t> &aux, long long dir_cap)
+    {
+        size_t a = 0;
+        std::vector<mtr_wdp_job> part;
+        while (a < jobs.size()) {
+            size_t b = a;
+            long long dir = 0, aux_lo = -1, aux_hi = 0;
+            while (b < jobs.size()) {
+                const long long need = wdp_dir_bytes(jobs[b].ulen, jobs[b].rows) * jobs[b].n_param;
+                if (b > a && dir + need > dir_cap) break;
+                dir += need;
+                if (jobs[b].mode != MTR_TB_COUNTS) {
+                    const long long lo = jobs[b].mode == MTR_TB_CONSENSUS ? jobs[b].aux_off * 4 : jobs[b].aux_off;
+                    const long long sz = jobs[b].mode == MTR_TB_CONSENSUS ? jobs[b].aux_cap * 4 : jobs[b].aux_cap;
+                    if (aux_lo < 0) aux_lo = lo;
+                    aux_hi = lo + sz;
+                }
+                b++;
+            }
+            part.assign(jobs.begin() + a, jobs.begin() + b);
+            if (aux_lo > 0)
+                for (mtr_wdp_job &j : part)
+                    if (j.mode != MTR_TB_COUNTS) j.aux_off -= j.mode == MTR_TB_CONSENSUS ? aux_lo / 4 : aux_lo;
+            const double t0 = now_s();
+            const int rc = mtr_wdp_run(ctx, part.data(), (int)part.size(), units.data(), (int64_t)units.size(), res.data() + 2 * a,
+                                       aux_lo >= 0 ? aux.data() + aux_lo : nullptr, aux_lo >= 0 ? aux_hi - aux_lo : 0);
+            if (rc) die(ctx, "mtr_wdp_run", rc);
+            t_dp += now_s() - t0;
+            a = b;
+        }
+    }
+};
+
+// ---------------------------------------------------------------- cross-read stale state
+// The reference never clears orgInputString / inputString_w_rand between reads, and reads past the part it
+// rewrites.  Both effects depend only on the sequence of reads, so they are reproduced while parsing: every
+// read gets the two bases beyond its end and the k = 5 coded values beyond len + 4r that an earlier, longer
+// read left behind (zeros in a fresh process).
+struct StaleTracker {
+    std::vector<uint8_t> org;          // shadow of orgInputString
+    std::vector<uint16_t> padded;      // shadow of inputString_w_rand after the k = 5 pass
+    std::vector<uint8_t> mt;           // genrand_int32() % 4 after init_genrand(0)
+    StaleTracker() : org(kMaxLen + 8, 0), padded(3 * (size_t)kMaxLen, 0)
+    {
+        mt.resize(1300000);
+        uint32_t s[624];
+        s[0] = 0;
+        for (int i = 1; i < 624; i++) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+        int pos = 624;
+        for (size_t t = 0; t < mt.size(); t++) {
+            if (pos == 624) {
+                for (int i = 0; i < 624; i++) {
+                    const uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+                    s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+                }
+                pos = 0;
+            }
+            uint32_t y = s[pos++];
+            y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+            mt[t] = (uint8_t)(y & 3u);
+        }
+    }
+    // fills in.bases[len], [len+1] and in.stale, then records what this read leaves behind
+    void visit(ReadInput &in, const int *tail_override)
+    {
+        const int L = in.len, r = L < 1000 ? 100 : L / 10, N = L + 2 * r;
+        const int written = std::min(L + 4 * r, kMaxLen);
+        in.bases.resize(L + 2);
+        in.bases[L] = tail_override ? (uint8_t)(tail_override[0] & 3) : org[L];
+        in.bases[L + 1] = tail_override ? (uint8_t)(tail_override[1] & 3) : org[L + 1];
+        int wmax = 0;
+        for (int w = 5; w <= 10240 && w < L / 2; w *= 2) wmax = w;
+        const int need = L + r + 2 * wmax + 8;              // last index the k = 5 passes touch
+        in.stale.clear();
+        if (need > written) in.stale.assign(padded.begin() + written, padded.begin() + need);
+        memcpy(org.data(), in.bases.data(), (size_t)L);
+        // inputString_w_rand after init_inputString_surrounded_by_random_seq(k = 5) (fill_directional_index.c:137-169)
+        const int c = written;
+        auto base = [&](int i) -> int {
+            if (i < r) return mt[c + i];
+            if (i < r + L) return in.bases[i - r];
+            if (i < N) return mt[c + r + (i - r - L)];
+            return mt[i];
+        };
+        int code = 0;
+        for (int i = 0; i < 4 && i < written; i++) code = code * 4 + base(i);
+        for (int i = 0; i < written; i++) {
+            if (i < N - 4) { code = (code % 256) * 4 + base(i + 4); padded[i] = (uint16_t)code; }
+            else padded[i] = (uint16_t)base(i);
+        }
+    }
+};
+
+// ---------------------------------------------------------------- FASTA reader (handle_one_file.c:169-269)
+struct FastaReader {
+    FILE *fp = nullptr;
+    std::string next_id;
+    bool started = false, eof = false;
+    std::vector<char> buf;
+    explicit FastaReader(const char *path) : buf(1 << 20)
+    {
+        fp = fopen(path, "r");
+        if (!fp) { fprintf(stderr, "fatal error: cannot open %s\n", path); fflush(stderr); exit(EXIT_FAILURE); }
+    }
+    ~FastaReader() { if (fp) fclose(fp); }
+    // Returns false at the end of input or at a zero-length read (which ends the run in the reference, :283).
+    bool next(ReadInput &out)
+    {
+        if (eof) return false;
+        out.id.clear(); out.bases.clear(); out.len = 0;
+        bool any = false;
+        while (fgets(buf.data(), (int)buf.size(), fp)) {
+            any = true;
+            char *s = buf.data();
+            if (s[0] == '>' ) {
+                std::string id;
+                for (int i = 1; s[i] && s[i] != '\n' && s[i] != '\r'; i++) id += s[i];
+                if (!started) { started = true; next_id = id; continue; }
+                out.id = next_id; next_id = id;
+                out.len = (int)out.bases.size();
+                return out.len > 0;
+            }
+            for (int i = 0; s[i] && s[i] != '\n' && s[i] != '\r'; i++) {
+                uint8_t b;
+                switch (s[i]) {
+                case 'A': case 'a': b = 0; break;
+                case 'C': case 'c': b = 1; break;
+                case 'G': case 'g': b = 2; break;
+                case 'T': case 't': b = 3; break;
+                default: fprintf(stderr, "Invalid character: %c \n", s[i]); exit(EXIT_FAILURE);
+                }
+                out.bases.push_back(b);
+                if (kMaxLen <= (int)out.bases.size()) {
+                    fprintf(stderr, "fatal error: The length %d is tentatively at most %i.\nread ID = %s\nSet MAX_INPUT_LENGTH to a larger value",
+                            (int)out.bases.size(), kMaxLen, out.id.c_str());
+                    fprintf(stderr, "cannot allocate space for one of global variables in the heap.\n");
+                    exit(EXIT_FAILURE);
+                }
+            }
+        }
+        eof = true;
+        if (!any) return false;
+        out.id = next_id;
+        out.len = (int)out.bases.size();
+        return out.len > 0;
+    }
+};
+
+// ---------------------------------------------------------------- process-wide state behind the C entry points
+struct Runtime {
+    std::vector<Engine *> engines;
+    StaleTracker stale;
+    std::vector<ReadInput> pending;
+    long long pending_bases = 0;
+    int batch_reads = 2048;
+    long long batch_bases = 64LL << 20;
+    int print_alignment = 0;
+
+    Runtime()
+    {
+        int ngpu = 1;
+        if (const char *e = getenv("MTR_GPUS")) ngpu = std::max(1, atoi(e));
+        if (const char *e = getenv("MTR_BATCH_READS")) batch_reads = std::max(1, atoi(e));
+        if (const char *e = getenv("MTR_BATCH_MBASES")) batch_bases = std::max(1LL, atoll(e)) << 20;
+        int base = 0;
+        if (const char *e = getenv("MTR_DEVICE")) base = atoi(e);
+        int threads = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("MTR_THREADS")) threads = atoi(e);
+        threads = std::max(1, threads / ngpu);
+        for (int g = 0; g < ngpu; g++) engines.push_back(new Engine(base + g, threads));
+    }
+    ~Runtime() { for (Engine *e : engines) delete e; }
+};
+
+Runtime *g_rt = nullptr;
+Runtime &runtime()
+{
+    if (!g_rt) g_rt = new Runtime();
+    return *g_rt;
+}
+
+void publish_timers(Runtime &rt)
+{
+    for (Engine *e : rt.engines) {
+        time_range += (float)e->t_di; time_wrap_around_DP += (float)e->t_dp; time_period += (float)e->t_rounds;
+        query_counter += (int)e->candidates;
+        e->t_di = e->t_dp = e->t_rounds = 0; e->candidates = 0;
+    }
+}
+
+struct GlobalsInit {
+    GlobalsInit() { orgInputString = (int *)calloc(kMaxLen + 8, sizeof(int)); }
+} g_globals_init;
+
+}  // namespace
+
+// ================================================================ the reference's entry points
+extern "C" void mtr_flush(void)
+{
+    Runtime &rt = runtime();
+    if (rt.pending.empty()) return;
+    const std::string out = rt.engines[0]->process(rt.pending, rt.print_alignment);
+    fwrite(out.data(), 1, out.size(), stdout);
+    fflush(stdout);
+    rt.pending.clear();
+    rt.pending_bases = 0;
+    publish_timers(rt);
+}
+
+// handle_one_read.c:263: the read is orgInputString[0..inputLen)
+extern "C" void handle_one_read(char *readID, int inputLen, int read_cnt, int print_alignment)
+{
+    (void)read_cnt;
+    if (inputLen <= 0) return;
+    Runtime &rt = runtime();
+    if (!rt.pending.empty() && rt.print_alignment != print_alignment) mtr_flush();
+    rt.print_alignment = print_alignment;
+    ReadInput in;
+    in.id = readID ? readID : "";
+    in.len = inputLen;
+    in.bases.resize(inputLen + 2);
+    for (int i = 0; i < inputLen; i++) in.bases[i] = (uint8_t)(orgInputString[i] & 3);
+    const int tail[2] = {orgInputString[inputLen], orgInputString[inputLen + 1]};
+    rt.stale.visit(in, tail);
+    rt.pending_bases += inputLen;
+    rt.pending.push_back(std::move(in));
+    if ((int)rt.pending.size() >= rt.batch_reads || rt.pending_bases >= rt.batch_bases) mtr_flush();
+}
+
+// handle_one_file.c:271: batches go to the GPUs round-robin, output is printed in input order
+extern "C" int handle_one_file(char *inputFile, int print_alignment)
+{
+    Runtime &rt = runtime();
+    mtr_flush();
+    FastaReader reader(inputFile);
+    const int ngpu = (int)rt.engines.size();
+    struct Slot { std::thread th; std::string out; std::vector<ReadInput> reads; };
+    std::vector<Slot *> inflight;
+    auto drain_front = [&]() {
+        Slot *s = inflight.front();
+        s->th.join();
+        fwrite(s->out.data(), 1, s->out.size(), stdout);
+        fflush(stdout);
+        delete s;
+        inflight.erase(inflight.begin());
+    };
+    int n_reads = 0;
+    long long batch_index = 0;
+    bool more = true;
+    while (more) {
+        Slot *s = new Slot();
+        long long bases = 0;
+        while ((int)s->reads.size() < rt.batch_reads && bases < rt.batch_bases) {
+            ReadInput in;
+            if (!reader.next(in)) { more = false; break; }
+            rt.stale.visit(in, nullptr);
+            bases += in.len;
+            s->reads.push_back(std::move(in));
+            n_reads++;
+        }
+        if (s->reads.empty()) { delete s; break; }
+        while ((int)inflight.size() >= ngpu) drain_front();
+        Engine *eng = rt.engines[batch_index % ngpu];
+        batch_index++;
+        s->th = std::thread([eng, s, print_alignment] { s->out = eng->process(s->reads, print_alignment); });
+        inflight.push_back(s);
+    }
+    while (!inflight.empty()) drain_front();
+    publish_timers(rt);
+    return n_reads;
+}

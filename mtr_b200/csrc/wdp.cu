@@ -46,6 +46,13 @@ static int class_of(int ulen, int paired)
     return -1;
 }
 
+long long wdp_dir_bytes(int ulen, int rows)
+{
+    const int k = class_of(ulen, 0);
+    if (k < 0) return 0;
+    return ((long long)rows * (kClasses[k].G * kClasses[k].C / 4) + 15) & ~15LL;
+}
+
 #define NEG_INF (-(1 << 28))
 
 __device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, long long b)

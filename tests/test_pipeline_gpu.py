@@ -1,0 +1,74 @@
+"""End-to-end parity of the drop-in: bin/mTR (libmtr_b200.so: CUDA directional index + CUDA wrap-around DP +
+host control) must print exactly what the reference prints -- checked as md5 against the digests taken from the
+reference binary (tests/golden/digests.json) and, on a mismatch, diffed against the oracle for a readable report."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MTR = os.path.join(ROOT, "bin", "mTR")
+ORACLE_BIN = os.path.join(ROOT, "oracle", "mtr_oracle")
+DIGESTS = json.load(open(os.path.join(golden_cases.GOLDEN, "digests.json")))
+
+
+def run(binary, flags, path, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([binary] + flags + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return p.stdout
+
+
+def explain(out, flags, path):
+    exp = run(ORACLE_BIN, flags, path).decode().splitlines()
+    got = out.decode().splitlines()
+    for i, (a, b) in enumerate(zip(got, exp)):
+        if a != b:
+            return "first difference at line %d:\n got: %s\n exp: %s\n(%d vs %d lines)" % (i + 1, a[:300], b[:300], len(got), len(exp))
+    return "outputs differ in length: %d vs %d lines" % (len(got), len(exp))
+
+
+@pytest.fixture(scope="module")
+def shipped_dir(tmp_path_factory, oracle_so):
+    d = tmp_path_factory.mktemp("shipped")
+    golden_cases.extract_shipped(str(d))
+    return str(d)
+
+
+@pytest.fixture(scope="module")
+def synthetic_dir(tmp_path_factory, oracle_so):
+    d = tmp_path_factory.mktemp("synthetic")
+    for name, (reads, lw) in golden_cases.synthetic_cases().items():
+        golden_cases.write_case(os.path.join(str(d), name + ".fa"), reads, lw)
+    return str(d)
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS["shipped"]))
+def test_shipped_multiple_TRs(shipped_dir, name):
+    path = os.path.join(shipped_dir, name)
+    for mode, flags in golden_cases.MODES.items():
+        out = run(MTR, flags, path)
+        assert hashlib.md5(out).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode, explain(out, flags, path))
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS["synthetic"]))
+def test_synthetic_cases(synthetic_dir, name):
+    path = os.path.join(synthetic_dir, name + ".fa")
+    for mode, flags in golden_cases.MODES.items():
+        out = run(MTR, flags, path)
+        assert hashlib.md5(out).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode, explain(out, flags, path))
+
+
+def test_small_batches_give_identical_output(synthetic_dir):
+    """Batch boundaries (and with them the round structure) must not change a byte."""
+    path = os.path.join(synthetic_dir, "mixed.fa")
+    ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
+    for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_DIR_BUDGET_MB": "1"}):
+        assert hashlib.md5(run(MTR, [], path, env)).hexdigest() == ref, env
