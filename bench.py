@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s and wrap-around-DP GCUPS of the mTR hot path on B200, beside the reference on the host CPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one batch of R synthetic C5 reads (BASELINE.json configs[4]: 10-20 kb reads carrying one tandem repeat,
+unit 2-500 bp, 5-15 % sub/ins/del noise) through the whole per-read path: directional index, candidate loop, unit
+finder, wrap-around DP, chaining, formatted TSV.  Every rank runs the same step shape on its own reads (weak
+scaling, no collective on the data path; torch.distributed is used only for the barrier and the max over ranks).
+
+  value : reads/s with the batch already 2-bit packed and resident in HBM when the clock starts (mtr_pipeline_run)
+  e2e   : reads/s from FASTA text in host memory to the output text in host memory (mtr_pipeline_load_fasta +
+          mtr_pipeline_run): parse, pack, H2D, every per-round H2D/D2H, formatting
+  roofline     : the dominant kernel (K3 wrap-around DP fill): algorithmic cell updates / CUDA-event kernel time
+                 against the integer-ALU issue ceiling measured on this GPU by mtr_alu_probe
+  roofline_di  : the directional-index kernels against measured HBM bandwidth (reported for completeness: that
+                 stage is LSU/shared-memory bound, not HBM bound)
+  cpu_baseline : oracle/_ref/mTR_ref_O3 (the unmodified reference, -O3) on a bounded sample of the same workload
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from mtr_b200 import synth  # noqa: E402
+
+I_CELL_INT32 = 15.0     # integer instructions per cell update with full reference semantics
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "mTR_ref_O3")
+ORACLE_BIN = os.path.join(ROOT, "oracle", "mtr_oracle")
+
+
+def fasta_bytes(reads, first_id=0):
+    return "".join(">%d\n%s\n" % (first_id + i, synth.to_text(r)) for i, r in enumerate(reads)).encode()
+
+
+def step_reads(n, rank, step):
+    return synth.long_reads(n, seed=1000 + 10007 * rank + step)[0]
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.p, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.p = None
+
+    def _pump(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm = [int(r[0]) for r in self.rows if r and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference_cli(binary, reads, cores, flags=()):
+    """Times the reference CLI on `reads`, split into `cores` contiguous chunks run concurrently (the reference
+    is single-threaded and non-reentrant: process-level sharding is its only multi-core mode)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        chunks = [c for c in np.array_split(np.arange(len(reads)), cores) if len(c)]
+        paths = []
+        for ci, idx in enumerate(chunks):
+            p = os.path.join(tmp, "c%d.fa" % ci)
+            synth.write_fasta(p, [reads[i] for i in idx], ids=[int(i) for i in idx])
+            paths.append(p)
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([binary] + list(flags) + [p], stdout=open(p + ".out", "wb"), stderr=subprocess.DEVNULL) for p in paths]
+        for pr in procs:
+            pr.wait()
+        dt = time.perf_counter() - t0
+        out = b"".join(open(p + ".out", "rb").read() for p in paths)
+        assert all(pr.returncode == 0 for pr in procs)
+    return dt, out
+
+
+def reference_arm(a, rank, world):
+    """--impl reference: the reference's own CPU implementation on the box's host cores, same workload."""
+    if rank != 0:
+        return
+    binary, kind = (REF_BIN, "reference") if os.path.exists(REF_BIN) else (ORACLE_BIN, "port")
+    if not os.path.exists(binary):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    cores = os.cpu_count() or 1
+    n = max(cores, min(a.reads, 2 * cores))              # bounded sample: ~0.3 s of CPU per read per core
+    times = []
+    for step in range(a.warmup + a.steps):
+        reads = step_reads(n, 0, step)
+        dt, _ = run_reference_cli(binary, reads, cores)
+        if step >= a.warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    v = n / per_step
+    line = {"impl": "reference", "metric": "reads_per_s", "value": round(v, 3), "unit": "reads/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(per_step * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "C5 synthetic long reads 10-20 kb, unit 2-500 bp, 5-15% noise", "reads_per_step": n,
+                       "mode": "default (Manhattan), -m 0.6"},
+            "cpu_baseline": {"value": round(v, 3), "unit": "reads/s", "cores": cores, "kind": kind,
+                             "sample": "%d reads per step, split over %d processes" % (n, cores)},
+            "e2e": {"value": round(v, 3), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "512")), help="reads per step per GPU")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = 2 x cores)")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        reference_arm(a, rank, world)
+        return
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from mtr_b200 import capi
+    threads = max(1, (os.cpu_count() or 1) // world)
+    pipe = capi.Pipeline(local_rank, threads=threads)
+    ctx = capi.Context(local_rank)
+    alu = {k: ctx.alu_probe(i) for i, k in enumerate(("viaddmnmx_s32", "lop3_iadd", "viaddmnmx_s16x2"))}
+    ctx.close()
+
+    R = a.reads
+    total = a.warmup + a.steps
+    texts = [fasta_bytes(step_reads(R, rank, s)) for s in range(total)]
+    keys = ("reads", "bases", "candidates", "rounds", "rounds_fast", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
+            "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "wdp_fill_ms",
+            "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms")
+
+    # ---- device-resident loop: the batch is packed and in HBM before the clock starts
+    acc = dict.fromkeys(keys, 0.0)
+    t_res = 0.0
+    digest = hashlib.md5()
+    for s in range(a.warmup):
+        pipe.load_fasta(texts[s]); pipe.run()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    for s in range(a.warmup, total):
+        pipe.load_fasta(texts[s])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = pipe.run()
+        torch.cuda.synchronize()
+        t_res += time.perf_counter() - t0
+        digest.update(out)
+        st = pipe.stats()
+        for k in keys:
+            acc[k] += st[k]
+    barrier()
+    t_res = max_over_ranks(t_res)
+
+    # ---- end-to-end loop: FASTA text in host memory -> output text in host memory
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for s in range(a.warmup, total):
+        pipe.load_fasta(texts[s])
+        out = pipe.run()
+        st = pipe.stats()
+        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()
+    pipe.close()
+
+    reads_all = sum_over_ranks(R * a.steps)
+    cells_all = sum_over_ranks(acc["wdp_cells"])
+    kernel_ms = acc["wdp_fill_ms"] + acc["wdp_tb_ms"]
+    gcups_rank = acc["wdp_cells"] / max(kernel_ms, 1e-9) / 1e6
+    fill_gcups = acc["wdp_cells"] / max(acc["wdp_fill_ms"], 1e-9) / 1e6
+    peak_gcups = alu["viaddmnmx_s32"] / I_CELL_INT32
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    di_bytes = acc["di_bytes_in"] + acc["di_bytes_out"]
+    di_gbs = di_bytes / max(acc["di_kernel_ms"], 1e-9) / 1e6
+
+    line = {
+        "metric": "reads_per_s", "value": round(reads_all / t_res, 3), "unit": "reads/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": round(t_res / a.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "C5 synthetic long reads 10-20 kb, unit 2-500 bp, 5-15% noise", "reads_per_step_per_gpu": R,
+                   "mode": "default (Manhattan), -m 0.6", "host_threads_per_gpu": threads,
+                   "l2": "working set per step (direction matrices, %d MB) exceeds the 126 MB L2" % (acc["wdp_dir_bytes"] / a.steps / 2 ** 20)},
+        "e2e": {"value": round(reads_all / t_e2e, 3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d / a.steps),
+                "d2h_bytes_per_step": int(d2h / a.steps)},
+        "gpu_launches": int(acc["launches"]),
+        "gcups": {"wrap_around_dp": round(gcups_rank, 2), "fill_only": round(fill_gcups, 2),
+                  "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3), "algorithmic_cells_per_step": int(acc["wdp_cells"] / a.steps)},
+        "roofline": {"kernel": "wdp_fill_* (K3 wrap-around DP)", "bound": "int-alu", "achieved": round(fill_gcups, 2),
+                     "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4), "traffic": None,
+                     "peak_how": "mtr_alu_probe: %.0f G lane-ops/s VIADDMNMX.RELU measured now / %.0f instr per cell (SURVEY.md 8(d))"
+                                 % (alu["viaddmnmx_s32"], I_CELL_INT32),
+                     "alu_probe_gops": {k: round(v, 1) for k, v in alu.items()},
+                     "dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3)},
+        "roofline_di": {"kernel": "di_codes + di_slide + di_merge (K1/K2)", "bound": "hbm", "achieved": round(di_gbs, 3),
+                        "peak": hbm_peak, "unit": "GB/s", "frac": round(di_gbs / hbm_peak, 6), "traffic": None,
+                        "note": "algorithmic bytes = packed reads in + 16 B per position out; the stage is LSU/shared-memory bound"},
+        "breakdown_ms_per_step": {k: round(acc[k] / a.steps, 2) for k in ("di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms",
+                                                                         "wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms")},
+        "rounds_per_step": int(acc["rounds"] / a.steps), "fast_lane_rounds_per_step": int(acc["rounds_fast"] / a.steps), "dp_jobs_per_step": int(acc["jobs"] / a.steps),
+        "clocks": clk, "output_md5": digest.hexdigest(),
+    }
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        n = a.cpu_sample or 2 * cores
+        binary, kind = (REF_BIN, "reference") if os.path.exists(REF_BIN) else (ORACLE_BIN, "port")
+        sample = step_reads(n, 0, a.warmup)[:n] if n <= R else step_reads(n, 0, a.warmup)
+        dt, ref_out = run_reference_cli(binary, sample, cores)
+        line["cpu_baseline"] = {"value": round(len(sample) / dt, 3), "unit": "reads/s", "cores": cores, "kind": kind,
+                                "sample": "%d reads of the step's workload (seed of step %d), %d processes, %.1f s" % (len(sample), a.warmup, cores, dt)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

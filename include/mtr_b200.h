@@ -49,6 +49,10 @@ int  mtr_device_count(void);
 int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int64_t *word_off, const int32_t *len,
                      int n_reads);
 
+/* Makes dst use the read batch resident in src (same device) without copying it; dst does not own the memory,
+ * so src must outlive dst's use of the batch.  Lets several contexts run DP batches concurrently on one GPU. */
+int mtr_reads_share(mtr_ctx *dst, const mtr_ctx *src);
+
 /* ------------------------------------------------------------------ K3: wrap-around DP */
 /* One job = one call of wrap_around_DP_sub (wrap_around_DP.c:222-354), of the DP inside
  * revise_representative_unit_sub (consensus.c:851-962, mode CONSENSUS) or of pretty_print_alignment
@@ -132,6 +136,33 @@ typedef struct {
     int32_t  n_sm;
 } mtr_stats;
 int mtr_get_stats(const mtr_ctx *ctx, mtr_stats *out);
+
+/* Integer-ALU issue microbenchmark: giga lane-operations per second of VIADDMNMX.RELU (kind 0), LOP3/IADD
+ * (kind 1) and VIADDMNMX.S16x2 (kind 2) with every SM busy -- the denominator of the DP roofline. */
+int mtr_alu_probe(mtr_ctx *ctx, int kind, double *gops);
+
+/* ------------------------------------------------------------------ batch-level pipeline */
+/* The whole per-read path of handle_one_file (handle_one_file.c:271-293 -> handle_one_read.c:190-261) on FASTA
+ * text that is already in host memory, split so that the host<->device boundary can be timed separately:
+ *   load_fasta : parse + stale-state tracking + 2-bit pack + H2D   (afterwards the batch is resident in HBM)
+ *   run        : directional index, candidate rounds (unit finder on the host cores, DP on the GPU), chaining;
+ *                returns the text the reference would print for these reads (TSV records, alignments with -a)
+ * Uses the globals Manhattan_Distance and min_match_ratio like the reference. */
+typedef struct mtr_pipeline mtr_pipeline;
+typedef struct {
+    int64_t reads, bases, candidates, rounds, rounds_fast, jobs, wdp_calls;
+    int64_t wdp_cells, wdp_slot_cells, wdp_dir_bytes;      /* algorithmic cells = sum rows * ulen over every DP run */
+    int64_t di_position_passes, di_bytes_in, di_bytes_out;
+    int64_t h2d_bytes, d2h_bytes;
+    int64_t launches;                                      /* CUDA kernels launched by run() */
+    double  wdp_fill_ms, wdp_tb_ms, di_kernel_ms;          /* CUDA-event time on the launching streams */
+    double  di_wall_ms, rounds_wall_ms, host_step_ms, wdp_wall_ms;
+} mtr_pipeline_stats;
+int  mtr_pipeline_open(int device, int threads, mtr_pipeline **out);
+void mtr_pipeline_close(mtr_pipeline *p);
+int  mtr_pipeline_load_fasta(mtr_pipeline *p, const char *text, int64_t len);
+int  mtr_pipeline_run(mtr_pipeline *p, int print_alignment, const char **out_text, int64_t *out_len);
+int  mtr_pipeline_get_stats(const mtr_pipeline *p, mtr_pipeline_stats *out);
 
 /* ------------------------------------------------------------------ the reference's entry points */
 /* mTR.h:126  handle_one_file(char *inputFile, int print_alignment): parses the FASTA, runs the pipeline on

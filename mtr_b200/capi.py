@@ -18,9 +18,10 @@ TB_COUNTS, TB_CONSENSUS, TB_PATH = 0, 1, 2
 
 # every symbol include/mtr_b200.h declares (tests check that the library exports all of them)
 ABI_FUNCTIONS = [
-    "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_reads_upload",
+    "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_di_run", "mtr_get_stats",
-    "handle_one_file", "handle_one_read", "mtr_flush",
+    "mtr_alu_probe", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_run",
+    "mtr_pipeline_get_stats", "handle_one_file", "handle_one_read", "mtr_flush",
 ]
 ABI_GLOBALS = [
     "Manhattan_Distance", "min_match_ratio", "orgInputString", "time_all", "time_memory", "time_range",
@@ -50,6 +51,14 @@ class Stats(C.Structure):
         ("di_position_passes", C.c_int64), ("di_bytes_in", C.c_int64), ("di_bytes_out", C.c_int64),
         ("launches", C.c_int32), ("n_sm", C.c_int32),
     ]
+
+
+class PipelineStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "reads", "bases", "candidates", "rounds", "rounds_fast", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
+        "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches")] + \
+        [(n, C.c_double) for n in ("wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms",
+                                   "host_step_ms", "wdp_wall_ms")]
 
 
 JOB_DTYPE = np.dtype([
@@ -89,11 +98,19 @@ def load_library() -> C.CDLL:
     lib.mtr_wdp_download.argtypes = [vp, vp, vp, i64]
     lib.mtr_di_run.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.mtr_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.mtr_alu_probe.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.mtr_pipeline_open.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
+    lib.mtr_pipeline_close.argtypes = [vp]
+    lib.mtr_pipeline_close.restype = None
+    lib.mtr_pipeline_load_fasta.argtypes = [vp, C.c_char_p, i64]
+    lib.mtr_pipeline_run.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(i64)]
+    lib.mtr_pipeline_get_stats.argtypes = [vp, C.POINTER(PipelineStats)]
     lib.handle_one_file.argtypes = [C.c_char_p, C.c_int]
     lib.handle_one_file.restype = C.c_int
     lib.mtr_flush.restype = None
     for f in ("mtr_reads_upload", "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download",
-              "mtr_di_run", "mtr_get_stats"):
+              "mtr_di_run", "mtr_get_stats", "mtr_alu_probe", "mtr_pipeline_open", "mtr_pipeline_load_fasta",
+              "mtr_pipeline_run", "mtr_pipeline_get_stats"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
     return lib
@@ -211,3 +228,49 @@ class Context:
         s = Stats()
         self._check(self.lib.mtr_get_stats(self.h, C.byref(s)), "mtr_get_stats")
         return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    def alu_probe(self, kind: int) -> float:
+        """Giga lane-ops/s of the integer pipe (0: VIADDMNMX.RELU s32, 1: LOP3+IADD, 2: VIADDMNMX s16x2)."""
+        g = C.c_double()
+        self._check(self.lib.mtr_alu_probe(self.h, kind, C.byref(g)), "mtr_alu_probe")
+        return g.value
+
+
+class Pipeline:
+    """Batch-level mirror of handle_one_file: FASTA text in host memory -> the text mTR prints.
+
+    The reference reads its two options from globals (main.c:53-56); so does the library."""
+
+    def __init__(self, device: int = 0, threads: int = 0, manhattan: bool = True, min_match_ratio: float = 0.6):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.mtr_pipeline_open(device, threads, C.byref(h))
+        if rc != 0:
+            raise MtrError("mtr_pipeline_open(%d) failed (%d): %s" % (device, rc, self.lib.mtr_last_error(None).decode()))
+        self.h = h
+        C.c_int.in_dll(self.lib, "Manhattan_Distance").value = 1 if manhattan else 0
+        C.c_float.in_dll(self.lib, "min_match_ratio").value = min_match_ratio
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mtr_pipeline_close(self.h)
+            self.h = None
+
+    def load_fasta(self, text: bytes) -> int:
+        n = self.lib.mtr_pipeline_load_fasta(self.h, text, len(text))
+        if n < 0:
+            raise MtrError("mtr_pipeline_load_fasta failed (%d)" % n)
+        return n
+
+    def run(self, print_alignment: bool = False) -> bytes:
+        out = C.c_char_p()
+        n = C.c_int64()
+        rc = self.lib.mtr_pipeline_run(self.h, 1 if print_alignment else 0, C.byref(out), C.byref(n))
+        if rc != 0:
+            raise MtrError("mtr_pipeline_run failed (%d)" % rc)
+        return C.string_at(out, n.value)
+
+    def stats(self) -> dict:
+        s = PipelineStats()
+        self.lib.mtr_pipeline_get_stats(self.h, C.byref(s))
+        return {n: getattr(s, n) for n, _ in PipelineStats._fields_}

@@ -119,6 +119,21 @@ extern "C" int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int6
     return MTR_OK;
 }
 
+extern "C" int mtr_reads_share(mtr_ctx *dst, const mtr_ctx *src)
+{
+    if (!dst || !src || dst == src) return MTR_EINVAL;
+    if (dst->device != src->device) { mtr_set_error(dst, "reads_share: contexts are on different devices"); return MTR_EINVAL; }
+    dst->d_packed.borrow(src->d_packed.p, src->d_packed.cap);
+    dst->d_word_off.borrow(src->d_word_off.p, src->d_word_off.cap);
+    dst->d_len.borrow(src->d_len.p, src->d_len.cap);
+    dst->word_off = src->word_off;
+    dst->len = src->len;
+    dst->n_reads = src->n_reads;
+    dst->n_words = src->n_words;
+    dst->wdp.uploaded = false;
+    return MTR_OK;
+}
+
 extern "C" int mtr_wdp_upload(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len, int64_t aux_bytes)
 {
     if (!ctx) return MTR_EINVAL;

@@ -40,7 +40,7 @@ struct DiTask {             // one chunk of one pass
 
 struct DiState {
     DevBuf d_mt, d_reads, d_passes, d_tasks[3], d_s1, d_s3, d_s5, d_stream, d_stale;
-    DevBuf d_di, d_end, d_w, d_work_di, d_work_end, d_work_w;
+    DevBuf d_di, d_end, d_w, d_work_di, d_work_end, d_work_w, d_work_tmp;
     bool mt_ready = false;
 };
 
@@ -52,7 +52,7 @@ void di_state_free(mtr_ctx *ctx)
     for (int i = 0; i < 3; i++) d->d_tasks[i].release();
     d->d_s1.release(); d->d_s3.release(); d->d_s5.release(); d->d_stream.release(); d->d_stale.release();
     d->d_di.release(); d->d_end.release(); d->d_w.release();
-    d->d_work_di.release(); d->d_work_end.release(); d->d_work_w.release();
+    d->d_work_di.release(); d->d_work_end.release(); d->d_work_w.release(); d->d_work_tmp.release();
     delete d;
     ctx->di = nullptr;
 }
@@ -194,67 +194,117 @@ __device__ __forceinline__ double di_value(const DiPass &ps, const int *__restri
     return sd[ps.stream_off + i + ps.w] - sd[ps.stream_off + i];          // P_12 - P_01, :355
 }
 
+// One warp per read.  Per pass the 32 lanes first materialise directional_index_tmp[0..N) as fp64 (two loads and
+// one divide per position, in parallel), then lane 0 runs the reference's sequential state machine over it.
 template <bool MANHATTAN>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 di_merge(const DiRead *__restrict__ reads, int n_reads, const DiPass *__restrict__ passes,
          const int *__restrict__ si, const double *__restrict__ sd,
-         double *__restrict__ wdi, int *__restrict__ wend, int *__restrict__ ww,
+         double *__restrict__ wdi, int *__restrict__ wend, int *__restrict__ ww, double *__restrict__ wtmp,
          double *__restrict__ odi, int *__restrict__ oend, int *__restrict__ ow)
 {
-    const int rdi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rdi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (rdi >= n_reads) return;
     const DiRead rd = reads[rdi];
     const int N = rd.N, L = rd.len, r = rd.r;
-    double *DI = wdi + rd.work_off;
+    double *DI = wdi + rd.work_off, *tmp = wtmp + rd.work_off;
     int *EN = wend + rd.work_off, *WW = ww + rd.work_off;
-    for (int i = 0; i < N; i++) { DI[i] = -1; EN[i] = -1; WW[i] = -1; }
+    for (int i = lane; i < N; i += 32) { DI[i] = -1; EN[i] = -1; WW[i] = -1; }
     for (int pi = 0; pi < rd.npass; pi++) {
         const DiPass ps = passes[rd.pass_begin + pi];
         const int w = ps.w;
-        // put_local_maximum_into_directional_index, :467-503
-        double local_max = -1;
-        int local_max_i = -1;
-        for (int i = 0; i < N; i++) {
-            const double t = di_value<MANHATTAN>(ps, si, sd, i);
-            if (local_max < t) { local_max = t; local_max_i = i; }
-            if (local_max_i >= 0 && local_max_i + w < i && DI[local_max_i] < local_max && 0 < local_max) {
-                double local_min = 1;
-                int local_min_j = local_max_i;
-                for (int j = local_max_i; j < N; j++) {
-                    const double tj = di_value<MANHATTAN>(ps, si, sd, j);
-                    if (local_min > tj) { local_min = tj; local_min_j = j; }
-                    if (local_min_j + w < j) {
-                        DI[local_max_i] = local_max;
-                        WW[local_max_i] = w;
-                        EN[local_max_i] = local_min_j + w;
-                        i = local_min_j + w;
-                        break;
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) tmp[i] = di_value<MANHATTAN>(ps, si, sd, i);
+        __syncwarp();
+        if (lane == 0) {
+            // put_local_maximum_into_directional_index, :467-503
+            double local_max = -1;
+            int local_max_i = -1;
+            for (int i = 0; i < N; i++) {
+                const double t = tmp[i];
+                if (local_max < t) { local_max = t; local_max_i = i; }
+                if (local_max_i >= 0 && local_max_i + w < i && DI[local_max_i] < local_max && 0 < local_max) {
+                    double local_min = 1;
+                    int local_min_j = local_max_i;
+                    for (int j = local_max_i; j < N; j++) {
+                        const double tj = tmp[j];
+                        if (local_min > tj) { local_min = tj; local_min_j = j; }
+                        if (local_min_j + w < j) {
+                            DI[local_max_i] = local_max;
+                            WW[local_max_i] = w;
+                            EN[local_max_i] = local_min_j + w;
+                            i = local_min_j + w;
+                            break;
+                        }
                     }
+                    local_max = -1;
                 }
-                local_max = -1;
             }
         }
     }
+    __syncwarp();
     // unshift (:587-597) into the output arrays (only [0, L) is ever read again)
     double *O = odi + rd.pos_off;
     int *OE = oend + rd.pos_off, *OW = ow + rd.pos_off;
-    for (int i = 0; i < L; i++) { O[i] = DI[i + r]; OE[i] = EN[i + r] - r; OW[i] = WW[i + r]; }
-    // remove_redundant_ranges (:505-546); entries at or beyond L are -1 in the reference
-    for (int i = 0; i < L; i++) {
-        const int ie = OE[i];
-        const double idi = O[i];
+    for (int i = lane; i < L; i += 32) { O[i] = DI[i + r]; OE[i] = EN[i + r] - r; OW[i] = WW[i + r]; }
+}
+
+// remove_redundant_ranges (fill_directional_index.c:505-546), one warp per read.  The outer loop over range
+// starts i is sequential (an earlier iteration may have removed i or j); for a fixed i every later range j is
+// judged against i's cached values only, so the j loop is data-parallel: the warp tests 32 live ranges at a
+// time, applies "remove j" up to the first lane that says "remove i", and stops there like the reference's break.
+__global__ void __launch_bounds__(128)
+di_prune(const DiRead *__restrict__ reads, int n_reads, double *__restrict__ wdi, int *__restrict__ wend, int *__restrict__ wpos,
+         double *__restrict__ odi, int *__restrict__ oend)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_reads) return;
+    const DiRead rd = reads[warp];
+    const int L = rd.len;
+    double *O = odi + rd.pos_off;
+    int *OE = oend + rd.pos_off;
+    double *LD = wdi + rd.work_off;                 // compacted live ranges: DI, end, start
+    int *LE = wend + rd.work_off, *LP = wpos + rd.work_off;
+    int n = 0;
+    for (int base = 0; base < L; base += 32) {
+        const int i = base + lane;
+        const double v = i < L ? O[i] : -1.0;
+        const bool live = 0 < v;
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int at = n + __popc(m & ((1u << lane) - 1u));
+            LD[at] = v; LE[at] = OE[i]; LP[at] = i;
+        }
+        n += __popc(m);
+    }
+    __syncwarp();
+    for (int a = 0; a < n; a++) {
+        const double idi = LD[a];
         if (!(0 < idi)) continue;
-        for (int j = i + 1; j <= ie && j < L; j++) {
-            const int je = OE[j];
-            const double jdi = O[j];
-            if (!(0 < jdi)) continue;
-            const double jac = (double)(min(ie, je) - j) / (double)(max(ie, je) - i);
-            if (0.98 < jac) {
-                if (idi < jdi) { O[i] = -1; OE[i] = -1; break; }
-                O[j] = -1; OE[j] = -1;
-            } else if (ie >= je && idi > jdi) {
-                O[j] = -1; OE[j] = -1;
+        const int i = LP[a], ie = LE[a];
+        bool i_dead = false;
+        for (int b0 = a + 1; b0 < n && !i_dead; b0 += 32) {
+            const int b = b0 + lane;
+            int outcome = 0;                        // 1: remove j, 2: remove i
+            bool in_range = false;
+            if (b < n) {
+                const int j = LP[b];
+                in_range = j <= ie;
+                const double jdi = LD[b];
+                if (in_range && 0 < jdi) {
+                    const int je = LE[b];
+                    const double jac = (double)(min(ie, je) - j) / (double)(max(ie, je) - i);
+                    if (0.98 < jac) outcome = idi < jdi ? 2 : 1;
+                    else if (ie >= je && idi > jdi) outcome = 1;
+                }
             }
+            const unsigned kill_i = __ballot_sync(0xffffffffu, outcome == 2);
+            const unsigned beyond = __ballot_sync(0xffffffffu, b < n && !in_range);
+            const int first = kill_i ? __ffs(kill_i) - 1 : 32;
+            if (outcome == 1 && lane < first) { LD[b] = -1; O[LP[b]] = -1; OE[LP[b]] = -1; }
+            if (kill_i) { i_dead = true; if (lane == 0) { LD[a] = -1; O[i] = -1; OE[i] = -1; } }
+            __syncwarp();
+            if (beyond) break;                      // starts are sorted: nothing further can be <= ie
         }
     }
 }
@@ -338,6 +388,7 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     MTR_CUDA(ctx, d.d_end.reserve((size_t)std::max<long long>(total_pos, 1) * 4));
     MTR_CUDA(ctx, d.d_w.reserve((size_t)std::max<long long>(total_pos, 1) * 4));
     MTR_CUDA(ctx, d.d_work_di.reserve((size_t)work_total * 8));
+    MTR_CUDA(ctx, d.d_work_tmp.reserve((size_t)work_total * 8));
     MTR_CUDA(ctx, d.d_work_end.reserve((size_t)work_total * 4));
     MTR_CUDA(ctx, d.d_work_w.reserve((size_t)work_total * 4));
     MTR_CUDA(ctx, cudaMemcpyAsync(d.d_reads.p, reads.data(), sizeof(DiRead) * (size_t)n, cudaMemcpyHostToDevice, s));
@@ -382,11 +433,15 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     SLIDE(5, 48, uint16_t, d.d_s5.p, 2)
 #undef SLIDE
     if (manhattan)
-        di_merge<true><<<(n + 63) / 64, 64, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
-                                                   (double *)d.d_di.p, (int *)d.d_end.p, (int *)d.d_w.p);
+        di_merge<true><<<(n * 32 + 127) / 128, 128, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
+                                                           (double *)d.d_work_tmp.p, (double *)d.d_di.p, (int *)d.d_end.p, (int *)d.d_w.p);
     else
-        di_merge<false><<<(n + 63) / 64, 64, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
-                                                    (double *)d.d_di.p, (int *)d.d_end.p, (int *)d.d_w.p);
+        di_merge<false><<<(n * 32 + 127) / 128, 128, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
+                                                            (double *)d.d_work_tmp.p, (double *)d.d_di.p, (int *)d.d_end.p, (int *)d.d_w.p);
+    MTR_CUDA(ctx, cudaGetLastError());
+    launches++;
+    di_prune<<<(n * 32 + 127) / 128, 128, 0, s>>>(dr, n, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
+                                                 (double *)d.d_di.p, (int *)d.d_end.p);
     MTR_CUDA(ctx, cudaGetLastError());
     launches++;
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));

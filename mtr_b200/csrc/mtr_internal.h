@@ -22,8 +22,11 @@ void mtr_set_error(mtr_ctx *ctx, const char *fmt, ...);
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;      // points into another context's allocation
+    void borrow(void *q, size_t c) { release(); p = q; cap = c; borrowed = true; }
     cudaError_t reserve(size_t bytes)
     {
+        if (borrowed) { p = nullptr; cap = 0; borrowed = false; }
         if (bytes <= cap) return cudaSuccess;
         size_t want = bytes + bytes / 4 + 4096;
         if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
@@ -31,7 +34,7 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
 };
 
 struct PinBuf {

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -428,7 +429,7 @@ struct ReadState {
     long long candidates = 0;
 };
 
-struct Worker { Counter cnt; };
+struct Worker { Counter cnt; double t_build = 0, t_list = 0, t_walk = 0, t_polish = 0, t_step = 0; long long n_chain = 0, n_walk = 0; };
 
 struct RoundResults {
     const mtr_wdp_result *res = nullptr;   // [2 * job]
@@ -472,15 +473,22 @@ void start_chain(ReadState &rs, Chain &ch, Worker &wk)
     ch.rr.inputLen = rs.L; ch.rr.kmer = ch.k;
     ch.dir_found[0] = ch.dir_found[1] = false;
     ch.found_last = false;
+    double tp0 = now_s();
     wk.cnt.build(rs.org, rs.L, ch.k, rs.qs, rs.qe);
+    double tp1 = now_s();
+    wk.t_build += tp1 - tp0; wk.n_chain++;
     const int maxf = wk.cnt.max_freq();
     int nodes[100];
     const int nn = wk.cnt.list_max_nodes(nodes, 100, maxf);
+    tp0 = now_s();
+    wk.t_list += tp0 - tp1;
+    struct WalkTimer { Worker &w; double t0; ~WalkTimer() { w.t_walk += now_s() - t0; } } walk_timer{wk, tp0};
     bool any = false;
     if (5 < maxf) {
         for (int d = 0; d < 2; d++)
             for (int i = 0; i < nn; i++) {
                 Rec r = ch.rr;
+                wk.n_walk++;
                 const bool found = walk(wk.cnt, rs.qs, rs.qe, nodes[i], ch.k, d == 1, r);
                 ch.found_last = found;
                 if (!found) continue;
@@ -526,7 +534,7 @@ void advance_chain(ReadState &rs, Chain &ch, Worker &wk, const RoundResults &rr)
         const int coverage = ch.rr.repeat_len / ch.rr.period;
         if (!(5 <= coverage && coverage <= 20 && 5 < ch.rr.period)) { ch.stage = Chain::DONE; return; }
         // revise_representative_unit (consensus.c:1048-1087)
-        polish(wk.cnt, rs.org, rs.L, ch.rr);
+        { const double tq = now_s(); polish(wk.cnt, rs.org, rs.L, ch.rr); wk.t_polish += now_s() - tq; }
         ch.ratio0 = ch.rr.ratio();
         ch.pass = 0;
         emit_revise_cons(rs, ch);
@@ -702,7 +710,8 @@ struct ReadInput {
 }
 
 struct Engine {
-    mtr_ctx *ctx = nullptr;
+    mtr_ctx *ctx = nullptr;            // directional index + the lane of long DP jobs
+    mtr_ctx *ctx_fast = nullptr;       // the lane of short DP jobs (shares the resident reads of ctx)
     Pool *pool = nullptr;
     std::vector<Worker> workers;
     double t_di = 0, t_dp = 0, t_rounds = 0;
@@ -710,46 +719,82 @@ struct Engine {
 
     Engine(int device, int threads)
     {
-        const int rc = mtr_cuda_init(device, &ctx);
+        int rc = mtr_cuda_init(device, &ctx);
+        if (rc) die(nullptr, "mtr_cuda_init", rc);
+        rc = mtr_cuda_init(device, &ctx_fast);
         if (rc) die(nullptr, "mtr_cuda_init", rc);
         pool = new Pool(threads);
         workers.resize(pool->size());
     }
-    ~Engine() { delete pool; mtr_cuda_shutdown(ctx); }
+    ~Engine() { delete pool; mtr_cuda_shutdown(ctx_fast); mtr_cuda_shutdown(ctx); }
+
+    // resident batch (prepare) + statistics of the last run
+    std::vector<int64_t> b_word_off, b_stale_off, b_pos_off;
+    std::vector<uint16_t> b_stale;
+    mtr_pipeline_stats ps = {};
 
     // Processes one batch; returns the text the reference would have printed for these reads, in order.
     std::string process(std::vector<ReadInput> &in, int print_alignment)
     {
+        prepare(in);
+        return run(in, print_alignment);
+    }
+
+    // 2-bit packs the reads and uploads them: after this the batch is resident in HBM.
+    void prepare(std::vector<ReadInput> &in)
+    {
         const int n = (int)in.size();
-        std::string out;
-        if (n == 0) return out;
-        // ---- pack (2 bit) and upload; directional index on the GPU
-        std::vector<int64_t> word_off(n + 1, 0), stale_off(n + 1, 0), pos_off(n + 1, 0);
+        if (n == 0) return;
+        b_word_off.assign(n + 1, 0); b_stale_off.assign(n + 1, 0); b_pos_off.assign(n + 1, 0);
         std::vector<int32_t> lens(n);
         for (int r = 0; r < n; r++) {
             lens[r] = in[r].len;
             const int64_t words = (in[r].len + 2 + 15) / 16;
-            word_off[r + 1] = word_off[r] + ((words + 3) / 4) * 4;
-            stale_off[r + 1] = stale_off[r] + (int64_t)in[r].stale.size();
-            pos_off[r + 1] = pos_off[r] + in[r].len;
+            b_word_off[r + 1] = b_word_off[r] + ((words + 3) / 4) * 4;
+            b_stale_off[r + 1] = b_stale_off[r] + (int64_t)in[r].stale.size();
+            b_pos_off[r + 1] = b_pos_off[r] + in[r].len;
         }
-        std::vector<uint32_t> packed((size_t)word_off[n], 0u);
-        std::vector<uint16_t> stale((size_t)stale_off[n]);
+        std::vector<uint32_t> packed((size_t)b_word_off[n], 0u);
+        b_stale.assign((size_t)b_stale_off[n], 0);
         pool->run(n, [&](int, int r) {
-            uint32_t *dst = packed.data() + word_off[r];
+            uint32_t *dst = packed.data() + b_word_off[r];
             const uint8_t *b = in[r].bases.data();
             const int nb = in[r].len + 2;
             for (int i = 0; i < nb; i++) dst[i >> 4] |= (uint32_t)b[i] << ((i & 15) * 2);
-            if (!in[r].stale.empty()) memcpy(stale.data() + stale_off[r], in[r].stale.data(), in[r].stale.size() * 2);
+            if (!in[r].stale.empty()) memcpy(b_stale.data() + b_stale_off[r], in[r].stale.data(), in[r].stale.size() * 2);
         });
-        int rc = mtr_reads_upload(ctx, packed.data(), word_off.data(), lens.data(), n);
+        int rc = mtr_reads_upload(ctx, packed.data(), b_word_off.data(), lens.data(), n);
         if (rc) die(ctx, "mtr_reads_upload", rc);
+        rc = mtr_reads_share(ctx_fast, ctx);
+        if (rc) die(ctx_fast, "mtr_reads_share", rc);
+        ps.h2d_bytes = (int64_t)packed.size() * 4 + (int64_t)(n + 1) * 12;
+    }
+
+    // Directional index + candidate rounds + chaining for the resident batch.
+    std::string run(std::vector<ReadInput> &in, int print_alignment)
+    {
+        const int n = (int)in.size();
+        std::string out;
+        if (n == 0) return out;
+        const std::vector<int64_t> &pos_off = b_pos_off;
+        const int64_t h2d_prepare = ps.h2d_bytes;
+        memset(&ps, 0, sizeof ps);
+        ps.h2d_bytes = h2d_prepare;
+        ps.reads = n; ps.bases = pos_off[n];
         std::vector<double> di((size_t)pos_off[n]);
         std::vector<int32_t> end((size_t)pos_off[n]), ww((size_t)pos_off[n]);
         double t0 = now_s();
-        rc = mtr_di_run(ctx, Manhattan_Distance, stale.data(), stale_off.data(), pos_off.data(), di.data(), end.data(), ww.data());
+        int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), di.data(), end.data(), ww.data());
         if (rc) die(ctx, "mtr_di_run", rc);
         t_di += now_s() - t0;
+        {
+            mtr_stats s;
+            mtr_get_stats(ctx, &s);
+            ps.di_kernel_ms = s.di_ms; ps.di_position_passes = s.di_position_passes; ps.launches += s.launches;
+            ps.di_bytes_in = s.di_bytes_in; ps.di_bytes_out = s.di_bytes_out;
+            ps.h2d_bytes += (int64_t)b_stale.size() * 2; ps.d2h_bytes += pos_off[n] * 16;
+            ps.di_wall_ms = (now_s() - t0) * 1e3;
+        }
         // ---- per-read state machines
         std::vector<ReadState> st(n);
         for (int r = 0; r < n; r++) {
@@ -758,54 +803,129 @@ struct Engine {
             rs.end.assign(end.begin() + pos_off[r], end.begin() + pos_off[r + 1]);
             rs.w.assign(ww.begin() + pos_off[r], ww.begin() + pos_off[r + 1]);
         }
-        std::vector<int> active(n);
-        for (int r = 0; r < n; r++) active[r] = r;
-        std::vector<mtr_wdp_job> jobs;
-        std::vector<uint8_t> units, aux;
-        std::vector<mtr_wdp_result> res;
-        RoundResults cur;
+        // Asynchronous rounds: host workers advance whichever reads have their DP results, the dispatcher thread
+        // sends everything queued so far to the GPU as soon as the previous batch is back.  No barrier: a read with
+        // an expensive host step (a de Bruijn walk with many tie-breaks) delays only itself.
         const long long dir_cap = dir_budget();
         t0 = now_s();
-        while (!active.empty()) {
-            pool->run((int)active.size(), [&](int tid, int i) { step_read(st[active[i]], workers[tid], cur, print_alignment); });
-            jobs.clear(); units.clear();
-            long long aux_bytes = 0;
-            size_t keep = 0;
-            for (size_t a = 0; a < active.size(); a++) {
-                ReadState &rs = st[active[a]];
-                if (rs.phase == ReadState::FINISHED) continue;
-                active[keep++] = active[a];
-                rs.job_base = (long long)jobs.size();
-                rs.job_aux.assign(rs.jobs.size(), 0);
-                for (size_t j = 0; j < rs.jobs.size(); j++) {
-                    const JobReq &q = rs.jobs[j];
-                    mtr_wdp_job g;
-                    memset(&g, 0, sizeof g);
-                    g.read = rs.index; g.first = q.first; g.rows = q.rows; g.ulen = q.ulen;
-                    g.unit_off = (int32_t)(units.size() + (size_t)q.unit_off);
-                    for (int s = 0; s < 2; s++) { g.gain[s] = q.g[s]; g.mis[s] = q.m[s]; g.indel[s] = q.in[s]; }
-                    g.n_param = q.n_param; g.mode = q.mode;
-                    if (q.mode != MTR_TB_COUNTS) {
-                        aux_bytes = (aux_bytes + 15) & ~15LL;
-                        rs.job_aux[j] = aux_bytes;
-                        g.aux_off = q.mode == MTR_TB_CONSENSUS ? aux_bytes / 4 : aux_bytes;
-                        g.aux_cap = q.aux_need;
-                        aux_bytes += q.mode == MTR_TB_CONSENSUS ? q.aux_need * 4 : q.aux_need;
-                    }
-                    jobs.push_back(g);
+        double host_ms = 0, wdp_ms = 0;
+        struct BatchResult { std::vector<mtr_wdp_result> res; std::vector<uint8_t> aux; };
+        std::vector<std::shared_ptr<BatchResult>> result_of(n);
+        std::mutex mu;
+        std::condition_variable cv_ready, cv_submit;
+        std::vector<int> ready(n), submitted[2];                  // lane 0: long jobs, lane 1: short jobs
+        for (int r = 0; r < n; r++) ready[r] = n - 1 - r;         // popped from the back: read 0 first
+        int remaining = n;
+        const int fast_rows = getenv("MTR_FAST_ROWS") ? atoi(getenv("MTR_FAST_ROWS")) : 1536;
+        auto worker_loop = [&](int tid) {
+            for (;;) {
+                int idx;
+                {
+                    std::unique_lock<std::mutex> g(mu);
+                    cv_ready.wait(g, [&] { return !ready.empty() || remaining == 0; });
+                    if (ready.empty()) return;
+                    idx = ready.back();
+                    ready.pop_back();
                 }
-                units.insert(units.end(), rs.units.begin(), rs.units.end());
+                ReadState &rs = st[idx];
+                RoundResults cur;
+                if (result_of[idx]) { cur.res = result_of[idx]->res.data(); cur.aux = result_of[idx]->aux.data(); }
+                const double ts = now_s();
+                step_read(rs, workers[tid], cur, print_alignment);
+                workers[tid].t_step += now_s() - ts;
+                result_of[idx].reset();
+                int lane = 1;
+                for (const JobReq &q : rs.jobs) if (q.rows > fast_rows) { lane = 0; break; }
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (rs.phase == ReadState::FINISHED) { if (--remaining == 0) { cv_ready.notify_all(); cv_submit.notify_all(); } }
+                    else { submitted[lane].push_back(idx); cv_submit.notify_all(); }
+                }
             }
-            active.resize(keep);
-            if (jobs.empty()) break;
-            rounds++; jobs_total += (long long)jobs.size();
-            res.resize(jobs.size() * 2);
-            aux.assign((size_t)aux_bytes, 0);
-            run_jobs(jobs, units, res, aux, dir_cap);
-            cur.res = res.data(); cur.aux = aux.data();
+        };
+        auto dispatch_loop = [&](int lane) {
+            mtr_ctx *lctx = lane ? ctx_fast : ctx;
+            cudaSetDevice(lctx->device);
+            std::vector<mtr_wdp_job> jobs;
+            std::vector<uint8_t> units;
+            std::vector<int> batch;
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> g(mu);
+                    cv_submit.wait(g, [&] { return !submitted[lane].empty() || remaining == 0; });
+                    if (submitted[lane].empty()) return;
+                    batch.swap(submitted[lane]);
+                    submitted[lane].clear();
+                }
+                jobs.clear(); units.clear();
+                long long aux_bytes = 0;
+                for (int idx : batch) {
+                    ReadState &rs = st[idx];
+                    rs.job_base = (long long)jobs.size();
+                    rs.job_aux.assign(rs.jobs.size(), 0);
+                    for (size_t j = 0; j < rs.jobs.size(); j++) {
+                        const JobReq &q = rs.jobs[j];
+                        mtr_wdp_job gj;
+                        memset(&gj, 0, sizeof gj);
+                        gj.read = rs.index; gj.first = q.first; gj.rows = q.rows; gj.ulen = q.ulen;
+                        gj.unit_off = (int32_t)(units.size() + (size_t)q.unit_off);
+                        for (int s = 0; s < 2; s++) { gj.gain[s] = q.g[s]; gj.mis[s] = q.m[s]; gj.indel[s] = q.in[s]; }
+                        gj.n_param = q.n_param; gj.mode = q.mode;
+                        if (q.mode != MTR_TB_COUNTS) {
+                            aux_bytes = (aux_bytes + 15) & ~15LL;
+                            rs.job_aux[j] = aux_bytes;
+                            gj.aux_off = q.mode == MTR_TB_CONSENSUS ? aux_bytes / 4 : aux_bytes;
+                            gj.aux_cap = q.aux_need;
+                            aux_bytes += q.mode == MTR_TB_CONSENSUS ? q.aux_need * 4 : q.aux_need;
+                        }
+                        jobs.push_back(gj);
+                    }
+                    units.insert(units.end(), rs.units.begin(), rs.units.end());
+                }
+                auto br = std::make_shared<BatchResult>();
+                br->res.resize(jobs.size() * 2);
+                br->aux.assign((size_t)aux_bytes, 0);
+                const double tg0 = now_s();
+                mtr_pipeline_stats local;
+                memset(&local, 0, sizeof local);
+                run_jobs(lctx, jobs, units, br->res, br->aux, dir_cap, local);
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    wdp_ms += (now_s() - tg0) * 1e3;
+                    rounds++; jobs_total += (long long)jobs.size();
+                    ps.rounds++; ps.jobs += (int64_t)jobs.size();
+                    if (lane) ps.rounds_fast++;
+                    ps.h2d_bytes += (int64_t)jobs.size() * sizeof(mtr_wdp_job) + (int64_t)units.size();
+                    ps.d2h_bytes += (int64_t)jobs.size() * 2 * sizeof(mtr_wdp_result) + aux_bytes;
+                    ps.wdp_fill_ms += local.wdp_fill_ms; ps.wdp_tb_ms += local.wdp_tb_ms; ps.wdp_cells += local.wdp_cells;
+                    ps.wdp_slot_cells += local.wdp_slot_cells; ps.wdp_dir_bytes += local.wdp_dir_bytes;
+                    ps.launches += local.launches; ps.wdp_calls += local.wdp_calls;
+                    for (int idx : batch) { result_of[idx] = br; ready.push_back(idx); }
+                }
+                cv_ready.notify_all();
+                batch.clear();
+            }
+        };
+        std::thread dispatcher0([&] { dispatch_loop(0); }), dispatcher1([&] { dispatch_loop(1); });
+        {
+            const double th0 = now_s();
+            pool->run(pool->size(), [&](int tid, int) { worker_loop(tid); });
+            host_ms += (now_s() - th0) * 1e3;
         }
+        dispatcher0.join();
+        dispatcher1.join();
         t_rounds += now_s() - t0;
-        for (int r = 0; r < n; r++) { out += st[r].out; candidates += st[r].candidates; }
+        t_dp += wdp_ms / 1e3;
+        ps.rounds_wall_ms = (now_s() - t0) * 1e3;
+        for (int r = 0; r < n; r++) { out += st[r].out; candidates += st[r].candidates; ps.candidates += st[r].candidates; }
+        ps.host_step_ms = host_ms; ps.wdp_wall_ms = wdp_ms;
+        if (getenv("MTR_PROFILE")) {
+            double b = 0, l = 0, w = 0, p = 0, t = 0; long long nc = 0, nw = 0;
+            for (Worker &k : workers) { b += k.t_build; l += k.t_list; w += k.t_walk; p += k.t_polish; t += k.t_step; nc += k.n_chain; nw += k.n_walk;
+                                        k.t_build = k.t_list = k.t_walk = k.t_polish = k.t_step = 0; k.n_chain = k.n_walk = 0; }
+            fprintf(stderr, "[mtr profile] reads %d rounds %lld | host cpu-s: step %.3f build %.3f maxlist %.3f walk %.3f polish %.3f | chains %lld walks %lld | wall: host %.3f s gpu %.3f s\n",
+                    n, (long long)ps.rounds, t, b, l, w, p, nc, nw, host_ms / 1e3, wdp_ms / 1e3);
+        }
         return out;
     }
 
@@ -816,8 +936,8 @@ struct Engine {
     }
 
     // Runs the round's jobs in sub-batches whose direction matrices fit the budget.
-    void run_jobs(std::vector<mtr_wdp_job> &jobs, std::vector<uint8_t> &units, std::vector<mtr_wdp_result> &res,
-                  std::vector<uint8_t> &aux, long long dir_cap)
+    void run_jobs(mtr_ctx *lctx, std::vector<mtr_wdp_job> &jobs, std::vector<uint8_t> &units, std::vector<mtr_wdp_result> &res,
+                  std::vector<uint8_t> &aux, long long dir_cap, mtr_pipeline_stats &acc)
     {
         size_t a = 0;
         std::vector<mtr_wdp_job> part;
@@ -841,10 +961,17 @@ struct Engine {
                 for (mtr_wdp_job &j : part)
                     if (j.mode != MTR_TB_COUNTS) j.aux_off -= j.mode == MTR_TB_CONSENSUS ? aux_lo / 4 : aux_lo;
             const double t0 = now_s();
-            const int rc = mtr_wdp_run(ctx, part.data(), (int)part.size(), units.data(), (int64_t)units.size(), res.data() + 2 * a,
+            const int rc = mtr_wdp_run(lctx, part.data(), (int)part.size(), units.data(), (int64_t)units.size(), res.data() + 2 * a,
                                        aux_lo >= 0 ? aux.data() + aux_lo : nullptr, aux_lo >= 0 ? aux_hi - aux_lo : 0);
-            if (rc) die(ctx, "mtr_wdp_run", rc);
-            t_dp += now_s() - t0;
+            if (rc) die(lctx, "mtr_wdp_run", rc);
+            (void)t0;
+            {
+                mtr_stats s;
+                mtr_get_stats(lctx, &s);
+                acc.wdp_fill_ms += s.wdp_fill_ms; acc.wdp_tb_ms += s.wdp_tb_ms; acc.wdp_cells += s.wdp_cells;
+                acc.wdp_slot_cells += s.wdp_slot_cells; acc.wdp_dir_bytes += s.wdp_dir_bytes; acc.launches += s.launches;
+                acc.wdp_calls++;
+            }
             a = b;
         }
     }
@@ -1087,4 +1214,99 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     while (!inflight.empty()) drain_front();
     publish_timers(rt);
     return n_reads;
+}
+
+// ================================================================ batch-level pipeline ABI (bench, tests, embedding)
+struct mtr_pipeline {
+    Engine *eng = nullptr;
+    StaleTracker *stale = nullptr;
+    std::vector<ReadInput> reads;
+    std::string out;
+};
+
+extern "C" int mtr_pipeline_open(int device, int threads, mtr_pipeline **out)
+{
+    if (!out) return MTR_EINVAL;
+    *out = nullptr;
+    mtr_ctx *probe = nullptr;
+    const int rc = mtr_cuda_init(device, &probe);       // fail with a code instead of exiting
+    if (rc) return rc;
+    mtr_cuda_shutdown(probe);
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    mtr_pipeline *p = new mtr_pipeline();
+    p->eng = new Engine(device, std::max(1, threads));
+    p->stale = new StaleTracker();
+    *out = p;
+    return MTR_OK;
+}
+
+extern "C" void mtr_pipeline_close(mtr_pipeline *p)
+{
+    if (!p) return;
+    delete p->eng; delete p->stale; delete p;
+}
+
+// Parses FASTA text held in host memory (same rules as handle_one_file), reproduces the cross-read stale state,
+// packs the reads to 2 bit and uploads them.  Returns the number of reads now resident, or a negative code.
+extern "C" int mtr_pipeline_load_fasta(mtr_pipeline *p, const char *text, int64_t len)
+{
+    if (!p || (!text && len > 0)) return MTR_EINVAL;
+    p->reads.clear();
+    ReadInput cur;
+    bool have = false;
+    auto flush = [&]() -> bool {
+        if (!have) return true;
+        cur.len = (int)cur.bases.size();
+        if (cur.len == 0) return false;                     // a zero-length read ends the run (handle_one_file.c:283)
+        p->stale->visit(cur, nullptr);
+        p->reads.push_back(std::move(cur));
+        cur = ReadInput();
+        return true;
+    };
+    int64_t i = 0;
+    bool stop = false;
+    while (i < len && !stop) {
+        int64_t e = i;
+        while (e < len && text[e] != '\n') e++;
+        if (text[i] == '>') {
+            if (!flush()) { stop = true; break; }
+            have = true;
+            cur.id.clear();
+            for (int64_t t = i + 1; t < e && text[t] != '\r'; t++) cur.id += text[t];
+        } else {
+            for (int64_t t = i; t < e && text[t] != '\r'; t++) {
+                uint8_t b;
+                switch (text[t]) {
+                case 'A': case 'a': b = 0; break;
+                case 'C': case 'c': b = 1; break;
+                case 'G': case 'g': b = 2; break;
+                case 'T': case 't': b = 3; break;
+                default: return MTR_EINVAL;
+                }
+                cur.bases.push_back(b);
+                if ((int)cur.bases.size() >= kMaxLen) return MTR_ERANGE;
+            }
+        }
+        i = e + 1;
+    }
+    if (!stop) flush();
+    p->eng->prepare(p->reads);
+    return (int)p->reads.size();
+}
+
+// Runs the pipeline on the resident batch (may be called repeatedly).  *out_text stays valid until the next call.
+extern "C" int mtr_pipeline_run(mtr_pipeline *p, int print_alignment, const char **out_text, int64_t *out_len)
+{
+    if (!p) return MTR_EINVAL;
+    p->out = p->eng->run(p->reads, print_alignment);
+    if (out_text) *out_text = p->out.data();
+    if (out_len) *out_len = (int64_t)p->out.size();
+    return MTR_OK;
+}
+
+extern "C" int mtr_pipeline_get_stats(const mtr_pipeline *p, mtr_pipeline_stats *out)
+{
+    if (!p || !out) return MTR_EINVAL;
+    *out = p->eng->ps;
+    return MTR_OK;
 }

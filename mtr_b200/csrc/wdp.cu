@@ -33,16 +33,19 @@
 #include "mtr_internal.h"
 
 // ---------------------------------------------------------------- job classes
-// U <= G*C.  Small C for tiny units (many tiny jobs per warp), C = 16 for long units.
+// U <= G*C, capacities 16 .. 512.  Classes 0-5 maximise throughput (few lanes per job, long register chains:
+// more jobs per warp, less scan overhead); classes 6-11 minimise the latency of one row (many lanes, C = 4
+// where possible) and are used when a batch is too small to fill the GPU anyway.  Both variants of a capacity
+// write the same direction-matrix layout.
 static const WdpClass kClasses[WDP_NCLASS] = {
     {4, 4, 0},  {4, 8, 0},  {8, 8, 0},  {8, 16, 0}, {16, 16, 0}, {32, 16, 0},
-    {4, 4, 1},  {4, 8, 1},  {8, 8, 1},  {8, 16, 1}, {16, 16, 1}, {32, 16, 1},
+    {4, 4, 0},  {8, 4, 0},  {16, 4, 0}, {32, 4, 0}, {32, 8, 0},  {32, 16, 0},
 };
 
-static int class_of(int ulen, int paired)
+static int class_of(int ulen, int latency)
 {
     for (int k = 0; k < 6; k++)
-        if (ulen <= kClasses[k].G * kClasses[k].C) return k + (paired ? 6 : 0);
+        if (ulen <= kClasses[k].G * kClasses[k].C) return k + (latency ? 6 : 0);
     return -1;
 }
 
@@ -280,6 +283,13 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
     w.cells = 0; w.slot_cells = 0;
     std::vector<int> cls;
     cls.reserve((size_t)n_jobs * 2);
+    // latency classes if the whole batch fits the resident warps of the GPU even with one warp-row per job
+    long long lat_warps = 0;
+    for (int jn = 0; jn < n_jobs; jn++) {
+        const int k = class_of(std::max(1, std::min(jobs[jn].ulen, 499)), 1);
+        lat_warps += (long long)jobs[jn].n_param * kClasses[k].G;
+    }
+    const int latency = (lat_warps / 32) <= (long long)ctx->n_sm * 24 ? 1 : 0;
     for (int jn = 0; jn < n_jobs; jn++) {
         const mtr_wdp_job &j = jobs[jn];
         if (j.read < 0 || j.read >= ctx->n_reads || j.ulen < 1 || j.ulen >= 500 || j.rows < 0 ||
@@ -311,7 +321,7 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
             t.n_param = 1; t.mode = j.mode;
             t.aux_off = j.aux_off; t.aux_cap = j.aux_cap;
             t.result_idx = jn * 2 + p;
-            const int k = class_of(j.ulen, 0);
+            const int k = class_of(j.ulen, latency);
             t.dir_stride = kClasses[k].G * kClasses[k].C / 4;
             t.dir_bytes = (long long)t.rows * t.dir_stride;
             cls.push_back(k);
@@ -389,6 +399,12 @@ int wdp_launch_impl(mtr_ctx *ctx)
         case 3: launch_fill<8, 16>(ctx, k, dt, n, s); break;
         case 4: launch_fill<16, 16>(ctx, k, dt, n, s); break;
         case 5: launch_fill<32, 16>(ctx, k, dt, n, s); break;
+        case 6: launch_fill<4, 4>(ctx, k, dt, n, s); break;
+        case 7: launch_fill<8, 4>(ctx, k, dt, n, s); break;
+        case 8: launch_fill<16, 4>(ctx, k, dt, n, s); break;
+        case 9: launch_fill<32, 4>(ctx, k, dt, n, s); break;
+        case 10: launch_fill<32, 8>(ctx, k, dt, n, s); break;
+        case 11: launch_fill<32, 16>(ctx, k, dt, n, s); break;
         default: mtr_set_error(ctx, "wdp_launch: class %d has no kernel", k); return MTR_EINVAL;
         }
         MTR_CUDA(ctx, cudaGetLastError());

@@ -46,19 +46,18 @@ def mutate_repeat(rng: np.random.Generator, unit: np.ndarray, copies: int,
     kind[pos[:n_sub]] = 1
     kind[pos[n_sub:n_sub + n_ins]] = 2
     kind[pos[n_sub + n_ins:]] = 3
-    out = []
     sub_shift = rng.integers(1, 4, n, dtype=np.int8)
     ins_base = rng.integers(0, 4, n, dtype=np.int8)
-    for i in range(n):
-        k = kind[i]
-        if k == 0:
-            out.append(rep[i])
-        elif k == 1:
-            out.append((rep[i] + sub_shift[i]) % 4)
-        elif k == 2:
-            out.append(rep[i]); out.append(ins_base[i])
-        # k == 3: deleted
-    return np.asarray(out, dtype=np.int8)
+    counts = np.ones(n, dtype=np.int64)
+    counts[kind == 2] = 2
+    counts[kind == 3] = 0
+    out = np.repeat(rep, counts)
+    start = np.cumsum(counts) - counts
+    sub = kind == 1
+    out[start[sub]] = (rep[sub] + sub_shift[sub]) % 4
+    ins = kind == 2
+    out[start[ins] + 1] = ins_base[ins]
+    return out.astype(np.int8)
 
 
 def rand_seq_reads(unit_len: int, copies: int, sub: float, ins: float, dele: float,
