@@ -44,6 +44,7 @@ constexpr int kMaxLen = 1000000;      // MAX_INPUT_LENGTH, mTR.h:31
 constexpr int kMaxPeriod = 500;       // MAX_PERIOD, mTR.h:34
 constexpr int kMaxTies = 1024;        // MAX_tiebreaks, mTR.h:46
 constexpr long long kWrapCap = 200000000LL;   // WrapDPsize, mTR.h:51
+constexpr int kMaxInflightCands = 24;         // per read; bounds the jobs a read can queue in one round
 
 struct Pow4 { int v[16]; Pow4() { v[0] = 1; for (int i = 1; i < 16; i++) v[i] = v[i - 1] * 4; } };
 const Pow4 P4;
@@ -414,9 +415,8 @@ struct ReadState {
     int L = 0, index = 0;
     std::vector<int> end, w;           // directional_index_end / _w; dead entries have end < 0
     int cursor = 0;
-    bool in_candidate = false;
-    int qs = 0, qe = 0;
-    std::vector<Chain> chains;
+    struct Cand { int qs = 0, qe = 0; std::vector<Chain> chains; };
+    std::vector<Cand> cands;           // candidates in flight, in candidate order (front commits first)
     std::vector<ChainItem> accepted;
     std::vector<Rec> printing;         // -a: the chain waiting for its PATH jobs
     enum Phase { RUN, PRINT_WAIT, FINISHED } phase = RUN;
@@ -467,14 +467,14 @@ void emit_revise_cons(ReadState &rs, Chain &ch)
 }
 
 // search_De_Bruijn_graph up to the point where it needs wrap_around_DP (consensus.c:507-549)
-void start_chain(ReadState &rs, Chain &ch, Worker &wk)
+void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
 {
     ch.rr.clear();
     ch.rr.inputLen = rs.L; ch.rr.kmer = ch.k;
     ch.dir_found[0] = ch.dir_found[1] = false;
     ch.found_last = false;
     double tp0 = now_s();
-    wk.cnt.build(rs.org, rs.L, ch.k, rs.qs, rs.qe);
+    wk.cnt.build(rs.org, rs.L, ch.k, qs, qe);
     double tp1 = now_s();
     wk.t_build += tp1 - tp0; wk.n_chain++;
     const int maxf = wk.cnt.max_freq();
@@ -489,11 +489,11 @@ void start_chain(ReadState &rs, Chain &ch, Worker &wk)
             for (int i = 0; i < nn; i++) {
                 Rec r = ch.rr;
                 wk.n_walk++;
-                const bool found = walk(wk.cnt, rs.qs, rs.qe, nodes[i], ch.k, d == 1, r);
+                const bool found = walk(wk.cnt, qs, qe, nodes[i], ch.k, d == 1, r);
                 ch.found_last = found;
                 if (!found) continue;
                 ch.dir[d] = r; ch.dir_found[d] = true;
-                ch.dir_job[d] = add_job(rs, rs.qs, rs.qe - rs.qs + 1, r.unit, 2, kSearchParams, MTR_TB_COUNTS);
+                ch.dir_job[d] = add_job(rs, qs, qe - qs + 1, r.unit, 2, kSearchParams, MTR_TB_COUNTS);
                 any = true;
                 break;
             }
@@ -503,7 +503,7 @@ void start_chain(ReadState &rs, Chain &ch, Worker &wk)
     ch.stage = Chain::DONE;
 }
 
-void advance_chain(ReadState &rs, Chain &ch, Worker &wk, const RoundResults &rr)
+void advance_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk, const RoundResults &rr)
 {
     const mtr_wdp_result *res = rr.res + 2 * rs.job_base;
     if (ch.stage == Chain::SEARCH_WAIT) {
@@ -516,7 +516,7 @@ void advance_chain(ReadState &rs, Chain &ch, Worker &wk, const RoundResults &rr)
             float pick_ratio = -1;
             for (int s = 0; s < 2; s++) {
                 Rec t = ch.dir[d];
-                apply_dp(t, rs.qs, res[2 * ch.dir_job[d] + s], kSearchParams[s][0], kSearchParams[s][1], kSearchParams[s][2]);
+                apply_dp(t, qs, res[2 * ch.dir_job[d] + s], kSearchParams[s][0], kSearchParams[s][1], kSearchParams[s][2]);
                 const float ratio = t.ratio();
                 if (pick_ratio < ratio) { pick = t; pick_ratio = ratio; }
             }
@@ -527,7 +527,7 @@ void advance_chain(ReadState &rs, Chain &ch, Worker &wk, const RoundResults &rr)
         }
         ch.rr = best;
         if (!ch.found_last) { ch.rr.clear(); ch.stage = Chain::DONE; return; }            // Q4
-        if ((long long)ch.rr.period * (rs.qe - rs.qs + 1) > kWrapCap) {
+        if ((long long)ch.rr.period * (qe - qs + 1) > kWrapCap) {
             fprintf(stderr, "You need to increse the value of WrapDPsize.\n");
             ch.rr.clear(); ch.stage = Chain::DONE; return;
         }
@@ -594,17 +594,20 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
         rs.phase = ReadState::FINISHED;
         return;
     }
-    if (rs.in_candidate)
-        for (Chain &ch : rs.chains)
-            if (ch.stage != Chain::DONE) advance_chain(rs, ch, wk, rr);
+    for (ReadState::Cand &cd : rs.cands)
+        for (Chain &ch : cd.chains)
+            if (ch.stage != Chain::DONE) advance_chain(rs, cd.qs, cd.qe, ch, wk, rr);
     for (;;) {
-        if (rs.in_candidate) {
-            for (const Chain &ch : rs.chains)
-                if (ch.stage != Chain::DONE) return;        // its jobs are queued in rs.jobs
+        // commit finished candidates in candidate order
+        while (!rs.cands.empty()) {
+            ReadState::Cand &cd = rs.cands.front();
+            bool done = true;
+            for (const Chain &ch : cd.chains) if (ch.stage != Chain::DONE) { done = false; break; }
+            if (!done) break;
             // find_tandem_repeat's pick over k (handle_one_read.c:135-146), then handle_one_TR's accept (:236-243)
             Rec pick;
             float best_ratio = -1;
-            for (const Chain &ch : rs.chains) {
+            for (const Chain &ch : cd.chains) {
                 const float ratio = ch.rr.ratio();
                 if (best_ratio < ratio && min_match_ratio <= ratio && 5 < ch.rr.units && 2 <= ch.rr.period) {
                     best_ratio = ratio; pick = ch.rr;
@@ -618,22 +621,34 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
                 it.rec = pick; it.start = pick.rep_start; it.end = pick.rep_end; it.score = pick.nm; it.pred = nullptr;
                 rs.accepted.push_back(it);
             }
-            rs.in_candidate = false;
+            rs.cands.erase(rs.cands.begin());
         }
+        // Start further candidates.  An accepted repeat of an in-flight candidate (qs', qe') ends at rep_end <= qe'+1
+        // and prunes only ranges that end before rep_end (:181-182); a later candidate whose range ends beyond
+        // every in-flight qe' can therefore never be pruned by them and is evaluated concurrently -- same results,
+        // fewer sequential rounds.  Candidates that could still be pruned wait, exactly as in the reference.
         while (rs.cursor < rs.L && !(rs.end[rs.cursor] > -1 && rs.end[rs.cursor] < rs.L)) rs.cursor++;
-        if (rs.cursor >= rs.L) { finish_read(rs, print_alignment); return; }
-        rs.qs = rs.cursor; rs.qe = rs.end[rs.cursor];
+        if (rs.cursor >= rs.L) {
+            if (rs.cands.empty()) finish_read(rs, print_alignment);
+            return;
+        }
+        const int qs = rs.cursor, qe = rs.end[rs.cursor];
+        bool safe = (int)rs.cands.size() < kMaxInflightCands;
+        for (const ReadState::Cand &cd : rs.cands) if (cd.qe >= qe) { safe = false; break; }
+        if (!safe) return;                                  // wait for the in-flight candidates (they have jobs queued)
         const int cw = rs.w[rs.cursor];
         rs.cursor++;
         int min_k, max_k;                                   // handle_one_read.c:105-120
         if (cw < 100) { min_k = 2; max_k = 10; } else if (cw < 1000) { min_k = 2; max_k = 12; } else { min_k = 5; max_k = 15; }
-        rs.chains.resize(max_k - min_k + 1);
+        rs.cands.emplace_back();
+        ReadState::Cand &cd = rs.cands.back();
+        cd.qs = qs; cd.qe = qe;
+        cd.chains.resize(max_k - min_k + 1);
         for (int k = min_k; k <= max_k; k++) {
-            Chain &ch = rs.chains[k - min_k];
+            Chain &ch = cd.chains[k - min_k];
             ch.k = k;
-            start_chain(rs, ch, wk);
+            start_chain(rs, qs, qe, ch, wk);
         }
-        rs.in_candidate = true;
     }
 }
 
