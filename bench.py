@@ -183,7 +183,7 @@ def main():
     R = a.reads
     total = a.warmup + a.steps
     texts = [fasta_bytes(step_reads(R, rank, s)) for s in range(total)]
-    keys = ("reads", "bases", "candidates", "rounds", "rounds_fast", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
+    keys = ("reads", "bases", "candidates", "rounds", "rounds_fast", "rounds_uf", "uf_tasks", "uf_kernel_ms", "uf_wall_ms", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
             "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "wdp_fill_ms",
             "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms")
 
@@ -260,9 +260,9 @@ def main():
         "roofline_di": {"kernel": "di_codes + di_slide + di_merge (K1/K2)", "bound": "hbm", "achieved": round(di_gbs, 3),
                         "peak": hbm_peak, "unit": "GB/s", "frac": round(di_gbs / hbm_peak, 6), "traffic": None,
                         "note": "algorithmic bytes = packed reads in + 16 B per position out; the stage is LSU/shared-memory bound"},
-        "breakdown_ms_per_step": {k: round(acc[k] / a.steps, 2) for k in ("di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms",
-                                                                         "wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms")},
-        "rounds_per_step": int(acc["rounds"] / a.steps), "fast_lane_rounds_per_step": int(acc["rounds_fast"] / a.steps), "dp_jobs_per_step": int(acc["jobs"] / a.steps),
+        "breakdown_ms_per_step": {k: round(acc[k] / a.steps, 2) for k in ("di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms", "uf_wall_ms",
+                                                                         "wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms", "uf_kernel_ms")},
+        "rounds_per_step": int(acc["rounds"] / a.steps), "fast_lane_rounds_per_step": int(acc["rounds_fast"] / a.steps), "uf_rounds_per_step": int(acc["rounds_uf"] / a.steps), "uf_tasks_per_step": int(acc["uf_tasks"] / a.steps), "dp_jobs_per_step": int(acc["jobs"] / a.steps),
         "clocks": clk, "output_md5": digest.hexdigest(),
     }
 

@@ -124,6 +124,29 @@ int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t a
 int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
                const int64_t *pos_off, double *di, int32_t *end, int32_t *w);
 
+/* ------------------------------------------------------------------ K4: unit finder */
+/* One task = search_De_Bruijn_graph (consensus.c:507-549) for one candidate range [qs, qe] of one resident read
+ * and one k, up to the point where it would call wrap_around_DP: k-mer counts of the window (init_inputString
+ * :37-60, generate_freqNode_return_list_maxNodes :132-229), then the greedy forward walk over the maximum-
+ * frequency nodes until the first loop, then the backward walk likewise (:269-505). */
+typedef struct {
+    int32_t read, qs, qe, k;   /* k in 2..15 */
+} mtr_uf_task;
+
+typedef struct {
+    int32_t max_freq;          /* maxFreq; the walks run only if it exceeds MIN_NUM_FREQ_UNIT = 5 (:532) */
+    int32_t found_last;        /* foundLoop of the LAST walk attempted: search_De_Bruijn_graph's return value (Q4) */
+    int32_t found[2];          /* forward, backward: a loop was found */
+    int32_t period[2];         /* its length (1..499) */
+    int64_t unit_off[2];       /* offset of the unit (bytes 0..3) in `units` and of its node counts
+                                  (string_score, :350-352) in `scores`; -1 if not found */
+} mtr_uf_result;
+
+/* Synchronous.  units / scores must hold out_cap entries with out_cap >= sum over tasks of 2*min(500,(qe-qs)/5);
+ * *out_used receives the number of entries written. */
+int mtr_uf_run(mtr_ctx *ctx, const mtr_uf_task *tasks, int n_tasks, mtr_uf_result *results,
+               uint8_t *units, int32_t *scores, int64_t out_cap, int64_t *out_used);
+
 /* ------------------------------------------------------------------ counters for the roofline */
 typedef struct {
     double   wdp_fill_ms, wdp_tb_ms, di_ms;      /* CUDA-event time of the last launch of each stage */
@@ -134,6 +157,8 @@ typedef struct {
     int64_t  di_bytes_in, di_bytes_out;
     int32_t  launches;                           /* kernels launched by the last call */
     int32_t  n_sm;
+    double   uf_ms;                              /* CUDA-event time of the last unit-finder launch */
+    int64_t  uf_tasks, uf_table_bytes;
 } mtr_stats;
 int mtr_get_stats(const mtr_ctx *ctx, mtr_stats *out);
 
@@ -150,13 +175,13 @@ int mtr_alu_probe(mtr_ctx *ctx, int kind, double *gops);
  * Uses the globals Manhattan_Distance and min_match_ratio like the reference. */
 typedef struct mtr_pipeline mtr_pipeline;
 typedef struct {
-    int64_t reads, bases, candidates, rounds, rounds_fast, jobs, wdp_calls;
+    int64_t reads, bases, candidates, rounds, rounds_fast, rounds_uf, jobs, uf_tasks, wdp_calls;
     int64_t wdp_cells, wdp_slot_cells, wdp_dir_bytes;      /* algorithmic cells = sum rows * ulen over every DP run */
     int64_t di_position_passes, di_bytes_in, di_bytes_out;
     int64_t h2d_bytes, d2h_bytes;
     int64_t launches;                                      /* CUDA kernels launched by run() */
-    double  wdp_fill_ms, wdp_tb_ms, di_kernel_ms;          /* CUDA-event time on the launching streams */
-    double  di_wall_ms, rounds_wall_ms, host_step_ms, wdp_wall_ms;
+    double  wdp_fill_ms, wdp_tb_ms, di_kernel_ms, uf_kernel_ms;   /* CUDA-event time on the launching streams */
+    double  di_wall_ms, rounds_wall_ms, host_step_ms, wdp_wall_ms, uf_wall_ms;
 } mtr_pipeline_stats;
 int  mtr_pipeline_open(int device, int threads, mtr_pipeline **out);
 void mtr_pipeline_close(mtr_pipeline *p);

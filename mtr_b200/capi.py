@@ -20,7 +20,7 @@ TB_COUNTS, TB_CONSENSUS, TB_PATH = 0, 1, 2
 ABI_FUNCTIONS = [
     "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_di_run", "mtr_get_stats",
-    "mtr_alu_probe", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_run",
+    "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_run",
     "mtr_pipeline_get_stats", "handle_one_file", "handle_one_read", "mtr_flush",
 ]
 ABI_GLOBALS = [
@@ -50,17 +50,21 @@ class Stats(C.Structure):
         ("wdp_cells", C.c_int64), ("wdp_slot_cells", C.c_int64), ("wdp_dir_bytes", C.c_int64),
         ("di_position_passes", C.c_int64), ("di_bytes_in", C.c_int64), ("di_bytes_out", C.c_int64),
         ("launches", C.c_int32), ("n_sm", C.c_int32),
+        ("uf_ms", C.c_double), ("uf_tasks", C.c_int64), ("uf_table_bytes", C.c_int64),
     ]
 
 
 class PipelineStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
-        "reads", "bases", "candidates", "rounds", "rounds_fast", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
+        "reads", "bases", "candidates", "rounds", "rounds_fast", "rounds_uf", "jobs", "uf_tasks", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
         "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches")] + \
-        [(n, C.c_double) for n in ("wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms",
-                                   "host_step_ms", "wdp_wall_ms")]
+        [(n, C.c_double) for n in ("wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms", "uf_kernel_ms", "di_wall_ms", "rounds_wall_ms",
+                                   "host_step_ms", "wdp_wall_ms", "uf_wall_ms")]
 
 
+UF_TASK_DTYPE = np.dtype([("read", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("k", "<i4")])
+UF_RESULT_DTYPE = np.dtype([("max_freq", "<i4"), ("found_last", "<i4"), ("found", "<i4", (2,)), ("period", "<i4", (2,)),
+                            ("unit_off", "<i8", (2,))])
 JOB_DTYPE = np.dtype([
     ("read", "<i4"), ("first", "<i4"), ("rows", "<i4"), ("unit_off", "<i4"), ("ulen", "<i4"),
     ("gain", "i1", (2,)), ("mis", "i1", (2,)), ("indel", "i1", (2,)), ("n_param", "u1"), ("mode", "u1"),
@@ -99,6 +103,8 @@ def load_library() -> C.CDLL:
     lib.mtr_di_run.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.mtr_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mtr_alu_probe.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.mtr_uf_run.argtypes = [vp, vp, C.c_int, vp, vp, vp, i64, C.POINTER(i64)]
+    lib.mtr_uf_run.restype = C.c_int
     lib.mtr_pipeline_open.argtypes = [C.c_int, C.c_int, C.POINTER(vp)]
     lib.mtr_pipeline_close.argtypes = [vp]
     lib.mtr_pipeline_close.restype = None
@@ -109,7 +115,7 @@ def load_library() -> C.CDLL:
     lib.handle_one_file.restype = C.c_int
     lib.mtr_flush.restype = None
     for f in ("mtr_reads_upload", "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download",
-              "mtr_di_run", "mtr_get_stats", "mtr_alu_probe", "mtr_pipeline_open", "mtr_pipeline_load_fasta",
+              "mtr_di_run", "mtr_get_stats", "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_load_fasta",
               "mtr_pipeline_run", "mtr_pipeline_get_stats"):
         getattr(lib, f).restype = C.c_int
     _lib = lib
@@ -228,6 +234,18 @@ class Context:
         s = Stats()
         self._check(self.lib.mtr_get_stats(self.h, C.byref(s)), "mtr_get_stats")
         return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    def uf_run(self, tasks: np.ndarray):
+        """tasks: array of UF_TASK_DTYPE.  Returns (results, units uint8, scores int32)."""
+        tasks = np.ascontiguousarray(tasks, dtype=UF_TASK_DTYPE)
+        cap = int(np.sum(2 * np.minimum(500, (tasks["qe"] - tasks["qs"]) // 5))) + 16
+        res = np.zeros(len(tasks), dtype=UF_RESULT_DTYPE)
+        units = np.zeros(cap, dtype=np.uint8)
+        scores = np.zeros(cap, dtype=np.int32)
+        used = C.c_int64()
+        self._check(self.lib.mtr_uf_run(self.h, _ptr(tasks), len(tasks), _ptr(res), _ptr(units), _ptr(scores), cap,
+                                        C.byref(used)), "mtr_uf_run")
+        return res, units[:used.value], scores[:used.value]
 
     def alu_probe(self, kind: int) -> float:
         """Giga lane-ops/s of the integer pipe (0: VIADDMNMX.RELU s32, 1: LOP3+IADD, 2: VIADDMNMX s16x2)."""

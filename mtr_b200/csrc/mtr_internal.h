@@ -99,6 +99,7 @@ struct mtr_ctx {
     int64_t n_words = 0;
     WdpState wdp;
     struct DiState *di = nullptr;
+    struct UfState *uf = nullptr;
     mtr_stats stats = {};
 };
 
@@ -107,4 +108,5 @@ int  wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const ui
 int  wdp_launch_impl(mtr_ctx *ctx);
 int  wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes);
 void di_state_free(mtr_ctx *ctx);
+void uf_state_free(mtr_ctx *ctx);
 long long wdp_dir_bytes(int ulen, int rows);   // bytes of one direction matrix (per penalty set)

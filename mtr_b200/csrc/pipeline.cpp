@@ -79,15 +79,19 @@ void apply_dp(Rec &r, int qs, const mtr_wdp_result &d, int g, int m, int in)
 // (init_inputString + generate_freqNode_*, consensus.c:37-253; the hash layout is unobservable)
 struct Counter {
     std::vector<int> codes;           // codes[i - qs] for i in [qs, qe]
-    std::vector<int> direct;          // k <= 6
-    std::vector<uint32_t> hkey, hstamp;
-    std::vector<int> hval;
-    uint32_t epoch = 0;
+    std::vector<int> direct;          // k <= 6: 4^k counters
+    // k > 6: open addressing, one 8-byte slot per node (key + 1 in the high word so that 0 means empty); the slots
+    // a window touched are cleared again from `codes`, so a build costs O(window), not O(table)
+    std::vector<uint64_t> slots;
+    std::vector<uint32_t> touched;
     uint32_t hmask = 0;
-    int k = 0;
+    int k = 0, maxf = -1;
 
+    static inline uint32_t hash(uint32_t node) { return node * 2654435761u; }
     void build(const uint8_t *org, int L, int kk, int qs, int qe)
     {
+        for (uint32_t h : touched) slots[h] = 0;
+        touched.clear();
         k = kk;
         const int n = qe - qs + 1;
         codes.resize(n);
@@ -105,42 +109,55 @@ struct Counter {
                 codes[i - qs] = i < L ? org[i] : 0;
             }
         }
+        maxf = -1;
         if (k <= 6) {
             direct.assign(P4.v[k], 0);
-            for (int c : codes) direct[c]++;
+            for (int c : codes) maxf = std::max(maxf, ++direct[c]);
         } else {
             uint32_t cap = 1024;
             while (cap < 2u * (uint32_t)(n + 1)) cap <<= 1;
-            if (hkey.size() < cap) { hkey.assign(cap, 0); hval.assign(cap, 0); hstamp.assign(cap, 0); epoch = 0; }
+            if (slots.size() < cap) slots.assign(cap, 0);
             hmask = cap - 1;
-            if (++epoch == 0) { std::fill(hstamp.begin(), hstamp.end(), 0u); epoch = 1; }
-            for (int c : codes) (*slot(c, true))++;
+            touched.reserve(n);
+            for (int c : codes) {
+                const uint64_t key = ((uint64_t)(uint32_t)c + 1) << 32;
+                uint32_t h = hash((uint32_t)c) & hmask;
+                for (;;) {
+                    const uint64_t sl = slots[h];
+                    if (sl == 0) { slots[h] = key | 1u; touched.push_back(h); maxf = std::max(maxf, 1); break; }
+                    if ((sl & 0xffffffff00000000ull) == key) { slots[h] = sl + 1; maxf = std::max(maxf, (int)(uint32_t)(sl + 1)); break; }
+                    h = (h + 1) & hmask;
+                }
+            }
         }
     }
-    int *slot(int node, bool create)
+    int get(int node)                                          // freq_node, consensus.c:231-253
     {
-        if (k <= 6) return (node >= 0 && node < P4.v[k]) ? &direct[node] : nullptr;
-        uint32_t h = ((uint32_t)node * 2654435761u) & hmask;
+        if (k <= 6) return (node >= 0 && node < P4.v[k]) ? direct[node] : 0;
+        const uint64_t key = ((uint64_t)(uint32_t)node + 1) << 32;
+        uint32_t h = hash((uint32_t)node) & hmask;
         for (;;) {
-            if (hstamp[h] != epoch) {
-                if (!create) return nullptr;
-                hstamp[h] = epoch; hkey[h] = (uint32_t)node; hval[h] = 0;
-                return &hval[h];
-            }
-            if (hkey[h] == (uint32_t)node) return &hval[h];
+            const uint64_t sl = slots[h];
+            if (sl == 0) return 0;
+            if ((sl & 0xffffffff00000000ull) == key) return (int)(uint32_t)sl;
             h = (h + 1) & hmask;
         }
     }
-    int get(int node) { int *p = slot(node, false); return p ? *p : 0; }      // freq_node, consensus.c:231-253
-    int max_freq() { int m = -1; for (int c : codes) m = std::max(m, get(c)); return m; }
+    void decrement(int node)
+    {
+        if (k <= 6) { direct[node]--; return; }
+        const uint64_t key = ((uint64_t)(uint32_t)node + 1) << 32;
+        uint32_t h = hash((uint32_t)node) & hmask;
+        while ((slots[h] & 0xffffffff00000000ull) != key) h = (h + 1) & hmask;
+        slots[h]--;
+    }
+    int max_freq() const { return maxf; }                      // counts only grow while building: running max == final max
     // generate_freqNode_return_list_maxNodes (:132-229): listing a node decrements its count
-    int list_max_nodes(int *list, int cap, int maxf)
+    int list_max_nodes(int *list, int cap, int maxfreq)
     {
         int n = 0;
-        for (int c : codes) {
-            int *p = slot(c, false);
-            if (p && *p == maxf) { list[n++] = c; (*p)--; if (cap <= n) break; }
-        }
+        for (int c : codes)
+            if (get(c) == maxfreq) { list[n++] = c; decrement(c); if (cap <= n) break; }
         return n;
     }
 };
@@ -399,7 +416,8 @@ struct JobReq {
 };
 
 struct Chain {                  // one k of one candidate: find_tandem_repeat_sub (handle_one_read.c:77-100)
-    enum Stage { SEARCH_WAIT, CONS_WAIT, DP_WAIT, DONE } stage = DONE;
+    enum Stage { UF_WAIT, SEARCH_WAIT, CONS_WAIT, DP_WAIT, DONE } stage = DONE;
+    int uf_task = -1;
     int k = 0, pass = 0;
     Rec rr, tmp, dir[2];
     bool dir_found[2] = {false, false};
@@ -423,18 +441,28 @@ struct ReadState {
     // round I/O
     std::vector<JobReq> jobs;
     std::vector<uint8_t> units;
+    std::vector<mtr_uf_task> uf_tasks; // unit-finder tasks of this round (K4)
+    long long uf_base = 0;             // global index of this read's first unit-finder task of the previous round
     long long job_base = 0;            // global index of this read's first job of the previous round
     std::vector<long long> job_aux;    // byte offset in the round's aux buffer of each job of the previous round
     std::string out;
     long long candidates = 0;
 };
 
-struct Worker { Counter cnt; double t_build = 0, t_list = 0, t_walk = 0, t_polish = 0, t_step = 0; long long n_chain = 0, n_walk = 0; };
+struct Worker { Counter cnt; double t_build = 0, t_list = 0, t_walk = 0, t_polish = 0, t_step = 0; long long n_chain = 0, n_walk = 0;
+                double hb_t[8] = {0}, hw_t[8] = {0}, hw_max[8] = {0}; long long hb_n[8] = {0}, hw_n[8] = {0}; };
+
+int size_bucket(int n) { int b = 0; while (b < 7 && n > (64 << b)) b++; return b; }   // <=64, 128, ..., >4096
 
 struct RoundResults {
     const mtr_wdp_result *res = nullptr;   // [2 * job]
     const uint8_t *aux = nullptr;
+    const mtr_uf_result *uf = nullptr;     // [unit-finder task]
+    const uint8_t *uf_units = nullptr;
+    const int32_t *uf_scores = nullptr;
 };
+
+bool g_uf_on_gpu = false;                  // MTR_UNITFINDER=gpu runs the unit finder as K4 on the GPU
 
 int add_job(ReadState &rs, int first, int rows, const std::vector<uint8_t> &unit, int n_param, const int (*p)[3], int mode)
 {
@@ -473,16 +501,28 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
     ch.rr.inputLen = rs.L; ch.rr.kmer = ch.k;
     ch.dir_found[0] = ch.dir_found[1] = false;
     ch.found_last = false;
+    if (g_uf_on_gpu) {
+        mtr_uf_task t;
+        t.read = rs.index; t.qs = qs; t.qe = qe; t.k = ch.k;
+        ch.uf_task = (int)rs.uf_tasks.size();
+        rs.uf_tasks.push_back(t);
+        ch.stage = Chain::UF_WAIT;
+        wk.n_chain++;
+        return;
+    }
     double tp0 = now_s();
     wk.cnt.build(rs.org, rs.L, ch.k, qs, qe);
     double tp1 = now_s();
     wk.t_build += tp1 - tp0; wk.n_chain++;
     const int maxf = wk.cnt.max_freq();
     int nodes[100];
-    const int nn = wk.cnt.list_max_nodes(nodes, 100, maxf);
+    // the listing decrements counts (Q8), which only the walks can observe: skip it when they do not run (:532)
+    const int nn = 5 < maxf ? wk.cnt.list_max_nodes(nodes, 100, maxf) : 0;
     tp0 = now_s();
     wk.t_list += tp0 - tp1;
-    struct WalkTimer { Worker &w; double t0; ~WalkTimer() { w.t_walk += now_s() - t0; } } walk_timer{wk, tp0};
+    const int sb = size_bucket(qe - qs + 1);
+    wk.hb_n[sb]++; wk.hb_t[sb] += tp0 - (tp1 - (tp1 - tp0 > 0 ? 0 : 0));
+    struct WalkTimer { Worker &w; double t0; int sb; bool walked; ~WalkTimer() { const double d = now_s() - t0; w.t_walk += d; if (walked) { w.hw_n[sb]++; w.hw_t[sb] += d; if (d > w.hw_max[sb]) w.hw_max[sb] = d; } } } walk_timer{wk, tp0, sb, 5 < maxf};
     bool any = false;
     if (5 < maxf) {
         for (int d = 0; d < 2; d++)
@@ -506,6 +546,25 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
 void advance_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk, const RoundResults &rr)
 {
     const mtr_wdp_result *res = rr.res + 2 * rs.job_base;
+    if (ch.stage == Chain::UF_WAIT) {
+        const mtr_uf_result &u = rr.uf[rs.uf_base + ch.uf_task];
+        ch.found_last = u.found_last != 0;
+        bool any = false;
+        for (int d = 0; d < 2; d++) {
+            if (!u.found[d]) continue;
+            Rec r = ch.rr;
+            r.period = u.period[d];
+            r.unit.assign(rr.uf_units + u.unit_off[d], rr.uf_units + u.unit_off[d] + u.period[d]);
+            r.score.assign(rr.uf_scores + u.unit_off[d], rr.uf_scores + u.unit_off[d] + u.period[d]);
+            ch.dir[d] = r; ch.dir_found[d] = true;
+            ch.dir_job[d] = add_job(rs, qs, qe - qs + 1, r.unit, 2, kSearchParams, MTR_TB_COUNTS);
+            any = true;
+        }
+        if (any) { ch.stage = Chain::SEARCH_WAIT; return; }
+        ch.rr.clear();
+        ch.stage = Chain::DONE;
+        return;
+    }
     if (ch.stage == Chain::SEARCH_WAIT) {
         Rec best;                                           // max_rr of search_De_Bruijn_graph, starts cleared
         float best_ratio = -1;
@@ -585,6 +644,7 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
 {
     rs.jobs.clear();
     rs.units.clear();
+    rs.uf_tasks.clear();
     if (rs.phase == ReadState::PRINT_WAIT) {
         const mtr_wdp_result *res = rr.res + 2 * rs.job_base;
         for (size_t i = 0; i < rs.printing.size(); i++) {
@@ -727,6 +787,7 @@ struct ReadInput {
 struct Engine {
     mtr_ctx *ctx = nullptr;            // directional index + the lane of long DP jobs
     mtr_ctx *ctx_fast = nullptr;       // the lane of short DP jobs (shares the resident reads of ctx)
+    mtr_ctx *ctx_uf = nullptr;         // the lane of unit-finder tasks (K4)
     Pool *pool = nullptr;
     std::vector<Worker> workers;
     double t_di = 0, t_dp = 0, t_rounds = 0;
@@ -738,10 +799,13 @@ struct Engine {
         if (rc) die(nullptr, "mtr_cuda_init", rc);
         rc = mtr_cuda_init(device, &ctx_fast);
         if (rc) die(nullptr, "mtr_cuda_init", rc);
+        rc = mtr_cuda_init(device, &ctx_uf);
+        if (rc) die(nullptr, "mtr_cuda_init", rc);
+        if (const char *e = getenv("MTR_UNITFINDER")) g_uf_on_gpu = strcmp(e, "gpu") == 0;
         pool = new Pool(threads);
         workers.resize(pool->size());
     }
-    ~Engine() { delete pool; mtr_cuda_shutdown(ctx_fast); mtr_cuda_shutdown(ctx); }
+    ~Engine() { delete pool; mtr_cuda_shutdown(ctx_uf); mtr_cuda_shutdown(ctx_fast); mtr_cuda_shutdown(ctx); }
 
     // resident batch (prepare) + statistics of the last run
     std::vector<int64_t> b_word_off, b_stale_off, b_pos_off;
@@ -782,6 +846,8 @@ struct Engine {
         if (rc) die(ctx, "mtr_reads_upload", rc);
         rc = mtr_reads_share(ctx_fast, ctx);
         if (rc) die(ctx_fast, "mtr_reads_share", rc);
+        rc = mtr_reads_share(ctx_uf, ctx);
+        if (rc) die(ctx_uf, "mtr_reads_share", rc);
         ps.h2d_bytes = (int64_t)packed.size() * 4 + (int64_t)(n + 1) * 12;
     }
 
@@ -823,12 +889,15 @@ struct Engine {
         // an expensive host step (a de Bruijn walk with many tie-breaks) delays only itself.
         const long long dir_cap = dir_budget();
         t0 = now_s();
-        double host_ms = 0, wdp_ms = 0;
+        double host_ms = 0, wdp_ms = 0, uf_ms = 0;
         struct BatchResult { std::vector<mtr_wdp_result> res; std::vector<uint8_t> aux; };
+        struct UfBatchResult { std::vector<mtr_uf_result> res; std::vector<uint8_t> units; std::vector<int32_t> scores; };
         std::vector<std::shared_ptr<BatchResult>> result_of(n);
+        std::vector<std::shared_ptr<UfBatchResult>> uf_result_of(n);
+        std::vector<int> pending(n, 0);                           // lanes a read is still waiting for
         std::mutex mu;
         std::condition_variable cv_ready, cv_submit;
-        std::vector<int> ready(n), submitted[2];                  // lane 0: long jobs, lane 1: short jobs
+        std::vector<int> ready(n), submitted[3];                  // lane 0: long DP jobs, 1: short DP jobs, 2: unit finder
         for (int r = 0; r < n; r++) ready[r] = n - 1 - r;         // popped from the back: read 0 first
         int remaining = n;
         const int fast_rows = getenv("MTR_FAST_ROWS") ? atoi(getenv("MTR_FAST_ROWS")) : 1536;
@@ -845,16 +914,26 @@ struct Engine {
                 ReadState &rs = st[idx];
                 RoundResults cur;
                 if (result_of[idx]) { cur.res = result_of[idx]->res.data(); cur.aux = result_of[idx]->aux.data(); }
+                if (uf_result_of[idx]) {
+                    cur.uf = uf_result_of[idx]->res.data(); cur.uf_units = uf_result_of[idx]->units.data();
+                    cur.uf_scores = uf_result_of[idx]->scores.data();
+                }
                 const double ts = now_s();
                 step_read(rs, workers[tid], cur, print_alignment);
                 workers[tid].t_step += now_s() - ts;
                 result_of[idx].reset();
+                uf_result_of[idx].reset();
                 int lane = 1;
                 for (const JobReq &q : rs.jobs) if (q.rows > fast_rows) { lane = 0; break; }
                 {
                     std::lock_guard<std::mutex> g(mu);
                     if (rs.phase == ReadState::FINISHED) { if (--remaining == 0) { cv_ready.notify_all(); cv_submit.notify_all(); } }
-                    else { submitted[lane].push_back(idx); cv_submit.notify_all(); }
+                    else {
+                        if (!rs.jobs.empty()) { pending[idx]++; submitted[lane].push_back(idx); }
+                        if (!rs.uf_tasks.empty()) { pending[idx]++; submitted[2].push_back(idx); }
+                        if (pending[idx] == 0) { fprintf(stderr, "mTR (B200): internal error: read %d stalled\n", idx); exit(EXIT_FAILURE); }
+                        cv_submit.notify_all();
+                    }
                 }
             }
         };
@@ -915,13 +994,54 @@ struct Engine {
                     ps.wdp_fill_ms += local.wdp_fill_ms; ps.wdp_tb_ms += local.wdp_tb_ms; ps.wdp_cells += local.wdp_cells;
                     ps.wdp_slot_cells += local.wdp_slot_cells; ps.wdp_dir_bytes += local.wdp_dir_bytes;
                     ps.launches += local.launches; ps.wdp_calls += local.wdp_calls;
-                    for (int idx : batch) { result_of[idx] = br; ready.push_back(idx); }
+                    for (int idx : batch) { result_of[idx] = br; if (--pending[idx] == 0) ready.push_back(idx); }
                 }
                 cv_ready.notify_all();
                 batch.clear();
             }
         };
-        std::thread dispatcher0([&] { dispatch_loop(0); }), dispatcher1([&] { dispatch_loop(1); });
+        auto uf_dispatch_loop = [&]() {
+            cudaSetDevice(ctx_uf->device);
+            std::vector<mtr_uf_task> tasks;
+            std::vector<int> batch;
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> g(mu);
+                    cv_submit.wait(g, [&] { return !submitted[2].empty() || remaining == 0; });
+                    if (submitted[2].empty()) return;
+                    batch.swap(submitted[2]);
+                    submitted[2].clear();
+                }
+                tasks.clear();
+                long long cap = 16;
+                for (int idx : batch) {
+                    ReadState &rs = st[idx];
+                    rs.uf_base = (long long)tasks.size();
+                    for (const mtr_uf_task &t : rs.uf_tasks) { tasks.push_back(t); cap += 2LL * std::min(kMaxPeriod, (t.qe - t.qs) / 5); }
+                }
+                auto br = std::make_shared<UfBatchResult>();
+                br->res.resize(tasks.size());
+                br->units.resize((size_t)cap);
+                br->scores.resize((size_t)cap);
+                int64_t used = 0;
+                const double tg0 = now_s();
+                const int rc = mtr_uf_run(ctx_uf, tasks.data(), (int)tasks.size(), br->res.data(), br->units.data(), br->scores.data(), cap, &used);
+                if (rc) die(ctx_uf, "mtr_uf_run", rc);
+                mtr_stats us;
+                mtr_get_stats(ctx_uf, &us);
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    uf_ms += (now_s() - tg0) * 1e3;
+                    ps.rounds_uf++; ps.uf_tasks += (int64_t)tasks.size(); ps.uf_kernel_ms += us.uf_ms; ps.launches += 1;
+                    ps.h2d_bytes += (int64_t)tasks.size() * sizeof(mtr_uf_task);
+                    ps.d2h_bytes += (int64_t)tasks.size() * sizeof(mtr_uf_result) + used * 5;
+                    for (int idx : batch) { uf_result_of[idx] = br; if (--pending[idx] == 0) ready.push_back(idx); }
+                }
+                cv_ready.notify_all();
+                batch.clear();
+            }
+        };
+        std::thread dispatcher0([&] { dispatch_loop(0); }), dispatcher1([&] { dispatch_loop(1); }), dispatcher2([&] { uf_dispatch_loop(); });
         {
             const double th0 = now_s();
             pool->run(pool->size(), [&](int tid, int) { worker_loop(tid); });
@@ -929,15 +1049,21 @@ struct Engine {
         }
         dispatcher0.join();
         dispatcher1.join();
+        dispatcher2.join();
         t_rounds += now_s() - t0;
         t_dp += wdp_ms / 1e3;
         ps.rounds_wall_ms = (now_s() - t0) * 1e3;
         for (int r = 0; r < n; r++) { out += st[r].out; candidates += st[r].candidates; ps.candidates += st[r].candidates; }
-        ps.host_step_ms = host_ms; ps.wdp_wall_ms = wdp_ms;
+        ps.host_step_ms = host_ms; ps.wdp_wall_ms = wdp_ms; ps.uf_wall_ms = uf_ms;
         if (getenv("MTR_PROFILE")) {
             double b = 0, l = 0, w = 0, p = 0, t = 0; long long nc = 0, nw = 0;
             for (Worker &k : workers) { b += k.t_build; l += k.t_list; w += k.t_walk; p += k.t_polish; t += k.t_step; nc += k.n_chain; nw += k.n_walk;
                                         k.t_build = k.t_list = k.t_walk = k.t_polish = k.t_step = 0; k.n_chain = k.n_walk = 0; }
+            for (int b = 0; b < 8; b++) {
+                long long bn = 0, wn = 0; double wt = 0, wm = 0;
+                for (Worker &k : workers) { bn += k.hb_n[b]; wn += k.hw_n[b]; wt += k.hw_t[b]; wm = std::max(wm, k.hw_max[b]); k.hb_n[b] = k.hw_n[b] = 0; k.hw_t[b] = k.hw_max[b] = 0; }
+                fprintf(stderr, "[mtr profile]   window <= %5d: chains %9lld  with walks %8lld  walk cpu-s %8.3f  max walk ms %8.2f\n", 64 << b, bn, wn, wt, wm * 1e3);
+            }
             fprintf(stderr, "[mtr profile] reads %d rounds %lld | host cpu-s: step %.3f build %.3f maxlist %.3f walk %.3f polish %.3f | chains %lld walks %lld | wall: host %.3f s gpu %.3f s\n",
                     n, (long long)ps.rounds, t, b, l, w, p, nc, nw, host_ms / 1e3, wdp_ms / 1e3);
         }

@@ -689,6 +689,31 @@ static int search_unit(mtro_ctx *c, int qs, int qe, mtro_rr *rr)
     return found;                                   /* flag of the LAST attempt (Q4) */
 }
 
+void mtro_unit_walks(mtro_ctx *c, int qs, int qe, int k, mtro_walk_result *res,
+                     unsigned char *unit_fwd, int *score_fwd, unsigned char *unit_bwd, int *score_bwd)
+{
+    kmer_window(c, k, qs, qe);
+    int nodes[100], maxfreq;
+    int nn = list_max_nodes(c, k, qs, qe, nodes, 100, &maxfreq);
+    memset(res, 0, sizeof *res);
+    res->max_freq = maxfreq;
+    if (!(5 < maxfreq)) return;
+    mtro_rr tmp;
+    for (int dir = 0; dir < 2; dir++) {
+        for (int i = 0; i < nn; i++) {
+            rr_clear(&tmp);
+            int found = walk(c, qs, qe, nodes[i], k, dir, &tmp);
+            res->found_last = found;
+            if (!found) continue;
+            res->found[dir] = 1; res->period[dir] = tmp.rep_period;
+            unsigned char *u = dir ? unit_bwd : unit_fwd;
+            int *sc = dir ? score_bwd : score_fwd;
+            for (int j = 0; j < tmp.rep_period; j++) { u[j] = (unsigned char)base_of_char(tmp.unit[j]); sc[j] = tmp.unit_score[j]; }
+            break;
+        }
+    }
+}
+
 /* ================================================================ polish + revise (consensus.c:584-1087) */
 
 static int align_score(mtro_ctx *c, int start, int k, int node, int period, const int *unit)  /* :584-596 */

@@ -83,6 +83,13 @@ void mtro_wrap_dp(mtro_ctx *c, const int *x, int rows, const int *u, int ulen,
 /* Unit finder for one candidate range of the loaded read (handle_one_read.c:102-154). */
 void mtro_find_tandem_repeat(mtro_ctx *c, int query_start, int query_end, int w, mtro_rr *out);
 
+/* The part of search_De_Bruijn_graph (consensus.c:507-549) that precedes wrap_around_DP, for the loaded read:
+ * counts, maximum-frequency node list, first looping forward walk and first looping backward walk.
+ * unit[d] / score[d] must hold 500 entries each. */
+typedef struct { int max_freq, found_last, found[2], period[2]; } mtro_walk_result;
+void mtro_unit_walks(mtro_ctx *c, int query_start, int query_end, int k, mtro_walk_result *res,
+                     unsigned char *unit_fwd, int *score_fwd, unsigned char *unit_bwd, int *score_bwd);
+
 /* min_missing table lookup (consensus.c:714-820). */
 int mtro_min_missing(int rep_period, double error, int coverage);
 int mtro_min_missing_raw(int i, int j, int k);

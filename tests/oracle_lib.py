@@ -24,6 +24,10 @@ class Rr(C.Structure):
                [("unit", C.c_char * 1024), ("unit_score", C.c_int * 500)]
 
 
+class WalkResult(C.Structure):
+    _fields_ = [("max_freq", C.c_int), ("found_last", C.c_int), ("found", C.c_int * 2), ("period", C.c_int * 2)]
+
+
 class OStats(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in ("dp_calls", "dp_cells", "revise_calls", "revise_cells", "print_calls",
                                             "print_cells", "di_position_passes", "candidates", "searches", "reads", "bases")]
@@ -55,6 +59,7 @@ def lib():
         L.mtro_wrap_dp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.POINTER(DpResult), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mtro_find_tandem_repeat.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(Rr)]
+        L.mtro_unit_walks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(WalkResult), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mtro_min_missing.argtypes = [C.c_int, C.c_double, C.c_int]
         L.mtro_min_missing.restype = C.c_int
         L.mtro_min_missing_raw.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -158,6 +163,16 @@ class Oracle:
             out["path"] = path[:res.path_len].copy()
         if want_dirs:
             out["dirs"] = dirs.reshape(R + 1, U + 1)
+        return out
+
+    def unit_walks(self, qs, qe, k):
+        res = WalkResult()
+        uf = np.zeros(500, np.uint8); sf = np.zeros(500, np.int32); ub = np.zeros(500, np.uint8); sb = np.zeros(500, np.int32)
+        self.L.mtro_unit_walks(self.h, qs, qe, k, C.byref(res), uf.ctypes.data, sf.ctypes.data, ub.ctypes.data, sb.ctypes.data)
+        out = dict(max_freq=res.max_freq, found_last=res.found_last, found=(res.found[0], res.found[1]),
+                   period=(res.period[0], res.period[1]))
+        out["units"] = (uf[:res.period[0]].copy(), ub[:res.period[1]].copy())
+        out["scores"] = (sf[:res.period[0]].copy(), sb[:res.period[1]].copy())
         return out
 
     def stats(self):
