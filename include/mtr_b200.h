@@ -39,6 +39,9 @@ int  mtr_cuda_init(int device, mtr_ctx **out);
 void mtr_cuda_shutdown(mtr_ctx *ctx);
 const char *mtr_last_error(const mtr_ctx *ctx);   /* ctx may be NULL: error of the last failed init */
 int  mtr_device_count(void);
+/* on != 0: host threads waiting for this context sleep (cudaEventBlockingSync) instead of spinning; worth it for
+ * contexts whose calls take milliseconds (adds tens of microseconds of wake-up latency per call). Default off. */
+int  mtr_set_blocking_sync(mtr_ctx *ctx, int on);
 
 /* ------------------------------------------------------------------ reads (orgInputString, mTR.h:65) */
 /* A batch of reads, 2-bit packed (A,C,G,T = 0..3; base b of a read is bits [2*(b%16), 2*(b%16)+2) of word

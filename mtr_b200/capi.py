@@ -18,7 +18,7 @@ TB_COUNTS, TB_CONSENSUS, TB_PATH = 0, 1, 2
 
 # every symbol include/mtr_b200.h declares (tests check that the library exports all of them)
 ABI_FUNCTIONS = [
-    "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_reads_upload", "mtr_reads_share",
+    "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_di_run", "mtr_get_stats",
     "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_run",
     "mtr_pipeline_get_stats", "handle_one_file", "handle_one_read", "mtr_flush",

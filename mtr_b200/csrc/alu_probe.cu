@@ -42,7 +42,7 @@ extern "C" int mtr_alu_probe(mtr_ctx *ctx, int kind, double *gops)
         else alu_probe_kernel<2><<<blocks, threads, 0, s>>>(iters, rep + 1, (int *)ctx->wdp.d_counters.p);
         MTR_CUDA(ctx, cudaGetLastError());
         MTR_CUDA(ctx, cudaEventRecord(ctx->ev[6], s));
-        MTR_CUDA(ctx, cudaStreamSynchronize(s));
+        MTR_CUDA(ctx, mtr_sync(ctx));
         float ms = 0;
         MTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));
         if (rep > 0 && ms < best) best = ms;

@@ -62,6 +62,7 @@ extern "C" int mtr_cuda_init(int device, mtr_ctx **out)
              cudaEventCreateWithFlags(&ctx->class_done[k], cudaEventDisableTiming) == cudaSuccess;
     }
     for (int k = 0; ok && k < 8; k++) ok = cudaEventCreate(&ctx->ev[k]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         mtr_set_error(nullptr, "mtr_cuda_init: stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -87,6 +88,7 @@ extern "C" void mtr_cuda_shutdown(mtr_ctx *ctx)
         if (ctx->class_done[k]) cudaEventDestroy(ctx->class_done[k]);
     }
     for (int k = 0; k < 8; k++) if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     delete ctx;
 }
@@ -110,13 +112,20 @@ extern "C" int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int6
         MTR_CUDA(ctx, cudaMemsetAsync((char *)ctx->d_packed.p + (size_t)nw * 4, 0, 64, ctx->main_stream));
         MTR_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_off.p, word_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->main_stream));
         MTR_CUDA(ctx, cudaMemcpyAsync(ctx->d_len.p, len, (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->main_stream));
-        MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+        MTR_CUDA(ctx, mtr_sync(ctx));
     }
     ctx->word_off.assign(word_off, word_off + (n_reads ? n_reads + 1 : 0));
     ctx->len.assign(len, len + n_reads);
     ctx->n_reads = n_reads;
     ctx->n_words = nw;
     ctx->wdp.uploaded = false;
+    return MTR_OK;
+}
+
+extern "C" int mtr_set_blocking_sync(mtr_ctx *ctx, int on)
+{
+    if (!ctx) return MTR_EINVAL;
+    ctx->blocking_sync = on != 0;
     return MTR_OK;
 }
 

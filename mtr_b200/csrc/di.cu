@@ -448,7 +448,7 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     MTR_CUDA(ctx, cudaMemcpyAsync(di, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, cudaMemcpyAsync(end, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, cudaMemcpyAsync(w_out, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
-    MTR_CUDA(ctx, cudaStreamSynchronize(s));
+    MTR_CUDA(ctx, mtr_sync(ctx));
     float ms = 0;
     MTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
     ctx->stats.di_ms = ms;

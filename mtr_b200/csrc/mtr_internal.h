@@ -90,6 +90,8 @@ struct mtr_ctx {
     cudaStream_t main_stream = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t class_done[WDP_NCLASS] = {};
+    cudaEvent_t sync_ev = nullptr;          // blocking-sync event: waiting threads sleep instead of spinning
+    bool blocking_sync = false;             // mtr_set_blocking_sync
     std::string err;
     // resident reads
     DevBuf d_packed, d_word_off, d_len;
@@ -107,6 +109,15 @@ int  wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const ui
                      int64_t aux_bytes);
 int  wdp_launch_impl(mtr_ctx *ctx);
 int  wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes);
+// waits for everything queued on main_stream without burning a host core (the dispatcher threads of the pipeline
+// would otherwise spin next to the host workers)
+inline cudaError_t mtr_sync(mtr_ctx *ctx)
+{
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(ctx->main_stream);
+    cudaError_t e = cudaEventRecord(ctx->sync_ev, ctx->main_stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->sync_ev);
+}
 void di_state_free(mtr_ctx *ctx);
 void uf_state_free(mtr_ctx *ctx);
 long long wdp_dir_bytes(int ulen, int rows);   // bytes of one direction matrix (per penalty set)

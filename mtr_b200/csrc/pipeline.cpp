@@ -163,39 +163,77 @@ struct Counter {
 };
 
 // ---------------------------------------------------------------- greedy de Bruijn walk (consensus.c:269-505)
-bool walk(Counter &cnt, int qs, int qe, int start, int k, bool backward, Rec &out)
+// From step 10 on the look-ahead depth is constant (k), so the next node is a pure function of the current node
+// and of the (now frozen) count table.  WalkMemo caches that function across the <= 100 start nodes of one
+// (window, k, direction) and marks the nodes a walk has visited: coming back to a visited node means the walk is
+// caught in a cycle that does not contain its start node, i.e. it can only run out its step limit -- the result
+// ("no loop") is returned at once.  Both shortcuts leave every observable result unchanged.
+struct WalkMemo {
+    struct Entry { uint32_t key, epoch; int next, seen; };
+    std::vector<Entry> tab;
+    uint32_t epoch = 0, mask = 0;
+    int serial = 0;
+    void reset()
+    {
+        if (tab.empty()) { tab.assign(1u << 17, Entry{0, 0, 0, 0}); mask = (1u << 17) - 1; }
+        if (++epoch == 0) { for (Entry &e : tab) e.epoch = 0; epoch = 1; }
+        serial = 0;
+    }
+    Entry *slot(uint32_t node)
+    {
+        uint32_t h = (node * 2654435761u) & mask;
+        for (;;) {
+            Entry &e = tab[h];
+            if (e.epoch != epoch) { e.epoch = epoch; e.key = node; e.seen = -1; e.next = -1; return &e; }
+            if (e.key == node) return &e;
+            h = (h + 1) & mask;
+        }
+    }
+};
+
+bool walk(Counter &cnt, WalkMemo &memo, int qs, int qe, int start, int k, bool backward, Rec &out)
 {
     int ustr[kMaxPeriod], uscore[kMaxPeriod];
     int ties[kMaxTies], fresh[kMaxTies];
     int node = start, period = 0;
     const int limit = (qe - qs) / 5;                       // MIN_NUM_FREQ_UNIT
+    const int serial = memo.serial++;
     for (int l = 0; l < kMaxPeriod && l < limit; l++) {
         if (!backward) { ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node); }
-        int m, pick = 0, nties = 1;
-        ties[0] = 0;
-        const int depth = l < 10 ? 1 : k;
-        for (m = 1; m <= depth; m++) {
-            int best = -1, nf = 0;
-            pick = 0;
-            for (int t = 0; t < nties; t++)
-                for (int b = 0; b < 4; b++) {
-                    const int digits = backward ? b * P4.v[m - 1] + ties[t] : 4 * ties[t] + b;
-                    const int cand = backward ? digits * P4.v[k - m] + node / P4.v[m]
-                                              : P4.v[m] * (node % P4.v[k - m]) + digits;
-                    const int c = cnt.get(cand);
-                    if (best < c) { best = c; pick = digits; nf = 0; fresh[nf++] = digits; }
-                    else if (best == c && nf < kMaxTies) fresh[nf++] = digits;
-                }
-            if (backward ? nf <= 1 : nf == 1) break;
-            std::copy(fresh, fresh + nf, ties);
-            nties = nf;
+        WalkMemo::Entry *me = nullptr;
+        int next = -1;
+        if (l >= 10) {
+            me = memo.slot((uint32_t)node);
+            if (me->seen == serial) return false;           // cycle without the start node
+            me->seen = serial;
+            next = me->next;
         }
-        if (!backward) {
-            node = 4 * (node % P4.v[k - 1]) + pick / P4.v[m - 1];       // unresolved ties append 'A' (:336)
-        } else {
-            node = (pick % 4) * P4.v[k - 1] + node / 4;
-            ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node);
+        if (next < 0) {
+            int m, pick = 0, nties = 1;
+            ties[0] = 0;
+            const int depth = l < 10 ? 1 : k;
+            for (m = 1; m <= depth; m++) {
+                int best = -1, nf = 0;
+                pick = 0;
+                for (int t = 0; t < nties; t++)
+                    for (int b = 0; b < 4; b++) {
+                        const int digits = backward ? b * P4.v[m - 1] + ties[t] : 4 * ties[t] + b;
+                        const int cand = backward ? digits * P4.v[k - m] + node / P4.v[m]
+                                                  : P4.v[m] * (node % P4.v[k - m]) + digits;
+                        const int c = cnt.get(cand);
+                        if (best < c) { best = c; pick = digits; nf = 0; fresh[nf++] = digits; }
+                        else if (best == c && nf < kMaxTies) fresh[nf++] = digits;
+                    }
+                if (backward ? nf <= 1 : nf == 1) break;
+                std::copy(fresh, fresh + nf, ties);
+                nties = nf;
+            }
+            next = backward ? (pick % 4) * P4.v[k - 1] + node / 4
+                            : 4 * (node % P4.v[k - 1]) + pick / P4.v[m - 1];      // unresolved ties append 'A' (:336)
+            if (me) me->next = next;
         }
+        node = next;
+        if (backward) { ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node); }
         if (node == start) { period = l + 1; if (kMaxPeriod <= period) period = 0; break; }
     }
     if (period == 0) return false;
@@ -449,7 +487,7 @@ struct ReadState {
     long long candidates = 0;
 };
 
-struct Worker { Counter cnt; double t_build = 0, t_list = 0, t_walk = 0, t_polish = 0, t_step = 0; long long n_chain = 0, n_walk = 0;
+struct Worker { Counter cnt; WalkMemo memo; double t_build = 0, t_list = 0, t_walk = 0, t_polish = 0, t_step = 0; long long n_chain = 0, n_walk = 0;
                 double hb_t[8] = {0}, hw_t[8] = {0}, hw_max[8] = {0}; long long hb_n[8] = {0}, hw_n[8] = {0}; };
 
 int size_bucket(int n) { int b = 0; while (b < 7 && n > (64 << b)) b++; return b; }   // <=64, 128, ..., >4096
@@ -463,6 +501,7 @@ struct RoundResults {
 };
 
 bool g_uf_on_gpu = false;                  // MTR_UNITFINDER=gpu runs the unit finder as K4 on the GPU
+int g_uf_gpu_min_window = 0;               // ... for candidate windows of at least this many bases (MTR_UF_GPU_MIN_WINDOW)
 
 int add_job(ReadState &rs, int first, int rows, const std::vector<uint8_t> &unit, int n_param, const int (*p)[3], int mode)
 {
@@ -501,7 +540,7 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
     ch.rr.inputLen = rs.L; ch.rr.kmer = ch.k;
     ch.dir_found[0] = ch.dir_found[1] = false;
     ch.found_last = false;
-    if (g_uf_on_gpu) {
+    if (g_uf_on_gpu && qe - qs + 1 >= g_uf_gpu_min_window) {
         mtr_uf_task t;
         t.read = rs.index; t.qs = qs; t.qe = qe; t.k = ch.k;
         ch.uf_task = (int)rs.uf_tasks.size();
@@ -525,11 +564,12 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
     struct WalkTimer { Worker &w; double t0; int sb; bool walked; ~WalkTimer() { const double d = now_s() - t0; w.t_walk += d; if (walked) { w.hw_n[sb]++; w.hw_t[sb] += d; if (d > w.hw_max[sb]) w.hw_max[sb] = d; } } } walk_timer{wk, tp0, sb, 5 < maxf};
     bool any = false;
     if (5 < maxf) {
-        for (int d = 0; d < 2; d++)
+        for (int d = 0; d < 2; d++) {
+            wk.memo.reset();
             for (int i = 0; i < nn; i++) {
                 Rec r = ch.rr;
                 wk.n_walk++;
-                const bool found = walk(wk.cnt, qs, qe, nodes[i], ch.k, d == 1, r);
+                const bool found = walk(wk.cnt, wk.memo, qs, qe, nodes[i], ch.k, d == 1, r);
                 ch.found_last = found;
                 if (!found) continue;
                 ch.dir[d] = r; ch.dir_found[d] = true;
@@ -537,6 +577,7 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
                 any = true;
                 break;
             }
+        }
     }
     if (any) { ch.stage = Chain::SEARCH_WAIT; return; }
     ch.rr.clear();                                          // nothing found: find_tandem_repeat_sub clears (:86-88)
@@ -785,9 +826,9 @@ struct ReadInput {
 }
 
 struct Engine {
-    mtr_ctx *ctx = nullptr;            // directional index + the lane of long DP jobs
-    mtr_ctx *ctx_fast = nullptr;       // the lane of short DP jobs (shares the resident reads of ctx)
-    mtr_ctx *ctx_uf = nullptr;         // the lane of unit-finder tasks (K4)
+    mtr_ctx *ctx = nullptr;            // owns the resident reads; directional index; first long-DP lane
+    std::vector<mtr_ctx *> lanes[3];   // dispatch lanes: [0] long DP jobs, [1] short DP jobs, [2] unit finder (K4);
+                                       // every lane context shares the reads of ctx and runs concurrently on the GPU
     Pool *pool = nullptr;
     std::vector<Worker> workers;
     double t_di = 0, t_dp = 0, t_rounds = 0;
@@ -797,15 +838,33 @@ struct Engine {
     {
         int rc = mtr_cuda_init(device, &ctx);
         if (rc) die(nullptr, "mtr_cuda_init", rc);
-        rc = mtr_cuda_init(device, &ctx_fast);
-        if (rc) die(nullptr, "mtr_cuda_init", rc);
-        rc = mtr_cuda_init(device, &ctx_uf);
-        if (rc) die(nullptr, "mtr_cuda_init", rc);
         if (const char *e = getenv("MTR_UNITFINDER")) g_uf_on_gpu = strcmp(e, "gpu") == 0;
+        if (const char *e = getenv("MTR_UF_GPU_MIN_WINDOW")) g_uf_gpu_min_window = atoi(e);
+        int want[3] = {1, 1, g_uf_on_gpu ? 2 : 0};
+        if (const char *e = getenv("MTR_UF_LANES")) want[2] = g_uf_on_gpu ? std::max(1, atoi(e)) : 0;
+        if (const char *e = getenv("MTR_LONG_LANES")) want[0] = std::max(1, atoi(e));
+        if (const char *e = getenv("MTR_SHORT_LANES")) want[1] = std::max(1, atoi(e));
+        lanes[0].push_back(ctx);
+        for (int kind = 0; kind < 3; kind++)
+            while ((int)lanes[kind].size() < want[kind]) {
+                mtr_ctx *c = nullptr;
+                rc = mtr_cuda_init(device, &c);
+                if (rc) die(nullptr, "mtr_cuda_init", rc);
+                lanes[kind].push_back(c);
+            }
+        // long-lane calls take milliseconds: their dispatcher threads sleep while waiting, leaving the cores to the workers
+        if (!getenv("MTR_SPIN_LONG")) for (mtr_ctx *c : lanes[0]) if (c != ctx || lanes[0].size() > 1) mtr_set_blocking_sync(c, 1);
+        for (mtr_ctx *c : lanes[2]) mtr_set_blocking_sync(c, 1);
         pool = new Pool(threads);
         workers.resize(pool->size());
     }
-    ~Engine() { delete pool; mtr_cuda_shutdown(ctx_uf); mtr_cuda_shutdown(ctx_fast); mtr_cuda_shutdown(ctx); }
+    ~Engine()
+    {
+        delete pool;
+        for (int kind = 0; kind < 3; kind++)
+            for (mtr_ctx *c : lanes[kind]) if (c != ctx) mtr_cuda_shutdown(c);
+        mtr_cuda_shutdown(ctx);
+    }
 
     // resident batch (prepare) + statistics of the last run
     std::vector<int64_t> b_word_off, b_stale_off, b_pos_off;
@@ -844,10 +903,12 @@ struct Engine {
         });
         int rc = mtr_reads_upload(ctx, packed.data(), b_word_off.data(), lens.data(), n);
         if (rc) die(ctx, "mtr_reads_upload", rc);
-        rc = mtr_reads_share(ctx_fast, ctx);
-        if (rc) die(ctx_fast, "mtr_reads_share", rc);
-        rc = mtr_reads_share(ctx_uf, ctx);
-        if (rc) die(ctx_uf, "mtr_reads_share", rc);
+        for (int kind = 0; kind < 3; kind++)
+            for (mtr_ctx *c : lanes[kind]) {
+                if (c == ctx) continue;
+                rc = mtr_reads_share(c, ctx);
+                if (rc) die(c, "mtr_reads_share", rc);
+            }
         ps.h2d_bytes = (int64_t)packed.size() * 4 + (int64_t)(n + 1) * 12;
     }
 
@@ -890,6 +951,7 @@ struct Engine {
         const long long dir_cap = dir_budget();
         t0 = now_s();
         double host_ms = 0, wdp_ms = 0, uf_ms = 0;
+        double lane_ms[3] = {0, 0, 0}; long long lane_batches[3] = {0, 0, 0}, lane_items[3] = {0, 0, 0}, lane_reads[3] = {0, 0, 0};
         struct BatchResult { std::vector<mtr_wdp_result> res; std::vector<uint8_t> aux; };
         struct UfBatchResult { std::vector<mtr_uf_result> res; std::vector<uint8_t> units; std::vector<int32_t> scores; };
         std::vector<std::shared_ptr<BatchResult>> result_of(n);
@@ -937,8 +999,7 @@ struct Engine {
                 }
             }
         };
-        auto dispatch_loop = [&](int lane) {
-            mtr_ctx *lctx = lane ? ctx_fast : ctx;
+        auto dispatch_loop = [&](int lane, mtr_ctx *lctx) {
             cudaSetDevice(lctx->device);
             std::vector<mtr_wdp_job> jobs;
             std::vector<uint8_t> units;
@@ -986,6 +1047,7 @@ struct Engine {
                 {
                     std::lock_guard<std::mutex> g(mu);
                     wdp_ms += (now_s() - tg0) * 1e3;
+                    lane_ms[lane] += (now_s() - tg0) * 1e3; lane_batches[lane]++; lane_items[lane] += (long long)jobs.size(); lane_reads[lane] += (long long)batch.size();
                     rounds++; jobs_total += (long long)jobs.size();
                     ps.rounds++; ps.jobs += (int64_t)jobs.size();
                     if (lane) ps.rounds_fast++;
@@ -1000,7 +1062,7 @@ struct Engine {
                 batch.clear();
             }
         };
-        auto uf_dispatch_loop = [&]() {
+        auto uf_dispatch_loop = [&](mtr_ctx *ctx_uf) {
             cudaSetDevice(ctx_uf->device);
             std::vector<mtr_uf_task> tasks;
             std::vector<int> batch;
@@ -1032,6 +1094,7 @@ struct Engine {
                 {
                     std::lock_guard<std::mutex> g(mu);
                     uf_ms += (now_s() - tg0) * 1e3;
+                    lane_ms[2] += (now_s() - tg0) * 1e3; lane_batches[2]++; lane_items[2] += (long long)tasks.size(); lane_reads[2] += (long long)batch.size();
                     ps.rounds_uf++; ps.uf_tasks += (int64_t)tasks.size(); ps.uf_kernel_ms += us.uf_ms; ps.launches += 1;
                     ps.h2d_bytes += (int64_t)tasks.size() * sizeof(mtr_uf_task);
                     ps.d2h_bytes += (int64_t)tasks.size() * sizeof(mtr_uf_result) + used * 5;
@@ -1041,15 +1104,16 @@ struct Engine {
                 batch.clear();
             }
         };
-        std::thread dispatcher0([&] { dispatch_loop(0); }), dispatcher1([&] { dispatch_loop(1); }), dispatcher2([&] { uf_dispatch_loop(); });
+        std::vector<std::thread> dispatchers;
+        for (int kind = 0; kind < 2; kind++)
+            for (mtr_ctx *c : lanes[kind]) dispatchers.emplace_back([&, kind, c] { dispatch_loop(kind, c); });
+        for (mtr_ctx *c : lanes[2]) dispatchers.emplace_back([&, c] { uf_dispatch_loop(c); });
         {
             const double th0 = now_s();
             pool->run(pool->size(), [&](int tid, int) { worker_loop(tid); });
             host_ms += (now_s() - th0) * 1e3;
         }
-        dispatcher0.join();
-        dispatcher1.join();
-        dispatcher2.join();
+        for (std::thread &t : dispatchers) t.join();
         t_rounds += now_s() - t0;
         t_dp += wdp_ms / 1e3;
         ps.rounds_wall_ms = (now_s() - t0) * 1e3;
@@ -1059,6 +1123,11 @@ struct Engine {
             double b = 0, l = 0, w = 0, p = 0, t = 0; long long nc = 0, nw = 0;
             for (Worker &k : workers) { b += k.t_build; l += k.t_list; w += k.t_walk; p += k.t_polish; t += k.t_step; nc += k.n_chain; nw += k.n_walk;
                                         k.t_build = k.t_list = k.t_walk = k.t_polish = k.t_step = 0; k.n_chain = k.n_walk = 0; }
+            for (int l = 0; l < 3; l++)
+                fprintf(stderr, "[mtr profile]   lane %d (%s): batches %6lld  busy %8.1f ms  items/batch %8.1f  reads/batch %6.1f  ms/batch %6.3f\n", l,
+                        l == 0 ? "long DP" : (l == 1 ? "short DP" : "unit finder"), lane_batches[l], lane_ms[l],
+                        lane_batches[l] ? (double)lane_items[l] / lane_batches[l] : 0.0, lane_batches[l] ? (double)lane_reads[l] / lane_batches[l] : 0.0,
+                        lane_batches[l] ? lane_ms[l] / lane_batches[l] : 0.0);
             for (int b = 0; b < 8; b++) {
                 long long bn = 0, wn = 0; double wt = 0, wm = 0;
                 for (Worker &k : workers) { bn += k.hb_n[b]; wn += k.hw_n[b]; wt += k.hw_t[b]; wm = std::max(wm, k.hw_max[b]); k.hb_n[b] = k.hw_n[b] = 0; k.hw_t[b] = k.hw_max[b] = 0; }

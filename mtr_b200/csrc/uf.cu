@@ -314,12 +314,12 @@ extern "C" int mtr_uf_run(mtr_ctx *ctx, const mtr_uf_task *tasks, int n_tasks, m
     unsigned long long used = 0;
     MTR_CUDA(ctx, cudaMemcpyAsync(results, u.d_results.p, sizeof(mtr_uf_result) * (size_t)n_tasks, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, cudaMemcpyAsync(&used, u.d_used.p, 8, cudaMemcpyDeviceToHost, s));
-    MTR_CUDA(ctx, cudaStreamSynchronize(s));
+    MTR_CUDA(ctx, mtr_sync(ctx));
     if ((long long)used > need_out) { mtr_set_error(ctx, "uf_run: device wrote %llu > %lld unit bytes", used, need_out); return MTR_ECUDA; }
     if (used > 0) {
         MTR_CUDA(ctx, cudaMemcpyAsync(units, u.d_units.p, (size_t)used, cudaMemcpyDeviceToHost, s));
         MTR_CUDA(ctx, cudaMemcpyAsync(scores, u.d_scores.p, (size_t)used * 4, cudaMemcpyDeviceToHost, s));
-        MTR_CUDA(ctx, cudaStreamSynchronize(s));
+        MTR_CUDA(ctx, mtr_sync(ctx));
     }
     float ms = 0;
     MTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]));

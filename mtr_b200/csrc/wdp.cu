@@ -366,7 +366,7 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
         MTR_CUDA(ctx, cudaMemcpyAsync(w.d_tasks.p, w.h_tasks.p, sizeof(WdpTask) * (size_t)nt, cudaMemcpyHostToDevice, ctx->main_stream));
         MTR_CUDA(ctx, cudaMemcpyAsync(w.d_units.p, units, (size_t)units_len, cudaMemcpyHostToDevice, ctx->main_stream));
     }
-    MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+    MTR_CUDA(ctx, mtr_sync(ctx));
     w.uploaded = true;
     return MTR_OK;
 }
@@ -421,7 +421,7 @@ int wdp_launch_impl(mtr_ctx *ctx)
         ctx->stats.launches++;
     }
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[2], ms));
-    MTR_CUDA(ctx, cudaStreamSynchronize(ms));
+    MTR_CUDA(ctx, mtr_sync(ctx));
     float f0 = 0, f1 = 0;
     MTR_CUDA(ctx, cudaEventElapsedTime(&f0, ctx->ev[0], ctx->ev[1]));
     MTR_CUDA(ctx, cudaEventElapsedTime(&f1, ctx->ev[1], ctx->ev[2]));
@@ -443,7 +443,7 @@ int wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t 
     }
     if (aux && aux_bytes > 0)
         MTR_CUDA(ctx, cudaMemcpyAsync(aux, w.d_aux.p, (size_t)aux_bytes, cudaMemcpyDeviceToHost, ctx->main_stream));
-    MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+    MTR_CUDA(ctx, mtr_sync(ctx));
     if (w.n_results > 0) memcpy(results, w.h_results.p, sizeof(mtr_wdp_result) * (size_t)w.n_results);
     return MTR_OK;
 }
