@@ -122,67 +122,82 @@ wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
         for (int off = 16; off >= G; off >>= 1) maxrows = max(maxrows, __shfl_xor_sync(FULL, maxrows, off));
 
         unsigned xw = 0;
-        for (int i = 1; i <= maxrows; i++) {
+        // One row.  Ws = row i-1 of my columns (scores x4, untagged), Wd receives row i.
+        auto row = [&](const int (&Ws)[C], int (&Wd)[C], const int i) {
             const bool act = i <= rows;
             const long long bi = base0 + i;
             if (act && (i == 1 || (bi & 15) == 0)) xw = packed[bi >> 4];
             const int xi = (int)((xw >> ((int)(bi & 15) * 2)) & 3u);
-            const unsigned m = ((xi & 2) ? eq23 : eq01) >> ((xi & 1) * 16);
+            const unsigned m = (((xi & 2) ? eq23 : eq01) >> ((xi & 1) * 16)) & ((1u << C) - 1u);
 
-            // phase A: left-independent candidates
-            int A[C];
+            // pass 1: every cell once, speculating that no left-carry enters the lane
+            int R[C];                                       // tagged results (low 2 bits = direction code)
+            int left = NEG_INF;
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                const int dg = (c == 0) ? dgin : Wp[c - 1];
-                const int a = __viaddmax_s32_relu(dg, cD, Wp[c] + cU);
-                A[c] = (m & (1u << c)) ? dg + g4 : a;
+                const int dg = (c == 0) ? dgin : Ws[c - 1];
+                const int a = __viaddmax_s32_relu(dg, cD, Ws[c] + cU);
+                const int t = __viaddmax_s32(left, cL, a);
+                const int r = (m & (1u << c)) ? dg + g4 : t;
+                R[c] = r;
+                Wd[c] = r & ~3;
+                left = Wd[c];
             }
-            // phase B: left chain with speculative lane-boundary carries
-            int r[C], v[C];
-            int carry = NEG_INF, cn;
+            // exact lane-boundary carries from the lane summaries: a lane passes its carry-in on (minus C
+            // indels) only if it holds no match cell; iterate to the fixpoint (monotone, <= G rounds)
+            const int out0 = Wd[C - 1];
+            int out = out0, cin;
             for (;;) {
-                int left = carry;
+                cin = __shfl_up_sync(FULL, out, 1, G);
+                if (gl == 0) cin = NEG_INF;
+                const int nout = m ? out0 : max(out0, cin - in4 * C);
+                const bool changed = nout != out;
+                out = nout;
+                if (!__any_sync(FULL, changed)) break;
+            }
+            // fix-up: cells before the lane's first match see the carry; cell c gets cin - (c+1) indels, tag "left"
+            if (__any_sync(FULL, !(m & 1u) && cin + cL > R[0])) {
+                const int f = m ? __ffs(m) - 1 : C;
+                int cand = cin + cL;
 #pragma unroll
                 for (int c = 0; c < C; c++) {
-                    int t = __viaddmax_s32(left, cL, A[c]);
-                    t = (m & (1u << c)) ? A[c] : t;
-                    r[c] = t;
-                    v[c] = t & ~3;
-                    left = v[c];
+                    const int ce = c < f ? cand : NEG_INF;
+                    if (ce > R[c]) { R[c] = ce; Wd[c] = ce & ~3; }
+                    cand -= in4;
                 }
-                cn = __shfl_up_sync(FULL, v[C - 1], 1, G);
-                if (gl == 0) cn = NEG_INF;
-                const bool need = (cn != carry) && !(m & 1u) && (cn + cL > r[0]);
-                if (!__any_sync(FULL, need)) break;
-                carry = cn;
             }
             // W[i][U] -> everybody (lane 0 needs it as next row's diagonal and for the j == 1 quirk)
             int mine = 0;
 #pragma unroll
-            for (int c = 0; c < C; c++) mine |= v[c] & sel[c];
+            for (int c = 0; c < C; c++) mine |= Wd[c] & sel[c];
             const int wU = __shfl_sync(FULL, mine, lu, G);
 
-            unsigned bits = 0;
+            // direction codes = tagged - untagged, packed 2 bits per cell with two multiply-add chains
+            // (sum (R_c - W_c) 4^c is exact modulo 2^32); argmax key on the same pipe
+            unsigned accR = 0, accW = 0;
+            int key = 0;
 #pragma unroll
-            for (int c = 0; c < C; c++) bits |= (unsigned)(r[c] & 3) << (2 * c);
+            for (int c = C - 1; c >= 0; c--) {
+                accR = accR * 4u + (unsigned)R[c];
+                accW = accW * 4u + (unsigned)Wd[c];
+                key = max(key, Wd[c] * 4 + (15 - c));
+            }
+            unsigned bits = accR - accW;
             // traceback at j == 1 tests "deletion" against W[i][0] == W[i][U] before insertion
-            if (gl == 0 && (bits & 3u) == 1u && v[0] == wU - in4) bits ^= 3u;
-
+            if (gl == 0 && (bits & 3u) == 1u && Wd[0] == wU - in4) bits ^= 3u;
             if (act) {
                 uint8_t *p = drow + (size_t)(i - 1) * dstride;
                 if (C == 4) *p = (uint8_t)bits;
                 else if (C == 8) *(uint16_t *)p = (uint16_t)bits;
                 else *(uint32_t *)p = bits;
             }
-
-            int key = 0;
-#pragma unroll
-            for (int c = 0; c < C; c++) key = max(key, (v[c] << 2) | (15 - c));
             if (act && (key >> 4) > best_v) { best_v = key >> 4; best_i = i; best_c = 15 - (key & 15); }
-
-#pragma unroll
-            for (int c = 0; c < C; c++) Wp[c] = v[c];
-            dgin = (gl == 0) ? wU : cn;
+            dgin = (gl == 0) ? wU : cin;
+        };
+        int Wq[C];
+        for (int i = 1; i <= maxrows; i += 2) {
+            row(Wp, Wq, i);
+            if (i + 1 <= maxrows) row(Wq, Wp, i + 1);
         }
 
         // first row-major argmax over the group: larger value, then smaller row, then smaller column
