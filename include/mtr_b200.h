@@ -123,7 +123,8 @@ int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t a
  *
  * Output, per read r, for positions [0, len[r]): di (fp64), end, w -- exactly the reference's
  * directional_index / directional_index_end / directional_index_w after the call; pos_off[r] is the offset
- * of read r in the three arrays (pos_off[n] = total). */
+ * of read r in the three arrays (pos_off[n] = total).  di may be NULL: a range is live iff end >= 0 (the pipeline
+ * only needs end and w). */
 int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
                const int64_t *pos_off, double *di, int32_t *end, int32_t *w);
 

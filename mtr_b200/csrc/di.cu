@@ -323,7 +323,7 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
 {
     if (!ctx) return MTR_EINVAL;
     if (ctx->n_reads == 0) return MTR_OK;
-    if (!pos_off || !di || !end || !w_out) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
+    if (!pos_off || !end || !w_out) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
     MTR_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->di) ctx->di = new DiState();
     DiState &d = *ctx->di;
@@ -445,7 +445,7 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     MTR_CUDA(ctx, cudaGetLastError());
     launches++;
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-    MTR_CUDA(ctx, cudaMemcpyAsync(di, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
+    if (di) MTR_CUDA(ctx, cudaMemcpyAsync(di, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, cudaMemcpyAsync(end, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, cudaMemcpyAsync(w_out, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, mtr_sync(ctx));
@@ -454,7 +454,7 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     ctx->stats.di_ms = ms;
     ctx->stats.di_position_passes = pp;
     ctx->stats.di_bytes_in = ctx->n_words * 4 + nstale_total * 2;
-    ctx->stats.di_bytes_out = total_pos * 16;
+    ctx->stats.di_bytes_out = total_pos * (di ? 16 : 8);
     ctx->stats.launches = launches;
     return MTR_OK;
 }

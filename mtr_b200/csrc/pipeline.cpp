@@ -90,8 +90,8 @@ struct Counter {
     static inline uint32_t hash(uint32_t node) { return node * 2654435761u; }
     void build(const uint8_t *org, int L, int kk, int qs, int qe)
     {
-        for (uint32_t h : touched) slots[h] = 0;
-        touched.clear();
+        if (k <= 6) { for (int c : codes) direct[c] = 0; }      // undo the previous window (O(window), not O(4^k))
+        else { for (uint32_t h : touched) slots[h] = 0; touched.clear(); }
         k = kk;
         const int n = qe - qs + 1;
         codes.resize(n);
@@ -111,7 +111,7 @@ struct Counter {
         }
         maxf = -1;
         if (k <= 6) {
-            direct.assign(P4.v[k], 0);
+            if (direct.size() < 4096) direct.assign(4096, 0);
             for (int c : codes) maxf = std::max(maxf, ++direct[c]);
         } else {
             uint32_t cap = 1024;
@@ -745,10 +745,22 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
         ReadState::Cand &cd = rs.cands.back();
         cd.qs = qs; cd.qe = qe;
         cd.chains.resize(max_k - min_k + 1);
+        // A k'-mer that occurs c times has a k-prefix (k < k') that occurs at least c times at the same coded
+        // positions, so maxFreq(k') <= maxFreq(k) + (number of raw-base entries of the k' window, Q7).  Once that
+        // bound is <= 5 the search cannot pass the maxFreq gate (consensus.c:532) for any larger k: those chains
+        // end "not found" without building their count tables.
+        int low_maxf = 1 << 30;
         for (int k = min_k; k <= max_k; k++) {
             Chain &ch = cd.chains[k - min_k];
             ch.k = k;
+            const int raw = qe - std::min(qe, rs.L - k + 1) + 1;
+            if (!g_uf_on_gpu && low_maxf + raw <= 5) {
+                ch.rr.clear(); ch.found_last = false; ch.dir_found[0] = ch.dir_found[1] = false;
+                ch.stage = Chain::DONE;
+                continue;
+            }
             start_chain(rs, qs, qe, ch, wk);
+            if (!g_uf_on_gpu) low_maxf = std::min(low_maxf, wk.cnt.max_freq());
         }
     }
 }
@@ -840,7 +852,7 @@ struct Engine {
         if (rc) die(nullptr, "mtr_cuda_init", rc);
         if (const char *e = getenv("MTR_UNITFINDER")) g_uf_on_gpu = strcmp(e, "gpu") == 0;
         if (const char *e = getenv("MTR_UF_GPU_MIN_WINDOW")) g_uf_gpu_min_window = atoi(e);
-        int want[3] = {1, 1, g_uf_on_gpu ? 2 : 0};
+        int want[3] = {2, 2, g_uf_on_gpu ? 2 : 0};
         if (const char *e = getenv("MTR_UF_LANES")) want[2] = g_uf_on_gpu ? std::max(1, atoi(e)) : 0;
         if (const char *e = getenv("MTR_LONG_LANES")) want[0] = std::max(1, atoi(e));
         if (const char *e = getenv("MTR_SHORT_LANES")) want[1] = std::max(1, atoi(e));
@@ -923,10 +935,9 @@ struct Engine {
         memset(&ps, 0, sizeof ps);
         ps.h2d_bytes = h2d_prepare;
         ps.reads = n; ps.bases = pos_off[n];
-        std::vector<double> di((size_t)pos_off[n]);
         std::vector<int32_t> end((size_t)pos_off[n]), ww((size_t)pos_off[n]);
         double t0 = now_s();
-        int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), di.data(), end.data(), ww.data());
+        int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), nullptr, end.data(), ww.data());
         if (rc) die(ctx, "mtr_di_run", rc);
         t_di += now_s() - t0;
         {
@@ -934,7 +945,7 @@ struct Engine {
             mtr_get_stats(ctx, &s);
             ps.di_kernel_ms = s.di_ms; ps.di_position_passes = s.di_position_passes; ps.launches += s.launches;
             ps.di_bytes_in = s.di_bytes_in; ps.di_bytes_out = s.di_bytes_out;
-            ps.h2d_bytes += (int64_t)b_stale.size() * 2; ps.d2h_bytes += pos_off[n] * 16;
+            ps.h2d_bytes += (int64_t)b_stale.size() * 2; ps.d2h_bytes += pos_off[n] * 8;
             ps.di_wall_ms = (now_s() - t0) * 1e3;
         }
         // ---- per-read state machines
