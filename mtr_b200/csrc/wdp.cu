@@ -244,24 +244,47 @@ wdp_traceback(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__r
         } else if (t.mode == MTR_TB_PATH) {
             path = (uint8_t *)aux + t.aux_off;
         }
-        while (i > 0 && run > 0) {
-            const int xi = read_base(packed, t.base0 + i);
-            const int uj = units[t.unit_off + j - 1];
-            int op;
-            if (xi == uj) {
-                op = 0;
-            } else {
-                const int code = (d[(size_t)(i - 1) * t.dir_stride + ((j - 1) >> 2)] >> (((j - 1) & 3) * 2)) & 3;
-                if (code == 0) { flags |= 2; break; }       // cannot happen: run > 0 means W[i][j] > 0
-                op = code == 3 ? 1 : (code == 2 ? 2 : 3);
+        // The walk is a chain of dependent loads (read base, unit base, direction byte).  ~85 % of the steps of a
+        // real alignment are diagonal, so the operands of the next TB_DEPTH cells down the diagonal are fetched
+        // together (independent loads in flight) and consumed until the path leaves the diagonal.
+        constexpr int TB_DEPTH = 8;
+        bool alive = i > 0 && run > 0;
+        while (alive) {
+            int qx[TB_DEPTH], qu[TB_DEPTH], qd[TB_DEPTH];
+            {
+                int jt = j;
+#pragma unroll
+                for (int q = 0; q < TB_DEPTH; q++) {
+                    const int it = i - q;
+                    const bool ok = it >= 1;
+                    qx[q] = ok ? read_base(packed, t.base0 + it) : 0;
+                    qu[q] = units[t.unit_off + jt - 1];
+                    qd[q] = ok ? d[(size_t)(it - 1) * t.dir_stride + ((jt - 1) >> 2)] : 0;
+                    jt = jt == 1 ? t.ulen : jt - 1;
+                }
             }
-            if (path) { if (steps < t.aux_cap) path[steps] = (uint8_t)op; else flags |= 1; }
-            steps++;
-            if (op == 0)      { if (cons) cons[j * 5 + xi]++; run -= G;  i--; j--; nm++; }
-            else if (op == 1) { if (cons) cons[j * 5 + xi]++; run += MM; i--; j--; nx++; }
-            else if (op == 2) { if (cons) cons[j * 5 + 4]++;  run += IN; j--;      nd++; }
-            else              { if (miss) miss[j * 4 + xi]++; run += IN; i--;      ni++; }
-            if (j == 0) j = t.ulen;
+#pragma unroll
+            for (int q = 0; q < TB_DEPTH; q++) {
+                if (!(i > 0 && run > 0)) { alive = false; break; }
+                const int xi = qx[q], uj = qu[q];
+                int op;
+                if (xi == uj) {
+                    op = 0;
+                } else {
+                    const int code = (qd[q] >> (((j - 1) & 3) * 2)) & 3;
+                    if (code == 0) { flags |= 2; alive = false; break; }       // cannot happen: run > 0 means W[i][j] > 0
+                    op = code == 3 ? 1 : (code == 2 ? 2 : 3);
+                }
+                if (path) { if (steps < t.aux_cap) path[steps] = (uint8_t)op; else flags |= 1; }
+                steps++;
+                if (op == 0)      { if (cons) cons[j * 5 + xi]++; run -= G;  i--; j--; nm++; }
+                else if (op == 1) { if (cons) cons[j * 5 + xi]++; run += MM; i--; j--; nx++; }
+                else if (op == 2) { if (cons) cons[j * 5 + 4]++;  run += IN; j--;      nd++; }
+                else              { if (miss) miss[j * 4 + xi]++; run += IN; i--;      ni++; }
+                if (j == 0) j = t.ulen;
+                if (op >= 2) break;                         // left the diagonal: refill from the new cell
+            }
+            if (!(i > 0 && run > 0)) alive = false;
         }
         res->end_i = i; res->end_j = j;
         res->n_match = nm; res->n_mismatch = nx; res->n_ins = ni; res->n_del = nd;
