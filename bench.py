@@ -222,6 +222,15 @@ def main():
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     clk = clocks.stop()
+
+    # ---- K3 alone on exactly one step's DP jobs, replayed as a single batch (operands resident in HBM)
+    alone = None
+    if rank == 0:
+        pipe.log_jobs(True)
+        pipe.load_fasta(texts[a.warmup])
+        pipe.run()
+        pipe.log_jobs(False)
+        alone = pipe.replay_logged_jobs(iters=3)
     pipe.close()
 
     reads_all = sum_over_ranks(R * a.steps)
@@ -257,6 +266,13 @@ def main():
                                  % (alu["viaddmnmx_s32"], I_CELL_INT32),
                      "alu_probe_gops": {k: round(v, 1) for k, v in alu.items()},
                      "dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3)},
+        "roofline_kernel_alone": None if alone is None else {
+            "what": "the same K3 kernels on all DP jobs of one step replayed as ONE batch (%d jobs), timed alone with CUDA events" % alone["jobs"],
+            "bound": "int-alu", "achieved": round(alone["wdp_cells"] / max(alone["wdp_fill_ms"], 1e-9) / 1e6, 2), "peak": round(peak_gcups, 1),
+            "unit": "GCUPS", "frac": round(alone["wdp_cells"] / max(alone["wdp_fill_ms"], 1e-9) / 1e6 / peak_gcups, 4),
+            "with_traceback_gcups": round(alone["wdp_cells"] / max(alone["wdp_fill_ms"] + alone["wdp_tb_ms"], 1e-9) / 1e6, 2),
+            "fill_ms": round(alone["wdp_fill_ms"], 3), "tb_ms": round(alone["wdp_tb_ms"], 3), "cells": int(alone["wdp_cells"]),
+            "slot_cells": int(alone["wdp_slot_cells"]), "dir_bytes": int(alone["wdp_dir_bytes"])},
         "roofline_di": {"kernel": "di_codes + di_slide + di_merge (K1/K2)", "bound": "hbm", "achieved": round(di_gbs, 3),
                         "peak": hbm_peak, "unit": "GB/s", "frac": round(di_gbs / hbm_peak, 6), "traffic": None,
                         "note": "algorithmic bytes = packed reads in + 16 B per position out; the stage is LSU/shared-memory bound"},

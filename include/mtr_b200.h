@@ -192,6 +192,12 @@ void mtr_pipeline_close(mtr_pipeline *p);
 int  mtr_pipeline_load_fasta(mtr_pipeline *p, const char *text, int64_t len);
 int  mtr_pipeline_run(mtr_pipeline *p, int print_alignment, const char **out_text, int64_t *out_len);
 int  mtr_pipeline_get_stats(const mtr_pipeline *p, mtr_pipeline_stats *out);
+/* Measurement support: log every DP job run() sends to the GPU (as COUNTS jobs), read the log back, and get the
+ * context that holds the resident reads so that the logged jobs can be replayed as ONE batch with mtr_wdp_upload /
+ * mtr_wdp_launch -- K3 timed alone on exactly the step's jobs. */
+int  mtr_pipeline_log_jobs(mtr_pipeline *p, int on);
+int  mtr_pipeline_get_job_log(mtr_pipeline *p, const mtr_wdp_job **jobs, int64_t *n_jobs, const uint8_t **units, int64_t *units_len);
+mtr_ctx *mtr_pipeline_ctx(mtr_pipeline *p);
 
 /* ------------------------------------------------------------------ the reference's entry points */
 /* mTR.h:126  handle_one_file(char *inputFile, int print_alignment): parses the FASTA, runs the pipeline on

@@ -21,7 +21,7 @@ ABI_FUNCTIONS = [
     "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_di_run", "mtr_get_stats",
     "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_run",
-    "mtr_pipeline_get_stats", "handle_one_file", "handle_one_read", "mtr_flush",
+    "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush",
 ]
 ABI_GLOBALS = [
     "Manhattan_Distance", "min_match_ratio", "orgInputString", "time_all", "time_memory", "time_range",
@@ -111,6 +111,10 @@ def load_library() -> C.CDLL:
     lib.mtr_pipeline_load_fasta.argtypes = [vp, C.c_char_p, i64]
     lib.mtr_pipeline_run.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(i64)]
     lib.mtr_pipeline_get_stats.argtypes = [vp, C.POINTER(PipelineStats)]
+    lib.mtr_pipeline_log_jobs.argtypes = [vp, C.c_int]
+    lib.mtr_pipeline_get_job_log.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
+    lib.mtr_pipeline_ctx.argtypes = [vp]
+    lib.mtr_pipeline_ctx.restype = vp
     lib.handle_one_file.argtypes = [C.c_char_p, C.c_int]
     lib.handle_one_file.restype = C.c_int
     lib.mtr_flush.restype = None
@@ -287,6 +291,28 @@ class Pipeline:
         if rc != 0:
             raise MtrError("mtr_pipeline_run failed (%d)" % rc)
         return C.string_at(out, n.value)
+
+    def log_jobs(self, on: bool = True):
+        self.lib.mtr_pipeline_log_jobs(self.h, 1 if on else 0)
+
+    def replay_logged_jobs(self, iters: int = 2) -> dict:
+        """Replays the DP jobs logged by the last run() as ONE batch on the pipeline's own context (K3 alone,
+        operands resident); returns the library's kernel statistics of the last replay."""
+        jobs, n, units, ul = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
+        rc = self.lib.mtr_pipeline_get_job_log(self.h, C.byref(jobs), C.byref(n), C.byref(units), C.byref(ul))
+        if rc != 0 or n.value == 0:
+            raise MtrError("no logged jobs")
+        ctx = self.lib.mtr_pipeline_ctx(self.h)
+        rc = self.lib.mtr_wdp_upload(ctx, jobs, int(n.value), units, ul.value, 0)
+        if rc != 0:
+            raise MtrError("replay upload failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))
+        st = Stats()
+        for _ in range(iters):
+            rc = self.lib.mtr_wdp_launch(ctx)
+            if rc != 0:
+                raise MtrError("replay launch failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))
+        self.lib.mtr_get_stats(ctx, C.byref(st))
+        return {k: getattr(st, k) for k, _ in Stats._fields_} | {"jobs": int(n.value)}
 
     def stats(self) -> dict:
         s = PipelineStats()

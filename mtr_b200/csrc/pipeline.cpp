@@ -878,6 +878,10 @@ struct Engine {
         mtr_cuda_shutdown(ctx);
     }
 
+    // optional log of every DP job of the last run (bench: replay them as one batch to time K3 alone)
+    bool log_jobs = false;
+    std::vector<mtr_wdp_job> job_log;
+    std::vector<uint8_t> unit_log;
     // resident batch (prepare) + statistics of the last run
     std::vector<int64_t> b_word_off, b_stale_off, b_pos_off;
     std::vector<uint16_t> b_stale;
@@ -935,6 +939,7 @@ struct Engine {
         memset(&ps, 0, sizeof ps);
         ps.h2d_bytes = h2d_prepare;
         ps.reads = n; ps.bases = pos_off[n];
+        job_log.clear(); unit_log.clear();
         std::vector<int32_t> end((size_t)pos_off[n]), ww((size_t)pos_off[n]);
         double t0 = now_s();
         int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), nullptr, end.data(), ww.data());
@@ -1059,6 +1064,11 @@ struct Engine {
                     std::lock_guard<std::mutex> g(mu);
                     wdp_ms += (now_s() - tg0) * 1e3;
                     lane_ms[lane] += (now_s() - tg0) * 1e3; lane_batches[lane]++; lane_items[lane] += (long long)jobs.size(); lane_reads[lane] += (long long)batch.size();
+                    if (log_jobs) {
+                        const int32_t shift = (int32_t)unit_log.size();
+                        for (mtr_wdp_job j : jobs) { j.unit_off += shift; j.mode = MTR_TB_COUNTS; j.aux_off = 0; j.aux_cap = 0; job_log.push_back(j); }
+                        unit_log.insert(unit_log.end(), units.begin(), units.end());
+                    }
                     rounds++; jobs_total += (long long)jobs.size();
                     ps.rounds++; ps.jobs += (int64_t)jobs.size();
                     if (lane) ps.rounds_fast++;
@@ -1531,3 +1541,22 @@ extern "C" int mtr_pipeline_get_stats(const mtr_pipeline *p, mtr_pipeline_stats 
     *out = p->eng->ps;
     return MTR_OK;
 }
+
+// Bench support: log the DP jobs of the next runs / hand the log out (valid until the next run).
+extern "C" int mtr_pipeline_log_jobs(mtr_pipeline *p, int on)
+{
+    if (!p) return MTR_EINVAL;
+    p->eng->log_jobs = on != 0;
+    return MTR_OK;
+}
+
+extern "C" int mtr_pipeline_get_job_log(mtr_pipeline *p, const mtr_wdp_job **jobs, int64_t *n_jobs, const uint8_t **units, int64_t *units_len)
+{
+    if (!p || !jobs || !n_jobs || !units || !units_len) return MTR_EINVAL;
+    *jobs = p->eng->job_log.data(); *n_jobs = (int64_t)p->eng->job_log.size();
+    *units = p->eng->unit_log.data(); *units_len = (int64_t)p->eng->unit_log.size();
+    return MTR_OK;
+}
+
+// The context that owns the resident reads of the pipeline's batch (for replaying logged jobs with mtr_wdp_*).
+extern "C" mtr_ctx *mtr_pipeline_ctx(mtr_pipeline *p) { return p ? p->eng->ctx : nullptr; }

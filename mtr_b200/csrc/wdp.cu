@@ -33,19 +33,22 @@
 #include "mtr_internal.h"
 
 // ---------------------------------------------------------------- job classes
-// U <= G*C, capacities 16 .. 512.  Classes 0-5 maximise throughput (few lanes per job, long register chains:
-// more jobs per warp, less scan overhead); classes 6-11 minimise the latency of one row (many lanes, C = 4
-// where possible) and are used when a batch is too small to fill the GPU anyway.  Both variants of a capacity
-// write the same direction-matrix layout.
+// U <= G*C.  Classes 0-9 maximise throughput (few lanes per job, long register chains: more jobs per warp, less
+// carry traffic), with capacities 16, 32, 48, 64, 96, 128, 192, 256, 384, 512 so that at most a third of the slots
+// is padding; classes 10-15 minimise the latency of one row (many lanes, C = 4 where possible) and are used when a
+// batch is too small to fill the GPU anyway.  Every class writes the same direction-matrix layout (slot s of a row
+// at bit 2*(s%4) of byte s/4).
 static const WdpClass kClasses[WDP_NCLASS] = {
-    {4, 4, 0},  {4, 8, 0},  {8, 8, 0},  {8, 16, 0}, {16, 16, 0}, {32, 16, 0},
+    {4, 4, 0},  {4, 8, 0},  {4, 12, 0}, {8, 8, 0},  {8, 12, 0},  {8, 16, 0}, {16, 12, 0}, {16, 16, 0}, {32, 12, 0}, {32, 16, 0},
     {4, 4, 0},  {8, 4, 0},  {16, 4, 0}, {32, 4, 0}, {32, 8, 0},  {32, 16, 0},
 };
+constexpr int kThroughputClasses = 10, kLatencyClasses = 6;
 
 static int class_of(int ulen, int latency)
 {
-    for (int k = 0; k < 6; k++)
-        if (ulen <= kClasses[k].G * kClasses[k].C) return k + (latency ? 6 : 0);
+    const int lo = latency ? kThroughputClasses : 0, n = latency ? kLatencyClasses : kThroughputClasses;
+    for (int k = lo; k < lo + n; k++)
+        if (ulen <= kClasses[k].G * kClasses[k].C) return k;
     return -1;
 }
 
@@ -189,6 +192,7 @@ wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
                 uint8_t *p = drow + (size_t)(i - 1) * dstride;
                 if (C == 4) *p = (uint8_t)bits;
                 else if (C == 8) *(uint16_t *)p = (uint16_t)bits;
+                else if (C == 12) { p[0] = (uint8_t)bits; p[1] = (uint8_t)(bits >> 8); p[2] = (uint8_t)(bits >> 16); }
                 else *(uint32_t *)p = bits;
             }
             if (act && (key >> 4) > best_v) { best_v = key >> 4; best_i = i; best_c = 15 - (key & 15); }
@@ -433,16 +437,20 @@ int wdp_launch_impl(mtr_ctx *ctx)
         switch (k) {
         case 0: launch_fill<4, 4>(ctx, k, dt, n, s); break;
         case 1: launch_fill<4, 8>(ctx, k, dt, n, s); break;
-        case 2: launch_fill<8, 8>(ctx, k, dt, n, s); break;
-        case 3: launch_fill<8, 16>(ctx, k, dt, n, s); break;
-        case 4: launch_fill<16, 16>(ctx, k, dt, n, s); break;
-        case 5: launch_fill<32, 16>(ctx, k, dt, n, s); break;
-        case 6: launch_fill<4, 4>(ctx, k, dt, n, s); break;
-        case 7: launch_fill<8, 4>(ctx, k, dt, n, s); break;
-        case 8: launch_fill<16, 4>(ctx, k, dt, n, s); break;
-        case 9: launch_fill<32, 4>(ctx, k, dt, n, s); break;
-        case 10: launch_fill<32, 8>(ctx, k, dt, n, s); break;
-        case 11: launch_fill<32, 16>(ctx, k, dt, n, s); break;
+        case 2: launch_fill<4, 12>(ctx, k, dt, n, s); break;
+        case 3: launch_fill<8, 8>(ctx, k, dt, n, s); break;
+        case 4: launch_fill<8, 12>(ctx, k, dt, n, s); break;
+        case 5: launch_fill<8, 16>(ctx, k, dt, n, s); break;
+        case 6: launch_fill<16, 12>(ctx, k, dt, n, s); break;
+        case 7: launch_fill<16, 16>(ctx, k, dt, n, s); break;
+        case 8: launch_fill<32, 12>(ctx, k, dt, n, s); break;
+        case 9: launch_fill<32, 16>(ctx, k, dt, n, s); break;
+        case 10: launch_fill<4, 4>(ctx, k, dt, n, s); break;
+        case 11: launch_fill<8, 4>(ctx, k, dt, n, s); break;
+        case 12: launch_fill<16, 4>(ctx, k, dt, n, s); break;
+        case 13: launch_fill<32, 4>(ctx, k, dt, n, s); break;
+        case 14: launch_fill<32, 8>(ctx, k, dt, n, s); break;
+        case 15: launch_fill<32, 16>(ctx, k, dt, n, s); break;
         default: mtr_set_error(ctx, "wdp_launch: class %d has no kernel", k); return MTR_EINVAL;
         }
         MTR_CUDA(ctx, cudaGetLastError());
