@@ -109,7 +109,7 @@ def reference_arm(a, rank, world):
     if not os.path.exists(binary):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     cores = os.cpu_count() or 1
-    n = max(cores, min(a.reads, 2 * cores))              # bounded sample: ~0.3 s of CPU per read per core
+    n = max(cores, min(a.reads, 8 * cores))              # bounded sample: ~0.3 s of CPU per read, 8 reads per core per step
     times = []
     for step in range(a.warmup + a.steps):
         reads = step_reads(n, 0, step)
@@ -284,7 +284,7 @@ def main():
 
     if rank == 0:
         cores = os.cpu_count() or 1
-        n = a.cpu_sample or 2 * cores
+        n = a.cpu_sample or 8 * cores
         binary, kind = (REF_BIN, "reference") if os.path.exists(REF_BIN) else (ORACLE_BIN, "port")
         sample = step_reads(n, 0, a.warmup)[:n] if n <= R else step_reads(n, 0, a.warmup)
         dt, ref_out = run_reference_cli(binary, sample, cores)

@@ -190,6 +190,9 @@ typedef struct {
 int  mtr_pipeline_open(int device, int threads, mtr_pipeline **out);
 void mtr_pipeline_close(mtr_pipeline *p);
 int  mtr_pipeline_load_fasta(mtr_pipeline *p, const char *text, int64_t len);
+/* Sharding: keep reads [first, first+count) only (count < 0: to the end); earlier reads are parsed just to carry the
+ * reference's cross-read stale state, so concatenating the shards' outputs equals the whole file's output. */
+int  mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, int64_t len, int first, int count);
 int  mtr_pipeline_run(mtr_pipeline *p, int print_alignment, const char **out_text, int64_t *out_len);
 int  mtr_pipeline_get_stats(const mtr_pipeline *p, mtr_pipeline_stats *out);
 /* Measurement support: log every DP job run() sends to the GPU (as COUNTS jobs), read the log back, and get the

@@ -20,8 +20,8 @@ TB_COUNTS, TB_CONSENSUS, TB_PATH = 0, 1, 2
 ABI_FUNCTIONS = [
     "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_di_run", "mtr_get_stats",
-    "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_run",
-    "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush",
+    "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_load_fasta_shard",
+    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush",
 ]
 ABI_GLOBALS = [
     "Manhattan_Distance", "min_match_ratio", "orgInputString", "time_all", "time_memory", "time_range",
@@ -109,6 +109,8 @@ def load_library() -> C.CDLL:
     lib.mtr_pipeline_close.argtypes = [vp]
     lib.mtr_pipeline_close.restype = None
     lib.mtr_pipeline_load_fasta.argtypes = [vp, C.c_char_p, i64]
+    lib.mtr_pipeline_load_fasta_shard.argtypes = [vp, C.c_char_p, i64, C.c_int, C.c_int]
+    lib.mtr_pipeline_load_fasta_shard.restype = C.c_int
     lib.mtr_pipeline_run.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(i64)]
     lib.mtr_pipeline_get_stats.argtypes = [vp, C.POINTER(PipelineStats)]
     lib.mtr_pipeline_log_jobs.argtypes = [vp, C.c_int]
@@ -278,8 +280,9 @@ class Pipeline:
             self.lib.mtr_pipeline_close(self.h)
             self.h = None
 
-    def load_fasta(self, text: bytes) -> int:
-        n = self.lib.mtr_pipeline_load_fasta(self.h, text, len(text))
+    def load_fasta(self, text: bytes, first: int = 0, count: int = -1) -> int:
+        """Loads the reads [first, first+count) of the FASTA text (default: all) and makes them resident."""
+        n = self.lib.mtr_pipeline_load_fasta_shard(self.h, text, len(text), first, count)
         if n < 0:
             raise MtrError("mtr_pipeline_load_fasta failed (%d)" % n)
         return n

@@ -1479,18 +1479,30 @@ extern "C" void mtr_pipeline_close(mtr_pipeline *p)
 
 // Parses FASTA text held in host memory (same rules as handle_one_file), reproduces the cross-read stale state,
 // packs the reads to 2 bit and uploads them.  Returns the number of reads now resident, or a negative code.
+extern "C" int mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, int64_t len, int first, int count);
+
 extern "C" int mtr_pipeline_load_fasta(mtr_pipeline *p, const char *text, int64_t len)
 {
-    if (!p || (!text && len > 0)) return MTR_EINVAL;
+    return mtr_pipeline_load_fasta_shard(p, text, len, 0, -1);
+}
+
+// Keeps reads [first, first + count) of the text (count < 0: to the end).  The reads before `first` are still
+// visited by the stale-state tracker, so a shard behaves exactly as it would inside the whole file (H3/H4a).
+extern "C" int mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, int64_t len, int first, int count)
+{
+    if (!p || (!text && len > 0) || first < 0) return MTR_EINVAL;
     p->reads.clear();
+    int ordinal = 0;
     ReadInput cur;
     bool have = false;
     auto flush = [&]() -> bool {
         if (!have) return true;
         cur.len = (int)cur.bases.size();
         if (cur.len == 0) return false;                     // a zero-length read ends the run (handle_one_file.c:283)
+        if (count >= 0 && ordinal >= first + count) return false;
         p->stale->visit(cur, nullptr);
-        p->reads.push_back(std::move(cur));
+        if (ordinal >= first) p->reads.push_back(std::move(cur));
+        ordinal++;
         cur = ReadInput();
         return true;
     };

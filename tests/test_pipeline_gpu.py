@@ -72,3 +72,31 @@ def test_small_batches_give_identical_output(synthetic_dir):
     ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
     for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_DIR_BUDGET_MB": "1"}):
         assert hashlib.md5(run(MTR, [], path, env)).hexdigest() == ref, env
+
+
+def test_sharded_pipeline_equals_whole_file(synthetic_dir):
+    """Two shards of the mixed-length file (stale state crosses the cut) through the pipeline ABI: the concatenation
+    must be the whole file's output."""
+    from mtr_b200 import capi, shard
+    text = open(os.path.join(synthetic_dir, "mixed.fa"), "rb").read()
+    plan = shard.plan_shards(shard.read_lengths(text), 2)
+    parts = []
+    for start, end in plan:
+        pipe = capi.Pipeline(0)
+        assert pipe.load_fasta(text, first=start, count=end - start) == end - start
+        parts.append(pipe.run())
+        pipe.close()
+    assert hashlib.md5(shard.merge_outputs(parts)).hexdigest() == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
+
+
+def test_pipeline_abi_alignment_and_pearson_modes(synthetic_dir):
+    from mtr_b200 import capi
+    text = open(os.path.join(synthetic_dir, "single_TR_20.fa"), "rb").read()
+    pipe = capi.Pipeline(0)
+    pipe.load_fasta(text)
+    assert hashlib.md5(pipe.run(print_alignment=True)).hexdigest() == DIGESTS["synthetic"]["single_TR_20"]["a"]["md5"]
+    pipe.close()
+    pipe = capi.Pipeline(0, manhattan=False, min_match_ratio=0.7)
+    pipe.load_fasta(text)
+    assert hashlib.md5(pipe.run()).hexdigest() == DIGESTS["synthetic"]["single_TR_20"]["p_m07"]["md5"]
+    pipe.close()
