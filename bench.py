@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "2048")), help="reads per step per GPU")
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "4096")), help="reads per step per GPU")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = 2 x cores)")
     a = ap.parse_args()

@@ -1125,9 +1125,14 @@ struct Engine {
                 batch.clear();
             }
         };
+        // Large batches keep one lane of each kind busy with big launches; small batches are latency-bound and gain
+        // from a second concurrent lane (MTR_LANES_FULL_BELOW reads).
+        const int full_below = getenv("MTR_LANES_FULL_BELOW") ? atoi(getenv("MTR_LANES_FULL_BELOW")) : 4096;
         std::vector<std::thread> dispatchers;
-        for (int kind = 0; kind < 2; kind++)
-            for (mtr_ctx *c : lanes[kind]) dispatchers.emplace_back([&, kind, c] { dispatch_loop(kind, c); });
+        for (int kind = 0; kind < 2; kind++) {
+            size_t use = n < full_below ? lanes[kind].size() : 1;
+            for (size_t li = 0; li < use; li++) { mtr_ctx *c = lanes[kind][li]; dispatchers.emplace_back([&, kind, c] { dispatch_loop(kind, c); }); }
+        }
         for (mtr_ctx *c : lanes[2]) dispatchers.emplace_back([&, c] { uf_dispatch_loop(c); });
         {
             const double th0 = now_s();
@@ -1237,33 +1242,75 @@ struct StaleTracker {
             mt[t] = (uint8_t)(y & 3u);
         }
     }
-    // fills in.bases[len], [len+1] and in.stale, then records what this read leaves behind
-    void visit(ReadInput &in, const int *tail_override)
+    struct Geom { int L, r, N, ext, need; };
+    static Geom geom(int L)
     {
-        const int L = in.len, r = L < 1000 ? 100 : L / 10, N = L + 2 * r;
-        const int written = std::min(L + 4 * r, kMaxLen);
-        in.bases.resize(L + 2);
-        in.bases[L] = tail_override ? (uint8_t)(tail_override[0] & 3) : org[L];
-        in.bases[L + 1] = tail_override ? (uint8_t)(tail_override[1] & 3) : org[L + 1];
+        Geom g;
+        g.L = L; g.r = L < 1000 ? 100 : L / 10; g.N = L + 2 * g.r;
+        g.ext = std::min(L + 4 * g.r, kMaxLen);             // area the read re-initialises (:143)
         int wmax = 0;
         for (int w = 5; w <= 10240 && w < L / 2; w *= 2) wmax = w;
-        const int need = L + r + 2 * wmax + 8;              // last index the k = 5 passes touch
-        in.stale.clear();
-        if (need > written) in.stale.assign(padded.begin() + written, padded.begin() + need);
-        memcpy(org.data(), in.bases.data(), (size_t)L);
-        // inputString_w_rand after init_inputString_surrounded_by_random_seq(k = 5) (fill_directional_index.c:137-169)
-        const int c = written;
+        g.need = L + g.r + 2 * wmax + 8;                    // last index the k = 5 passes touch
+        return g;
+    }
+    // inputString_w_rand[x] (x < ext) after init_inputString_surrounded_by_random_seq(k = 5) of this read
+    // (fill_directional_index.c:137-169): 5-mer code below N-4, raw padded base above
+    int s5_at(const ReadInput &in, const Geom &g, int x) const
+    {
         auto base = [&](int i) -> int {
-            if (i < r) return mt[c + i];
-            if (i < r + L) return in.bases[i - r];
-            if (i < N) return mt[c + r + (i - r - L)];
+            if (i < g.r) return mt[g.ext + i];
+            if (i < g.r + g.L) return in.bases[i - g.r];
+            if (i < g.N) return mt[g.ext + g.r + (i - g.r - g.L)];
             return mt[i];
         };
-        int code = 0;
-        for (int i = 0; i < 4 && i < written; i++) code = code * 4 + base(i);
-        for (int i = 0; i < written; i++) {
-            if (i < N - 4) { code = (code % 256) * 4 + base(i + 4); padded[i] = (uint16_t)code; }
-            else padded[i] = (uint16_t)base(i);
+        if (x >= g.N - 4) return base(x);
+        return (((base(x) * 4 + base(x + 1)) * 4 + base(x + 2)) * 4 + base(x + 3)) * 4 + base(x + 4);
+    }
+    // Processes reads v[b..e) as they follow each other in the input: every read gets the two bases past its end
+    // and the k = 5 codes beyond its own area that the latest earlier, longer read left behind -- looked up
+    // directly in the earlier reads of the batch (in parallel over reads) or in the state carried over from
+    // earlier batches; afterwards the carried state is advanced past the batch in O(longest read).
+    void visit_batch(std::vector<ReadInput> &v, size_t b, size_t e, int threads, const int *tail_override)
+    {
+        const int n = (int)(e - b);
+        if (n <= 0) return;
+        std::vector<Geom> g(n);
+        for (int i = 0; i < n; i++) { g[i] = geom(v[b + i].len); v[b + i].bases.resize(v[b + i].len + 2); }
+        auto work = [&](int i) {
+            ReadInput &in = v[b + i];
+            const int L = g[i].L;
+            for (int t = 0; t < 2; t++) {
+                const int x = L + t;
+                int val = org[x];
+                for (int m = i - 1; m >= 0; m--) if (g[m].L > x) { val = v[b + m].bases[x]; break; }
+                in.bases[x] = tail_override && n == 1 ? (uint8_t)(tail_override[t] & 3) : (uint8_t)val;
+            }
+            const int lo = g[i].ext, hi = g[i].need;
+            in.stale.assign(hi > lo ? hi - lo : 0, 0);
+            if (hi <= lo) return;
+            int maxext = 0;
+            for (int m = i - 1; m >= 0 && maxext < hi; m--) {
+                if (g[m].ext <= maxext) continue;
+                for (int x = std::max(lo, maxext); x < std::min(g[m].ext, hi); x++) in.stale[x - lo] = (uint16_t)s5_at(v[b + m], g[m], x);
+                maxext = g[m].ext;
+            }
+            for (int x = std::max(lo, maxext); x < hi; x++) in.stale[x - lo] = padded[x];
+        };
+        const int T = std::max(1, std::min(threads, n / 8));
+        if (T <= 1) { for (int i = 0; i < n; i++) work(i); }
+        else {
+            std::atomic<int> next{0};
+            std::vector<std::thread> th;
+            for (int t = 0; t < T; t++) th.emplace_back([&] { for (int i; (i = next.fetch_add(1)) < n;) work(i); });
+            for (auto &x : th) x.join();
+        }
+        int maxext = 0, maxlen = 0;
+        for (int i = n - 1; i >= 0; i--) {
+            if (g[i].ext > maxext) {
+                for (int x = maxext; x < g[i].ext; x++) padded[x] = (uint16_t)s5_at(v[b + i], g[i], x);
+                maxext = g[i].ext;
+            }
+            if (g[i].L > maxlen) { memcpy(org.data() + maxlen, v[b + i].bases.data() + maxlen, (size_t)(g[i].L - maxlen)); maxlen = g[i].L; }
         }
     }
 };
@@ -1329,7 +1376,8 @@ struct Runtime {
     StaleTracker stale;
     std::vector<ReadInput> pending;
     long long pending_bases = 0;
-    int batch_reads = 2048;
+    int batch_reads = 4096;
+    int prep_threads = 4;
     long long batch_bases = 64LL << 20;
     int print_alignment = 0;
 
@@ -1343,6 +1391,7 @@ struct Runtime {
         if (const char *e = getenv("MTR_DEVICE")) base = atoi(e);
         int threads = (int)std::thread::hardware_concurrency();
         if (const char *e = getenv("MTR_THREADS")) threads = atoi(e);
+        prep_threads = std::max(1, std::min(8, threads / 2));
         threads = std::max(1, threads / ngpu);
         for (int g = 0; g < ngpu; g++) engines.push_back(new Engine(base + g, threads));
     }
@@ -1398,9 +1447,9 @@ extern "C" void handle_one_read(char *readID, int inputLen, int read_cnt, int pr
     in.bases.resize(inputLen + 2);
     for (int i = 0; i < inputLen; i++) in.bases[i] = (uint8_t)(orgInputString[i] & 3);
     const int tail[2] = {orgInputString[inputLen], orgInputString[inputLen + 1]};
-    rt.stale.visit(in, tail);
     rt.pending_bases += inputLen;
     rt.pending.push_back(std::move(in));
+    rt.stale.visit_batch(rt.pending, rt.pending.size() - 1, rt.pending.size(), 1, tail);
     if ((int)rt.pending.size() >= rt.batch_reads || rt.pending_bases >= rt.batch_bases) mtr_flush();
 }
 
@@ -1430,12 +1479,12 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
         while ((int)s->reads.size() < rt.batch_reads && bases < rt.batch_bases) {
             ReadInput in;
             if (!reader.next(in)) { more = false; break; }
-            rt.stale.visit(in, nullptr);
             bases += in.len;
             s->reads.push_back(std::move(in));
             n_reads++;
         }
         if (s->reads.empty()) { delete s; break; }
+        rt.stale.visit_batch(s->reads, 0, s->reads.size(), rt.prep_threads, nullptr);
         while ((int)inflight.size() >= ngpu) drain_front();
         Engine *eng = rt.engines[batch_index % ngpu];
         batch_index++;
@@ -1492,47 +1541,55 @@ extern "C" int mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, 
 {
     if (!p || (!text && len > 0) || first < 0) return MTR_EINVAL;
     p->reads.clear();
-    int ordinal = 0;
-    ReadInput cur;
-    bool have = false;
-    auto flush = [&]() -> bool {
-        if (!have) return true;
-        cur.len = (int)cur.bases.size();
-        if (cur.len == 0) return false;                     // a zero-length read ends the run (handle_one_file.c:283)
-        if (count >= 0 && ordinal >= first + count) return false;
-        p->stale->visit(cur, nullptr);
-        if (ordinal >= first) p->reads.push_back(std::move(cur));
-        ordinal++;
-        cur = ReadInput();
-        return true;
-    };
-    int64_t i = 0;
-    bool stop = false;
-    while (i < len && !stop) {
-        int64_t e = i;
-        while (e < len && text[e] != '\n') e++;
-        if (text[i] == '>') {
-            if (!flush()) { stop = true; break; }
-            have = true;
-            cur.id.clear();
-            for (int64_t t = i + 1; t < e && text[t] != '\r'; t++) cur.id += text[t];
-        } else {
-            for (int64_t t = i; t < e && text[t] != '\r'; t++) {
-                uint8_t b;
-                switch (text[t]) {
-                case 'A': case 'a': b = 0; break;
-                case 'C': case 'c': b = 1; break;
-                case 'G': case 'g': b = 2; break;
-                case 'T': case 't': b = 3; break;
-                default: return MTR_EINVAL;
-                }
-                cur.bases.push_back(b);
-                if ((int)cur.bases.size() >= kMaxLen) return MTR_ERANGE;
-            }
-        }
-        i = e + 1;
+    // record boundaries: '>' at the start of a line
+    std::vector<int64_t> starts;
+    for (const char *q = text; q && q < text + len;) {
+        q = (const char *)memchr(q, '>', (size_t)(text + len - q));
+        if (!q) break;
+        if (q == text || q[-1] == '\n') starts.push_back(q - text);
+        q++;
     }
-    if (!stop) flush();
+    int nrec = (int)starts.size();
+    if (count >= 0) nrec = std::min(nrec, first + count);
+    starts.push_back(nrec < (int)starts.size() ? starts[nrec] : len);
+    p->reads.resize(nrec);
+    static const struct Lut { int8_t v[256]; Lut() { memset(v, -1, sizeof v); v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; v['\n'] = v['\r'] = -2; } } lut;
+    std::atomic<int> next{0}, bad{0};
+    auto parse = [&] {
+        for (int i; (i = next.fetch_add(1)) < nrec;) {
+            ReadInput &in = p->reads[i];
+            const char *q = text + starts[i] + 1, *end = text + starts[i + 1];
+            const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
+            const char *hend = nl ? nl : end;
+            const char *idend = hend;
+            for (const char *c = q; c < hend; c++) if (*c == '\r') { idend = c; break; }
+            in.id.assign(q, idend);
+            in.bases.resize((size_t)(end - hend) + 2);
+            uint8_t *dst = in.bases.data();
+            for (const char *c = hend; c < end; c++) {
+                const int8_t b = lut.v[(unsigned char)*c];
+                if (b >= 0) *dst++ = (uint8_t)b;
+                else if (b == -1) { bad.store(1); break; }
+            }
+            in.len = (int)(dst - in.bases.data());
+            in.bases.resize((size_t)in.len + 2);
+            if (in.len >= kMaxLen) bad.store(2);
+        }
+    };
+    {
+        const int T = std::max(1, std::min(p->eng->pool->size(), nrec / 16));
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(parse);
+        parse();
+        for (auto &x : th) x.join();
+    }
+    if (bad.load() == 1) return MTR_EINVAL;                 // the reference aborts: "Invalid character"
+    if (bad.load() == 2) return MTR_ERANGE;
+    for (int i = 0; i < nrec; i++)
+        if (p->reads[i].len == 0) { p->reads.resize(i); break; }   // a zero-length read ends the run (handle_one_file.c:283)
+    // the reads before `first` only carry the stale state forward
+    p->stale->visit_batch(p->reads, 0, p->reads.size(), p->eng->pool->size(), nullptr);
+    if (first > 0) p->reads.erase(p->reads.begin(), p->reads.begin() + std::min<size_t>((size_t)first, p->reads.size()));
     p->eng->prepare(p->reads);
     return (int)p->reads.size();
 }
