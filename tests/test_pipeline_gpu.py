@@ -100,3 +100,13 @@ def test_pipeline_abi_alignment_and_pearson_modes(synthetic_dir):
     pipe.load_fasta(text)
     assert hashlib.md5(pipe.run()).hexdigest() == DIGESTS["synthetic"]["single_TR_20"]["p_m07"]["md5"]
     pipe.close()
+
+
+def test_cli_on_two_gpus_matches_digest(synthetic_dir):
+    """handle_one_file with MTR_GPUS=2: batches alternate between the GPUs, output is merged in input order."""
+    from mtr_b200 import capi
+    if capi.load_library().mtr_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    path = os.path.join(synthetic_dir, "mixed.fa")
+    out = run(MTR, [], path, {"MTR_GPUS": "2", "MTR_BATCH_READS": "5"})
+    assert hashlib.md5(out).hexdigest() == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
