@@ -16,6 +16,7 @@
 #include "mtr_internal.h"
 
 #define MT_TABLE_LEN 1300000
+#define FULLMASK 0xffffffffu
 
 struct DiRead {
     long long word_off;     // first word of the packed read
@@ -195,7 +196,8 @@ __device__ __forceinline__ double di_value(const DiPass &ps, const int *__restri
 }
 
 // One warp per read.  Per pass the 32 lanes first materialise directional_index_tmp[0..N) as fp64 (two loads and
-// one divide per position, in parallel), then lane 0 runs the reference's sequential state machine over it.
+// one divide per position, in parallel), then the warp runs the reference's sequential state machine over it,
+// 32 positions per step.
 template <bool MANHATTAN>
 __global__ void __launch_bounds__(128)
 di_merge(const DiRead *__restrict__ reads, int n_reads, const DiPass *__restrict__ passes,
@@ -216,30 +218,67 @@ di_merge(const DiRead *__restrict__ reads, int n_reads, const DiPass *__restrict
         __syncwarp();
         for (int i = lane; i < N; i += 32) tmp[i] = di_value<MANHATTAN>(ps, si, sd, i);
         __syncwarp();
-        if (lane == 0) {
-            // put_local_maximum_into_directional_index, :467-503
-            double local_max = -1;
-            int local_max_i = -1;
-            for (int i = 0; i < N; i++) {
-                const double t = tmp[i];
-                if (local_max < t) { local_max = t; local_max_i = i; }
-                if (local_max_i >= 0 && local_max_i + w < i && DI[local_max_i] < local_max && 0 < local_max) {
-                    double local_min = 1;
-                    int local_min_j = local_max_i;
-                    for (int j = local_max_i; j < N; j++) {
-                        const double tj = tmp[j];
-                        if (local_min > tj) { local_min = tj; local_min_j = j; }
-                        if (local_min_j + w < j) {
-                            DI[local_max_i] = local_max;
-                            WW[local_max_i] = w;
-                            EN[local_max_i] = local_min_j + w;
-                            i = local_min_j + w;
-                            break;
-                        }
-                    }
-                    local_max = -1;
-                }
+        // put_local_maximum_into_directional_index (:467-503), 32 positions per step.  The sequential state machine
+        // is a running (max, first argmax) with a trigger test per position, then a running (min, first argmin) with
+        // another trigger: both are inclusive prefix scans with a first-wins combiner, and the first lane whose
+        // trigger fires is the event the sequential loop would have reached.
+        double local_max = -1;
+        int lmi = -1, i = 0;
+        while (i < N) {
+            const int p = i + lane;
+            double v = p < N ? tmp[p] : -2.0;
+            int vi = p;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double ov = __shfl_up_sync(FULLMASK, v, o);
+                const int oi = __shfl_up_sync(FULLMASK, vi, o);
+                if (lane >= o && !(v > ov)) { v = ov; vi = oi; }          // the earlier position wins ties
             }
+            const bool beats = local_max < v;
+            const double pm = beats ? v : local_max;
+            const int pmi = beats ? vi : lmi;
+            bool trig = false;
+            if (p < N && pmi >= 0 && pmi + w < p && 0 < pm) trig = DI[pmi] < pm;
+            const unsigned tb = __ballot_sync(FULLMASK, trig);
+            if (!tb) {
+                local_max = __shfl_sync(FULLMASK, pm, 31);
+                lmi = __shfl_sync(FULLMASK, pmi, 31);
+                i += 32;
+                continue;
+            }
+            const int e = __ffs(tb) - 1;
+            local_max = __shfl_sync(FULLMASK, pm, e);
+            lmi = __shfl_sync(FULLMASK, pmi, e);
+            int next_i = i + e + 1;                                       // if no end is found the loop just goes on
+            double local_min = 1;
+            int lmj = lmi;
+            for (int j0 = lmi; j0 < N; j0 += 32) {
+                const int q = j0 + lane;
+                double u = q < N ? tmp[q] : 2.0;
+                int ui = q;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double ou = __shfl_up_sync(FULLMASK, u, o);
+                    const int oi = __shfl_up_sync(FULLMASK, ui, o);
+                    if (lane >= o && !(u < ou)) { u = ou; ui = oi; }
+                }
+                const bool lower = local_min > u;
+                const double qm = lower ? u : local_min;
+                const int qmi = lower ? ui : lmj;
+                const unsigned fb = __ballot_sync(FULLMASK, q < N && qmi + w < q);
+                if (fb) {
+                    const int f = __ffs(fb) - 1;
+                    const int end_j = __shfl_sync(FULLMASK, qmi, f) + w;
+                    if (lane == 0) { DI[lmi] = local_max; WW[lmi] = w; EN[lmi] = end_j; }
+                    next_i = end_j + 1;                                   // i = local_min_j + w, then the for's i++
+                    break;
+                }
+                local_min = __shfl_sync(FULLMASK, qm, 31);
+                lmj = __shfl_sync(FULLMASK, qmi, 31);
+            }
+            __syncwarp();
+            local_max = -1;                                               // local_max_i keeps its value (Q2)
+            i = next_i;
         }
     }
     __syncwarp();
