@@ -469,7 +469,7 @@ struct ReadState {
     std::string id;
     const uint8_t *org = nullptr;      // len + 2 bases (two stale tail bases, H4a)
     int L = 0, index = 0;
-    std::vector<int> end, w;           // directional_index_end / _w; dead entries have end < 0
+    int32_t *end = nullptr, *w = nullptr; // directional_index_end / _w of this read (views into the batch arrays); dead entries have end < 0
     int cursor = 0;
     struct Cand { int qs = 0, qe = 0; std::vector<Chain> chains; };
     std::vector<Cand> cands;           // candidates in flight, in candidate order (front commits first)
@@ -852,7 +852,7 @@ struct Engine {
         if (rc) die(nullptr, "mtr_cuda_init", rc);
         if (const char *e = getenv("MTR_UNITFINDER")) g_uf_on_gpu = strcmp(e, "gpu") == 0;
         if (const char *e = getenv("MTR_UF_GPU_MIN_WINDOW")) g_uf_gpu_min_window = atoi(e);
-        int want[3] = {2, 2, g_uf_on_gpu ? 2 : 0};
+        int want[3] = {2, 3, g_uf_on_gpu ? 2 : 0};
         if (const char *e = getenv("MTR_UF_LANES")) want[2] = g_uf_on_gpu ? std::max(1, atoi(e)) : 0;
         if (const char *e = getenv("MTR_LONG_LANES")) want[0] = std::max(1, atoi(e));
         if (const char *e = getenv("MTR_SHORT_LANES")) want[1] = std::max(1, atoi(e));
@@ -873,6 +873,7 @@ struct Engine {
     ~Engine()
     {
         delete pool;
+        h_end.release(); h_w.release();
         for (int kind = 0; kind < 3; kind++)
             for (mtr_ctx *c : lanes[kind]) if (c != ctx) mtr_cuda_shutdown(c);
         mtr_cuda_shutdown(ctx);
@@ -886,6 +887,7 @@ struct Engine {
     std::vector<int64_t> b_word_off, b_stale_off, b_pos_off;
     std::vector<uint16_t> b_stale;
     mtr_pipeline_stats ps = {};
+    PinBuf h_end, h_w;
 
     // Processes one batch; returns the text the reference would have printed for these reads, in order.
     std::string process(std::vector<ReadInput> &in, int print_alignment)
@@ -940,9 +942,11 @@ struct Engine {
         ps.h2d_bytes = h2d_prepare;
         ps.reads = n; ps.bases = pos_off[n];
         job_log.clear(); unit_log.clear();
-        std::vector<int32_t> end((size_t)pos_off[n]), ww((size_t)pos_off[n]);
+        // pinned, reused across batches: the D2H copy of end / w (8 bytes per base) runs at PCIe speed
+        if (h_end.reserve(((size_t)pos_off[n] + 1) * 4) != cudaSuccess || h_w.reserve(((size_t)pos_off[n] + 1) * 4) != cudaSuccess) die(ctx, "cudaMallocHost", MTR_ENOMEM);
+        int32_t *end = (int32_t *)h_end.p, *ww = (int32_t *)h_w.p;
         double t0 = now_s();
-        int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), nullptr, end.data(), ww.data());
+        int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), nullptr, end, ww);
         if (rc) die(ctx, "mtr_di_run", rc);
         t_di += now_s() - t0;
         {
@@ -958,8 +962,8 @@ struct Engine {
         for (int r = 0; r < n; r++) {
             ReadState &rs = st[r];
             rs.id = in[r].id; rs.org = in[r].bases.data(); rs.L = in[r].len; rs.index = r;
-            rs.end.assign(end.begin() + pos_off[r], end.begin() + pos_off[r + 1]);
-            rs.w.assign(ww.begin() + pos_off[r], ww.begin() + pos_off[r + 1]);
+            rs.end = end + pos_off[r];
+            rs.w = ww + pos_off[r];
         }
         // Asynchronous rounds: host workers advance whichever reads have their DP results, the dispatcher thread
         // sends everything queued so far to the GPU as soon as the previous batch is back.  No barrier: a read with
@@ -1127,7 +1131,7 @@ struct Engine {
         };
         // Large batches keep one lane of each kind busy with big launches; small batches are latency-bound and gain
         // from a second concurrent lane (MTR_LANES_FULL_BELOW reads).
-        const int full_below = getenv("MTR_LANES_FULL_BELOW") ? atoi(getenv("MTR_LANES_FULL_BELOW")) : 4096;
+        const int full_below = getenv("MTR_LANES_FULL_BELOW") ? atoi(getenv("MTR_LANES_FULL_BELOW")) : (1 << 30);
         std::vector<std::thread> dispatchers;
         for (int kind = 0; kind < 2; kind++) {
             size_t use = n < full_below ? lanes[kind].size() : 1;
