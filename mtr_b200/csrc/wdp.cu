@@ -159,14 +159,20 @@ wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
                 if (!__any_sync(FULL, changed)) break;
             }
             // fix-up: cells before the lane's first match see the carry; cell c gets cin - (c+1) indels, tag "left"
-            if (__any_sync(FULL, !(m & 1u) && cin + cL > R[0])) {
-                const int f = m ? __ffs(m) - 1 : C;
+            // (the carry decays by one indel per cell, so it usually dies within the first few cells: the cells
+            // are visited in groups of four and the warp leaves as soon as no lane's carry is alive any more)
+            bool live = !(m & 1u) && cin + cL > R[0];
+            if (__any_sync(FULL, live)) {
                 int cand = cin + cL;
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    const int ce = c < f ? cand : NEG_INF;
-                    if (ce > R[c]) { R[c] = ce; Wd[c] = ce & ~3; }
-                    cand -= in4;
+                for (int c0 = 0; c0 < C; c0 += 4) {
+#pragma unroll
+                    for (int c = c0; c < c0 + 4; c++) {
+                        live = live && !(m & (1u << c)) && cand > R[c];
+                        if (live) { R[c] = cand; Wd[c] = cand & ~3; }
+                        cand -= in4;
+                    }
+                    if (c0 + 4 < C && !__any_sync(FULL, live)) break;
                 }
             }
             // W[i][U] -> everybody (lane 0 needs it as next row's diagonal and for the j == 1 quirk)
