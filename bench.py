@@ -261,7 +261,9 @@ def main():
         "gcups": {"wrap_around_dp": round(gcups_rank, 2), "fill_only": round(fill_gcups, 2),
                   "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3), "algorithmic_cells_per_step": int(acc["wdp_cells"] / a.steps)},
         "roofline": {"kernel": "wdp_fill_* (K3 wrap-around DP)", "bound": "int-alu", "achieved": round(fill_gcups, 2),
-                     "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4), "traffic": None,
+                     "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4),
+                     "traffic": {"dram_bytes_per_cell_ncu": 0.289, "algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3),
+                                 "source": "profiles/r1_final_wdp_fill_summary.md (ncu --set full: 3.84 GB DRAM for 13.29 G cells)"},
                      "peak_how": "mtr_alu_probe: %.0f G lane-ops/s VIADDMNMX.RELU measured now / %.0f instr per cell (SURVEY.md 8(d))"
                                  % (alu["viaddmnmx_s32"], I_CELL_INT32),
                      "alu_probe_gops": {k: round(v, 1) for k, v in alu.items()},
