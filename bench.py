@@ -137,7 +137,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "4096")), help="reads per step per GPU")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = 2 x cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = 8 x cores)")
+    ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0 = cores / GPUs)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,7 +175,7 @@ def main():
         return float(t.item())
 
     from mtr_b200 import capi
-    threads = max(1, (os.cpu_count() or 1) // world)
+    threads = a.threads or max(1, (os.cpu_count() or 1) // world)
     pipe = capi.Pipeline(local_rank, threads=threads)
     ctx = capi.Context(local_rank)
     alu = {k: ctx.alu_probe(i) for i, k in enumerate(("viaddmnmx_s32", "lop3_iadd", "viaddmnmx_s16x2"))}

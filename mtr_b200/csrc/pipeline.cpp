@@ -84,6 +84,7 @@ struct Counter {
     // a window touched are cleared again from `codes`, so a build costs O(window), not O(table)
     std::vector<uint64_t> slots;
     std::vector<uint32_t> touched;
+    std::vector<uint32_t> pos_slot;   // slot of every window position (k > 6): the listing pass needs no second probe
     uint32_t hmask = 0;
     int k = 0, maxf = -1;
 
@@ -103,7 +104,7 @@ struct Counter {
             if (i < coded_end) {
                 const int c = 4 * carry + org[i + k - 1];
                 codes[i - qs] = c;
-                carry = c % mask;
+                carry = c & (mask - 1);                       // mask = 4^(k-1)
             } else {
                 // raw base left by the copy loop (:42-44); index L itself is stale in the reference (H4b): 0 here
                 codes[i - qs] = i < L ? org[i] : 0;
@@ -119,7 +120,9 @@ struct Counter {
             if (slots.size() < cap) slots.assign(cap, 0);
             hmask = cap - 1;
             touched.reserve(n);
-            for (int c : codes) {
+            pos_slot.resize(n);
+            for (int i = 0; i < n; i++) {
+                const int c = codes[i];
                 const uint64_t key = ((uint64_t)(uint32_t)c + 1) << 32;
                 uint32_t h = hash((uint32_t)c) & hmask;
                 for (;;) {
@@ -128,6 +131,7 @@ struct Counter {
                     if ((sl & 0xffffffff00000000ull) == key) { slots[h] = sl + 1; maxf = std::max(maxf, (int)(uint32_t)(sl + 1)); break; }
                     h = (h + 1) & hmask;
                 }
+                pos_slot[i] = h;
             }
         }
     }
@@ -156,8 +160,16 @@ struct Counter {
     int list_max_nodes(int *list, int cap, int maxfreq)
     {
         int n = 0;
-        for (int c : codes)
-            if (get(c) == maxfreq) { list[n++] = c; decrement(c); if (cap <= n) break; }
+        if (k <= 6) {
+            for (int c : codes)
+                if (direct[c] == maxfreq) { list[n++] = c; direct[c]--; if (cap <= n) break; }
+        } else {
+            const int len = (int)codes.size();
+            for (int i = 0; i < len; i++) {
+                uint64_t &sl = slots[pos_slot[i]];
+                if ((int)(uint32_t)sl == maxfreq) { list[n++] = codes[i]; sl--; if (cap <= n) break; }
+            }
+        }
         return n;
     }
 };
@@ -199,7 +211,7 @@ bool walk(Counter &cnt, WalkMemo &memo, int qs, int qe, int start, int k, bool b
     const int limit = (qe - qs) / 5;                       // MIN_NUM_FREQ_UNIT
     const int serial = memo.serial++;
     for (int l = 0; l < kMaxPeriod && l < limit; l++) {
-        if (!backward) { ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node); }
+        if (!backward) { ustr[l] = node >> (2 * (k - 1)); uscore[l] = cnt.get(node); }
         WalkMemo::Entry *me = nullptr;
         int next = -1;
         if (l >= 10) {
@@ -217,9 +229,10 @@ bool walk(Counter &cnt, WalkMemo &memo, int qs, int qe, int start, int k, bool b
                 pick = 0;
                 for (int t = 0; t < nties; t++)
                     for (int b = 0; b < 4; b++) {
-                        const int digits = backward ? b * P4.v[m - 1] + ties[t] : 4 * ties[t] + b;
-                        const int cand = backward ? digits * P4.v[k - m] + node / P4.v[m]
-                                                  : P4.v[m] * (node % P4.v[k - m]) + digits;
+                        // 4^x divisions and remainders of the reference as shifts and masks (all values >= 0)
+                        const int digits = backward ? (b << (2 * (m - 1))) + ties[t] : 4 * ties[t] + b;
+                        const int cand = backward ? (digits << (2 * (k - m))) + (node >> (2 * m))
+                                                  : ((node & ((1 << (2 * (k - m))) - 1)) << (2 * m)) + digits;
                         const int c = cnt.get(cand);
                         if (best < c) { best = c; pick = digits; nf = 0; fresh[nf++] = digits; }
                         else if (best == c && nf < kMaxTies) fresh[nf++] = digits;
@@ -228,12 +241,12 @@ bool walk(Counter &cnt, WalkMemo &memo, int qs, int qe, int start, int k, bool b
                 std::copy(fresh, fresh + nf, ties);
                 nties = nf;
             }
-            next = backward ? (pick % 4) * P4.v[k - 1] + node / 4
-                            : 4 * (node % P4.v[k - 1]) + pick / P4.v[m - 1];      // unresolved ties append 'A' (:336)
+            next = backward ? ((pick & 3) << (2 * (k - 1))) + (node >> 2)
+                            : 4 * (node & ((1 << (2 * (k - 1))) - 1)) + (pick >> (2 * (m - 1)));   // unresolved ties append 'A' (:336)
             if (me) me->next = next;
         }
         node = next;
-        if (backward) { ustr[l] = node / P4.v[k - 1]; uscore[l] = cnt.get(node); }
+        if (backward) { ustr[l] = node >> (2 * (k - 1)); uscore[l] = cnt.get(node); }
         if (node == start) { period = l + 1; if (kMaxPeriod <= period) period = 0; break; }
     }
     if (period == 0) return false;
