@@ -1,6 +1,7 @@
 // ctx.cu -- context, resident read batch and the kernel-level C ABI of libmtr_b200.so.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "mtr_internal.h"
 

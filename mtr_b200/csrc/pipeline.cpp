@@ -121,7 +121,9 @@ struct Counter {
             hmask = cap - 1;
             touched.reserve(n);
             pos_slot.resize(n);
+            constexpr int kAhead = 12;                          // the table of a long window does not fit L1/L2: prefetch
             for (int i = 0; i < n; i++) {
+                if (i + kAhead < n) __builtin_prefetch(&slots[hash((uint32_t)codes[i + kAhead]) & hmask], 1, 1);
                 const int c = codes[i];
                 const uint64_t key = ((uint64_t)(uint32_t)c + 1) << 32;
                 uint32_t h = hash((uint32_t)c) & hmask;
@@ -1032,6 +1034,8 @@ struct Engine {
                 }
             }
         };
+        const int gather_min[2] = {getenv("MTR_GATHER_LONG") ? atoi(getenv("MTR_GATHER_LONG")) : 0, getenv("MTR_GATHER_SHORT") ? atoi(getenv("MTR_GATHER_SHORT")) : 0};
+        const int gather_us[2] = {getenv("MTR_GATHER_LONG_US") ? atoi(getenv("MTR_GATHER_LONG_US")) : 2000, getenv("MTR_GATHER_SHORT_US") ? atoi(getenv("MTR_GATHER_SHORT_US")) : 300};
         auto dispatch_loop = [&](int lane, mtr_ctx *lctx) {
             cudaSetDevice(lctx->device);
             std::vector<mtr_wdp_job> jobs;
@@ -1041,6 +1045,11 @@ struct Engine {
                 {
                     std::unique_lock<std::mutex> g(mu);
                     cv_submit.wait(g, [&] { return !submitted[lane].empty() || remaining == 0; });
+                    if (submitted[lane].empty()) return;
+                    // a launch costs the same for 10 reads as for 300: give the workers a moment to fill the batch
+                    if ((int)submitted[lane].size() < gather_min[lane] && gather_us[lane] > 0)
+                        cv_submit.wait_for(g, std::chrono::microseconds(gather_us[lane]),
+                                           [&] { return (int)submitted[lane].size() >= gather_min[lane] || remaining == 0; });
                     if (submitted[lane].empty()) return;
                     batch.swap(submitted[lane]);
                     submitted[lane].clear();
