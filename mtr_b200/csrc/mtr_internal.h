@@ -68,7 +68,7 @@ struct WdpTask {
     unsigned char pad_[2];
 };
 
-constexpr int WDP_NCLASS = 16;
+constexpr int WDP_NCLASS = 26;
 struct WdpClass { int G, C, paired; };          // lanes per job, cells per lane, int16x2 pairing
 
 struct WdpState {

@@ -29,6 +29,7 @@
 // tracking the running score exactly as the reference does (max_wrd), so no "stop" code is needed.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "mtr_internal.h"
 
@@ -43,6 +44,7 @@ static const WdpClass kClasses[WDP_NCLASS] = {
     {4, 4, 0},  {8, 4, 0},  {16, 4, 0}, {32, 4, 0}, {32, 8, 0},  {32, 16, 0},
 };
 constexpr int kThroughputClasses = 10, kLatencyClasses = 6;
+constexpr int kPairedBase = 16;          // classes 16..25: the throughput classes as paired int16x2 kernels
 
 static int class_of(int ulen, int latency)
 {
@@ -229,6 +231,187 @@ wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
     }
 }
 
+// ---------------------------------------------------------------- fill kernel, paired int16x2 scores
+// wrap_around_DP (wrap_around_DP.c:357-429) always runs the same window and unit under two penalty sets.  When
+// 4 * gain * rows fits int16 both DPs share one register per cell (low half: set 0, high half: set 1) and every
+// score operation is one VIADDMNMX.S16x2: the match mask, the carries' control flow and the wrap shuffle are
+// common, only the constants differ per half.  Same tagged-score scheme and direction layout as wdp_fill_i32;
+// the two direction matrices of a task lie dir_bytes apart.
+#define P16_NEG 0x8ad08ad0u            /* (-30000, -30000): multiple of 4, far from wrapping */
+#define P16_MIN 0x80008000u            /* (-32768, -32768): max(x + b, MIN) == x + b */
+
+__device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+
+template <int G, int C>
+__global__ void __launch_bounds__(128)
+wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
+             const uint8_t *__restrict__ units, uint8_t *__restrict__ dirs,
+             mtr_wdp_result *__restrict__ results, int *__restrict__ counter)
+{
+    constexpr int JPW = 32 / G;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr unsigned UNTAG = 0xfffcfffcu;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int grp = lane / G;
+    const int nslots = (ntasks + JPW - 1) / JPW;
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(counter, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= nslots) break;
+        const int tidx = slot * JPW + grp;
+        const bool have = tidx < ntasks;
+        const WdpTask *tp = tasks + (have ? tidx : 0);
+        const int rows = have ? tp->rows : 0;
+        const int ulen = tp->ulen;
+        const long long base0 = tp->base0;
+        const unsigned g42 = pack2(4 * tp->gain[0], 4 * tp->gain[1]);
+        const unsigned cD = pack2(-4 * tp->mis[0] + 3, -4 * tp->mis[1] + 3);
+        const unsigned cL = pack2(-4 * tp->indel[0] + 2, -4 * tp->indel[1] + 2);
+        const unsigned cU = pack2(-4 * tp->indel[0] + 1, -4 * tp->indel[1] + 1);
+        const unsigned nin4 = pack2(-4 * tp->indel[0], -4 * tp->indel[1]);
+        const unsigned nspan = pack2(-4 * tp->indel[0] * C, -4 * tp->indel[1] * C);
+        uint8_t *drow = dirs + tp->dir_off + (size_t)gl * (C / 4);
+        const long long dbytes = tp->dir_bytes;
+        const int dstride = tp->dir_stride;
+
+        unsigned eq01 = 0, eq23 = 0;
+        const int lu = (ulen - 1) / C, cu = (ulen - 1) % C;
+        unsigned sel[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const int j = gl * C + c;
+            if (j < ulen) {
+                const int b = units[tp->unit_off + j];
+                const unsigned bit = 1u << (c + ((b & 1) ? 16 : 0));
+                if (b & 2) eq23 |= bit; else eq01 |= bit;
+            }
+            sel[c] = (gl == lu && c == cu) ? 0xffffffffu : 0u;
+        }
+
+        unsigned Wp[C], Wq[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) Wp[c] = 0;
+        unsigned dgin = 0;
+        int best_v[2] = {0, 0}, best_i[2] = {0, 0}, best_c[2] = {0, 0};
+
+        int maxrows = rows;
+#pragma unroll
+        for (int off = 16; off >= G; off >>= 1) maxrows = max(maxrows, __shfl_xor_sync(FULL, maxrows, off));
+
+        unsigned xw = 0;
+        auto row = [&](const unsigned (&Ws)[C], unsigned (&Wd)[C], const int i) {
+            const bool act = i <= rows;
+            const long long bi = base0 + i;
+            if (act && (i == 1 || (bi & 15) == 0)) xw = packed[bi >> 4];
+            const int xi = (int)((xw >> ((int)(bi & 15) * 2)) & 3u);
+            const unsigned m = (((xi & 2) ? eq23 : eq01) >> ((xi & 1) * 16)) & ((1u << C) - 1u);
+
+            unsigned R[C];
+            unsigned left = P16_NEG;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const unsigned dg = (c == 0) ? dgin : Ws[c - 1];
+                const unsigned up = __viaddmax_s16x2(Ws[c], cU, P16_MIN);
+                const unsigned a = __viaddmax_s16x2_relu(dg, cD, up);
+                const unsigned t = __viaddmax_s16x2(left, cL, a);
+                const unsigned vm = __viaddmax_s16x2(dg, g42, P16_MIN);
+                const unsigned r = (m & (1u << c)) ? vm : t;
+                R[c] = r;
+                Wd[c] = r & UNTAG;
+                left = Wd[c];
+            }
+            const unsigned out0 = Wd[C - 1];
+            unsigned out = out0, cin;
+            for (;;) {
+                cin = __shfl_up_sync(FULL, out, 1, G);
+                if (gl == 0) cin = P16_NEG;
+                const unsigned nout = m ? out0 : __viaddmax_s16x2(cin, nspan, out0);
+                const bool changed = nout != out;
+                out = nout;
+                if (!__any_sync(FULL, changed)) break;
+            }
+            bool live = !(m & 1u) && __viaddmax_s16x2(cin, cL, R[0]) != R[0];
+            if (__any_sync(FULL, live)) {
+                unsigned cand = __viaddmax_s16x2(cin, cL, P16_MIN);
+#pragma unroll
+                for (int c0 = 0; c0 < C; c0 += 4) {
+#pragma unroll
+                    for (int c = c0; c < c0 + 4; c++) {
+                        live = live && !(m & (1u << c));
+                        const unsigned rn = __viaddmax_s16x2(live ? cand : P16_NEG, 0u, R[c]);
+                        live = live && rn != R[c];
+                        R[c] = rn;
+                        Wd[c] = rn & UNTAG;
+                        cand = __viaddmax_s16x2(cand, nin4, P16_MIN);
+                    }
+                    if (c0 + 4 < C && !__any_sync(FULL, live)) break;
+                }
+            }
+            unsigned mine = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) mine |= Wd[c] & sel[c];
+            const unsigned wU = __shfl_sync(FULL, mine, lu, G);
+
+            // direction codes: (R - W) holds one 2-bit code per half; eight cells fit one accumulator
+            unsigned acc0 = 0, acc1 = 0;
+            int key0 = 0, key1 = 0;
+#pragma unroll
+            for (int c = C - 1; c >= 0; c--) {
+                const unsigned code2 = R[c] - Wd[c];
+                if (c >= 8) acc1 = acc1 * 4u + code2; else acc0 = acc0 * 4u + code2;
+                key0 = max(key0, (int)(Wd[c] & 0xffffu) * 4 + (15 - c));
+                key1 = max(key1, (int)(Wd[c] >> 16) * 4 + (15 - c));
+            }
+            unsigned bits0 = (acc0 & 0xffffu) | (acc1 << 16);
+            unsigned bits1 = (acc0 >> 16) | (acc1 & 0xffff0000u);
+            if (gl == 0) {
+                // traceback at j == 1 tests "deletion" against W[i][0] == W[i][U] before insertion
+                const unsigned wl = __viaddmax_s16x2(wU, nin4, P16_MIN);          // W[i][U] - IN per half
+                if ((bits0 & 3u) == 1u && (Wd[0] & 0xffffu) == (wl & 0xffffu)) bits0 ^= 3u;
+                if ((bits1 & 3u) == 1u && (Wd[0] >> 16) == (wl >> 16)) bits1 ^= 3u;
+            }
+            if (act) {
+                uint8_t *p = drow + (size_t)(i - 1) * dstride;
+                uint8_t *q = p + dbytes;
+                if (C == 4) { *p = (uint8_t)bits0; *q = (uint8_t)bits1; }
+                else if (C == 8) { *(uint16_t *)p = (uint16_t)bits0; *(uint16_t *)q = (uint16_t)bits1; }
+                else if (C == 12) {
+                    p[0] = (uint8_t)bits0; p[1] = (uint8_t)(bits0 >> 8); p[2] = (uint8_t)(bits0 >> 16);
+                    q[0] = (uint8_t)bits1; q[1] = (uint8_t)(bits1 >> 8); q[2] = (uint8_t)(bits1 >> 16);
+                } else { *(uint32_t *)p = bits0; *(uint32_t *)q = bits1; }
+                if ((key0 >> 4) > best_v[0]) { best_v[0] = key0 >> 4; best_i[0] = i; best_c[0] = 15 - (key0 & 15); }
+                if ((key1 >> 4) > best_v[1]) { best_v[1] = key1 >> 4; best_i[1] = i; best_c[1] = 15 - (key1 & 15); }
+            }
+            dgin = (gl == 0) ? wU : cin;
+        };
+        for (int i = 1; i <= maxrows; i += 2) {
+            row(Wp, Wq, i);
+            if (i + 1 <= maxrows) row(Wq, Wp, i + 1);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int bv = best_v[h], bi = best_i[h], bj = gl * C + best_c[h] + 1;
+#pragma unroll
+            for (int off = G / 2; off >= 1; off >>= 1) {
+                const int ov = __shfl_xor_sync(FULL, bv, off);
+                const int oi = __shfl_xor_sync(FULL, bi, off);
+                const int oj = __shfl_xor_sync(FULL, bj, off);
+                const bool take = (ov > bv) || (ov == bv && (oi < bi || (oi == bi && oj < bj)));
+                if (take) { bv = ov; bi = oi; bj = oj; }
+            }
+            if (have && gl == 0) {
+                mtr_wdp_result *res = results + tp->result_idx + h;
+                res->best = bv;
+                res->max_i = bv > 0 ? bi : 0;
+                res->max_j = bv > 0 ? bj : 0;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- traceback (one thread per task)
 // wrap_around_DP.c:288-333 (counts), consensus.c:919-962 (histograms), wrap_around_DP.c:123-186 (path).
 __global__ void __launch_bounds__(128)
@@ -317,6 +500,19 @@ static void launch_fill(mtr_ctx *ctx, int k, const WdpTask *d_tasks, int ntasks,
                                               (int *)ctx->wdp.d_counters.p + k);
 }
 
+template <int G, int C>
+static void launch_fill_p16(mtr_ctx *ctx, int k, const WdpTask *d_tasks, int ntasks, cudaStream_t s)
+{
+    const int jpw = 32 / G;
+    const int nslots = (ntasks + jpw - 1) / jpw;
+    int blocks = (nslots + 3) / 4;
+    blocks = std::min(blocks, ctx->n_sm * 8);
+    wdp_fill_p16<G, C><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p,
+                                              (const uint8_t *)ctx->wdp.d_units.p, (uint8_t *)ctx->wdp.d_dirs.p,
+                                              (mtr_wdp_result *)ctx->wdp.d_results.p,
+                                              (int *)ctx->wdp.d_counters.p + k);
+}
+
 int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
                     int64_t aux_bytes)
 {
@@ -337,7 +533,9 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
         const int k = class_of(std::max(1, std::min(jobs[jn].ulen, 499)), 1);
         lat_warps += (long long)jobs[jn].n_param * kClasses[k].G;
     }
-    const int latency = (lat_warps / 32) <= (long long)ctx->n_sm * 24 ? 1 : 0;
+    int latency = (lat_warps / 32) <= (long long)ctx->n_sm * 24 ? 1 : 0;
+    if (const char *e = getenv("MTR_WDP_MODE")) latency = strcmp(e, "latency") == 0 ? 1 : (strcmp(e, "throughput") == 0 ? 0 : latency);
+    const bool pair_ok = !getenv("MTR_NO_PAIRED");
     for (int jn = 0; jn < n_jobs; jn++) {
         const mtr_wdp_job &j = jobs[jn];
         if (j.read < 0 || j.read >= ctx->n_reads || j.ulen < 1 || j.ulen >= 500 || j.rows < 0 ||
@@ -359,6 +557,26 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
         if (j.mode == MTR_TB_PATH && (j.aux_off < 0 || j.aux_cap < 0 || j.aux_off + j.aux_cap > aux_bytes)) {
             mtr_set_error(ctx, "wdp_upload: job %d path block outside aux", jn);
             return MTR_EINVAL;
+        }
+        // both penalty sets in one int16x2 task when every score (x4, plus tag) fits 15 bits
+        const int gmax = std::max((int)j.gain[0], (int)j.gain[1]);
+        if (!latency && pair_ok && j.n_param == 2 && j.mode == MTR_TB_COUNTS && 4LL * gmax * j.rows <= 32760 &&
+            j.indel[0] * 64 < 8000 && j.indel[1] * 64 < 8000 && j.mis[0] < 64 && j.mis[1] < 64) {
+            WdpTask t;
+            memset(&t, 0, sizeof t);
+            t.base0 = ctx->word_off[j.read] * 16 + j.first;
+            t.rows = j.rows; t.ulen = j.ulen; t.unit_off = j.unit_off;
+            for (int p = 0; p < 2; p++) { t.gain[p] = j.gain[p]; t.mis[p] = j.mis[p]; t.indel[p] = j.indel[p]; }
+            t.n_param = 2; t.mode = j.mode;
+            t.result_idx = jn * 2;
+            const int k = class_of(j.ulen, 0);
+            t.dir_stride = kClasses[k].G * kClasses[k].C / 4;
+            t.dir_bytes = (long long)t.rows * t.dir_stride;
+            cls.push_back(kPairedBase + k);
+            w.tasks.push_back(t);
+            w.cells += 2LL * j.rows * j.ulen;
+            w.slot_cells += 2LL * j.rows * kClasses[k].G * kClasses[k].C;
+            continue;
         }
         for (int p = 0; p < j.n_param; p++) {
             WdpTask t;
@@ -457,6 +675,16 @@ int wdp_launch_impl(mtr_ctx *ctx)
         case 13: launch_fill<32, 4>(ctx, k, dt, n, s); break;
         case 14: launch_fill<32, 8>(ctx, k, dt, n, s); break;
         case 15: launch_fill<32, 16>(ctx, k, dt, n, s); break;
+        case 16: launch_fill_p16<4, 4>(ctx, k, dt, n, s); break;
+        case 17: launch_fill_p16<4, 8>(ctx, k, dt, n, s); break;
+        case 18: launch_fill_p16<4, 12>(ctx, k, dt, n, s); break;
+        case 19: launch_fill_p16<8, 8>(ctx, k, dt, n, s); break;
+        case 20: launch_fill_p16<8, 12>(ctx, k, dt, n, s); break;
+        case 21: launch_fill_p16<8, 16>(ctx, k, dt, n, s); break;
+        case 22: launch_fill_p16<16, 12>(ctx, k, dt, n, s); break;
+        case 23: launch_fill_p16<16, 16>(ctx, k, dt, n, s); break;
+        case 24: launch_fill_p16<32, 12>(ctx, k, dt, n, s); break;
+        case 25: launch_fill_p16<32, 16>(ctx, k, dt, n, s); break;
         default: mtr_set_error(ctx, "wdp_launch: class %d has no kernel", k); return MTR_EINVAL;
         }
         MTR_CUDA(ctx, cudaGetLastError());

@@ -41,6 +41,47 @@ def test_random_jobs_paired(gpu_ctx, oracle):
     assert not bad, bad[:10]
 
 
+@pytest.mark.parametrize("mode", ["throughput", "latency"])
+def test_kernel_families(gpu_ctx, oracle, mode, monkeypatch):
+    """Small batches default to the latency classes; force each family (throughput classes pair the two penalty sets
+    of a wrap_around_DP call into one int16x2 task when the scores fit) and check both against the oracle."""
+    import os
+    monkeypatch.setenv("MTR_WDP_MODE", mode)
+    os.environ["MTR_WDP_MODE"] = mode
+    rng = np.random.default_rng(31)
+    reads, tails, jobs = wdp_cases.random_jobs(rng, n_jobs=500, max_rows=1500)
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs, pair=True)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res, pair=True)
+    assert not bad, (mode, bad[:10])
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res)
+    assert not bad, (mode, bad[:10])
+    # adversarial ties in the paired kernels: homopolymer and dinucleotide reads, units AC / A / ACAC
+    reads2 = [np.zeros(900, np.int8), np.tile(np.array([0, 1], np.int8), 600)]
+    tails2 = [(0, 0), (1, 0)]
+    jobs2 = [dict(read=r, first=f, rows=rows, unit=np.array(u, np.uint8), gain=1, mis=1, indel=3)
+             for r in range(2) for u in ([0], [0, 1], [1, 0], [0, 1, 0, 1], [0, 0, 1]) for f, rows in ((-1, 900), (3, 500), (100, 37))]
+    arr, res, aux = _run(gpu_ctx, reads2, tails2, jobs2, pair=True)
+    bad = wdp_cases.check_against_oracle(oracle, reads2, tails2, jobs2, res, pair=True)
+    assert not bad, (mode, bad[:10])
+    os.environ.pop("MTR_WDP_MODE", None)
+
+
+def test_paired_range_limit(gpu_ctx, oracle, monkeypatch):
+    """Pairs with more than 8190 rows exceed int16 and must fall back to two int32 tasks; 8190 rows just fit."""
+    import os
+    os.environ["MTR_WDP_MODE"] = "throughput"
+    rd, _ = synth.rand_seq_reads(40, 260, 0.005, 0.01, 0.01, 50, 50, 1, seed=19)
+    reads, tails = [rd[0]], [(2, 3)]
+    unit = np.array(rd[0][50:90], dtype=np.uint8)
+    jobs = [dict(read=0, first=10, rows=r, unit=unit, gain=1, mis=1, indel=3) for r in (8189, 8190, 8191, 9000)]
+    arr, res, aux = _run(gpu_ctx, reads, tails, jobs, pair=True)
+    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res, pair=True)
+    os.environ.pop("MTR_WDP_MODE", None)
+    assert not bad, bad
+    assert res[1, 0]["best"] > 7000
+
+
 def test_consensus_and_path(gpu_ctx, oracle):
     rng = np.random.default_rng(21)
     reads, tails, jobs = wdp_cases.random_jobs(rng, n_jobs=150, max_ulen=300)
