@@ -110,3 +110,36 @@ def test_cli_on_two_gpus_matches_digest(synthetic_dir):
     path = os.path.join(synthetic_dir, "mixed.fa")
     out = run(MTR, [], path, {"MTR_GPUS": "2", "MTR_BATCH_READS": "5"})
     assert hashlib.md5(out).hexdigest() == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
+
+
+def test_handle_one_read_entry_point(synthetic_dir):
+    """The reference's per-read entry point (mTR.h:127): the caller puts the read into orgInputString and calls
+    handle_one_read; records appear on stdout at mtr_flush().  Driven through ctypes in a child process."""
+    import sys
+    path = os.path.join(synthetic_dir, "mixed.fa")
+    script = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from mtr_b200 import capi
+lib = capi.load_library()
+lib.handle_one_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+lib.handle_one_read.restype = None
+org = C.POINTER(C.c_int).in_dll(lib, "orgInputString")
+C.c_int.in_dll(lib, "Manhattan_Distance").value = 1
+C.c_float.in_dll(lib, "min_match_ratio").value = 0.6
+code = {"A": 0, "C": 1, "G": 2, "T": 3}
+rid, n = None, 0
+for line in open(%r):
+    line = line.strip()
+    if line.startswith(">"):
+        rid = line[1:]
+    elif line:
+        for i, ch in enumerate(line):
+            org[i] = code[ch]                       # like handle_one_file.c:284-285; the tail keeps older reads
+        n += 1
+        lib.handle_one_read(rid.encode(), len(line), n, 0)
+lib.mtr_flush()
+''' % (ROOT, path)
+    p = subprocess.run([sys.executable, "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0, p.stderr.decode()[-1500:]
+    assert hashlib.md5(p.stdout).hexdigest() == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
