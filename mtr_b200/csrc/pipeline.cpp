@@ -25,6 +25,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <time.h>
 #include <vector>
 #include "mtr_internal.h"
 
@@ -48,6 +49,13 @@ constexpr int kMaxInflightCands = 24;         // per read; bounds the jobs a rea
 
 struct Pow4 { int v[16]; Pow4() { v[0] = 1; for (int i = 1; i < 16; i++) v[i] = v[i - 1] * 4; } };
 const Pow4 P4;
+
+double thread_cpu_s()
+{
+    timespec ts;
+    clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
 
 double now_s()
 {
@@ -997,14 +1005,23 @@ struct Engine {
         std::vector<int> ready(n), submitted[3];                  // lane 0: long DP jobs, 1: short DP jobs, 2: unit finder
         for (int r = 0; r < n; r++) ready[r] = n - 1 - r;         // popped from the back: read 0 first
         int remaining = n;
+        const bool prof = getenv("MTR_PROFILE") != nullptr;
+        std::vector<double> finish_at(prof ? n : 0, 0.0);
+        double idle_s = 0, worker_cpu_s = 0, disp_cpu_s = 0;
         const int fast_rows = getenv("MTR_FAST_ROWS") ? atoi(getenv("MTR_FAST_ROWS")) : 1536;
         auto worker_loop = [&](int tid) {
+            const double cpu0 = prof ? thread_cpu_s() : 0.0;
             for (;;) {
                 int idx;
                 {
                     std::unique_lock<std::mutex> g(mu);
-                    cv_ready.wait(g, [&] { return !ready.empty() || remaining == 0; });
-                    if (ready.empty()) return;
+                    if (prof && ready.empty() && remaining != 0) {
+                        const double ti = now_s();
+                        cv_ready.wait(g, [&] { return !ready.empty() || remaining == 0; });
+                        idle_s += now_s() - ti;
+                    } else
+                        cv_ready.wait(g, [&] { return !ready.empty() || remaining == 0; });
+                    if (ready.empty()) { if (prof) worker_cpu_s += thread_cpu_s() - cpu0; return; }
                     idx = ready.back();
                     ready.pop_back();
                 }
@@ -1024,6 +1041,7 @@ struct Engine {
                 for (const JobReq &q : rs.jobs) if (q.rows > fast_rows) { lane = 0; break; }
                 {
                     std::lock_guard<std::mutex> g(mu);
+                    if (prof && rs.phase == ReadState::FINISHED) finish_at[idx] = now_s() - t0;
                     if (rs.phase == ReadState::FINISHED) { if (--remaining == 0) { cv_ready.notify_all(); cv_submit.notify_all(); } }
                     else {
                         if (!rs.jobs.empty()) { pending[idx]++; submitted[lane].push_back(idx); }
@@ -1041,6 +1059,8 @@ struct Engine {
             std::vector<mtr_wdp_job> jobs;
             std::vector<uint8_t> units;
             std::vector<int> batch;
+            const double cpu0 = prof ? thread_cpu_s() : 0.0;
+            struct CpuAcc { double &acc; double c0; bool on; std::mutex &m; ~CpuAcc() { if (on) { std::lock_guard<std::mutex> g(m); acc += thread_cpu_s() - c0; } } } cpu_acc{disp_cpu_s, cpu0, prof, mu};
             for (;;) {
                 {
                     std::unique_lock<std::mutex> g(mu);
@@ -1184,6 +1204,13 @@ struct Engine {
                 long long bn = 0, wn = 0; double wt = 0, wm = 0;
                 for (Worker &k : workers) { bn += k.hb_n[b]; wn += k.hw_n[b]; wt += k.hw_t[b]; wm = std::max(wm, k.hw_max[b]); k.hb_n[b] = k.hw_n[b] = 0; k.hw_t[b] = k.hw_max[b] = 0; }
                 fprintf(stderr, "[mtr profile]   window <= %5d: chains %9lld  with walks %8lld  walk cpu-s %8.3f  max walk ms %8.2f\n", 64 << b, bn, wn, wt, wm * 1e3);
+            }
+            {
+                std::vector<double> f = finish_at;
+                std::sort(f.begin(), f.end());
+                auto q = [&](double x) { return f.empty() ? 0.0 : f[std::min(f.size() - 1, (size_t)(x * f.size()))]; };
+                fprintf(stderr, "[mtr profile]   read finish times s: p10 %.3f p50 %.3f p90 %.3f p99 %.3f max %.3f | worker idle %.3f s  worker cpu %.3f s  dispatcher cpu %.3f s\n",
+                        q(0.10), q(0.50), q(0.90), q(0.99), f.empty() ? 0.0 : f.back(), idle_s, worker_cpu_s, disp_cpu_s);
             }
             fprintf(stderr, "[mtr profile] reads %d rounds %lld | host cpu-s: step %.3f build %.3f maxlist %.3f walk %.3f polish %.3f | chains %lld walks %lld | wall: host %.3f s gpu %.3f s\n",
                     n, (long long)ps.rounds, t, b, l, w, p, nc, nw, host_ms / 1e3, wdp_ms / 1e3);

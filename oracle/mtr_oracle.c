@@ -123,6 +123,8 @@ void mtro_set_output(mtro_ctx *c, FILE *out) { c->out = out; }
 void mtro_get_stats(const mtro_ctx *c, mtro_stats *s) { *s = c->st; }
 void mtro_set_dp_hook(mtro_ctx *c, mtro_dp_hook hook, void *user) { c->hook = hook; c->hook_user = user; }
 const int *mtro_org(const mtro_ctx *c) { return c->org; }
+int *mtro_org_mut(mtro_ctx *c) { return c->org; }
+int *mtro_padded_mut(mtro_ctx *c) { return c->padded; }
 
 static void rr_clear(mtro_rr *r)            /* clear_rr, fill_directional_index.c:40-60 */
 {

@@ -117,6 +117,11 @@ typedef void (*mtro_dp_hook)(void *user, int kind, const int *x, int rows, const
 void mtro_set_dp_hook(mtro_ctx *c, mtro_dp_hook hook, void *user);
 /* Base of the persistent read buffer (orgInputString); a hook's x pointer minus this is the job's `first`. */
 const int *mtro_org(const mtro_ctx *c);
+/* Mutable views of the persistent buffers orgInputString (MTRO_MAX_INPUT_LENGTH + 16 ints) and inputString_w_rand
+ * (3 * MTRO_MAX_INPUT_LENGTH + 64 ints): lets a test put the cross-read stale state in place
+ * explicitly instead of replaying the earlier reads. */
+int *mtro_org_mut(mtro_ctx *c);
+int *mtro_padded_mut(mtro_ctx *c);
 
 /* ---- chaining (C++ side, mtr_oracle_chain.cpp; chaining.cpp:43-363) ---- */
 typedef struct mtro_chain mtro_chain;

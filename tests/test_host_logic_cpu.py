@@ -1,0 +1,72 @@
+"""Host logic on the CPU: the product's pipeline.cpp + main.c (unmodified) linked against tests/hostsim/sim_device.cpp,
+a TEST-ONLY stand-in that answers the kernel-level ABI (mtr_di_run, mtr_wdp_run, ...) with the oracle.  Everything the
+host does -- FASTA reader, stale-state tracker, per-read state machines with candidate look-ahead, k-mer count tables,
+de Bruijn walks, polish / vote, chaining, TSV and alignment formatting, batch splitting -- must reproduce the digests
+taken from the reference binary (tests/golden/digests.json).  The GPU twins of these tests are in
+tests/test_pipeline_gpu.py; the simulator is never part of the product (tests/test_abi_cpu.py)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+import golden_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMDIR = os.path.join(ROOT, "tests", "hostsim")
+SIM = os.path.join(SIMDIR, "_build", "mTR_hostsim")
+DIGESTS = json.load(open(os.path.join(golden_cases.GOLDEN, "digests.json")))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.check_call(["make", "-s", "-C", SIMDIR])
+    return SIM
+
+
+def run(binary, flags, path, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([binary] + flags + [path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return p.stdout
+
+
+@pytest.fixture(scope="module")
+def shipped_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("shipped")
+    golden_cases.extract_shipped(str(d))
+    return str(d)
+
+
+@pytest.fixture(scope="module")
+def synthetic_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("synthetic")
+    for name, (reads, lw) in golden_cases.synthetic_cases().items():
+        golden_cases.write_case(os.path.join(str(d), name + ".fa"), reads, lw)
+    return str(d)
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS["shipped"]))
+def test_host_logic_on_shipped_files(sim, shipped_dir, name):
+    path = os.path.join(shipped_dir, name)
+    for mode, flags in golden_cases.MODES.items():
+        assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode)
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS["synthetic"]))
+def test_host_logic_on_synthetic_cases(sim, synthetic_dir, name):
+    path = os.path.join(synthetic_dir, name + ".fa")
+    for mode, flags in golden_cases.MODES.items():
+        assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
+
+
+def test_batching_threads_and_lanes_do_not_change_the_output(sim, synthetic_dir):
+    """Batch boundaries (stale state crosses them), worker count, dispatch lanes and the two-device round-robin are
+    scheduling only: not a byte may change."""
+    path = os.path.join(synthetic_dir, "mixed.fa")
+    ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
+    for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_BATCH_READS": "3", "MTR_GPUS": "2"},
+                {"MTR_LONG_LANES": "1", "MTR_SHORT_LANES": "1"}, {"MTR_FAST_ROWS": "100", "MTR_THREADS": "3"}):
+        assert hashlib.md5(run(sim, [], path, env)).hexdigest() == ref, env
