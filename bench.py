@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "4096")), help="reads per step per GPU")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = 8 x cores)")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("MTR_BENCH_INFLIGHT", "1")), help="batches in flight per GPU (pipelines run concurrently)")
+    ap.add_argument("--quick", action="store_true", help="tuning aid: resident loop only (no e2e, no replay, no CPU baseline); not a bench line")
     ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0 = cores / GPUs)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -176,7 +178,6 @@ def main():
 
     from mtr_b200 import capi
     threads = a.threads or max(1, (os.cpu_count() or 1) // world)
-    pipe = capi.Pipeline(local_rank, threads=threads)
     ctx = capi.Context(local_rank)
     alu = {k: ctx.alu_probe(i) for i, k in enumerate(("viaddmnmx_s32", "lop3_iadd", "viaddmnmx_s16x2"))}
     ctx.close()
@@ -188,50 +189,107 @@ def main():
             "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "wdp_fill_ms",
             "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms")
 
-    # ---- device-resident loop: the batch is packed and in HBM before the clock starts
+    # Batches in flight (--inflight, default 1; handle_one_file: MTR_INFLIGHT_PER_GPU): with more than one, each batch
+    # runs on its own pipeline object so that the ramp-down of one batch overlaps the ramp-up of the next.  Measured on
+    # B200 + 16 host cores this loses (the long-job lanes of the two batches slow each other down), hence the default.
+    inflight = max(1, a.inflight)
+    n_pipes = max(inflight, min(a.steps, 2 * inflight))       # resident loop: this many batches are resident at once
+    pipes = [capi.Pipeline(local_rank, threads=threads) for _ in range(n_pipes)]
+
+    def run_concurrently(work):
+        """work: list of callables; `inflight` threads, thread t takes items t, t + inflight, ... (ctypes drops the GIL)."""
+        errs = []
+
+        def loop(t):
+            try:
+                for i in range(t, len(work), inflight):
+                    work[i]()
+            except BaseException as e:      # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=loop, args=(t,)) for t in range(inflight)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if errs:
+            raise errs[0]
+
+    # ---- warm-up: every pipeline sees at least one batch (buffers grown, kernels loaded)
+    n_warm = max(a.warmup, n_pipes)
+    run_concurrently([(lambda s=s: (pipes[s % n_pipes].load_fasta(texts[s % max(a.warmup, 1)]), pipes[s % n_pipes].run())) for s in range(n_warm)])
+
+    # ---- device-resident loop: the batches are packed and in HBM before the clock starts
     acc = dict.fromkeys(keys, 0.0)
+    lock = threading.Lock()
+    outs = {}
     t_res = 0.0
-    digest = hashlib.md5()
-    for s in range(a.warmup):
-        pipe.load_fasta(texts[s]); pipe.run()
     clocks = ClockSampler(local_rank)
     clocks.start()
     barrier()
-    for s in range(a.warmup, total):
-        pipe.load_fasta(texts[s])
+    timed = list(range(a.warmup, total))
+    for g0 in range(0, len(timed), n_pipes):
+        group = timed[g0:g0 + n_pipes]
+        for i, s in enumerate(group):
+            pipes[i].load_fasta(texts[s])
         torch.cuda.synchronize()
+
+        def one(i, s):
+            out = pipes[i].run()
+            st = pipes[i].stats()
+            with lock:
+                outs[s] = out
+                for k in keys:
+                    acc[k] += st[k]
         t0 = time.perf_counter()
-        out = pipe.run()
+        run_concurrently([(lambda i=i, s=s: one(i, s)) for i, s in enumerate(group)])
         torch.cuda.synchronize()
         t_res += time.perf_counter() - t0
-        digest.update(out)
-        st = pipe.stats()
-        for k in keys:
-            acc[k] += st[k]
     barrier()
     t_res = max_over_ranks(t_res)
+    digest = hashlib.md5()
+    for s in timed:
+        digest.update(outs[s])
+    if a.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "reads_per_s": round(R * a.steps * world / t_res, 1), "ms_per_step": round(t_res / a.steps * 1e3, 1),
+                              "fill_gcups": round(acc["wdp_cells"] / max(acc["wdp_fill_ms"], 1e-9) / 1e6, 1), "rounds_per_step": int(acc["rounds"] / a.steps),
+                              "wdp_fill_ms": round(acc["wdp_fill_ms"] / a.steps, 1), "wdp_tb_ms": round(acc["wdp_tb_ms"] / a.steps, 1),
+                              "md5": digest.hexdigest(), "inflight": inflight, "env": {k: v for k, v in os.environ.items() if k.startswith("MTR_")}}), flush=True)
+        clocks.stop()
+        for p in pipes:
+            p.close()
+        return
 
-    # ---- end-to-end loop: FASTA text in host memory -> output text in host memory
+    # ---- end-to-end loop: FASTA text in host memory -> output text in host memory, `inflight` batches at a time
     barrier()
     t0 = time.perf_counter()
-    h2d = d2h = 0
-    for s in range(a.warmup, total):
-        pipe.load_fasta(texts[s])
-        out = pipe.run()
-        st = pipe.stats()
-        h2d += st["h2d_bytes"]; d2h += st["d2h_bytes"]
+    io = {"h2d": 0, "d2h": 0}
+
+    def e2e_one(s):
+        p = pipes[(s - a.warmup) % inflight]
+        p.load_fasta(texts[s])
+        p.run()
+        st = p.stats()
+        with lock:
+            io["h2d"] += st["h2d_bytes"]; io["d2h"] += st["d2h_bytes"]
+    run_concurrently([(lambda s=s: e2e_one(s)) for s in timed])
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    h2d, d2h = io["h2d"], io["d2h"]
     clk = clocks.stop()
+    pipe = pipes[0]
+    for p in pipes[1:]:
+        p.close()
 
     # ---- K3 alone on exactly one step's DP jobs, replayed as a single batch (operands resident in HBM)
-    alone = None
+    alone = alone_fused = None
     if rank == 0:
         pipe.log_jobs(True)
         pipe.load_fasta(texts[a.warmup])
         pipe.run()
         pipe.log_jobs(False)
-        alone = pipe.replay_logged_jobs(iters=3)
+        alone = pipe.replay_logged_jobs(iters=3, fused=False)
+        alone_fused = pipe.replay_logged_jobs(iters=3, fused=True)
     pipe.close()
 
     reads_all = sum_over_ranks(R * a.steps)
@@ -254,14 +312,14 @@ def main():
         "warmup": a.warmup, "ms_per_step": round(t_res / a.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "C5 synthetic long reads 10-20 kb, unit 2-500 bp, 5-15% noise", "reads_per_step_per_gpu": R,
-                   "mode": "default (Manhattan), -m 0.6", "host_threads_per_gpu": threads,
+                   "mode": "default (Manhattan), -m 0.6", "host_threads_per_gpu": threads, "batches_in_flight_per_gpu": inflight,
                    "l2": "working set per step (direction matrices, %d MB) exceeds the 126 MB L2" % (acc["wdp_dir_bytes"] / a.steps / 2 ** 20)},
         "e2e": {"value": round(reads_all / t_e2e, 3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d / a.steps),
                 "d2h_bytes_per_step": int(d2h / a.steps)},
         "gpu_launches": int(acc["launches"]),
         "gcups": {"wrap_around_dp": round(gcups_rank, 2), "fill_only": round(fill_gcups, 2),
                   "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3), "algorithmic_cells_per_step": int(acc["wdp_cells"] / a.steps)},
-        "roofline": {"kernel": "wdp_fill_* (K3 wrap-around DP)", "bound": "int-alu", "achieved": round(fill_gcups, 2),
+        "roofline": {"kernel": "wdp_fill_* (K3 wrap-around DP: fill with the traceback fused in), all launches of the timed steps", "bound": "int-alu", "achieved": round(fill_gcups, 2),
                      "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4),
                      "traffic": {"dram_bytes_per_cell_ncu": 0.289, "algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3),
                                  "source": "profiles/r1_final_wdp_fill_summary.md (ncu --set full: 3.84 GB DRAM for 13.29 G cells)"},
@@ -270,12 +328,15 @@ def main():
                      "alu_probe_gops": {k: round(v, 1) for k, v in alu.items()},
                      "dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3)},
         "roofline_kernel_alone": None if alone is None else {
-            "what": "the same K3 kernels on all DP jobs of one step replayed as ONE batch (%d jobs), timed alone with CUDA events" % alone["jobs"],
+            "what": "the same K3 kernels on all DP jobs of one step replayed as ONE batch (%d jobs), timed alone with CUDA events; "
+                    "fill and traceback launched separately here so that achieved = fill alone" % alone["jobs"],
             "bound": "int-alu", "achieved": round(alone["wdp_cells"] / max(alone["wdp_fill_ms"], 1e-9) / 1e6, 2), "peak": round(peak_gcups, 1),
             "unit": "GCUPS", "frac": round(alone["wdp_cells"] / max(alone["wdp_fill_ms"], 1e-9) / 1e6 / peak_gcups, 4),
             "with_traceback_gcups": round(alone["wdp_cells"] / max(alone["wdp_fill_ms"] + alone["wdp_tb_ms"], 1e-9) / 1e6, 2),
             "fill_ms": round(alone["wdp_fill_ms"], 3), "tb_ms": round(alone["wdp_tb_ms"], 3), "cells": int(alone["wdp_cells"]),
-            "slot_cells": int(alone["wdp_slot_cells"]), "dir_bytes": int(alone["wdp_dir_bytes"])},
+            "slot_cells": int(alone["wdp_slot_cells"]), "dir_bytes": int(alone["wdp_dir_bytes"]),
+            "fused_fill_plus_traceback_ms": round(alone_fused["wdp_fill_ms"] + alone_fused["wdp_tb_ms"], 3),
+            "fused_gcups": round(alone_fused["wdp_cells"] / max(alone_fused["wdp_fill_ms"] + alone_fused["wdp_tb_ms"], 1e-9) / 1e6, 2)},
         "roofline_di": {"kernel": "di_codes + di_slide + di_merge (K1/K2)", "bound": "hbm", "achieved": round(di_gbs, 3),
                         "peak": hbm_peak, "unit": "GB/s", "frac": round(di_gbs / hbm_peak, 6), "traffic": None,
                         "note": "algorithmic bytes = packed reads in + 16 B per position out; the stage is LSU/shared-memory bound"},

@@ -110,6 +110,10 @@ int mtr_wdp_upload(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint
                    int64_t aux_bytes);
 int mtr_wdp_launch(mtr_ctx *ctx);
 int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes);
+/* on != 0 (default): every fill kernel runs the traceback of a task as soon as that task's fill is done (no second
+ * launch, the direction rows are still in cache); on == 0: fill kernels, then one traceback kernel -- lets the fill
+ * be timed alone (mtr_stats.wdp_fill_ms / wdp_tb_ms; fused: wdp_fill_ms covers both, wdp_tb_ms ~ 0). */
+int mtr_wdp_set_fused_traceback(mtr_ctx *ctx, int on);
 
 /* ------------------------------------------------------------------ K1/K2: directional index */
 /* Replaces fill_directional_index_with_end (fill_directional_index.c:549-602) for every read of the

@@ -100,6 +100,7 @@ def load_library() -> C.CDLL:
     lib.mtr_wdp_upload.argtypes = [vp, vp, C.c_int, vp, i64, i64]
     lib.mtr_wdp_launch.argtypes = [vp]
     lib.mtr_wdp_download.argtypes = [vp, vp, vp, i64]
+    lib.mtr_wdp_set_fused_traceback.argtypes = [vp, C.c_int]
     lib.mtr_di_run.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.mtr_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mtr_alu_probe.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
@@ -215,6 +216,11 @@ class Context:
     def wdp_launch(self):
         self._check(self.lib.mtr_wdp_launch(self.h), "mtr_wdp_launch")
 
+    def wdp_set_fused_traceback(self, on: bool):
+        """True (default): the fill kernels run each task's traceback themselves; False: fill kernels, then one
+        traceback kernel (so that the fill can be timed alone)."""
+        self._check(self.lib.mtr_wdp_set_fused_traceback(self.h, 1 if on else 0), "mtr_wdp_set_fused_traceback")
+
     def wdp_download(self, aux_bytes: int = 0):
         res = np.zeros((self._njobs, 2), dtype=RESULT_DTYPE)
         aux = np.zeros(max(aux_bytes, 1), dtype=np.uint8) if aux_bytes else None
@@ -298,14 +304,16 @@ class Pipeline:
     def log_jobs(self, on: bool = True):
         self.lib.mtr_pipeline_log_jobs(self.h, 1 if on else 0)
 
-    def replay_logged_jobs(self, iters: int = 2) -> dict:
+    def replay_logged_jobs(self, iters: int = 2, fused: bool = True) -> dict:
         """Replays the DP jobs logged by the last run() as ONE batch on the pipeline's own context (K3 alone,
-        operands resident); returns the library's kernel statistics of the last replay."""
+        operands resident); returns the library's kernel statistics of the last replay.  fused=False: fill kernels
+        and traceback kernel launched separately, so wdp_fill_ms is the fill alone."""
         jobs, n, units, ul = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
         rc = self.lib.mtr_pipeline_get_job_log(self.h, C.byref(jobs), C.byref(n), C.byref(units), C.byref(ul))
         if rc != 0 or n.value == 0:
             raise MtrError("no logged jobs")
         ctx = self.lib.mtr_pipeline_ctx(self.h)
+        self.lib.mtr_wdp_set_fused_traceback(ctx, 1 if fused else 0)
         rc = self.lib.mtr_wdp_upload(ctx, jobs, int(n.value), units, ul.value, 0)
         if rc != 0:
             raise MtrError("replay upload failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))
@@ -315,6 +323,7 @@ class Pipeline:
             if rc != 0:
                 raise MtrError("replay launch failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))
         self.lib.mtr_get_stats(ctx, C.byref(st))
+        self.lib.mtr_wdp_set_fused_traceback(ctx, 1)
         return {k: getattr(st, k) for k, _ in Stats._fields_} | {"jobs": int(n.value)}
 
     def stats(self) -> dict:

@@ -3,9 +3,17 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <time.h>
 #include "mtr_internal.h"
 
 static std::string g_init_error;
+
+static double wall_s()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
 
 void mtr_set_error(mtr_ctx *ctx, const char *fmt, ...)
 {
@@ -76,12 +84,16 @@ extern "C" int mtr_cuda_init(int device, mtr_ctx **out)
 extern "C" void mtr_cuda_shutdown(mtr_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->prof_n)
+        fprintf(stderr, "[mtr profile] ctx %p: %lld wdp_run calls, host ms per call: upload %.3f (classify+sort %.3f, buffers %.3f, stage+enqueue %.3f) launch %.3f download+wait %.3f\n", (void *)ctx,
+                ctx->prof_n, ctx->prof_s[0] / ctx->prof_n * 1e3, ctx->prof_up[0] / ctx->prof_n * 1e3, ctx->prof_up[1] / ctx->prof_n * 1e3,
+                ctx->prof_up[2] / ctx->prof_n * 1e3, ctx->prof_s[1] / ctx->prof_n * 1e3, ctx->prof_s[2] / ctx->prof_n * 1e3);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     di_state_free(ctx);
     uf_state_free(ctx);
     WdpState &w = ctx->wdp;
-    w.d_tasks.release(); w.d_units.release(); w.d_dirs.release(); w.d_results.release(); w.d_aux.release();
+    w.d_tasks.release(); w.d_dirs.release(); w.d_results.release(); w.d_aux.release();
     w.d_counters.release(); w.h_tasks.release(); w.h_results.release();
     ctx->d_packed.release(); ctx->d_word_off.release(); ctx->d_len.release();
     for (int k = 0; k < WDP_NCLASS; k++) {
@@ -148,30 +160,44 @@ extern "C" int mtr_reads_share(mtr_ctx *dst, const mtr_ctx *src)
 extern "C" int mtr_wdp_upload(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len, int64_t aux_bytes)
 {
     if (!ctx) return MTR_EINVAL;
-    return wdp_upload_impl(ctx, jobs, n_jobs, units, units_len, aux_bytes);
+    return wdp_upload_impl(ctx, jobs, n_jobs, units, units_len, aux_bytes, true);
 }
 
 extern "C" int mtr_wdp_launch(mtr_ctx *ctx)
 {
     if (!ctx) return MTR_EINVAL;
-    return wdp_launch_impl(ctx);
+    return wdp_launch_impl(ctx, true);
 }
 
 extern "C" int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes)
 {
     if (!ctx) return MTR_EINVAL;
-    return wdp_download_impl(ctx, results, aux, aux_bytes);
+    return wdp_download_impl(ctx, results, aux, aux_bytes, false);
 }
 
 extern "C" int mtr_wdp_run(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
                            mtr_wdp_result *results, void *aux, int64_t aux_bytes)
 {
     if (!ctx) return MTR_EINVAL;
-    int rc = wdp_upload_impl(ctx, jobs, n_jobs, units, units_len, aux_bytes);
+    // everything is enqueued on one stream; the host waits once, in the download
+    static const bool prof = getenv("MTR_PROFILE") != nullptr;
+    const double t0 = prof ? wall_s() : 0;
+    int rc = wdp_upload_impl(ctx, jobs, n_jobs, units, units_len, aux_bytes, false);
     if (rc) return rc;
-    rc = wdp_launch_impl(ctx);
+    const double t1 = prof ? wall_s() : 0;
+    rc = wdp_launch_impl(ctx, false);
     if (rc) return rc;
-    return wdp_download_impl(ctx, results, aux, aux_bytes);
+    const double t2 = prof ? wall_s() : 0;
+    rc = wdp_download_impl(ctx, results, aux, aux_bytes, true);
+    if (prof) { ctx->prof_s[0] += t1 - t0; ctx->prof_s[1] += t2 - t1; ctx->prof_s[2] += wall_s() - t2; ctx->prof_n++; }
+    return rc;
+}
+
+extern "C" int mtr_wdp_set_fused_traceback(mtr_ctx *ctx, int on)
+{
+    if (!ctx) return MTR_EINVAL;
+    ctx->wdp.fused_tb = on != 0;
+    return MTR_OK;
 }
 
 extern "C" int mtr_get_stats(const mtr_ctx *ctx, mtr_stats *out)

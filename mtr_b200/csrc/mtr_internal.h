@@ -72,7 +72,7 @@ constexpr int WDP_NCLASS = 26;
 struct WdpClass { int G, C, paired; };          // lanes per job, cells per lane, int16x2 pairing
 
 struct WdpState {
-    DevBuf d_tasks, d_units, d_dirs, d_results, d_aux, d_counters;
+    DevBuf d_tasks, d_dirs, d_results, d_aux, d_counters;      // d_tasks holds [WdpTask x n | unit bases]
     PinBuf h_tasks, h_results;
     std::vector<WdpTask> tasks;                 // sorted by class, then by rows descending
     int class_begin[WDP_NCLASS + 1] = {0};
@@ -80,6 +80,11 @@ struct WdpState {
     long long dir_total = 0, aux_bytes = 0;
     long long cells = 0, slot_cells = 0;
     bool uploaded = false;
+    size_t units_dev_off = 0;                   // byte offset of the unit bases inside d_tasks
+    int latency = 0;                            // the uploaded batch uses the latency classes (one fused launch)
+    bool fused_tb = true;                       // traceback inside the fill kernels (mtr_wdp_set_fused_traceback)
+    unsigned counter_gen = 0;
+    std::vector<int> unused_results;            // result slots no task writes (second slot of one-set jobs)
 };
 
 // ---------------------------------------------------------------- context
@@ -103,12 +108,16 @@ struct mtr_ctx {
     struct DiState *di = nullptr;
     struct UfState *uf = nullptr;
     mtr_stats stats = {};
+    double prof_s[3] = {0, 0, 0};           // MTR_PROFILE: host seconds in upload / launch / download+wait of mtr_wdp_run
+    long long prof_n = 0;
+    double prof_up[3] = {0, 0, 0};          // ... inside upload: classify + sort / buffer growth / staging copy + enqueue
 };
 
+// sync == false: only enqueue on main_stream (mtr_wdp_run waits once, at the end)
 int  wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
-                     int64_t aux_bytes);
-int  wdp_launch_impl(mtr_ctx *ctx);
-int  wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes);
+                     int64_t aux_bytes, bool sync);
+int  wdp_launch_impl(mtr_ctx *ctx, bool sync);
+int  wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes, bool read_times);
 // waits for everything queued on main_stream without burning a host core (the dispatcher threads of the pipeline
 // would otherwise spin next to the host workers)
 inline cudaError_t mtr_sync(mtr_ctx *ctx)

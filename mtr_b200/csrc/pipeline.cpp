@@ -23,9 +23,13 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <queue>
 #include <string>
 #include <thread>
 #include <time.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #include <vector>
 #include "mtr_internal.h"
 
@@ -861,13 +865,32 @@ struct ReadInput {
 }
 
 struct Engine {
-    mtr_ctx *ctx = nullptr;            // owns the resident reads; directional index; first long-DP lane
-    std::vector<mtr_ctx *> lanes[3];   // dispatch lanes: [0] long DP jobs, [1] short DP jobs, [2] unit finder (K4);
-                                       // every lane context shares the reads of ctx and runs concurrently on the GPU
+    mtr_ctx *ctx = nullptr;            // owns the resident reads; directional index; first lane of the last tier
+    // DP dispatch lanes, grouped in tiers by the longest job (rows) a read queued this round: a batch is as slow as
+    // its longest job (rows are sequential in the fill and in the traceback), and 7 of 8 read-rounds carry only jobs
+    // of <= 256 rows.  Every lane is its own mtr_ctx (own streams and buffers) sharing the resident reads of ctx, so
+    // all lanes run concurrently on the GPU.  The last tier takes everything.
+    static constexpr int kMaxTiers = 6;
+    int n_tiers = 3;
+    int tier_rows[kMaxTiers] = {128, 1536, 1 << 30, 0, 0, 0};
+    int tier_spin[kMaxTiers] = {0, 0, 0, 0, 0, 0};     // 1: the tier's dispatcher threads spin on the stream instead of sleeping
+    std::vector<mtr_ctx *> tier_lanes[kMaxTiers];
+    std::vector<mtr_ctx *> uf_lanes;   // unit finder (K4), opt-in
     Pool *pool = nullptr;
     std::vector<Worker> workers;
     double t_di = 0, t_dp = 0, t_rounds = 0;
     long long candidates = 0, rounds = 0, jobs_total = 0;
+
+    static int parse_list(const char *e, int *out, int cap)
+    {
+        int n = 0;
+        while (e && *e && n < cap) {
+            out[n++] = atoi(e);
+            e = strchr(e, ',');
+            if (e) e++;
+        }
+        return n;
+    }
 
     Engine(int device, int threads)
     {
@@ -875,21 +898,37 @@ struct Engine {
         if (rc) die(nullptr, "mtr_cuda_init", rc);
         if (const char *e = getenv("MTR_UNITFINDER")) g_uf_on_gpu = strcmp(e, "gpu") == 0;
         if (const char *e = getenv("MTR_UF_GPU_MIN_WINDOW")) g_uf_gpu_min_window = atoi(e);
-        int want[3] = {2, 3, g_uf_on_gpu ? 2 : 0};
-        if (const char *e = getenv("MTR_UF_LANES")) want[2] = g_uf_on_gpu ? std::max(1, atoi(e)) : 0;
-        if (const char *e = getenv("MTR_LONG_LANES")) want[0] = std::max(1, atoi(e));
-        if (const char *e = getenv("MTR_SHORT_LANES")) want[1] = std::max(1, atoi(e));
-        lanes[0].push_back(ctx);
-        for (int kind = 0; kind < 3; kind++)
-            while ((int)lanes[kind].size() < want[kind]) {
+        int want_uf = g_uf_on_gpu ? 2 : 0;
+        if (const char *e = getenv("MTR_UF_LANES")) want_uf = g_uf_on_gpu ? std::max(1, atoi(e)) : 0;
+        // MTR_TIER_ROWS="128,1536": upper row bounds of all tiers but the last; MTR_TIER_LANES="2,2,2"; MTR_TIER_SPIN="0,0,0"
+        int want[kMaxTiers] = {2, 2, 2, 2, 2, 2};
+        if (const char *e = getenv("MTR_TIER_ROWS")) {
+            int v[kMaxTiers];
+            const int n = parse_list(e, v, kMaxTiers - 1);
+            n_tiers = 0;
+            for (int i = 0; i < n; i++) if (v[i] > 0 && (n_tiers == 0 || v[i] > tier_rows[n_tiers - 1])) tier_rows[n_tiers++] = v[i];
+            tier_rows[n_tiers++] = 1 << 30;
+        }
+        if (const char *e = getenv("MTR_TIER_LANES")) { int v[kMaxTiers]; const int n = parse_list(e, v, kMaxTiers); for (int i = 0; i < n; i++) want[i] = std::max(1, v[i]); }
+        if (const char *e = getenv("MTR_TIER_SPIN")) { int v[kMaxTiers]; const int n = parse_list(e, v, kMaxTiers); for (int i = 0; i < n; i++) tier_spin[i] = v[i] != 0; }
+        tier_lanes[n_tiers - 1].push_back(ctx);
+        for (int t = 0; t < n_tiers; t++)
+            while ((int)tier_lanes[t].size() < want[t]) {
                 mtr_ctx *c = nullptr;
                 rc = mtr_cuda_init(device, &c);
                 if (rc) die(nullptr, "mtr_cuda_init", rc);
-                lanes[kind].push_back(c);
+                tier_lanes[t].push_back(c);
             }
-        // long-lane calls take milliseconds: their dispatcher threads sleep while waiting, leaving the cores to the workers
-        if (!getenv("MTR_SPIN_LONG")) for (mtr_ctx *c : lanes[0]) if (c != ctx || lanes[0].size() > 1) mtr_set_blocking_sync(c, 1);
-        for (mtr_ctx *c : lanes[2]) mtr_set_blocking_sync(c, 1);
+        while ((int)uf_lanes.size() < want_uf) {
+            mtr_ctx *c = nullptr;
+            rc = mtr_cuda_init(device, &c);
+            if (rc) die(nullptr, "mtr_cuda_init", rc);
+            uf_lanes.push_back(c);
+        }
+        // a sleeping dispatcher leaves its core to the host workers (tens of microseconds of wake-up latency per call)
+        for (int t = 0; t < n_tiers; t++)
+            for (mtr_ctx *c : tier_lanes[t]) mtr_set_blocking_sync(c, tier_spin[t] ? 0 : 1);
+        for (mtr_ctx *c : uf_lanes) mtr_set_blocking_sync(c, 1);
         pool = new Pool(threads);
         workers.resize(pool->size());
     }
@@ -897,8 +936,9 @@ struct Engine {
     {
         delete pool;
         h_end.release(); h_w.release();
-        for (int kind = 0; kind < 3; kind++)
-            for (mtr_ctx *c : lanes[kind]) if (c != ctx) mtr_cuda_shutdown(c);
+        for (int t = 0; t < n_tiers; t++)
+            for (mtr_ctx *c : tier_lanes[t]) if (c != ctx) mtr_cuda_shutdown(c);
+        for (mtr_ctx *c : uf_lanes) mtr_cuda_shutdown(c);
         mtr_cuda_shutdown(ctx);
     }
 
@@ -944,12 +984,13 @@ struct Engine {
         });
         int rc = mtr_reads_upload(ctx, packed.data(), b_word_off.data(), lens.data(), n);
         if (rc) die(ctx, "mtr_reads_upload", rc);
-        for (int kind = 0; kind < 3; kind++)
-            for (mtr_ctx *c : lanes[kind]) {
-                if (c == ctx) continue;
-                rc = mtr_reads_share(c, ctx);
-                if (rc) die(c, "mtr_reads_share", rc);
-            }
+        std::vector<mtr_ctx *> others(uf_lanes);
+        for (int t = 0; t < n_tiers; t++) others.insert(others.end(), tier_lanes[t].begin(), tier_lanes[t].end());
+        for (mtr_ctx *c : others) {
+            if (c == ctx) continue;
+            rc = mtr_reads_share(c, ctx);
+            if (rc) die(c, "mtr_reads_share", rc);
+        }
         ps.h2d_bytes = (int64_t)packed.size() * 4 + (int64_t)(n + 1) * 12;
     }
 
@@ -994,7 +1035,8 @@ struct Engine {
         const long long dir_cap = dir_budget();
         t0 = now_s();
         double host_ms = 0, wdp_ms = 0, uf_ms = 0;
-        double lane_ms[3] = {0, 0, 0}; long long lane_batches[3] = {0, 0, 0}, lane_items[3] = {0, 0, 0}, lane_reads[3] = {0, 0, 0};
+        constexpr int UF = kMaxTiers;                             // index of the unit-finder queue / counters
+        double lane_ms[kMaxTiers + 1] = {0}; long long lane_batches[kMaxTiers + 1] = {0}, lane_items[kMaxTiers + 1] = {0}, lane_reads[kMaxTiers + 1] = {0};
         struct BatchResult { std::vector<mtr_wdp_result> res; std::vector<uint8_t> aux; };
         struct UfBatchResult { std::vector<mtr_uf_result> res; std::vector<uint8_t> units; std::vector<int32_t> scores; };
         std::vector<std::shared_ptr<BatchResult>> result_of(n);
@@ -1002,14 +1044,26 @@ struct Engine {
         std::vector<int> pending(n, 0);                           // lanes a read is still waiting for
         std::mutex mu;
         std::condition_variable cv_ready, cv_submit;
-        std::vector<int> ready(n), submitted[3];                  // lane 0: long DP jobs, 1: short DP jobs, 2: unit finder
-        for (int r = 0; r < n; r++) ready[r] = n - 1 - r;         // popped from the back: read 0 first
+        std::vector<int> submitted[kMaxTiers + 1];                // per DP tier, [UF]: unit finder
+        // Ready reads are served most-bases-left-to-scan first: every read is a chain of dependent rounds, so the batch
+        // ends when its slowest chain does; serving the reads with the most work left first keeps them from being
+        // starved behind reads that just came back (a LIFO stack left the cores idle at the end of every batch).
+        typedef std::pair<int, int> ReadyKey;                     // (bases left, -index)
+        std::priority_queue<ReadyKey> ready;
+        auto push_ready = [&](int idx) { ready.push(ReadyKey(st[idx].L - st[idx].cursor, -idx)); };
+        for (int r = 0; r < n; r++) push_ready(r);
         int remaining = n;
         const bool prof = getenv("MTR_PROFILE") != nullptr;
+        const int worker_nice = getenv("MTR_WORKER_NICE") ? atoi(getenv("MTR_WORKER_NICE")) : 10;
         std::vector<double> finish_at(prof ? n : 0, 0.0);
         double idle_s = 0, worker_cpu_s = 0, disp_cpu_s = 0;
-        const int fast_rows = getenv("MTR_FAST_ROWS") ? atoi(getenv("MTR_FAST_ROWS")) : 1536;
+        long long rows_hist_n[12] = {0}, rows_hist_cells[12] = {0}, readmax_hist[12] = {0};   // MTR_PROFILE: DP jobs by rows (<=32, 64, ...)
+        double lane_fill_ms[kMaxTiers + 1] = {0}, lane_tb_ms[kMaxTiers + 1] = {0};
         auto worker_loop = [&](int tid) {
+            // The workers are CPU-bound for the whole batch; the dispatcher threads wake up for microseconds at a time
+            // and every microsecond they wait for a core delays a GPU round.  Raising the workers' nice value (needs no
+            // privilege) lets the scheduler hand a waking dispatcher a core at once.
+            if (worker_nice > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), worker_nice);
             const double cpu0 = prof ? thread_cpu_s() : 0.0;
             for (;;) {
                 int idx;
@@ -1022,8 +1076,8 @@ struct Engine {
                     } else
                         cv_ready.wait(g, [&] { return !ready.empty() || remaining == 0; });
                     if (ready.empty()) { if (prof) worker_cpu_s += thread_cpu_s() - cpu0; return; }
-                    idx = ready.back();
-                    ready.pop_back();
+                    idx = -ready.top().second;
+                    ready.pop();
                 }
                 ReadState &rs = st[idx];
                 RoundResults cur;
@@ -1037,23 +1091,22 @@ struct Engine {
                 workers[tid].t_step += now_s() - ts;
                 result_of[idx].reset();
                 uf_result_of[idx].reset();
-                int lane = 1;
-                for (const JobReq &q : rs.jobs) if (q.rows > fast_rows) { lane = 0; break; }
+                int max_rows = 0, lane = 0;
+                for (const JobReq &q : rs.jobs) max_rows = std::max(max_rows, q.rows);
+                while (max_rows > tier_rows[lane]) lane++;
                 {
                     std::lock_guard<std::mutex> g(mu);
                     if (prof && rs.phase == ReadState::FINISHED) finish_at[idx] = now_s() - t0;
                     if (rs.phase == ReadState::FINISHED) { if (--remaining == 0) { cv_ready.notify_all(); cv_submit.notify_all(); } }
                     else {
                         if (!rs.jobs.empty()) { pending[idx]++; submitted[lane].push_back(idx); }
-                        if (!rs.uf_tasks.empty()) { pending[idx]++; submitted[2].push_back(idx); }
+                        if (!rs.uf_tasks.empty()) { pending[idx]++; submitted[UF].push_back(idx); }
                         if (pending[idx] == 0) { fprintf(stderr, "mTR (B200): internal error: read %d stalled\n", idx); exit(EXIT_FAILURE); }
                         cv_submit.notify_all();
                     }
                 }
             }
         };
-        const int gather_min[2] = {getenv("MTR_GATHER_LONG") ? atoi(getenv("MTR_GATHER_LONG")) : 0, getenv("MTR_GATHER_SHORT") ? atoi(getenv("MTR_GATHER_SHORT")) : 0};
-        const int gather_us[2] = {getenv("MTR_GATHER_LONG_US") ? atoi(getenv("MTR_GATHER_LONG_US")) : 2000, getenv("MTR_GATHER_SHORT_US") ? atoi(getenv("MTR_GATHER_SHORT_US")) : 300};
         auto dispatch_loop = [&](int lane, mtr_ctx *lctx) {
             cudaSetDevice(lctx->device);
             std::vector<mtr_wdp_job> jobs;
@@ -1065,11 +1118,6 @@ struct Engine {
                 {
                     std::unique_lock<std::mutex> g(mu);
                     cv_submit.wait(g, [&] { return !submitted[lane].empty() || remaining == 0; });
-                    if (submitted[lane].empty()) return;
-                    // a launch costs the same for 10 reads as for 300: give the workers a moment to fill the batch
-                    if ((int)submitted[lane].size() < gather_min[lane] && gather_us[lane] > 0)
-                        cv_submit.wait_for(g, std::chrono::microseconds(gather_us[lane]),
-                                           [&] { return (int)submitted[lane].size() >= gather_min[lane] || remaining == 0; });
                     if (submitted[lane].empty()) return;
                     batch.swap(submitted[lane]);
                     submitted[lane].clear();
@@ -1109,6 +1157,11 @@ struct Engine {
                 {
                     std::lock_guard<std::mutex> g(mu);
                     wdp_ms += (now_s() - tg0) * 1e3;
+                    lane_fill_ms[lane] += local.wdp_fill_ms; lane_tb_ms[lane] += local.wdp_tb_ms;
+                    if (prof) {
+                        for (const mtr_wdp_job &j : jobs) { int b = 0; while (b < 11 && j.rows > (32 << b)) b++; rows_hist_n[b]++; rows_hist_cells[b] += (long long)j.rows * j.ulen * j.n_param; }
+                        for (int idx : batch) { int mx = 0; for (const JobReq &q : st[idx].jobs) mx = std::max(mx, q.rows); int b = 0; while (b < 11 && mx > (32 << b)) b++; readmax_hist[b]++; }
+                    }
                     lane_ms[lane] += (now_s() - tg0) * 1e3; lane_batches[lane]++; lane_items[lane] += (long long)jobs.size(); lane_reads[lane] += (long long)batch.size();
                     if (log_jobs) {
                         const int32_t shift = (int32_t)unit_log.size();
@@ -1117,13 +1170,13 @@ struct Engine {
                     }
                     rounds++; jobs_total += (long long)jobs.size();
                     ps.rounds++; ps.jobs += (int64_t)jobs.size();
-                    if (lane) ps.rounds_fast++;
+                    if (lane < n_tiers - 1) ps.rounds_fast++;
                     ps.h2d_bytes += (int64_t)jobs.size() * sizeof(mtr_wdp_job) + (int64_t)units.size();
                     ps.d2h_bytes += (int64_t)jobs.size() * 2 * sizeof(mtr_wdp_result) + aux_bytes;
                     ps.wdp_fill_ms += local.wdp_fill_ms; ps.wdp_tb_ms += local.wdp_tb_ms; ps.wdp_cells += local.wdp_cells;
                     ps.wdp_slot_cells += local.wdp_slot_cells; ps.wdp_dir_bytes += local.wdp_dir_bytes;
                     ps.launches += local.launches; ps.wdp_calls += local.wdp_calls;
-                    for (int idx : batch) { result_of[idx] = br; if (--pending[idx] == 0) ready.push_back(idx); }
+                    for (int idx : batch) { result_of[idx] = br; if (--pending[idx] == 0) push_ready(idx); }
                 }
                 cv_ready.notify_all();
                 batch.clear();
@@ -1136,10 +1189,10 @@ struct Engine {
             for (;;) {
                 {
                     std::unique_lock<std::mutex> g(mu);
-                    cv_submit.wait(g, [&] { return !submitted[2].empty() || remaining == 0; });
-                    if (submitted[2].empty()) return;
-                    batch.swap(submitted[2]);
-                    submitted[2].clear();
+                    cv_submit.wait(g, [&] { return !submitted[UF].empty() || remaining == 0; });
+                    if (submitted[UF].empty()) return;
+                    batch.swap(submitted[UF]);
+                    submitted[UF].clear();
                 }
                 tasks.clear();
                 long long cap = 16;
@@ -1161,28 +1214,28 @@ struct Engine {
                 {
                     std::lock_guard<std::mutex> g(mu);
                     uf_ms += (now_s() - tg0) * 1e3;
-                    lane_ms[2] += (now_s() - tg0) * 1e3; lane_batches[2]++; lane_items[2] += (long long)tasks.size(); lane_reads[2] += (long long)batch.size();
+                    lane_ms[UF] += (now_s() - tg0) * 1e3; lane_batches[UF]++; lane_items[UF] += (long long)tasks.size(); lane_reads[UF] += (long long)batch.size();
                     ps.rounds_uf++; ps.uf_tasks += (int64_t)tasks.size(); ps.uf_kernel_ms += us.uf_ms; ps.launches += 1;
                     ps.h2d_bytes += (int64_t)tasks.size() * sizeof(mtr_uf_task);
                     ps.d2h_bytes += (int64_t)tasks.size() * sizeof(mtr_uf_result) + used * 5;
-                    for (int idx : batch) { uf_result_of[idx] = br; if (--pending[idx] == 0) ready.push_back(idx); }
+                    for (int idx : batch) { uf_result_of[idx] = br; if (--pending[idx] == 0) push_ready(idx); }
                 }
                 cv_ready.notify_all();
                 batch.clear();
             }
         };
-        // Large batches keep one lane of each kind busy with big launches; small batches are latency-bound and gain
-        // from a second concurrent lane (MTR_LANES_FULL_BELOW reads).
-        const int full_below = getenv("MTR_LANES_FULL_BELOW") ? atoi(getenv("MTR_LANES_FULL_BELOW")) : (1 << 30);
         std::vector<std::thread> dispatchers;
-        for (int kind = 0; kind < 2; kind++) {
-            size_t use = n < full_below ? lanes[kind].size() : 1;
-            for (size_t li = 0; li < use; li++) { mtr_ctx *c = lanes[kind][li]; dispatchers.emplace_back([&, kind, c] { dispatch_loop(kind, c); }); }
-        }
-        for (mtr_ctx *c : lanes[2]) dispatchers.emplace_back([&, c] { uf_dispatch_loop(c); });
+        for (int t = 0; t < n_tiers; t++)
+            for (mtr_ctx *c : tier_lanes[t]) dispatchers.emplace_back([&, t, c] { dispatch_loop(t, c); });
+        for (mtr_ctx *c : uf_lanes) dispatchers.emplace_back([&, c] { uf_dispatch_loop(c); });
         {
             const double th0 = now_s();
-            pool->run(pool->size(), [&](int tid, int) { worker_loop(tid); });
+            // fresh threads, not the pool: the nice value of a thread cannot be lowered again without privilege, and
+            // the caller's thread must not be touched
+            std::vector<std::thread> wt;
+            const int nw = pool->size();
+            for (int t = 0; t < nw; t++) wt.emplace_back([&, t] { worker_loop(t); });
+            for (std::thread &t : wt) t.join();
             host_ms += (now_s() - th0) * 1e3;
         }
         for (std::thread &t : dispatchers) t.join();
@@ -1195,11 +1248,19 @@ struct Engine {
             double b = 0, l = 0, w = 0, p = 0, t = 0; long long nc = 0, nw = 0;
             for (Worker &k : workers) { b += k.t_build; l += k.t_list; w += k.t_walk; p += k.t_polish; t += k.t_step; nc += k.n_chain; nw += k.n_walk;
                                         k.t_build = k.t_list = k.t_walk = k.t_polish = k.t_step = 0; k.n_chain = k.n_walk = 0; }
-            for (int l = 0; l < 3; l++)
-                fprintf(stderr, "[mtr profile]   lane %d (%s): batches %6lld  busy %8.1f ms  items/batch %8.1f  reads/batch %6.1f  ms/batch %6.3f\n", l,
-                        l == 0 ? "long DP" : (l == 1 ? "short DP" : "unit finder"), lane_batches[l], lane_ms[l],
+            for (int l = 0; l <= UF; l++) {
+                if (l >= n_tiers && l != UF) continue;
+                char name[64];
+                if (l == UF) snprintf(name, sizeof name, "unit finder");
+                else if (l == n_tiers - 1) snprintf(name, sizeof name, "DP, longer jobs");
+                else snprintf(name, sizeof name, "DP rows <= %d", tier_rows[l]);
+                fprintf(stderr, "[mtr profile]   tier %d (%s, %d lanes): batches %6lld  busy %8.1f ms  items/batch %8.1f  reads/batch %6.1f  ms/batch %6.3f  kernel ms: fill %.1f traceback %.1f\n", l, name,
+                        l == UF ? (int)uf_lanes.size() : (int)tier_lanes[l].size(), lane_batches[l], lane_ms[l],
                         lane_batches[l] ? (double)lane_items[l] / lane_batches[l] : 0.0, lane_batches[l] ? (double)lane_reads[l] / lane_batches[l] : 0.0,
-                        lane_batches[l] ? lane_ms[l] / lane_batches[l] : 0.0);
+                        lane_batches[l] ? lane_ms[l] / lane_batches[l] : 0.0, lane_fill_ms[l], lane_tb_ms[l]);
+            }
+            for (int b = 0; b < 12; b++)
+                fprintf(stderr, "[mtr profile]   DP jobs with rows <= %6d: %9lld jobs %8.2f Gcells | read-rounds whose longest job is in this bucket: %8lld\n", 32 << b, rows_hist_n[b], rows_hist_cells[b] / 1e9, readmax_hist[b]);
             for (int b = 0; b < 8; b++) {
                 long long bn = 0, wn = 0; double wt = 0, wm = 0;
                 for (Worker &k : workers) { bn += k.hb_n[b]; wn += k.hw_n[b]; wt += k.hw_t[b]; wm = std::max(wm, k.hw_max[b]); k.hb_n[b] = k.hw_n[b] = 0; k.hw_t[b] = k.hw_max[b] = 0; }
@@ -1221,7 +1282,7 @@ struct Engine {
     static long long dir_budget()
     {
         const char *e = getenv("MTR_DIR_BUDGET_MB");
-        return (e ? atoll(e) : 16384LL) << 20;
+        return (e ? atoll(e) : 8192LL) << 20;
     }
 
     // Runs the round's jobs in sub-batches whose direction matrices fit the budget.
@@ -1425,7 +1486,10 @@ struct FastaReader {
 
 // ---------------------------------------------------------------- process-wide state behind the C entry points
 struct Runtime {
-    std::vector<Engine *> engines;
+    std::vector<Engine *> engines;     // per_gpu engines for every GPU: engine e works on GPU e / per_gpu
+    int per_gpu = 1;                   // batches in flight per GPU (MTR_INFLIGHT_PER_GPU).  Measured on B200 + 16 cores: a second
+                                       // batch in flight doubles the long-job lanes on the GPU and slows every round more
+                                       // than the overlap of ramp-down and ramp-up gains
     StaleTracker stale;
     std::vector<ReadInput> pending;
     long long pending_bases = 0;
@@ -1444,9 +1508,11 @@ struct Runtime {
         if (const char *e = getenv("MTR_DEVICE")) base = atoi(e);
         int threads = (int)std::thread::hardware_concurrency();
         if (const char *e = getenv("MTR_THREADS")) threads = atoi(e);
+        if (const char *e = getenv("MTR_INFLIGHT_PER_GPU")) per_gpu = std::max(1, atoi(e));
         prep_threads = std::max(1, std::min(8, threads / 2));
         threads = std::max(1, threads / ngpu);
-        for (int g = 0; g < ngpu; g++) engines.push_back(new Engine(base + g, threads));
+        for (int g = 0; g < ngpu; g++)
+            for (int i = 0; i < per_gpu; i++) engines.push_back(new Engine(base + g, threads));
     }
     ~Runtime() { for (Engine *e : engines) delete e; }
 };
@@ -1512,7 +1578,8 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     Runtime &rt = runtime();
     mtr_flush();
     FastaReader reader(inputFile);
-    const int ngpu = (int)rt.engines.size();
+    const int n_eng = (int)rt.engines.size();      // engines = batches in flight (per_gpu for every GPU)
+    const int n_gpu = n_eng / rt.per_gpu;
     struct Slot { std::thread th; std::string out; std::vector<ReadInput> reads; };
     std::vector<Slot *> inflight;
     auto drain_front = [&]() {
@@ -1538,8 +1605,9 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
         }
         if (s->reads.empty()) { delete s; break; }
         rt.stale.visit_batch(s->reads, 0, s->reads.size(), rt.prep_threads, nullptr);
-        while ((int)inflight.size() >= ngpu) drain_front();
-        Engine *eng = rt.engines[batch_index % ngpu];
+        while ((int)inflight.size() >= n_eng) drain_front();
+        // consecutive batches alternate between the GPUs first, then between the engines of one GPU
+        Engine *eng = rt.engines[(batch_index % n_gpu) * rt.per_gpu + (batch_index / n_gpu) % rt.per_gpu];
         batch_index++;
         s->th = std::thread([eng, s, print_alignment] { s->out = eng->process(s->reads, print_alignment); });
         inflight.push_back(s);

@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <time.h>
 #include "mtr_internal.h"
 
 // ---------------------------------------------------------------- job classes
@@ -68,25 +69,108 @@ __device__ __forceinline__ int read_base(const uint32_t *__restrict__ packed, lo
     return (int)((packed[b >> 4] >> ((int)(b & 15) * 2)) & 3u);
 }
 
-// ---------------------------------------------------------------- fill kernel, int32 scores
-template <int G, int C>
+// ---------------------------------------------------------------- traceback of one (task, penalty set), one thread
+// wrap_around_DP.c:288-333 (counts), consensus.c:919-962 (histograms), wrap_around_DP.c:123-186 (path).
+// Called by the lane that owns the task right after its fill (fused: the direction rows are still in L1/L2 and the
+// other warps of the SM keep filling meanwhile), or by the stand-alone wdp_traceback kernel.
+__device__ __forceinline__ void traceback_one(const WdpTask &t, const int p, const int best, const int max_i, const int max_j,
+                                              const uint32_t *__restrict__ packed, const uint8_t *__restrict__ units,
+                                              const uint8_t *dirs, mtr_wdp_result *res, void *aux)
+{
+    const int G = t.gain[p], MM = t.mis[p], IN = t.indel[p];
+    const int ulen = t.ulen, dstride = t.dir_stride, unit_off = t.unit_off;
+    const long long base0 = t.base0, aux_cap = t.aux_cap;
+    const uint8_t *d = dirs + t.dir_off + (size_t)p * t.dir_bytes;
+    int i = max_i, j = max_j, run = best;
+    if (j == 0) j = ulen;                                   // wrap_around_DP.c:296
+    int nm = 0, nx = 0, ni = 0, nd = 0, steps = 0, flags = 0;
+    int *cons = nullptr, *miss = nullptr;
+    uint8_t *path = nullptr;
+    if (t.mode == MTR_TB_CONSENSUS) {
+        cons = (int *)aux + t.aux_off;
+        miss = cons + (size_t)(ulen + 1) * 5;
+    } else if (t.mode == MTR_TB_PATH) {
+        path = (uint8_t *)aux + t.aux_off;
+    }
+    // The walk is a chain of dependent loads (read base, unit base, direction byte).  ~85 % of the steps of a
+    // real alignment are diagonal, so the operands of the next TB_DEPTH cells down the diagonal are fetched
+    // together (independent loads in flight) and consumed until the path leaves the diagonal.
+    constexpr int TB_DEPTH = 8;
+    bool alive = i > 0 && run > 0;
+    while (alive) {
+        int qx[TB_DEPTH], qu[TB_DEPTH], qd[TB_DEPTH];
+        {
+            int jt = j;
+#pragma unroll
+            for (int q = 0; q < TB_DEPTH; q++) {
+                const int it = i - q;
+                const bool ok = it >= 1;
+                qx[q] = ok ? read_base(packed, base0 + it) : 0;
+                qu[q] = units[unit_off + jt - 1];
+                qd[q] = ok ? d[(size_t)(it - 1) * dstride + ((jt - 1) >> 2)] : 0;
+                jt = jt == 1 ? ulen : jt - 1;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < TB_DEPTH; q++) {
+            if (!(i > 0 && run > 0)) { alive = false; break; }
+            const int xi = qx[q], uj = qu[q];
+            int op;
+            if (xi == uj) {
+                op = 0;
+            } else {
+                const int code = (qd[q] >> (((j - 1) & 3) * 2)) & 3;
+                if (code == 0) { flags |= 2; alive = false; break; }       // cannot happen: run > 0 means W[i][j] > 0
+                op = code == 3 ? 1 : (code == 2 ? 2 : 3);
+            }
+            if (path) { if (steps < aux_cap) path[steps] = (uint8_t)op; else flags |= 1; }
+            steps++;
+            if (op == 0)      { if (cons) cons[j * 5 + xi]++; run -= G;  i--; j--; nm++; }
+            else if (op == 1) { if (cons) cons[j * 5 + xi]++; run += MM; i--; j--; nx++; }
+            else if (op == 2) { if (cons) cons[j * 5 + 4]++;  run += IN; j--;      nd++; }
+            else              { if (miss) miss[j * 4 + xi]++; run += IN; i--;      ni++; }
+            if (j == 0) j = ulen;
+            if (op >= 2) break;                             // left the diagonal: refill from the new cell
+        }
+        if (!(i > 0 && run > 0)) alive = false;
+    }
+    // 48 bytes as three 16-byte stores (the result array may be pinned host memory: few, wide PCIe writes)
+    static_assert(sizeof(mtr_wdp_result) == 48, "mtr_wdp_result layout");
+    int4 *o = reinterpret_cast<int4 *>(res);
+    o[0] = make_int4(best, max_i, max_j, i);
+    o[1] = make_int4(j, nm, nx, ni);
+    o[2] = make_int4(nd, nm + nx + nd, steps, flags);
+}
+
+// stand-alone traceback (split mode: lets the fill kernels be timed alone), one thread per task
 __global__ void __launch_bounds__(128)
-wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
-             const uint8_t *__restrict__ units, uint8_t *__restrict__ dirs,
-             mtr_wdp_result *__restrict__ results, int *__restrict__ counter)
+wdp_traceback(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
+              const uint8_t *__restrict__ units, const uint8_t *dirs, const mtr_wdp_result *__restrict__ partial,
+              mtr_wdp_result *results, void *aux)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ntasks) return;
+    const WdpTask &t = tasks[idx];
+    for (int p = 0; p < (t.n_param == 2 ? 2 : 1); p++) {
+        const mtr_wdp_result *in = partial + t.result_idx + p;      // argmax left by the fill kernel (device memory)
+        traceback_one(t, p, in->best, in->max_i, in->max_j, packed, units, dirs, results + t.result_idx + p, aux);
+    }
+}
+
+// ---------------------------------------------------------------- fill kernel, int32 scores
+// One warp-slot: 32/G tasks of one class, tasks[slot * (32/G) + group].  fused != 0: the group's first lane runs the
+// traceback of its task as soon as the fill is done.
+template <int G, int C, bool FUSED>
+__device__ __forceinline__ void fill_slot_i32(const WdpTask *__restrict__ tasks, const int ntasks, const int slot,
+                                              const uint32_t *__restrict__ packed, const uint8_t *__restrict__ units,
+                                              uint8_t *dirs, mtr_wdp_result *results, void *aux)
 {
     constexpr int JPW = 32 / G;                    // jobs per warp
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;                       // lane within its group
     const int grp = lane / G;
-    const int nslots = (ntasks + JPW - 1) / JPW;
-
-    for (;;) {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(counter, 1);
-        slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= nslots) break;
+    {
         const int tidx = slot * JPW + grp;
         const bool have = tidx < ntasks;
         const WdpTask *tp = tasks + (have ? tidx : 0);
@@ -222,11 +306,65 @@ wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
             const bool take = (ov > best_v) || (ov == best_v && (oi < best_i || (oi == best_i && oj < best_j)));
             if (take) { best_v = ov; best_i = oi; best_j = oj; }
         }
-        if (have && gl == 0) {
+        if (FUSED) {
+            __syncwarp();                                   // the direction rows written by the other lanes of the group
+            if (have && gl == 0)
+                traceback_one(*tp, 0, best_v, best_v > 0 ? best_i : 0, best_v > 0 ? best_j : 0, packed, units, dirs,
+                              results + tp->result_idx, aux);
+            __syncwarp();
+        } else if (have && gl == 0) {
             mtr_wdp_result *res = results + tp->result_idx;
             res->best = best_v;
             res->max_i = best_v > 0 ? best_i : 0;
             res->max_j = best_v > 0 ? best_j : 0;
+        }
+    }
+}
+
+template <int G, int C, bool FUSED>
+__global__ void __launch_bounds__(128)
+wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
+             const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counter,
+             void *aux)
+{
+    constexpr int JPW = 32 / G;
+    const int nslots = (ntasks + JPW - 1) / JPW;
+    for (;;) {
+        int slot = 0;
+        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counter, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= nslots) break;
+        fill_slot_i32<G, C, FUSED>(tasks, ntasks, slot, packed, units, dirs, results, aux);
+    }
+}
+
+// Latency mode: ONE launch for a whole small batch.  The tasks are sorted by latency class (10..15); a warp pulls the
+// next slot of the shared queue, finds its class from the slot prefix sums and runs that class's fill (+ traceback).
+struct WdpMultiParams { int task_begin[kLatencyClasses + 1]; int slot_begin[kLatencyClasses + 1]; };
+
+template <bool FUSED>
+__global__ void __launch_bounds__(128)
+wdp_fill_multi(const WdpTask *__restrict__ tasks, const WdpMultiParams mp, const uint32_t *__restrict__ packed,
+               const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counter,
+               void *aux)
+{
+    for (;;) {
+        int slot = 0;
+        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counter, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= mp.slot_begin[kLatencyClasses]) break;
+        int k = 0;
+        while (slot >= mp.slot_begin[k + 1]) k++;
+        const WdpTask *ct = tasks + mp.task_begin[k];
+        const int cn = mp.task_begin[k + 1] - mp.task_begin[k];
+        const int ls = slot - mp.slot_begin[k];
+        switch (k) {
+        case 0: fill_slot_i32<4, 4, FUSED>(ct, cn, ls, packed, units, dirs, results, aux); break;
+        case 1: fill_slot_i32<8, 4, FUSED>(ct, cn, ls, packed, units, dirs, results, aux); break;
+        case 2: fill_slot_i32<16, 4, FUSED>(ct, cn, ls, packed, units, dirs, results, aux); break;
+        case 3: fill_slot_i32<32, 4, FUSED>(ct, cn, ls, packed, units, dirs, results, aux); break;
+        case 4: fill_slot_i32<32, 8, FUSED>(ct, cn, ls, packed, units, dirs, results, aux); break;
+        default: fill_slot_i32<32, 16, FUSED>(ct, cn, ls, packed, units, dirs, results, aux); break;
         }
     }
 }
@@ -242,11 +380,11 @@ wdp_fill_i32(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
 
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 
-template <int G, int C>
+template <int G, int C, bool FUSED>
 __global__ void __launch_bounds__(128)
 wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
-             const uint8_t *__restrict__ units, uint8_t *__restrict__ dirs,
-             mtr_wdp_result *__restrict__ results, int *__restrict__ counter)
+             const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counter,
+             void *aux)
 {
     constexpr int JPW = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
@@ -391,6 +529,7 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
             row(Wp, Wq, i);
             if (i + 1 <= maxrows) row(Wq, Wp, i + 1);
         }
+        int my_v = 0, my_i = 0, my_j = 0;                   // lane gl == h keeps the argmax of penalty set h
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             int bv = best_v[h], bi = best_i[h], bj = gl * C + best_c[h] + 1;
@@ -402,122 +541,69 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
                 const bool take = (ov > bv) || (ov == bv && (oi < bi || (oi == bi && oj < bj)));
                 if (take) { bv = ov; bi = oi; bj = oj; }
             }
-            if (have && gl == 0) {
-                mtr_wdp_result *res = results + tp->result_idx + h;
-                res->best = bv;
-                res->max_i = bv > 0 ? bi : 0;
-                res->max_j = bv > 0 ? bj : 0;
-            }
+            if (gl == h) { my_v = bv; my_i = bv > 0 ? bi : 0; my_j = bv > 0 ? bj : 0; }
         }
-    }
-}
-
-// ---------------------------------------------------------------- traceback (one thread per task)
-// wrap_around_DP.c:288-333 (counts), consensus.c:919-962 (histograms), wrap_around_DP.c:123-186 (path).
-__global__ void __launch_bounds__(128)
-wdp_traceback(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
-              const uint8_t *__restrict__ units, const uint8_t *__restrict__ dirs,
-              mtr_wdp_result *__restrict__ results, void *__restrict__ aux)
-{
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= ntasks) return;
-    const WdpTask t = tasks[idx];
-    for (int p = 0; p < (t.n_param == 2 ? 2 : 1); p++) {
-        mtr_wdp_result *res = results + t.result_idx + p;
-        const int G = t.gain[p], MM = t.mis[p], IN = t.indel[p];
-        const uint8_t *d = dirs + t.dir_off + (size_t)p * t.dir_bytes;
-        int i = res->max_i, j = res->max_j, run = res->best;
-        if (j == 0) j = t.ulen;                             // wrap_around_DP.c:296
-        int nm = 0, nx = 0, ni = 0, nd = 0, steps = 0, flags = 0;
-        int *cons = nullptr, *miss = nullptr;
-        uint8_t *path = nullptr;
-        if (t.mode == MTR_TB_CONSENSUS) {
-            cons = (int *)aux + t.aux_off;
-            miss = cons + (size_t)(t.ulen + 1) * 5;
-        } else if (t.mode == MTR_TB_PATH) {
-            path = (uint8_t *)aux + t.aux_off;
+        if (FUSED) {
+            __syncwarp();                                   // the direction rows written by the other lanes of the group
+            if (have && gl < 2) traceback_one(*tp, gl, my_v, my_i, my_j, packed, units, dirs, results + tp->result_idx + gl, aux);
+            __syncwarp();
+        } else if (have && gl < 2) {
+            mtr_wdp_result *res = results + tp->result_idx + gl;
+            res->best = my_v; res->max_i = my_i; res->max_j = my_j;
         }
-        // The walk is a chain of dependent loads (read base, unit base, direction byte).  ~85 % of the steps of a
-        // real alignment are diagonal, so the operands of the next TB_DEPTH cells down the diagonal are fetched
-        // together (independent loads in flight) and consumed until the path leaves the diagonal.
-        constexpr int TB_DEPTH = 8;
-        bool alive = i > 0 && run > 0;
-        while (alive) {
-            int qx[TB_DEPTH], qu[TB_DEPTH], qd[TB_DEPTH];
-            {
-                int jt = j;
-#pragma unroll
-                for (int q = 0; q < TB_DEPTH; q++) {
-                    const int it = i - q;
-                    const bool ok = it >= 1;
-                    qx[q] = ok ? read_base(packed, t.base0 + it) : 0;
-                    qu[q] = units[t.unit_off + jt - 1];
-                    qd[q] = ok ? d[(size_t)(it - 1) * t.dir_stride + ((jt - 1) >> 2)] : 0;
-                    jt = jt == 1 ? t.ulen : jt - 1;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < TB_DEPTH; q++) {
-                if (!(i > 0 && run > 0)) { alive = false; break; }
-                const int xi = qx[q], uj = qu[q];
-                int op;
-                if (xi == uj) {
-                    op = 0;
-                } else {
-                    const int code = (qd[q] >> (((j - 1) & 3) * 2)) & 3;
-                    if (code == 0) { flags |= 2; alive = false; break; }       // cannot happen: run > 0 means W[i][j] > 0
-                    op = code == 3 ? 1 : (code == 2 ? 2 : 3);
-                }
-                if (path) { if (steps < t.aux_cap) path[steps] = (uint8_t)op; else flags |= 1; }
-                steps++;
-                if (op == 0)      { if (cons) cons[j * 5 + xi]++; run -= G;  i--; j--; nm++; }
-                else if (op == 1) { if (cons) cons[j * 5 + xi]++; run += MM; i--; j--; nx++; }
-                else if (op == 2) { if (cons) cons[j * 5 + 4]++;  run += IN; j--;      nd++; }
-                else              { if (miss) miss[j * 4 + xi]++; run += IN; i--;      ni++; }
-                if (j == 0) j = t.ulen;
-                if (op >= 2) break;                         // left the diagonal: refill from the new cell
-            }
-            if (!(i > 0 && run > 0)) alive = false;
-        }
-        res->end_i = i; res->end_j = j;
-        res->n_match = nm; res->n_mismatch = nx; res->n_ins = ni; res->n_del = nd;
-        res->n_scanned = nm + nx + nd;
-        res->path_len = steps; res->flags = flags;
     }
 }
 
 // ---------------------------------------------------------------- host side
+constexpr int kCounterGens = 128;      // ring of counter sets: one memset per kCounterGens launches instead of one per launch
+
+static inline const uint8_t *d_units_of(const WdpState &w) { return (const uint8_t *)w.d_tasks.p + w.units_dev_off; }
+// The thread that finishes a task's traceback stores the 48-byte result straight into the pinned host buffer (mapped
+// into the device address space): no device->host copy is queued behind the kernels, where it would sit at the head
+// of a copy-engine queue and hold up the copies of every other lane until this lane's kernels are done.
+// Small (latency-class) batches run the traceback inside the fill kernel: one launch per batch.  Large batches keep
+// a separate traceback kernel -- a lane that walks a 10 k-step traceback would hold its whole warp back from filling.
+static inline bool fused_now(const WdpState &w) { return w.fused_tb && w.latency; }
+static inline mtr_wdp_result *results_of(const WdpState &w) { return (mtr_wdp_result *)(fused_now(w) ? w.h_results.p : w.d_results.p); }
+
 template <int G, int C>
-static void launch_fill(mtr_ctx *ctx, int k, const WdpTask *d_tasks, int ntasks, cudaStream_t s)
+static void launch_fill(mtr_ctx *ctx, int *counter, const WdpTask *d_tasks, int ntasks, cudaStream_t s)
 {
     const int jpw = 32 / G;
     const int nslots = (ntasks + jpw - 1) / jpw;
     int blocks = (nslots + 3) / 4;
     blocks = std::min(blocks, ctx->n_sm * 8);
-    wdp_fill_i32<G, C><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p,
-                                              (const uint8_t *)ctx->wdp.d_units.p, (uint8_t *)ctx->wdp.d_dirs.p,
-                                              (mtr_wdp_result *)ctx->wdp.d_results.p,
-                                              (int *)ctx->wdp.d_counters.p + k);
+    if (fused_now(ctx->wdp))
+        wdp_fill_i32<G, C, true><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p, d_units_of(ctx->wdp),
+                                                        (uint8_t *)ctx->wdp.d_dirs.p, results_of(ctx->wdp), counter, ctx->wdp.d_aux.p);
+    else
+        wdp_fill_i32<G, C, false><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p, d_units_of(ctx->wdp),
+                                                         (uint8_t *)ctx->wdp.d_dirs.p, results_of(ctx->wdp), counter, ctx->wdp.d_aux.p);
 }
 
 template <int G, int C>
-static void launch_fill_p16(mtr_ctx *ctx, int k, const WdpTask *d_tasks, int ntasks, cudaStream_t s)
+static void launch_fill_p16(mtr_ctx *ctx, int *counter, const WdpTask *d_tasks, int ntasks, cudaStream_t s)
 {
     const int jpw = 32 / G;
     const int nslots = (ntasks + jpw - 1) / jpw;
     int blocks = (nslots + 3) / 4;
     blocks = std::min(blocks, ctx->n_sm * 8);
-    wdp_fill_p16<G, C><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p,
-                                              (const uint8_t *)ctx->wdp.d_units.p, (uint8_t *)ctx->wdp.d_dirs.p,
-                                              (mtr_wdp_result *)ctx->wdp.d_results.p,
-                                              (int *)ctx->wdp.d_counters.p + k);
+    if (fused_now(ctx->wdp))
+        wdp_fill_p16<G, C, true><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p, d_units_of(ctx->wdp),
+                                                        (uint8_t *)ctx->wdp.d_dirs.p, results_of(ctx->wdp), counter, ctx->wdp.d_aux.p);
+    else
+        wdp_fill_p16<G, C, false><<<blocks, 128, 0, s>>>(d_tasks, ntasks, (const uint32_t *)ctx->d_packed.p, d_units_of(ctx->wdp),
+                                                         (uint8_t *)ctx->wdp.d_dirs.p, results_of(ctx->wdp), counter, ctx->wdp.d_aux.p);
 }
 
 int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uint8_t *units, int64_t units_len,
-                    int64_t aux_bytes)
+                    int64_t aux_bytes, bool sync)
 {
     WdpState &w = ctx->wdp;
     w.uploaded = false;
+    static const bool prof = getenv("MTR_PROFILE") != nullptr;
+    auto wall = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; };
+    const double tp0 = prof ? wall() : 0;
     if (n_jobs < 0 || (n_jobs > 0 && (!jobs || !units))) { mtr_set_error(ctx, "wdp_upload: null argument"); return MTR_EINVAL; }
     if (n_jobs > 0 && ctx->n_reads == 0) { mtr_set_error(ctx, "wdp_upload: no resident read batch"); return MTR_EINVAL; }
     w.tasks.clear();
@@ -534,6 +620,7 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
         lat_warps += (long long)jobs[jn].n_param * kClasses[k].G;
     }
     int latency = (lat_warps / 32) <= (long long)ctx->n_sm * 24 ? 1 : 0;
+    w.unused_results.clear();
     if (const char *e = getenv("MTR_WDP_MODE")) latency = strcmp(e, "latency") == 0 ? 1 : (strcmp(e, "throughput") == 0 ? 0 : latency);
     const bool pair_ok = !getenv("MTR_NO_PAIRED");
     for (int jn = 0; jn < n_jobs; jn++) {
@@ -578,6 +665,7 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
             w.slot_cells += 2LL * j.rows * kClasses[k].G * kClasses[k].C;
             continue;
         }
+        if (j.n_param == 1) w.unused_results.push_back(jn * 2 + 1);
         for (int p = 0; p < j.n_param; p++) {
             WdpTask t;
             memset(&t, 0, sizeof t);
@@ -618,26 +706,46 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
     w.tasks.swap(sorted);
     w.dir_total = off;
     w.aux_bytes = aux_bytes;
+    w.latency = latency;
 
+    const double tp1 = prof ? wall() : 0;
     MTR_CUDA(ctx, cudaSetDevice(ctx->device));
-    MTR_CUDA(ctx, w.d_tasks.reserve(sizeof(WdpTask) * (size_t)std::max(nt, 1)));
-    MTR_CUDA(ctx, w.d_units.reserve((size_t)std::max<int64_t>(units_len, 1)));
-    MTR_CUDA(ctx, w.d_dirs.reserve((size_t)std::max<long long>(w.dir_total, 16)));
+    // tasks and units travel as one block: [WdpTask x nt | units]
+    w.units_dev_off = sizeof(WdpTask) * (size_t)std::max(nt, 1);
+    const size_t in_bytes = w.units_dev_off + (size_t)std::max<int64_t>(units_len, 1);
+    MTR_CUDA(ctx, w.d_tasks.reserve(in_bytes));
+    // the direction matrices of a batch run to gigabytes and every regrowth is a device-wide cudaFree + cudaMalloc:
+    // grow in big steps so that a context reallocates a handful of times in its life
+    if ((size_t)w.dir_total > w.d_dirs.cap) MTR_CUDA(ctx, w.d_dirs.reserve((size_t)std::max<long long>(w.dir_total + w.dir_total / 2, 64 << 20)));
     MTR_CUDA(ctx, w.d_results.reserve(sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1)));
+    MTR_CUDA(ctx, w.h_results.reserve(sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1)));
     MTR_CUDA(ctx, w.d_aux.reserve((size_t)std::max<int64_t>(aux_bytes, 16)));
-    MTR_CUDA(ctx, w.d_counters.reserve(sizeof(int) * WDP_NCLASS));
+    MTR_CUDA(ctx, w.d_counters.reserve(sizeof(int) * WDP_NCLASS * kCounterGens));
+    const double tp2 = prof ? wall() : 0;
     if (nt > 0) {
-        MTR_CUDA(ctx, w.h_tasks.reserve(sizeof(WdpTask) * (size_t)nt));
+        MTR_CUDA(ctx, w.h_tasks.reserve(in_bytes));
         memcpy(w.h_tasks.p, w.tasks.data(), sizeof(WdpTask) * (size_t)nt);
-        MTR_CUDA(ctx, cudaMemcpyAsync(w.d_tasks.p, w.h_tasks.p, sizeof(WdpTask) * (size_t)nt, cudaMemcpyHostToDevice, ctx->main_stream));
-        MTR_CUDA(ctx, cudaMemcpyAsync(w.d_units.p, units, (size_t)units_len, cudaMemcpyHostToDevice, ctx->main_stream));
+        memcpy((char *)w.h_tasks.p + w.units_dev_off, units, (size_t)units_len);
+        MTR_CUDA(ctx, cudaMemcpyAsync(w.d_tasks.p, w.h_tasks.p, w.units_dev_off + (size_t)units_len, cudaMemcpyHostToDevice, ctx->main_stream));
     }
-    MTR_CUDA(ctx, mtr_sync(ctx));
+    if (sync) MTR_CUDA(ctx, mtr_sync(ctx));
+    if (prof) { const double tp3 = wall(); ctx->prof_up[0] += tp1 - tp0; ctx->prof_up[1] += tp2 - tp1; ctx->prof_up[2] += tp3 - tp2; }
     w.uploaded = true;
     return MTR_OK;
 }
 
-int wdp_launch_impl(mtr_ctx *ctx)
+// reads the CUDA-event times of the last launch (after a sync)
+static int wdp_read_times(mtr_ctx *ctx)
+{
+    float f0 = 0, f1 = 0;
+    MTR_CUDA(ctx, cudaEventElapsedTime(&f0, ctx->ev[0], ctx->ev[1]));
+    MTR_CUDA(ctx, cudaEventElapsedTime(&f1, ctx->ev[1], ctx->ev[2]));
+    ctx->stats.wdp_fill_ms = f0;
+    ctx->stats.wdp_tb_ms = f1;
+    return MTR_OK;
+}
+
+int wdp_launch_impl(mtr_ctx *ctx, bool sync)
 {
     WdpState &w = ctx->wdp;
     if (!w.uploaded) { mtr_set_error(ctx, "wdp_launch: nothing uploaded"); return MTR_EINVAL; }
@@ -648,82 +756,110 @@ int wdp_launch_impl(mtr_ctx *ctx)
     ctx->stats.wdp_slot_cells = w.slot_cells;
     ctx->stats.wdp_dir_bytes = w.dir_total;
     cudaStream_t ms = ctx->main_stream;
-    MTR_CUDA(ctx, cudaMemsetAsync(w.d_counters.p, 0, sizeof(int) * WDP_NCLASS, ms));
-    MTR_CUDA(ctx, cudaMemsetAsync(w.d_results.p, 0, sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1), ms));
+    // slot counters: a fresh, already-zero set per launch
+    if (w.counter_gen % kCounterGens == 0)
+        MTR_CUDA(ctx, cudaMemsetAsync(w.d_counters.p, 0, sizeof(int) * WDP_NCLASS * kCounterGens, ms));
+    int *counters = (int *)w.d_counters.p + (size_t)(w.counter_gen % kCounterGens) * WDP_NCLASS;
+    w.counter_gen++;
     if (w.aux_bytes > 0) MTR_CUDA(ctx, cudaMemsetAsync(w.d_aux.p, 0, (size_t)w.aux_bytes, ms));
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[0], ms));
-    for (int k = 0; k < WDP_NCLASS; k++) {
-        const int n = w.class_begin[k + 1] - w.class_begin[k];
-        if (n == 0) continue;
-        cudaStream_t s = ctx->stream[k];
-        MTR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev[0], 0));
-        const WdpTask *dt = (const WdpTask *)w.d_tasks.p + w.class_begin[k];
-        switch (k) {
-        case 0: launch_fill<4, 4>(ctx, k, dt, n, s); break;
-        case 1: launch_fill<4, 8>(ctx, k, dt, n, s); break;
-        case 2: launch_fill<4, 12>(ctx, k, dt, n, s); break;
-        case 3: launch_fill<8, 8>(ctx, k, dt, n, s); break;
-        case 4: launch_fill<8, 12>(ctx, k, dt, n, s); break;
-        case 5: launch_fill<8, 16>(ctx, k, dt, n, s); break;
-        case 6: launch_fill<16, 12>(ctx, k, dt, n, s); break;
-        case 7: launch_fill<16, 16>(ctx, k, dt, n, s); break;
-        case 8: launch_fill<32, 12>(ctx, k, dt, n, s); break;
-        case 9: launch_fill<32, 16>(ctx, k, dt, n, s); break;
-        case 10: launch_fill<4, 4>(ctx, k, dt, n, s); break;
-        case 11: launch_fill<8, 4>(ctx, k, dt, n, s); break;
-        case 12: launch_fill<16, 4>(ctx, k, dt, n, s); break;
-        case 13: launch_fill<32, 4>(ctx, k, dt, n, s); break;
-        case 14: launch_fill<32, 8>(ctx, k, dt, n, s); break;
-        case 15: launch_fill<32, 16>(ctx, k, dt, n, s); break;
-        case 16: launch_fill_p16<4, 4>(ctx, k, dt, n, s); break;
-        case 17: launch_fill_p16<4, 8>(ctx, k, dt, n, s); break;
-        case 18: launch_fill_p16<4, 12>(ctx, k, dt, n, s); break;
-        case 19: launch_fill_p16<8, 8>(ctx, k, dt, n, s); break;
-        case 20: launch_fill_p16<8, 12>(ctx, k, dt, n, s); break;
-        case 21: launch_fill_p16<8, 16>(ctx, k, dt, n, s); break;
-        case 22: launch_fill_p16<16, 12>(ctx, k, dt, n, s); break;
-        case 23: launch_fill_p16<16, 16>(ctx, k, dt, n, s); break;
-        case 24: launch_fill_p16<32, 12>(ctx, k, dt, n, s); break;
-        case 25: launch_fill_p16<32, 16>(ctx, k, dt, n, s); break;
-        default: mtr_set_error(ctx, "wdp_launch: class %d has no kernel", k); return MTR_EINVAL;
+    if (w.latency && nt > 0) {
+        // one launch for the whole batch
+        WdpMultiParams mp;
+        int slots = 0;
+        for (int q = 0; q <= kLatencyClasses; q++) {
+            mp.task_begin[q] = w.class_begin[kThroughputClasses + q] - w.class_begin[kThroughputClasses];
+            mp.slot_begin[q] = slots;
+            if (q < kLatencyClasses) {
+                const int n = w.class_begin[kThroughputClasses + q + 1] - w.class_begin[kThroughputClasses + q];
+                const int jpw = 32 / kClasses[kThroughputClasses + q].G;
+                slots += (n + jpw - 1) / jpw;
+            }
         }
+        const int blocks = std::min((slots + 3) / 4, ctx->n_sm * 4);
+        if (fused_now(w))
+            wdp_fill_multi<true><<<blocks, 128, 0, ms>>>((const WdpTask *)w.d_tasks.p + w.class_begin[kThroughputClasses], mp,
+                                                         (const uint32_t *)ctx->d_packed.p, d_units_of(w), (uint8_t *)w.d_dirs.p,
+                                                         results_of(w), counters, w.d_aux.p);
+        else
+            wdp_fill_multi<false><<<blocks, 128, 0, ms>>>((const WdpTask *)w.d_tasks.p + w.class_begin[kThroughputClasses], mp,
+                                                          (const uint32_t *)ctx->d_packed.p, d_units_of(w), (uint8_t *)w.d_dirs.p,
+                                                          results_of(w), counters, w.d_aux.p);
         MTR_CUDA(ctx, cudaGetLastError());
         ctx->stats.launches++;
-        MTR_CUDA(ctx, cudaEventRecord(ctx->class_done[k], s));
-        MTR_CUDA(ctx, cudaStreamWaitEvent(ms, ctx->class_done[k], 0));
+    } else {
+        for (int k = 0; k < WDP_NCLASS; k++) {
+            const int n = w.class_begin[k + 1] - w.class_begin[k];
+            if (n == 0) continue;
+            cudaStream_t s = ctx->stream[k];
+            MTR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev[0], 0));
+            const WdpTask *dt = (const WdpTask *)w.d_tasks.p + w.class_begin[k];
+            int *cnt = counters + k;
+            switch (k) {
+            case 0: launch_fill<4, 4>(ctx, cnt, dt, n, s); break;
+            case 1: launch_fill<4, 8>(ctx, cnt, dt, n, s); break;
+            case 2: launch_fill<4, 12>(ctx, cnt, dt, n, s); break;
+            case 3: launch_fill<8, 8>(ctx, cnt, dt, n, s); break;
+            case 4: launch_fill<8, 12>(ctx, cnt, dt, n, s); break;
+            case 5: launch_fill<8, 16>(ctx, cnt, dt, n, s); break;
+            case 6: launch_fill<16, 12>(ctx, cnt, dt, n, s); break;
+            case 7: launch_fill<16, 16>(ctx, cnt, dt, n, s); break;
+            case 8: launch_fill<32, 12>(ctx, cnt, dt, n, s); break;
+            case 9: launch_fill<32, 16>(ctx, cnt, dt, n, s); break;
+            case 10: launch_fill<4, 4>(ctx, cnt, dt, n, s); break;
+            case 11: launch_fill<8, 4>(ctx, cnt, dt, n, s); break;
+            case 12: launch_fill<16, 4>(ctx, cnt, dt, n, s); break;
+            case 13: launch_fill<32, 4>(ctx, cnt, dt, n, s); break;
+            case 14: launch_fill<32, 8>(ctx, cnt, dt, n, s); break;
+            case 15: launch_fill<32, 16>(ctx, cnt, dt, n, s); break;
+            case 16: launch_fill_p16<4, 4>(ctx, cnt, dt, n, s); break;
+            case 17: launch_fill_p16<4, 8>(ctx, cnt, dt, n, s); break;
+            case 18: launch_fill_p16<4, 12>(ctx, cnt, dt, n, s); break;
+            case 19: launch_fill_p16<8, 8>(ctx, cnt, dt, n, s); break;
+            case 20: launch_fill_p16<8, 12>(ctx, cnt, dt, n, s); break;
+            case 21: launch_fill_p16<8, 16>(ctx, cnt, dt, n, s); break;
+            case 22: launch_fill_p16<16, 12>(ctx, cnt, dt, n, s); break;
+            case 23: launch_fill_p16<16, 16>(ctx, cnt, dt, n, s); break;
+            case 24: launch_fill_p16<32, 12>(ctx, cnt, dt, n, s); break;
+            case 25: launch_fill_p16<32, 16>(ctx, cnt, dt, n, s); break;
+            default: mtr_set_error(ctx, "wdp_launch: class %d has no kernel", k); return MTR_EINVAL;
+            }
+            MTR_CUDA(ctx, cudaGetLastError());
+            ctx->stats.launches++;
+            MTR_CUDA(ctx, cudaEventRecord(ctx->class_done[k], s));
+            MTR_CUDA(ctx, cudaStreamWaitEvent(ms, ctx->class_done[k], 0));
+        }
     }
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[1], ms));
-    if (nt > 0) {
+    if (nt > 0 && !fused_now(w)) {
         wdp_traceback<<<(nt + 127) / 128, 128, 0, ms>>>((const WdpTask *)w.d_tasks.p, nt, (const uint32_t *)ctx->d_packed.p,
-                                                        (const uint8_t *)w.d_units.p, (const uint8_t *)w.d_dirs.p,
-                                                        (mtr_wdp_result *)w.d_results.p, w.d_aux.p);
+                                                        d_units_of(w), (const uint8_t *)w.d_dirs.p,
+                                                        (const mtr_wdp_result *)w.d_results.p, (mtr_wdp_result *)w.h_results.p, w.d_aux.p);
         MTR_CUDA(ctx, cudaGetLastError());
         ctx->stats.launches++;
     }
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[2], ms));
-    MTR_CUDA(ctx, mtr_sync(ctx));
-    float f0 = 0, f1 = 0;
-    MTR_CUDA(ctx, cudaEventElapsedTime(&f0, ctx->ev[0], ctx->ev[1]));
-    MTR_CUDA(ctx, cudaEventElapsedTime(&f1, ctx->ev[1], ctx->ev[2]));
-    ctx->stats.wdp_fill_ms = f0;
-    ctx->stats.wdp_tb_ms = f1;
+    if (sync) {
+        MTR_CUDA(ctx, mtr_sync(ctx));
+        return wdp_read_times(ctx);
+    }
     return MTR_OK;
 }
 
-int wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes)
+int wdp_download_impl(mtr_ctx *ctx, mtr_wdp_result *results, void *aux, int64_t aux_bytes, bool read_times)
 {
     WdpState &w = ctx->wdp;
     if (!w.uploaded) { mtr_set_error(ctx, "wdp_download: nothing uploaded"); return MTR_EINVAL; }
     if (aux_bytes > w.aux_bytes) { mtr_set_error(ctx, "wdp_download: aux_bytes larger than uploaded"); return MTR_EINVAL; }
     MTR_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (w.n_results > 0) {
-        MTR_CUDA(ctx, w.h_results.reserve(sizeof(mtr_wdp_result) * (size_t)w.n_results));
-        MTR_CUDA(ctx, cudaMemcpyAsync(w.h_results.p, w.d_results.p, sizeof(mtr_wdp_result) * (size_t)w.n_results,
-                                      cudaMemcpyDeviceToHost, ctx->main_stream));
-    }
-    if (aux && aux_bytes > 0)
+    // the results are already on their way into h_results; a copy is only issued once the kernels are done
+    if (aux && aux_bytes > 0) {
+        MTR_CUDA(ctx, mtr_sync(ctx));
         MTR_CUDA(ctx, cudaMemcpyAsync(aux, w.d_aux.p, (size_t)aux_bytes, cudaMemcpyDeviceToHost, ctx->main_stream));
+    }
     MTR_CUDA(ctx, mtr_sync(ctx));
     if (w.n_results > 0) memcpy(results, w.h_results.p, sizeof(mtr_wdp_result) * (size_t)w.n_results);
+    for (int idx : w.unused_results) memset(results + idx, 0, sizeof(mtr_wdp_result));     // second slot of a one-set job
+    if (read_times) return wdp_read_times(ctx);
     return MTR_OK;
 }

@@ -208,6 +208,13 @@ int mtr_uf_run(mtr_ctx *ctx, const mtr_uf_task *, int, mtr_uf_result *, uint8_t 
     return MTR_EINVAL;
 }
 
+// entry points the host pipeline never calls; present so that the ctypes binding (mtr_b200/capi.py) loads this library
+int mtr_wdp_upload(mtr_ctx *ctx, const mtr_wdp_job *, int, const uint8_t *, int64_t, int64_t) { mtr_set_error(ctx, "hostsim: not simulated"); return MTR_EINVAL; }
+int mtr_wdp_launch(mtr_ctx *ctx) { mtr_set_error(ctx, "hostsim: not simulated"); return MTR_EINVAL; }
+int mtr_wdp_download(mtr_ctx *ctx, mtr_wdp_result *, void *, int64_t) { mtr_set_error(ctx, "hostsim: not simulated"); return MTR_EINVAL; }
+int mtr_wdp_set_fused_traceback(mtr_ctx *ctx, int) { return ctx ? MTR_OK : MTR_EINVAL; }
+int mtr_alu_probe(mtr_ctx *ctx, int, double *gops) { if (!ctx || !gops) return MTR_EINVAL; *gops = 1.0; return MTR_OK; }
+
 int mtr_get_stats(const mtr_ctx *ctx, mtr_stats *out) { if (!ctx || !out) return MTR_EINVAL; *out = ctx->stats; return MTR_OK; }
 
 }  // extern "C"

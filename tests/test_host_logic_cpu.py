@@ -68,5 +68,5 @@ def test_batching_threads_and_lanes_do_not_change_the_output(sim, synthetic_dir)
     path = os.path.join(synthetic_dir, "mixed.fa")
     ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
     for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_BATCH_READS": "3", "MTR_GPUS": "2"},
-                {"MTR_LONG_LANES": "1", "MTR_SHORT_LANES": "1"}, {"MTR_FAST_ROWS": "100", "MTR_THREADS": "3"}):
+                {"MTR_TIER_ROWS": "1536", "MTR_TIER_LANES": "1,1"}, {"MTR_TIER_ROWS": "40,100,400", "MTR_TIER_SPIN": "1,1,0,0", "MTR_THREADS": "3"}):
         assert hashlib.md5(run(sim, [], path, env)).hexdigest() == ref, env

@@ -41,6 +41,31 @@ def test_random_jobs_paired(gpu_ctx, oracle):
     assert not bad, bad[:10]
 
 
+def test_fused_and_split_traceback_agree(gpu_ctx, oracle, monkeypatch):
+    """The fill kernels trace each task back themselves (default); the split mode (fill kernels + one traceback kernel,
+    used to time the fill alone) must give the same bytes, in both kernel families, incl. histograms and paths."""
+    import os
+    rng = np.random.default_rng(77)
+    reads, tails, jobs = wdp_cases.random_jobs(rng, n_jobs=400, max_rows=1200)
+    try:
+        for fam in ("latency", "throughput"):
+            monkeypatch.setenv("MTR_WDP_MODE", fam)
+            os.environ["MTR_WDP_MODE"] = fam
+            for mode, pair in ((capi.TB_COUNTS, True), (capi.TB_COUNTS, False), (capi.TB_CONSENSUS, False), (capi.TB_PATH, False)):
+                out = []
+                for fused in (True, False):
+                    gpu_ctx.wdp_set_fused_traceback(fused)
+                    arr, res, aux = _run(gpu_ctx, reads, tails, jobs, mode=mode, pair=pair)
+                    out.append((res.tobytes(), None if aux is None else aux.tobytes()))
+                assert out[0] == out[1], (fam, mode, pair)
+                if mode == capi.TB_COUNTS:
+                    bad = wdp_cases.check_against_oracle(oracle, reads, tails, jobs, res, pair=pair)
+                    assert not bad, (fam, pair, bad[:10])
+    finally:
+        gpu_ctx.wdp_set_fused_traceback(True)
+        os.environ.pop("MTR_WDP_MODE", None)
+
+
 @pytest.mark.parametrize("mode", ["throughput", "latency"])
 def test_kernel_families(gpu_ctx, oracle, mode, monkeypatch):
     """Small batches default to the latency classes; force each family (throughput classes pair the two penalty sets
