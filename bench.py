@@ -260,26 +260,34 @@ def main():
             p.close()
         return
 
-    # ---- end-to-end loop: FASTA text in host memory -> output text in host memory, `inflight` batches at a time
-    barrier()
-    t0 = time.perf_counter()
-    io = {"h2d": 0, "d2h": 0}
-
-    def e2e_one(s):
-        p = pipes[(s - a.warmup) % inflight]
-        p.load_fasta(texts[s])
-        p.run()
-        st = p.stats()
-        with lock:
-            io["h2d"] += st["h2d_bytes"]; io["d2h"] += st["d2h_bytes"]
-    run_concurrently([(lambda s=s: e2e_one(s)) for s in timed])
-    barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    h2d, d2h = io["h2d"], io["d2h"]
-    clk = clocks.stop()
-    pipe = pipes[0]
+    # ---- end to end through the reference's own entry point: handle_one_file(path) (mTR.h:126) on a FASTA file holding
+    # the K timed batches, exactly as main.c calls it -- parse, stale-state tracking, 2-bit pack, H2D, directional index,
+    # every per-round H2D / D2H, chaining, formatting, ordered stdout.  The entry point owns its engines (two per GPU:
+    # the next batch starts when the running one is down to its last reads); the pipelines above are closed first.
     for p in pipes[1:]:
         p.close()
+    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    e2e_path = os.path.join(shm, "mtr_bench_rank%d_%d.fa" % (rank, os.getpid()))
+    os.environ.setdefault("MTR_DEVICE", str(local_rank))
+    os.environ.setdefault("MTR_THREADS", str(threads))
+    os.environ.setdefault("MTR_BATCH_READS", str(R))
+    with open(e2e_path, "wb") as f:                      # warm-up file: one batch per engine
+        f.write(texts[0]); f.write(texts[0])
+    capi.run_file(e2e_path)
+    with open(e2e_path, "wb") as f:
+        for s in timed:
+            f.write(texts[s])
+    barrier()
+    t0 = time.perf_counter()
+    n_file, out_file, fst = capi.run_file(e2e_path)
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    os.unlink(e2e_path)
+    assert n_file == R * a.steps, (n_file, R, a.steps)
+    h2d, d2h = fst["h2d_bytes"], fst["d2h_bytes"]
+    e2e_md5 = hashlib.md5(out_file).hexdigest()
+    clk = clocks.stop()
+    pipe = pipes[0]
 
     # ---- K3 alone on exactly one step's DP jobs, replayed as a single batch (operands resident in HBM)
     alone = alone_fused = None
@@ -315,7 +323,9 @@ def main():
                    "mode": "default (Manhattan), -m 0.6", "host_threads_per_gpu": threads, "batches_in_flight_per_gpu": inflight,
                    "l2": "working set per step (direction matrices, %d MB) exceeds the 126 MB L2" % (acc["wdp_dir_bytes"] / a.steps / 2 ** 20)},
         "e2e": {"value": round(reads_all / t_e2e, 3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d / a.steps),
-                "d2h_bytes_per_step": int(d2h / a.steps)},
+                "d2h_bytes_per_step": int(d2h / a.steps), "ms_per_step": round(t_e2e / a.steps * 1e3, 2),
+                "how": "handle_one_file() on a FASTA file (tmpfs) with the K timed batches, stdout captured; parse, pack, every H2D/D2H inside",
+                "output_md5": e2e_md5},
         "gpu_launches": int(acc["launches"]),
         "gcups": {"wrap_around_dp": round(gcups_rank, 2), "fill_only": round(fill_gcups, 2),
                   "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3), "algorithmic_cells_per_step": int(acc["wdp_cells"] / a.steps)},

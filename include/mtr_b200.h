@@ -131,6 +131,10 @@ int mtr_wdp_set_fused_traceback(mtr_ctx *ctx, int on);
  * only needs end and w). */
 int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
                const int64_t *pos_off, double *di, int32_t *end, int32_t *w);
+/* The same for reads [first, first + count) of the resident batch only; every array is indexed as for the whole batch.
+ * Lets the host sweep a batch in slices and start on a slice while the next one is on the GPU. */
+int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
+                     const int64_t *pos_off, double *di, int32_t *end, int32_t *w, int first, int count);
 
 /* ------------------------------------------------------------------ K4: unit finder */
 /* One task = search_De_Bruijn_graph (consensus.c:507-549) for one candidate range [qs, qe] of one resident read
@@ -216,6 +220,9 @@ int  handle_one_file(char *inputFile, int print_alignment);
  * enqueued so far, in order. */
 void handle_one_read(char *readID, int inputLen, int read_cnt, int print_alignment);
 void mtr_flush(void);
+/* Counters (reads, cells, kernel launches, host<->device bytes ...) summed over everything the three entry points above
+ * have processed since the previous call; resets them.  The reference has only the -c timers (mTR.h:142-143). */
+int  mtr_file_stats(mtr_pipeline_stats *out);
 
 extern int   Manhattan_Distance;      /* mTR.h:61, set by main.c:56,77 */
 extern float min_match_ratio;         /* mTR.h:62, set by main.c:54,68 */

@@ -19,9 +19,9 @@ TB_COUNTS, TB_CONSENSUS, TB_PATH = 0, 1, 2
 # every symbol include/mtr_b200.h declares (tests check that the library exports all of them)
 ABI_FUNCTIONS = [
     "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_reads_upload", "mtr_reads_share",
-    "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_di_run", "mtr_get_stats",
+    "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_wdp_set_fused_traceback", "mtr_di_run", "mtr_di_run_range", "mtr_get_stats",
     "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_load_fasta_shard",
-    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush",
+    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush", "mtr_file_stats",
 ]
 ABI_GLOBALS = [
     "Manhattan_Distance", "min_match_ratio", "orgInputString", "time_all", "time_memory", "time_range",
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.mtr_wdp_download.argtypes = [vp, vp, vp, i64]
     lib.mtr_wdp_set_fused_traceback.argtypes = [vp, C.c_int]
     lib.mtr_di_run.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.mtr_di_run_range.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
     lib.mtr_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mtr_alu_probe.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.mtr_uf_run.argtypes = [vp, vp, C.c_int, vp, vp, vp, i64, C.POINTER(i64)]
@@ -118,6 +119,7 @@ def load_library() -> C.CDLL:
     lib.mtr_pipeline_get_job_log.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
     lib.mtr_pipeline_ctx.argtypes = [vp]
     lib.mtr_pipeline_ctx.restype = vp
+    lib.mtr_file_stats.argtypes = [C.POINTER(PipelineStats)]
     lib.handle_one_file.argtypes = [C.c_char_p, C.c_int]
     lib.handle_one_file.restype = C.c_int
     lib.mtr_flush.restype = None
@@ -330,3 +332,29 @@ class Pipeline:
         s = PipelineStats()
         self.lib.mtr_pipeline_get_stats(self.h, C.byref(s))
         return {n: getattr(s, n) for n, _ in PipelineStats._fields_}
+
+
+def run_file(path: str, print_alignment: bool = False, manhattan: bool = True, min_match_ratio: float = 0.6):
+    """handle_one_file (mTR.h:126) on a FASTA file, exactly as main.c calls it; what the library prints to stdout is
+    captured through a temporary file.  Returns (number of reads, stdout bytes, counters of the call).  The process-wide
+    runtime behind the entry point is configured by the MTR_* environment at its first use (MTR_DEVICE, MTR_GPUS,
+    MTR_THREADS, MTR_BATCH_READS ...)."""
+    import sys
+    import tempfile
+    lib = load_library()
+    C.c_int.in_dll(lib, "Manhattan_Distance").value = 1 if manhattan else 0
+    C.c_float.in_dll(lib, "min_match_ratio").value = min_match_ratio
+    sys.stdout.flush()
+    saved = os.dup(1)
+    with tempfile.TemporaryFile() as tf:
+        os.dup2(tf.fileno(), 1)
+        try:
+            n = lib.handle_one_file(path.encode(), 1 if print_alignment else 0)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tf.seek(0)
+        out = tf.read()
+    s = PipelineStats()
+    lib.mtr_file_stats(C.byref(s))
+    return n, out, {k: getattr(s, k) for k, _ in PipelineStats._fields_}

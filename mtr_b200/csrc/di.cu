@@ -361,7 +361,18 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
                           const int64_t *pos_off, double *di, int32_t *end, int32_t *w_out)
 {
     if (!ctx) return MTR_EINVAL;
-    if (ctx->n_reads == 0) return MTR_OK;
+    return mtr_di_run_range(ctx, manhattan, stale, stale_off, pos_off, di, end, w_out, 0, ctx->n_reads);
+}
+
+// Reads [first, first + count) of the resident batch only; stale_off / pos_off and the output arrays are indexed as
+// for the whole batch, so a caller can sweep the batch in slices and start working on a slice while the next one is
+// still on the GPU.
+extern "C" int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
+                                const int64_t *pos_off, double *di, int32_t *end, int32_t *w_out, int first, int count)
+{
+    if (!ctx) return MTR_EINVAL;
+    if (first < 0 || count < 0 || first + count > ctx->n_reads) { mtr_set_error(ctx, "di_run: read range outside the resident batch"); return MTR_EINVAL; }
+    if (count == 0) return MTR_OK;
     if (!pos_off || !end || !w_out) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
     MTR_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->di) ctx->di = new DiState();
@@ -374,7 +385,8 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
         MTR_CUDA(ctx, cudaMemcpy(d.d_mt.p, mt.data(), mt.size(), cudaMemcpyHostToDevice));
         d.mt_ready = true;
     }
-    const int n = ctx->n_reads;
+    const int n = count;
+    const int64_t pos0 = pos_off[first], stale0 = (stale && stale_off) ? stale_off[first] : 0;
     std::vector<DiRead> reads(n);
     std::vector<DiPass> passes;
     std::vector<DiTask> tasks[3];
@@ -382,8 +394,8 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     int max_M = 0;
     for (int r = 0; r < n; r++) {
         DiRead &rd = reads[r];
-        const int L = ctx->len[r];
-        rd.word_off = ctx->word_off[r];
+        const int L = ctx->len[first + r];
+        rd.word_off = ctx->word_off[first + r];
         rd.len = L;
         rd.r = L < 1000 ? 100 : L / 10;                       // handle_one_read.c:194-202
         rd.N = L + 2 * rd.r;
@@ -391,9 +403,9 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
         rd.M = std::max(rd.M, rd.N);
         rd.code_off = code_total; code_total += (rd.M + 15) & ~15;
         rd.work_off = work_total; work_total += rd.N;
-        rd.pos_off = pos_off[r];
-        rd.stale_off = stale_off ? stale_off[r] : 0;
-        rd.nstale = (stale && stale_off) ? (int)(stale_off[r + 1] - stale_off[r]) : 0;
+        rd.pos_off = pos_off[first + r] - pos0;
+        rd.stale_off = (stale && stale_off) ? stale_off[first + r] - stale0 : 0;
+        rd.nstale = (stale && stale_off) ? (int)(stale_off[first + r + 1] - stale_off[first + r]) : 0;
         rd.pass_begin = (int)passes.size();
         max_M = std::max(max_M, rd.M);
         for (int k = 1; k <= 5; k += 2) {
@@ -414,8 +426,8 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
         }
         rd.npass = (int)passes.size() - rd.pass_begin;
     }
-    const long long total_pos = pos_off[n];
-    const long long nstale_total = (stale && stale_off) ? stale_off[n] : 0;
+    const long long total_pos = pos_off[first + n] - pos0;
+    const long long nstale_total = (stale && stale_off) ? stale_off[first + n] - stale0 : 0;
     MTR_CUDA(ctx, d.d_reads.reserve(sizeof(DiRead) * (size_t)n));
     MTR_CUDA(ctx, d.d_passes.reserve(sizeof(DiPass) * std::max<size_t>(passes.size(), 1)));
     MTR_CUDA(ctx, d.d_s1.reserve((size_t)code_total + 64));
@@ -434,7 +446,7 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     if (!passes.empty())
         MTR_CUDA(ctx, cudaMemcpyAsync(d.d_passes.p, passes.data(), sizeof(DiPass) * passes.size(), cudaMemcpyHostToDevice, s));
     if (nstale_total > 0)
-        MTR_CUDA(ctx, cudaMemcpyAsync(d.d_stale.p, stale, (size_t)nstale_total * 2, cudaMemcpyHostToDevice, s));
+        MTR_CUDA(ctx, cudaMemcpyAsync(d.d_stale.p, stale + stale0, (size_t)nstale_total * 2, cudaMemcpyHostToDevice, s));
     for (int t = 0; t < 3; t++) {
         MTR_CUDA(ctx, d.d_tasks[t].reserve(sizeof(DiTask) * std::max<size_t>(tasks[t].size(), 1)));
         if (!tasks[t].empty())
@@ -484,15 +496,18 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
     MTR_CUDA(ctx, cudaGetLastError());
     launches++;
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-    if (di) MTR_CUDA(ctx, cudaMemcpyAsync(di, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
-    MTR_CUDA(ctx, cudaMemcpyAsync(end, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
-    MTR_CUDA(ctx, cudaMemcpyAsync(w_out, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
+    // the copies are issued only when the kernels are done: a copy waiting for its stream at the head of a copy-engine
+    // queue would hold up the copies of every other context on the GPU
+    MTR_CUDA(ctx, mtr_sync(ctx));
+    if (di) MTR_CUDA(ctx, cudaMemcpyAsync(di + pos0, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(end + pos0, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(w_out + pos0, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, mtr_sync(ctx));
     float ms = 0;
     MTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
     ctx->stats.di_ms = ms;
     ctx->stats.di_position_passes = pp;
-    ctx->stats.di_bytes_in = ctx->n_words * 4 + nstale_total * 2;
+    ctx->stats.di_bytes_in = (ctx->word_off[first + n] - ctx->word_off[first]) * 4 + nstale_total * 2;
     ctx->stats.di_bytes_out = total_pos * (di ? 16 : 8);
     ctx->stats.launches = launches;
     return MTR_OK;

@@ -196,21 +196,38 @@ struct Counter {
 // ("no loop") is returned at once.  Both shortcuts leave every observable result unchanged.
 struct WalkMemo {
     struct Entry { uint32_t key, epoch; int next, seen; };
+    // open addressing; the table starts small enough to stay in L1/L2 (most windows touch a few hundred nodes) and
+    // doubles when a (window, k, direction) fills it beyond a half
     std::vector<Entry> tab;
-    uint32_t epoch = 0, mask = 0;
+    uint32_t epoch = 0, mask = 0, used = 0;
     int serial = 0;
     void reset()
     {
-        if (tab.empty()) { tab.assign(1u << 17, Entry{0, 0, 0, 0}); mask = (1u << 17) - 1; }
+        if (tab.empty()) { tab.assign(1u << 10, Entry{0, 0, 0, 0}); mask = (1u << 10) - 1; }
         if (++epoch == 0) { for (Entry &e : tab) e.epoch = 0; epoch = 1; }
         serial = 0;
+        used = 0;
+    }
+    void grow()
+    {
+        std::vector<Entry> old;
+        old.swap(tab);
+        tab.assign(old.size() * 2, Entry{0, 0, 0, 0});
+        mask = (uint32_t)tab.size() - 1;
+        for (const Entry &e : old) {
+            if (e.epoch != epoch) continue;
+            uint32_t h = (e.key * 2654435761u) & mask;
+            while (tab[h].epoch == epoch) h = (h + 1) & mask;
+            tab[h] = e;
+        }
     }
     Entry *slot(uint32_t node)
     {
+        if (2 * used > mask) grow();
         uint32_t h = (node * 2654435761u) & mask;
         for (;;) {
             Entry &e = tab[h];
-            if (e.epoch != epoch) { e.epoch = epoch; e.key = node; e.seen = -1; e.next = -1; return &e; }
+            if (e.epoch != epoch) { e.epoch = epoch; e.key = node; e.seen = -1; e.next = -1; used++; return &e; }
             if (e.key == node) return &e;
             h = (h + 1) & mask;
         }
@@ -865,7 +882,7 @@ struct ReadInput {
 }
 
 struct Engine {
-    mtr_ctx *ctx = nullptr;            // owns the resident reads; directional index; first lane of the last tier
+    mtr_ctx *ctx = nullptr;            // owns the resident reads; runs the directional index
     // DP dispatch lanes, grouped in tiers by the longest job (rows) a read queued this round: a batch is as slow as
     // its longest job (rows are sequential in the fill and in the traceback), and 7 of 8 read-rounds carry only jobs
     // of <= 256 rows.  Every lane is its own mtr_ctx (own streams and buffers) sharing the resident reads of ctx, so
@@ -880,6 +897,7 @@ struct Engine {
     std::vector<Worker> workers;
     double t_di = 0, t_dp = 0, t_rounds = 0;
     long long candidates = 0, rounds = 0, jobs_total = 0;
+    std::atomic<int> unfinished{0}, batch_total{0};     // reads of the current batch still running (handle_one_file's stagger gate)
 
     static int parse_list(const char *e, int *out, int cap)
     {
@@ -911,7 +929,6 @@ struct Engine {
         }
         if (const char *e = getenv("MTR_TIER_LANES")) { int v[kMaxTiers]; const int n = parse_list(e, v, kMaxTiers); for (int i = 0; i < n; i++) want[i] = std::max(1, v[i]); }
         if (const char *e = getenv("MTR_TIER_SPIN")) { int v[kMaxTiers]; const int n = parse_list(e, v, kMaxTiers); for (int i = 0; i < n; i++) tier_spin[i] = v[i] != 0; }
-        tier_lanes[n_tiers - 1].push_back(ctx);
         for (int t = 0; t < n_tiers; t++)
             while ((int)tier_lanes[t].size() < want[t]) {
                 mtr_ctx *c = nullptr;
@@ -929,6 +946,7 @@ struct Engine {
         for (int t = 0; t < n_tiers; t++)
             for (mtr_ctx *c : tier_lanes[t]) mtr_set_blocking_sync(c, tier_spin[t] ? 0 : 1);
         for (mtr_ctx *c : uf_lanes) mtr_set_blocking_sync(c, 1);
+        mtr_set_blocking_sync(ctx, 1);
         pool = new Pool(threads);
         workers.resize(pool->size());
     }
@@ -937,7 +955,7 @@ struct Engine {
         delete pool;
         h_end.release(); h_w.release();
         for (int t = 0; t < n_tiers; t++)
-            for (mtr_ctx *c : tier_lanes[t]) if (c != ctx) mtr_cuda_shutdown(c);
+            for (mtr_ctx *c : tier_lanes[t]) mtr_cuda_shutdown(c);
         for (mtr_ctx *c : uf_lanes) mtr_cuda_shutdown(c);
         mtr_cuda_shutdown(ctx);
     }
@@ -999,6 +1017,7 @@ struct Engine {
     {
         const int n = (int)in.size();
         std::string out;
+        batch_total.store(n); unfinished.store(n);
         if (n == 0) return out;
         const std::vector<int64_t> &pos_off = b_pos_off;
         const int64_t h2d_prepare = ps.h2d_bytes;
@@ -1010,17 +1029,6 @@ struct Engine {
         if (h_end.reserve(((size_t)pos_off[n] + 1) * 4) != cudaSuccess || h_w.reserve(((size_t)pos_off[n] + 1) * 4) != cudaSuccess) die(ctx, "cudaMallocHost", MTR_ENOMEM);
         int32_t *end = (int32_t *)h_end.p, *ww = (int32_t *)h_w.p;
         double t0 = now_s();
-        int rc = mtr_di_run(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), nullptr, end, ww);
-        if (rc) die(ctx, "mtr_di_run", rc);
-        t_di += now_s() - t0;
-        {
-            mtr_stats s;
-            mtr_get_stats(ctx, &s);
-            ps.di_kernel_ms = s.di_ms; ps.di_position_passes = s.di_position_passes; ps.launches += s.launches;
-            ps.di_bytes_in = s.di_bytes_in; ps.di_bytes_out = s.di_bytes_out;
-            ps.h2d_bytes += (int64_t)b_stale.size() * 2; ps.d2h_bytes += pos_off[n] * 8;
-            ps.di_wall_ms = (now_s() - t0) * 1e3;
-        }
         // ---- per-read state machines
         std::vector<ReadState> st(n);
         for (int r = 0; r < n; r++) {
@@ -1051,12 +1059,12 @@ struct Engine {
         typedef std::pair<int, int> ReadyKey;                     // (bases left, -index)
         std::priority_queue<ReadyKey> ready;
         auto push_ready = [&](int idx) { ready.push(ReadyKey(st[idx].L - st[idx].cursor, -idx)); };
-        for (int r = 0; r < n; r++) push_ready(r);
         int remaining = n;
         const bool prof = getenv("MTR_PROFILE") != nullptr;
         const int worker_nice = getenv("MTR_WORKER_NICE") ? atoi(getenv("MTR_WORKER_NICE")) : 10;
         std::vector<double> finish_at(prof ? n : 0, 0.0);
         double idle_s = 0, worker_cpu_s = 0, disp_cpu_s = 0;
+        int active_workers = 0;                                   // MTR_PROFILE timeline
         long long rows_hist_n[12] = {0}, rows_hist_cells[12] = {0}, readmax_hist[12] = {0};   // MTR_PROFILE: DP jobs by rows (<=32, 64, ...)
         double lane_fill_ms[kMaxTiers + 1] = {0}, lane_tb_ms[kMaxTiers + 1] = {0};
         auto worker_loop = [&](int tid) {
@@ -1079,6 +1087,7 @@ struct Engine {
                     idx = -ready.top().second;
                     ready.pop();
                 }
+                if (prof) { std::lock_guard<std::mutex> g(mu); active_workers++; }
                 ReadState &rs = st[idx];
                 RoundResults cur;
                 if (result_of[idx]) { cur.res = result_of[idx]->res.data(); cur.aux = result_of[idx]->aux.data(); }
@@ -1096,7 +1105,9 @@ struct Engine {
                 while (max_rows > tier_rows[lane]) lane++;
                 {
                     std::lock_guard<std::mutex> g(mu);
+                    if (prof) active_workers--;
                     if (prof && rs.phase == ReadState::FINISHED) finish_at[idx] = now_s() - t0;
+                    if (rs.phase == ReadState::FINISHED) unfinished.store(remaining - 1, std::memory_order_relaxed);
                     if (rs.phase == ReadState::FINISHED) { if (--remaining == 0) { cv_ready.notify_all(); cv_submit.notify_all(); } }
                     else {
                         if (!rs.jobs.empty()) { pending[idx]++; submitted[lane].push_back(idx); }
@@ -1119,8 +1130,17 @@ struct Engine {
                     std::unique_lock<std::mutex> g(mu);
                     cv_submit.wait(g, [&] { return !submitted[lane].empty() || remaining == 0; });
                     if (submitted[lane].empty()) return;
-                    batch.swap(submitted[lane]);
-                    submitted[lane].clear();
+                    // a long queue (the first round of a batch: every read arrives at once) is shared with the other
+                    // lanes of the tier instead of going out as one huge launch that everybody waits for
+                    std::vector<int> &q = submitted[lane];
+                    const size_t lanes_here = tier_lanes[lane].size();
+                    const size_t take = q.size() <= 96 ? q.size() : std::max<size_t>(64, (q.size() + lanes_here - 1) / lanes_here);
+                    if (take >= q.size()) { batch.swap(q); q.clear(); }
+                    else {
+                        batch.assign(q.begin(), q.begin() + take);
+                        q.erase(q.begin(), q.begin() + take);
+                        cv_submit.notify_all();                 // the rest is for a sibling lane
+                    }
                 }
                 jobs.clear(); units.clear();
                 long long aux_bytes = 0;
@@ -1224,6 +1244,47 @@ struct Engine {
                 batch.clear();
             }
         };
+        // The directional index sweeps the batch in slices on its own context; the reads of a slice join the ready
+        // queue as soon as their candidate ranges are back, so the host workers and the DP lanes start while the
+        // later slices are still on the GPU.
+        // (default: one slice.  Measured on B200: in 512-read slices next to the busy DP lanes the index kernels take 4x
+        // longer in total and the last reads enter 0.45 s late, which costs more than the 0.1 s of overlap gains.)
+        const int di_slice = std::max(1, getenv("MTR_DI_SLICE") ? atoi(getenv("MTR_DI_SLICE")) : (1 << 30));
+        std::thread di_thread([&] {
+            cudaSetDevice(ctx->device);
+            const double td0 = now_s();
+            for (int first = 0; first < n; first += di_slice) {
+                const int count = std::min(di_slice, n - first);
+                const int rc = mtr_di_run_range(ctx, Manhattan_Distance, b_stale.data(), b_stale_off.data(), pos_off.data(), nullptr, end, ww, first, count);
+                if (rc) die(ctx, "mtr_di_run", rc);
+                mtr_stats s;
+                mtr_get_stats(ctx, &s);
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    ps.di_kernel_ms += s.di_ms; ps.di_position_passes += s.di_position_passes; ps.launches += s.launches;
+                    ps.di_bytes_in += s.di_bytes_in; ps.di_bytes_out += s.di_bytes_out;
+                    for (int r = first; r < first + count; r++) push_ready(r);
+                }
+                cv_ready.notify_all();
+            }
+            std::lock_guard<std::mutex> g(mu);
+            ps.h2d_bytes += (int64_t)b_stale.size() * 2; ps.d2h_bytes += pos_off[n] * 8;
+            ps.di_wall_ms = (now_s() - td0) * 1e3;
+            t_di += now_s() - td0;
+        });
+        std::thread monitor;
+        if (prof)
+            monitor = std::thread([&] {
+                for (;;) {
+                    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+                    std::lock_guard<std::mutex> g(mu);
+                    if (remaining == 0) return;
+                    size_t q[kMaxTiers] = {0};
+                    for (int t = 0; t < n_tiers; t++) q[t] = submitted[t].size();
+                    fprintf(stderr, "[mtr timeline] t %.2f s: unfinished %5d  ready %5zu  workers busy %2d  queued for tiers %zu/%zu/%zu/%zu\n", now_s() - t0, remaining,
+                            ready.size(), active_workers, q[0], q[1], q[2], q[3]);
+                }
+            });
         std::vector<std::thread> dispatchers;
         for (int t = 0; t < n_tiers; t++)
             for (mtr_ctx *c : tier_lanes[t]) dispatchers.emplace_back([&, t, c] { dispatch_loop(t, c); });
@@ -1239,6 +1300,8 @@ struct Engine {
             host_ms += (now_s() - th0) * 1e3;
         }
         for (std::thread &t : dispatchers) t.join();
+        di_thread.join();
+        if (monitor.joinable()) monitor.join();
         t_rounds += now_s() - t0;
         t_dp += wdp_ms / 1e3;
         ps.rounds_wall_ms = (now_s() - t0) * 1e3;
@@ -1458,22 +1521,24 @@ struct FastaReader {
                 out.len = (int)out.bases.size();
                 return out.len > 0;
             }
-            for (int i = 0; s[i] && s[i] != '\n' && s[i] != '\r'; i++) {
-                uint8_t b;
-                switch (s[i]) {
-                case 'A': case 'a': b = 0; break;
-                case 'C': case 'c': b = 1; break;
-                case 'G': case 'g': b = 2; break;
-                case 'T': case 't': b = 3; break;
-                default: fprintf(stderr, "Invalid character: %c \n", s[i]); exit(EXIT_FAILURE);
-                }
-                out.bases.push_back(b);
-                if (kMaxLen <= (int)out.bases.size()) {
-                    fprintf(stderr, "fatal error: The length %d is tentatively at most %i.\nread ID = %s\nSet MAX_INPUT_LENGTH to a larger value",
-                            (int)out.bases.size(), kMaxLen, out.id.c_str());
-                    fprintf(stderr, "cannot allocate space for one of global variables in the heap.\n");
-                    exit(EXIT_FAILURE);
-                }
+            // one line of bases: table lookup into the tail of out.bases (same checks, in the same order, as the
+            // per-character loop of handle_one_file.c:169-188,240-262)
+            static const struct Lut { int8_t v[256]; Lut() { memset(v, -1, sizeof v); v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; } } lut;
+            const size_t m = strcspn(s, "\r\n");
+            const size_t old = out.bases.size();
+            const size_t lim = std::min(m, (size_t)kMaxLen - old);
+            out.bases.resize(old + lim);
+            uint8_t *dst = out.bases.data() + old;
+            for (size_t i = 0; i < lim; i++) {
+                const int8_t b = lut.v[(unsigned char)s[i]];
+                if (b < 0) { fprintf(stderr, "Invalid character: %c \n", s[i]); exit(EXIT_FAILURE); }
+                dst[i] = (uint8_t)b;
+            }
+            if (kMaxLen <= (int)out.bases.size()) {
+                fprintf(stderr, "fatal error: The length %d is tentatively at most %i.\nread ID = %s\nSet MAX_INPUT_LENGTH to a larger value",
+                        (int)out.bases.size(), kMaxLen, out.id.c_str());
+                fprintf(stderr, "cannot allocate space for one of global variables in the heap.\n");
+                exit(EXIT_FAILURE);
             }
         }
         eof = true;
@@ -1487,9 +1552,11 @@ struct FastaReader {
 // ---------------------------------------------------------------- process-wide state behind the C entry points
 struct Runtime {
     std::vector<Engine *> engines;     // per_gpu engines for every GPU: engine e works on GPU e / per_gpu
-    int per_gpu = 1;                   // batches in flight per GPU (MTR_INFLIGHT_PER_GPU).  Measured on B200 + 16 cores: a second
-                                       // batch in flight doubles the long-job lanes on the GPU and slows every round more
-                                       // than the overlap of ramp-down and ramp-up gains
+    int per_gpu = 2;                   // engines per GPU (MTR_INFLIGHT_PER_GPU): the next batch starts on the sibling engine when
+                                       // the running one is down to its last reads (stagger_frac), so the ramp-down of one batch
+                                       // (a few chains of dependent rounds, cores idle) overlaps the ramp-up of the next.  Two
+                                       // batches in full flight would only slow each other's long-job lanes down.
+    double stagger_frac = 0.12;        // MTR_STAGGER_FRAC
     StaleTracker stale;
     std::vector<ReadInput> pending;
     long long pending_bases = 0;
@@ -1497,6 +1564,17 @@ struct Runtime {
     int prep_threads = 4;
     long long batch_bases = 64LL << 20;
     int print_alignment = 0;
+    mtr_pipeline_stats totals = {};    // summed over the batches of handle_one_file / mtr_flush since the last mtr_file_stats
+
+    void account(const mtr_pipeline_stats &p)
+    {
+        totals.reads += p.reads; totals.bases += p.bases; totals.candidates += p.candidates; totals.rounds += p.rounds;
+        totals.rounds_fast += p.rounds_fast; totals.jobs += p.jobs; totals.wdp_calls += p.wdp_calls; totals.wdp_cells += p.wdp_cells;
+        totals.wdp_slot_cells += p.wdp_slot_cells; totals.wdp_dir_bytes += p.wdp_dir_bytes; totals.di_position_passes += p.di_position_passes;
+        totals.di_bytes_in += p.di_bytes_in; totals.di_bytes_out += p.di_bytes_out; totals.h2d_bytes += p.h2d_bytes; totals.d2h_bytes += p.d2h_bytes;
+        totals.launches += p.launches; totals.wdp_fill_ms += p.wdp_fill_ms; totals.wdp_tb_ms += p.wdp_tb_ms; totals.di_kernel_ms += p.di_kernel_ms;
+        totals.di_wall_ms += p.di_wall_ms; totals.rounds_wall_ms += p.rounds_wall_ms; totals.host_step_ms += p.host_step_ms; totals.wdp_wall_ms += p.wdp_wall_ms;
+    }
 
     Runtime()
     {
@@ -1509,6 +1587,7 @@ struct Runtime {
         int threads = (int)std::thread::hardware_concurrency();
         if (const char *e = getenv("MTR_THREADS")) threads = atoi(e);
         if (const char *e = getenv("MTR_INFLIGHT_PER_GPU")) per_gpu = std::max(1, atoi(e));
+        if (const char *e = getenv("MTR_STAGGER_FRAC")) stagger_frac = atof(e);
         prep_threads = std::max(1, std::min(8, threads / 2));
         threads = std::max(1, threads / ngpu);
         for (int g = 0; g < ngpu; g++)
@@ -1545,6 +1624,7 @@ extern "C" void mtr_flush(void)
     Runtime &rt = runtime();
     if (rt.pending.empty()) return;
     const std::string out = rt.engines[0]->process(rt.pending, rt.print_alignment);
+    rt.account(rt.engines[0]->ps);
     fwrite(out.data(), 1, out.size(), stdout);
     fflush(stdout);
     rt.pending.clear();
@@ -1580,11 +1660,12 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     FastaReader reader(inputFile);
     const int n_eng = (int)rt.engines.size();      // engines = batches in flight (per_gpu for every GPU)
     const int n_gpu = n_eng / rt.per_gpu;
-    struct Slot { std::thread th; std::string out; std::vector<ReadInput> reads; };
+    struct Slot { std::thread th; std::string out; std::vector<ReadInput> reads; Engine *eng = nullptr; };
     std::vector<Slot *> inflight;
     auto drain_front = [&]() {
         Slot *s = inflight.front();
         s->th.join();
+        rt.account(s->eng->ps);
         fwrite(s->out.data(), 1, s->out.size(), stdout);
         fflush(stdout);
         delete s;
@@ -1593,6 +1674,7 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     int n_reads = 0;
     long long batch_index = 0;
     bool more = true;
+    std::vector<Engine *> last_on_gpu(n_gpu, nullptr);
     while (more) {
         Slot *s = new Slot();
         long long bases = 0;
@@ -1607,14 +1689,32 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
         rt.stale.visit_batch(s->reads, 0, s->reads.size(), rt.prep_threads, nullptr);
         while ((int)inflight.size() >= n_eng) drain_front();
         // consecutive batches alternate between the GPUs first, then between the engines of one GPU
-        Engine *eng = rt.engines[(batch_index % n_gpu) * rt.per_gpu + (batch_index / n_gpu) % rt.per_gpu];
+        const int gpu = (int)(batch_index % n_gpu);
+        Engine *eng = rt.engines[gpu * rt.per_gpu + (batch_index / n_gpu) % rt.per_gpu];
         batch_index++;
+        // stagger: the batch before this one on the same GPU must be down to its last reads
+        if (Engine *prev = last_on_gpu[gpu])
+            while (prev != eng && prev->unfinished.load() > (int)(rt.stagger_frac * prev->batch_total.load()))
+                std::this_thread::sleep_for(std::chrono::microseconds(500));
+        last_on_gpu[gpu] = eng;
+        eng->batch_total.store((int)s->reads.size()); eng->unfinished.store((int)s->reads.size());
+        s->eng = eng;
         s->th = std::thread([eng, s, print_alignment] { s->out = eng->process(s->reads, print_alignment); });
         inflight.push_back(s);
     }
     while (!inflight.empty()) drain_front();
     publish_timers(rt);
     return n_reads;
+}
+
+// Counters of everything handle_one_file / handle_one_read + mtr_flush processed since the last call (then reset).
+extern "C" int mtr_file_stats(mtr_pipeline_stats *out)
+{
+    if (!out) return MTR_EINVAL;
+    Runtime &rt = runtime();
+    *out = rt.totals;
+    memset(&rt.totals, 0, sizeof rt.totals);
+    return MTR_OK;
 }
 
 // ================================================================ batch-level pipeline ABI (bench, tests, embedding)

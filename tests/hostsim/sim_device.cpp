@@ -118,17 +118,28 @@ int mtr_reads_share(mtr_ctx *dst, const mtr_ctx *src)
 }
 
 // fill_directional_index_with_end for every resident read, each with exactly the stale state the host passed in
+int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off, const int64_t *pos_off,
+                     double *di, int32_t *end, int32_t *w, int first, int count);
 int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off, const int64_t *pos_off,
                double *di, int32_t *end, int32_t *w)
 {
-    if (!ctx || !pos_off || !end || !w) return MTR_EINVAL;
+    if (!ctx) return MTR_EINVAL;
+    return mtr_di_run_range(ctx, manhattan, stale, stale_off, pos_off, di, end, w, 0, ctx->n_reads);
+}
+
+int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off, const int64_t *pos_off,
+                     double *di, int32_t *end, int32_t *w, int first, int count)
+{
+    if (!ctx || first < 0 || count < 0 || first + count > ctx->n_reads) return MTR_EINVAL;
+    if (count == 0) return MTR_OK;
+    if (!pos_off || !end || !w) return MTR_EINVAL;
     const SimReads &rd = *ctx->di->reads;
     mtro_ctx *o = ctx->di->get(manhattan ? 1 : 0);
     int *org = mtro_org_mut(o), *padded = mtro_padded_mut(o);
     std::vector<int> bases;
     std::vector<double> dtmp;
     long long passes = 0;
-    for (int r = 0; r < ctx->n_reads; r++) {
+    for (int r = first; r < first + count; r++) {
         const int L = rd.len[r];
         bases.resize(L + 2);
         for (int i = 0; i < L + 2; i++) bases[i] = rd.base(r, i);
