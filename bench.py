@@ -47,6 +47,30 @@ def step_reads(n, rank, step):
     return synth.long_reads(n, seed=1000 + 10007 * rank + step)[0]
 
 
+def _text_chunk(args):
+    n, rank, step, chunk, first_id = args
+    # chunk c of a step has its own seed: the workload is defined by (reads per step, rank, step), not by the pool size
+    return fasta_bytes(synth.long_reads(n, seed=1000 + 10007 * rank + step + 7919 * chunk)[0], first_id)
+
+
+def make_texts(R, rank, total, chunk_reads=4096):
+    """FASTA text of every step (R reads each), generated in chunks of chunk_reads reads by a process pool: chunk 0 of a
+    step is exactly step_reads(chunk_reads, rank, step), so a 4096-read step is the same workload as before."""
+    import multiprocessing as mp
+    jobs = []
+    for s in range(total):
+        for c, first in enumerate(range(0, R, chunk_reads)):
+            jobs.append((min(chunk_reads, R - first), rank, s, c, first))
+    procs = max(1, min(len(jobs), (os.cpu_count() or 1) // max(1, int(os.environ.get("WORLD_SIZE", "1")))))
+    if procs == 1 or len(jobs) == 1:
+        parts = [_text_chunk(j) for j in jobs]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            parts = pool.map(_text_chunk, jobs)
+    per = (R + chunk_reads - 1) // chunk_reads
+    return [b"".join(parts[s * per:(s + 1) * per]) for s in range(total)]
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -149,6 +173,9 @@ def main():
         reference_arm(a, rank, world)
         return
 
+    # synthetic input first: the process pool forks before CUDA is initialised
+    texts = make_texts(a.reads, rank, a.warmup + a.steps)
+
     import torch
     dist = None
     if world > 1:
@@ -184,7 +211,6 @@ def main():
 
     R = a.reads
     total = a.warmup + a.steps
-    texts = [fasta_bytes(step_reads(R, rank, s)) for s in range(total)]
     keys = ("reads", "bases", "candidates", "rounds", "rounds_fast", "rounds_uf", "uf_tasks", "uf_kernel_ms", "uf_wall_ms", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
             "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "wdp_fill_ms",
             "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms")
@@ -193,7 +219,7 @@ def main():
     # runs on its own pipeline object so that the ramp-down of one batch overlaps the ramp-up of the next.  Measured on
     # B200 + 16 host cores this loses (the long-job lanes of the two batches slow each other down), hence the default.
     inflight = max(1, a.inflight)
-    n_pipes = max(inflight, min(a.steps, 2 * inflight))       # resident loop: this many batches are resident at once
+    n_pipes = 1 if inflight == 1 else max(inflight, min(a.steps, 2 * inflight))   # batches resident at once in the resident loop
     pipes = [capi.Pipeline(local_rank, threads=threads) for _ in range(n_pipes)]
 
     def run_concurrently(work):

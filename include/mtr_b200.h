@@ -42,6 +42,10 @@ int  mtr_device_count(void);
 /* on != 0: host threads waiting for this context sleep (cudaEventBlockingSync) instead of spinning; worth it for
  * contexts whose calls take milliseconds (adds tens of microseconds of wake-up latency per call). Default off. */
 int  mtr_set_blocking_sync(mtr_ctx *ctx, int on);
+/* CUDA stream priority of everything this context launches: level 0 = lowest (bulk work), higher = more urgent (clamped
+ * to the device's range).  The pipeline gives its short-job DP lanes a higher level than the long-job lanes and the
+ * directional index.  Call before the context has work in flight. */
+int  mtr_set_priority(mtr_ctx *ctx, int level);
 
 /* ------------------------------------------------------------------ reads (orgInputString, mTR.h:65) */
 /* A batch of reads, 2-bit packed (A,C,G,T = 0..3; base b of a read is bits [2*(b%16), 2*(b%16)+2) of word

@@ -18,7 +18,7 @@ TB_COUNTS, TB_CONSENSUS, TB_PATH = 0, 1, 2
 
 # every symbol include/mtr_b200.h declares (tests check that the library exports all of them)
 ABI_FUNCTIONS = [
-    "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_reads_upload", "mtr_reads_share",
+    "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_set_priority", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_wdp_set_fused_traceback", "mtr_di_run", "mtr_di_run_range", "mtr_get_stats",
     "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_load_fasta_shard",
     "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush", "mtr_file_stats",
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
     lib.mtr_wdp_launch.argtypes = [vp]
     lib.mtr_wdp_download.argtypes = [vp, vp, vp, i64]
     lib.mtr_wdp_set_fused_traceback.argtypes = [vp, C.c_int]
+    lib.mtr_set_priority.argtypes = [vp, C.c_int]
     lib.mtr_di_run.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.mtr_di_run_range.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
     lib.mtr_get_stats.argtypes = [vp, C.POINTER(Stats)]

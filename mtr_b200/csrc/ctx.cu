@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <time.h>
 #include "mtr_internal.h"
@@ -132,6 +133,29 @@ extern "C" int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int6
     ctx->n_reads = n_reads;
     ctx->n_words = nw;
     ctx->wdp.uploaded = false;
+    return MTR_OK;
+}
+
+// Recreates the context's streams with a CUDA stream priority: level 0 = lowest (bulk work: directional index, long DP
+// batches), higher levels = more urgent, clamped to what the device offers.  Pending thread blocks of a higher-priority
+// stream are placed before those of lower-priority streams, so a 0.1 ms latency-class batch does not queue behind the
+// thousands of blocks of a bulk kernel.  Call it before the context has work in flight.
+extern "C" int mtr_set_priority(mtr_ctx *ctx, int level)
+{
+    if (!ctx) return MTR_EINVAL;
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    int least = 0, greatest = 0;
+    MTR_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));     // numerically lower = higher priority
+    int prio = least - std::max(0, level);
+    if (prio < greatest) prio = greatest;
+    MTR_CUDA(ctx, cudaStreamSynchronize(ctx->main_stream));
+    MTR_CUDA(ctx, cudaStreamDestroy(ctx->main_stream));
+    MTR_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->main_stream, cudaStreamNonBlocking, prio));
+    for (int k = 0; k < WDP_NCLASS; k++) {
+        MTR_CUDA(ctx, cudaStreamSynchronize(ctx->stream[k]));
+        MTR_CUDA(ctx, cudaStreamDestroy(ctx->stream[k]));
+        MTR_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream[k], cudaStreamNonBlocking, prio));
+    }
     return MTR_OK;
 }
 

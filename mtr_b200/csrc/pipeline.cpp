@@ -651,25 +651,33 @@ void advance_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk, const R
         return;
     }
     if (ch.stage == Chain::SEARCH_WAIT) {
-        Rec best;                                           // max_rr of search_De_Bruijn_graph, starts cleared
+        // max_rr of search_De_Bruijn_graph starts cleared; wrap_around_DP (wrap_around_DP.c:357-429) keeps the strictly
+        // better of the two penalty sets of a direction.  Everything the comparisons need is in the DP results, so the
+        // record is materialised once, for the winner (a cleared record never qualifies: its Num_freq_unit is -1).
+        int best_d = -1, best_s = -1;
         float best_ratio = -1;
         for (int d = 0; d < 2; d++) {
             if (!ch.dir_found[d]) continue;
-            // wrap_around_DP (wrap_around_DP.c:357-429): keep the strictly better of the two penalty sets
-            Rec pick;
+            int pick_s = -1;
             float pick_ratio = -1;
             for (int s = 0; s < 2; s++) {
-                Rec t = ch.dir[d];
-                apply_dp(t, qs, res[2 * ch.dir_job[d] + s], kSearchParams[s][0], kSearchParams[s][1], kSearchParams[s][2]);
-                const float ratio = t.ratio();
-                if (pick_ratio < ratio) { pick = t; pick_ratio = ratio; }
+                const mtr_wdp_result &r = res[2 * ch.dir_job[d] + s];
+                const float ratio = (float)r.n_match / (r.n_match + r.n_mismatch + r.n_ins + r.n_del);
+                if (pick_ratio < ratio) { pick_s = s; pick_ratio = ratio; }
             }
-            const float ratio = pick.ratio();
-            if (best_ratio < ratio && min_match_ratio <= ratio && 5 < pick.units && 2 <= pick.period && pick.period < kMaxPeriod) {
-                best_ratio = ratio; best = pick;
+            if (pick_s < 0) continue;
+            const int period = ch.dir[d].period;
+            const int units = res[2 * ch.dir_job[d] + pick_s].n_scanned / period;
+            if (best_ratio < pick_ratio && min_match_ratio <= pick_ratio && 5 < units && 2 <= period && period < kMaxPeriod) {
+                best_ratio = pick_ratio; best_d = d; best_s = pick_s;
             }
         }
-        ch.rr = best;
+        if (best_d >= 0) {
+            ch.rr = std::move(ch.dir[best_d]);
+            apply_dp(ch.rr, qs, res[2 * ch.dir_job[best_d] + best_s], kSearchParams[best_s][0], kSearchParams[best_s][1], kSearchParams[best_s][2]);
+        } else {
+            ch.rr.clear();
+        }
         if (!ch.found_last) { ch.rr.clear(); ch.stage = Chain::DONE; return; }            // Q4
         if ((long long)ch.rr.period * (qe - qs + 1) > kWrapCap) {
             fprintf(stderr, "You need to increse the value of WrapDPsize.\n");
@@ -947,6 +955,10 @@ struct Engine {
             for (mtr_ctx *c : tier_lanes[t]) mtr_set_blocking_sync(c, tier_spin[t] ? 0 : 1);
         for (mtr_ctx *c : uf_lanes) mtr_set_blocking_sync(c, 1);
         mtr_set_blocking_sync(ctx, 1);
+        // short-job lanes outrank long-job lanes, which outrank the directional index (MTR_TIER_PRIO=0: all equal)
+        if (!getenv("MTR_TIER_PRIO") || atoi(getenv("MTR_TIER_PRIO")) != 0)
+            for (int t = 0; t < n_tiers; t++)
+                for (mtr_ctx *c : tier_lanes[t]) mtr_set_priority(c, n_tiers - t);
         pool = new Pool(threads);
         workers.resize(pool->size());
     }

@@ -87,6 +87,7 @@ void mtr_cuda_shutdown(mtr_ctx *ctx)
     delete ctx;
 }
 
+int mtr_set_priority(mtr_ctx *ctx, int) { return ctx ? MTR_OK : MTR_EINVAL; }
 int mtr_set_blocking_sync(mtr_ctx *ctx, int on) { if (!ctx) return MTR_EINVAL; ctx->blocking_sync = on != 0; return MTR_OK; }
 
 int mtr_reads_upload(mtr_ctx *ctx, const uint32_t *packed, const int64_t *word_off, const int32_t *len, int n_reads)

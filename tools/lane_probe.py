@@ -55,3 +55,27 @@ for tiny_fused in (True, False):
         th = threading.Thread(target=hog, args=(fused,)); th.start(); time.sleep(0.2)
         probe("tiny fused=%s, long lane fused=%s" % (tiny_fused, fused))
         stop = True; th.join()
+
+
+# ---- the directional index of 1024 reads looping on a third context next to the DP lanes
+print("--- DP lane latency next to a running directional index", flush=True)
+many = [synth.long_reads(256, seed=90)[0][i % 256] for i in range(1024)]
+pk, wo, ln = capi.pack_reads(many, [(0, 0)] * len(many))
+d = capi.Context(0)
+d.upload_reads(pk, wo, ln)
+def di_hog():
+    n = 0; t0 = time.perf_counter()
+    while not stop:
+        d.di_run(True); n += 1
+    print("   directional index: %d runs of 1024 reads, %.1f ms each" % (n, (time.perf_counter() - t0) / max(n, 1) * 1e3), flush=True)
+b.wdp_set_fused_traceback(True)
+for prio in (0, 3):
+    b.lib.mtr_set_priority(b.h, prio)
+    stop = False
+    th = threading.Thread(target=di_hog); th.start(); time.sleep(0.3)
+    probe("tiny batch, DI running, DP stream priority %d" % prio)
+    t0 = time.perf_counter(); k = 0
+    while time.perf_counter() - t0 < 0.5:
+        b.wdp_run(long_[0], long_[1]); k += 1
+    print("   long batch next to DI: %.2f ms each" % ((time.perf_counter() - t0) / k * 1e3), flush=True)
+    stop = True; th.join()
