@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- reads/s and wrap-around-DP GCUPS of the mTR hot path on B200, beside the reference on the host CPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference] [--quick] [--inflight B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One step = one batch of R synthetic C5 reads (BASELINE.json configs[4]: 10-20 kb reads carrying one tandem repeat,
@@ -10,8 +10,9 @@ finder, wrap-around DP, chaining, formatted TSV.  Every rank runs the same step 
 scaling, no collective on the data path; torch.distributed is used only for the barrier and the max over ranks).
 
   value : reads/s with the batch already 2-bit packed and resident in HBM when the clock starts (mtr_pipeline_run)
-  e2e   : reads/s from FASTA text in host memory to the output text in host memory (mtr_pipeline_load_fasta +
-          mtr_pipeline_run): parse, pack, H2D, every per-round H2D/D2H, formatting
+  e2e   : reads/s of handle_one_file() -- the reference's own entry point (mTR.h:126) -- on a FASTA file (tmpfs) holding
+          the K timed batches, stdout captured: parse, stale-state tracking, pack, H2D, every per-round H2D/D2H, chaining,
+          formatting, ordered output; byte counts from mtr_file_stats
   roofline     : the dominant kernel (K3 wrap-around DP fill): algorithmic cell updates / CUDA-event kernel time
                  against the integer-ALU issue ceiling measured on this GPU by mtr_alu_probe
   roofline_di  : the directional-index kernels against measured HBM bandwidth (reported for completeness: that

@@ -143,3 +143,24 @@ lib.mtr_flush()
     p = subprocess.run([sys.executable, "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert p.returncode == 0, p.stderr.decode()[-1500:]
     assert hashlib.md5(p.stdout).hexdigest() == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
+
+
+def test_handle_one_file_through_ctypes_with_counters(synthetic_dir):
+    """capi.run_file: handle_one_file exactly as main.c calls it, stdout captured, plus mtr_file_stats (child process:
+    the entry point's runtime is process-wide and reads MTR_* once)."""
+    import sys
+    path = os.path.join(synthetic_dir, "mixed.fa")
+    script = r'''
+import hashlib, json, sys
+sys.path.insert(0, %r)
+from mtr_b200 import capi
+n, out, st = capi.run_file(%r)
+print(json.dumps({"n": n, "md5": hashlib.md5(out).hexdigest(), "reads": st["reads"], "launches": st["launches"], "cells": st["wdp_cells"], "d2h": st["d2h_bytes"]}))
+''' % (ROOT, path)
+    for env in ({"MTR_BATCH_READS": "4"}, {"MTR_BATCH_READS": "3", "MTR_STAGGER_FRAC": "0.9", "MTR_TIER_PRIO": "0"}):
+        e = dict(os.environ); e.update(env)
+        p = subprocess.run([sys.executable, "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+        assert p.returncode == 0, p.stderr.decode()[-1500:]
+        r = json.loads(p.stdout.decode().strip().splitlines()[-1])
+        assert r["md5"] == DIGESTS["synthetic"]["mixed"]["default"]["md5"], env
+        assert r["n"] == r["reads"] > 0 and r["launches"] > 0 and r["cells"] > 0 and r["d2h"] > 0
