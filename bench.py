@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference] [--quick] [--inflight B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one batch of R synthetic C5 reads (BASELINE.json configs[4]: 10-20 kb reads carrying one tandem repeat,
+One step = one batch of R (default 8192) synthetic C5 reads (BASELINE.json configs[4]: 10-20 kb reads carrying one tandem repeat,
 unit 2-500 bp, 5-15 % sub/ins/del noise) through the whole per-read path: directional index, candidate loop, unit
 finder, wrap-around DP, chaining, formatted TSV.  Every rank runs the same step shape on its own reads (weak
 scaling, no collective on the data path; torch.distributed is used only for the barrier and the max over ranks).
@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "4096")), help="reads per step per GPU")
+    ap.add_argument("--reads", type=int, default=int(os.environ.get("MTR_BENCH_READS", "8192")), help="reads per step per GPU")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = 8 x cores)")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("MTR_BENCH_INFLIGHT", "1")), help="batches in flight per GPU (pipelines run concurrently)")
@@ -287,17 +287,29 @@ def main():
             p.close()
         return
 
+    # ---- K3 alone on exactly one step's DP jobs, replayed as a single batch (operands resident in HBM)
+    for p in pipes[1:]:
+        p.close()
+    alone = alone_fused = None
+    if rank == 0:
+        pipes[0].log_jobs(True)
+        pipes[0].load_fasta(texts[a.warmup])
+        pipes[0].run()
+        pipes[0].log_jobs(False)
+        alone = pipes[0].replay_logged_jobs(iters=3, fused=False)
+        alone_fused = pipes[0].replay_logged_jobs(iters=3, fused=True)
+    pipes[0].close()
+
     # ---- end to end through the reference's own entry point: handle_one_file(path) (mTR.h:126) on a FASTA file holding
     # the K timed batches, exactly as main.c calls it -- parse, stale-state tracking, 2-bit pack, H2D, directional index,
     # every per-round H2D / D2H, chaining, formatting, ordered stdout.  The entry point owns its engines (two per GPU:
     # the next batch starts when the running one is down to its last reads); the pipelines above are closed first.
-    for p in pipes[1:]:
-        p.close()
     shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
     e2e_path = os.path.join(shm, "mtr_bench_rank%d_%d.fa" % (rank, os.getpid()))
     os.environ.setdefault("MTR_DEVICE", str(local_rank))
     os.environ.setdefault("MTR_THREADS", str(threads))
     os.environ.setdefault("MTR_BATCH_READS", str(R))
+    os.environ.setdefault("MTR_BATCH_MBASES", str(max(64, (R * 21000) >> 20)))      # a batch of R reads of <= 20 kb must not be cut by the base cap
     with open(e2e_path, "wb") as f:                      # warm-up file: one batch per engine
         f.write(texts[0]); f.write(texts[0])
     capi.run_file(e2e_path)
@@ -314,18 +326,6 @@ def main():
     h2d, d2h = fst["h2d_bytes"], fst["d2h_bytes"]
     e2e_md5 = hashlib.md5(out_file).hexdigest()
     clk = clocks.stop()
-    pipe = pipes[0]
-
-    # ---- K3 alone on exactly one step's DP jobs, replayed as a single batch (operands resident in HBM)
-    alone = alone_fused = None
-    if rank == 0:
-        pipe.log_jobs(True)
-        pipe.load_fasta(texts[a.warmup])
-        pipe.run()
-        pipe.log_jobs(False)
-        alone = pipe.replay_logged_jobs(iters=3, fused=False)
-        alone_fused = pipe.replay_logged_jobs(iters=3, fused=True)
-    pipe.close()
 
     reads_all = sum_over_ranks(R * a.steps)
     cells_all = sum_over_ranks(acc["wdp_cells"])

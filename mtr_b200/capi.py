@@ -307,7 +307,7 @@ class Pipeline:
     def log_jobs(self, on: bool = True):
         self.lib.mtr_pipeline_log_jobs(self.h, 1 if on else 0)
 
-    def replay_logged_jobs(self, iters: int = 2, fused: bool = True) -> dict:
+    def replay_logged_jobs(self, iters: int = 2, fused: bool = True, max_jobs: int = 1_500_000) -> dict:
         """Replays the DP jobs logged by the last run() as ONE batch on the pipeline's own context (K3 alone,
         operands resident); returns the library's kernel statistics of the last replay.  fused=False: fill kernels
         and traceback kernel launched separately, so wdp_fill_ms is the fill alone."""
@@ -317,6 +317,11 @@ class Pipeline:
             raise MtrError("no logged jobs")
         ctx = self.lib.mtr_pipeline_ctx(self.h)
         self.lib.mtr_wdp_set_fused_traceback(ctx, 1 if fused else 0)
+        if n.value > max_jobs:        # bounded (the direction matrices of the replay must fit HBM): every stride-th job
+            stride = -(-int(n.value) // max_jobs)
+            all_jobs = np.frombuffer((C.c_char * (int(n.value) * JOB_DTYPE.itemsize)).from_address(jobs.value), dtype=JOB_DTYPE)
+            self._replay_subset = np.ascontiguousarray(all_jobs[::stride])
+            jobs, n = C.c_void_p(self._replay_subset.ctypes.data), C.c_int64(len(self._replay_subset))
         rc = self.lib.mtr_wdp_upload(ctx, jobs, int(n.value), units, ul.value, 0)
         if rc != 0:
             raise MtrError("replay upload failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))

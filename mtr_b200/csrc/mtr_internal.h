@@ -34,6 +34,15 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    cudaError_t reserve_exact(size_t bytes)     // no extra headroom: the caller chose the size
+    {
+        if (borrowed) { p = nullptr; cap = 0; borrowed = false; }
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
     void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
 };
 

@@ -1572,9 +1572,9 @@ struct Runtime {
     StaleTracker stale;
     std::vector<ReadInput> pending;
     long long pending_bases = 0;
-    int batch_reads = 4096;
+    int batch_reads = 8192;            // bigger batches amortise the ramp-up / ramp-down of a batch
     int prep_threads = 4;
-    long long batch_bases = 64LL << 20;
+    long long batch_bases = 192LL << 20;
     int print_alignment = 0;
     mtr_pipeline_stats totals = {};    // summed over the batches of handle_one_file / mtr_flush since the last mtr_file_stats
 

@@ -716,7 +716,8 @@ int wdp_upload_impl(mtr_ctx *ctx, const mtr_wdp_job *jobs, int n_jobs, const uin
     MTR_CUDA(ctx, w.d_tasks.reserve(in_bytes));
     // the direction matrices of a batch run to gigabytes and every regrowth is a device-wide cudaFree + cudaMalloc:
     // grow in big steps so that a context reallocates a handful of times in its life
-    if ((size_t)w.dir_total > w.d_dirs.cap) MTR_CUDA(ctx, w.d_dirs.reserve((size_t)std::max<long long>(w.dir_total + w.dir_total / 2, 64 << 20)));
+    if ((size_t)w.dir_total > w.d_dirs.cap)
+        MTR_CUDA(ctx, w.d_dirs.reserve_exact((size_t)std::max<long long>(w.dir_total + std::min<long long>(w.dir_total / 2, 2LL << 30), 64 << 20)));
     MTR_CUDA(ctx, w.d_results.reserve(sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1)));
     MTR_CUDA(ctx, w.h_results.reserve(sizeof(mtr_wdp_result) * (size_t)std::max(w.n_results, 1)));
     MTR_CUDA(ctx, w.d_aux.reserve((size_t)std::max<int64_t>(aux_bytes, 16)));
