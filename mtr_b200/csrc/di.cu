@@ -126,8 +126,10 @@ di_codes(const DiRead *__restrict__ reads, int n_reads, const uint32_t *__restri
 }
 
 // ---------------------------------------------------------------- K2: sliding two-window distance stream
-// One thread per chunk; the two histograms live in shared memory, bin-major so that a warp touching the
-// same bin is conflict-free.
+// One thread per chunk; the histograms live in shared memory, bin-major so that a warp touching the same bin is
+// conflict-free.  Pearson needs both windows' histograms (sum HA^2, sum HB^2, sum HA*HB); the Manhattan distance
+// sum |HA - HB| only needs their difference, so that mode keeps ONE table HA - HB per thread: half the shared-memory
+// traffic per position and twice the threads per SM (the k = 5 passes are bound by shared-memory capacity).
 template <int K, bool MANHATTAN, int T, typename CodeT>
 __global__ void __launch_bounds__(T)
 di_slide(const DiTask *__restrict__ tasks, int ntasks, const DiRead *__restrict__ reads,
@@ -136,8 +138,8 @@ di_slide(const DiTask *__restrict__ tasks, int ntasks, const DiRead *__restrict_
 {
     constexpr int BINS = K == 1 ? 4 : (K == 3 ? 64 : 1024);
     extern __shared__ short sh[];
-    short *HA = sh + threadIdx.x;                   // HA[bin * T]
-    short *HB = sh + BINS * T + threadIdx.x;
+    short *HA = sh + threadIdx.x;                   // HA[bin * T]   (Manhattan: HA - HB)
+    short *HB = sh + (MANHATTAN ? 0 : BINS * T) + threadIdx.x;
     const int tid = blockIdx.x * T + threadIdx.x;
     if (tid >= ntasks) return;
     const DiTask tk = tasks[tid];
@@ -145,21 +147,31 @@ di_slide(const DiTask *__restrict__ tasks, int ntasks, const DiRead *__restrict_
     const DiPass ps = passes[rd.pass_begin + tk.pass];
     const CodeT *S = codes + rd.code_off;
     const int w = ps.w;
-    for (int b = 0; b < BINS; b++) { HA[b * T] = 0; HB[b * T] = 0; }
+    for (int b = 0; b < BINS; b++) { HA[b * T] = 0; if (!MANHATTAN) HB[b * T] = 0; }
     // exact integer sums
     int D = 0;                                       // sum |HA - HB|
     long long SA = 0, SB = 0, IP = 0;                // sum HA^2, sum HB^2, sum HA*HB
     auto bumpA = [&](int bin, int delta) {
-        const int a = HA[bin * T], b = HB[bin * T];
-        if (MANHATTAN) D += abs(a + delta - b) - abs(a - b);
-        else { SA += 2 * a * delta + 1; IP += (long long)delta * b; }
-        HA[bin * T] = (short)(a + delta);
+        if (MANHATTAN) {
+            const int d = HA[bin * T];
+            D += abs(d + delta) - abs(d);
+            HA[bin * T] = (short)(d + delta);
+        } else {
+            const int a = HA[bin * T], b = HB[bin * T];
+            SA += 2 * a * delta + 1; IP += (long long)delta * b;
+            HA[bin * T] = (short)(a + delta);
+        }
     };
     auto bumpB = [&](int bin, int delta) {
-        const int a = HA[bin * T], b = HB[bin * T];
-        if (MANHATTAN) D += abs(a - b - delta) - abs(a - b);
-        else { SB += 2 * b * delta + 1; IP += (long long)delta * a; }
-        HB[bin * T] = (short)(b + delta);
+        if (MANHATTAN) {
+            const int d = HA[bin * T];
+            D += abs(d - delta) - abs(d);
+            HA[bin * T] = (short)(d - delta);
+        } else {
+            const int a = HA[bin * T], b = HB[bin * T];
+            SB += 2 * b * delta + 1; IP += (long long)delta * a;
+            HB[bin * T] = (short)(b + delta);
+        }
     };
     const int q0 = tk.q0;
     for (int t = 0; t < w; t++) { bumpA(S[q0 + t], +1); bumpB(S[q0 + w + t], +1); }
@@ -465,23 +477,25 @@ extern "C" int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *sta
     const DiPass *dp = (const DiPass *)d.d_passes.p;
     int *si = (int *)d.d_stream.p;
     double *sd = (double *)d.d_stream.p;
-#define SLIDE(K, T, CODET, CODES, IDX)                                                                         \
+#define SLIDE(K, TM, TP, CODET, CODES, IDX)                                                                    \
     if (!tasks[IDX].empty()) {                                                                                 \
         const int nt = (int)tasks[IDX].size();                                                                 \
-        const size_t smem = (size_t)2 * (K == 1 ? 4 : (K == 3 ? 64 : 1024)) * T * sizeof(short);               \
+        constexpr int BINS_ = (K == 1 ? 4 : (K == 3 ? 64 : 1024));                                             \
         if (manhattan) {                                                                                       \
-            MTR_CUDA(ctx, cudaFuncSetAttribute(di_slide<K, true, T, CODET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            di_slide<K, true, T, CODET><<<(nt + T - 1) / T, T, smem, s>>>((const DiTask *)d.d_tasks[IDX].p, nt, dr, dp, (const CODET *)CODES, si, sd); \
+            const size_t smem = (size_t)BINS_ * TM * sizeof(short);                                            \
+            MTR_CUDA(ctx, cudaFuncSetAttribute(di_slide<K, true, TM, CODET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            di_slide<K, true, TM, CODET><<<(nt + TM - 1) / TM, TM, smem, s>>>((const DiTask *)d.d_tasks[IDX].p, nt, dr, dp, (const CODET *)CODES, si, sd); \
         } else {                                                                                               \
-            MTR_CUDA(ctx, cudaFuncSetAttribute(di_slide<K, false, T, CODET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            di_slide<K, false, T, CODET><<<(nt + T - 1) / T, T, smem, s>>>((const DiTask *)d.d_tasks[IDX].p, nt, dr, dp, (const CODET *)CODES, si, sd); \
+            const size_t smem = (size_t)2 * BINS_ * TP * sizeof(short);                                        \
+            MTR_CUDA(ctx, cudaFuncSetAttribute(di_slide<K, false, TP, CODET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            di_slide<K, false, TP, CODET><<<(nt + TP - 1) / TP, TP, smem, s>>>((const DiTask *)d.d_tasks[IDX].p, nt, dr, dp, (const CODET *)CODES, si, sd); \
         }                                                                                                      \
         MTR_CUDA(ctx, cudaGetLastError());                                                                     \
         launches++;                                                                                            \
     }
-    SLIDE(1, 128, uint8_t, d.d_s1.p, 0)
-    SLIDE(3, 128, uint8_t, d.d_s3.p, 1)
-    SLIDE(5, 48, uint16_t, d.d_s5.p, 2)
+    SLIDE(1, 128, 128, uint8_t, d.d_s1.p, 0)
+    SLIDE(3, 128, 128, uint8_t, d.d_s3.p, 1)
+    SLIDE(5, 96, 48, uint16_t, d.d_s5.p, 2)
 #undef SLIDE
     if (manhattan)
         di_merge<true><<<(n * 32 + 127) / 128, 128, 0, s>>>(dr, n, dp, si, sd, (double *)d.d_work_di.p, (int *)d.d_work_end.p, (int *)d.d_work_w.p,
