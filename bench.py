@@ -310,8 +310,9 @@ def main():
     os.environ.setdefault("MTR_THREADS", str(threads))
     os.environ.setdefault("MTR_BATCH_READS", str(R))
     os.environ.setdefault("MTR_BATCH_MBASES", str(max(64, (R * 21000) >> 20)))      # a batch of R reads of <= 20 kb must not be cut by the base cap
-    with open(e2e_path, "wb") as f:                      # warm-up file: one batch per engine
-        f.write(texts[0]); f.write(texts[0])
+    with open(e2e_path, "wb") as f:                      # warm-up file: two batches per engine (buffers grown, pinned memory mapped)
+        for s in range(4):
+            f.write(texts[s % max(a.warmup, 1)])
     capi.run_file(e2e_path)
     with open(e2e_path, "wb") as f:
         for s in timed:

@@ -1672,12 +1672,14 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     FastaReader reader(inputFile);
     const int n_eng = (int)rt.engines.size();      // engines = batches in flight (per_gpu for every GPU)
     const int n_gpu = n_eng / rt.per_gpu;
+    const double t_file0 = now_s();
     struct Slot { std::thread th; std::string out; std::vector<ReadInput> reads; Engine *eng = nullptr; };
     std::vector<Slot *> inflight;
     auto drain_front = [&]() {
         Slot *s = inflight.front();
         s->th.join();
         rt.account(s->eng->ps);
+        if (getenv("MTR_PROFILE")) fprintf(stderr, "[mtr profile] batch of %zu reads done at %.3f s (di %.0f ms, rounds %.0f ms)\n", s->reads.size(), now_s() - t_file0, s->eng->ps.di_wall_ms, s->eng->ps.rounds_wall_ms);
         fwrite(s->out.data(), 1, s->out.size(), stdout);
         fflush(stdout);
         delete s;
@@ -1711,6 +1713,7 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
         last_on_gpu[gpu] = eng;
         eng->batch_total.store((int)s->reads.size()); eng->unfinished.store((int)s->reads.size());
         s->eng = eng;
+        if (getenv("MTR_PROFILE")) fprintf(stderr, "[mtr profile] batch %lld (%zu reads) starts on engine %d at %.3f s\n", batch_index - 1, s->reads.size(), (int)(eng == rt.engines[gpu * rt.per_gpu] ? 0 : 1), now_s() - t_file0);
         s->th = std::thread([eng, s, print_alignment] { s->out = eng->process(s->reads, print_alignment); });
         inflight.push_back(s);
     }
