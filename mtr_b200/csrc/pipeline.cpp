@@ -906,6 +906,8 @@ struct Engine {
     double t_di = 0, t_dp = 0, t_rounds = 0;
     long long candidates = 0, rounds = 0, jobs_total = 0;
     std::atomic<int> unfinished{0}, batch_total{0};     // reads of the current batch still running (handle_one_file's stagger gate)
+    std::atomic<long long> bases_left{0}, bases_total{0};   // ... and bases its reads have not scanned yet (reads all finish together
+                                                            // under most-work-left-first scheduling; the scan position is the progress)
 
     static int parse_list(const char *e, int *out, int cap)
     {
@@ -1030,6 +1032,7 @@ struct Engine {
         const int n = (int)in.size();
         std::string out;
         batch_total.store(n); unfinished.store(n);
+        { long long tb = 0; for (const ReadInput &r : in) tb += r.len; bases_total.store(tb); bases_left.store(tb); }
         if (n == 0) return out;
         const std::vector<int64_t> &pos_off = b_pos_off;
         const int64_t h2d_prepare = ps.h2d_bytes;
@@ -1108,7 +1111,9 @@ struct Engine {
                     cur.uf_scores = uf_result_of[idx]->scores.data();
                 }
                 const double ts = now_s();
+                const int left0 = rs.L - rs.cursor;
                 step_read(rs, workers[tid], cur, print_alignment);
+                bases_left.fetch_sub(left0 - (rs.phase == ReadState::FINISHED ? 0 : rs.L - rs.cursor), std::memory_order_relaxed);
                 workers[tid].t_step += now_s() - ts;
                 result_of[idx].reset();
                 uf_result_of[idx].reset();
@@ -1569,6 +1574,8 @@ struct Runtime {
                                        // (a few chains of dependent rounds, cores idle) overlaps the ramp-up of the next.  Two
                                        // batches in full flight would only slow each other's long-job lanes down.
     double stagger_frac = 0.12;        // MTR_STAGGER_FRAC
+    bool stagger_by_bases = true;      // the gate looks at the bases left to scan (MTR_STAGGER_BY=reads: at the reads left, which
+                                       // under most-work-left-first scheduling all finish in the last 0.1 s of a batch)
     StaleTracker stale;
     std::vector<ReadInput> pending;
     long long pending_bases = 0;
@@ -1600,6 +1607,7 @@ struct Runtime {
         if (const char *e = getenv("MTR_THREADS")) threads = atoi(e);
         if (const char *e = getenv("MTR_INFLIGHT_PER_GPU")) per_gpu = std::max(1, atoi(e));
         if (const char *e = getenv("MTR_STAGGER_FRAC")) stagger_frac = atof(e);
+        if (const char *e = getenv("MTR_STAGGER_BY")) stagger_by_bases = strcmp(e, "reads") != 0;
         prep_threads = std::max(1, std::min(8, threads / 2));
         threads = std::max(1, threads / ngpu);
         for (int g = 0; g < ngpu; g++)
@@ -1708,10 +1716,13 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
         batch_index++;
         // stagger: the batch before this one on the same GPU must be down to its last reads
         if (Engine *prev = last_on_gpu[gpu])
-            while (prev != eng && prev->unfinished.load() > (int)(rt.stagger_frac * prev->batch_total.load()))
+            while (prev != eng && prev->unfinished.load() > 0 &&
+                   (rt.stagger_by_bases ? prev->bases_left.load() > (long long)(rt.stagger_frac * prev->bases_total.load())
+                                        : prev->unfinished.load() > (int)(rt.stagger_frac * prev->batch_total.load())))
                 std::this_thread::sleep_for(std::chrono::microseconds(500));
         last_on_gpu[gpu] = eng;
         eng->batch_total.store((int)s->reads.size()); eng->unfinished.store((int)s->reads.size());
+        { long long tb = 0; for (const ReadInput &r : s->reads) tb += r.len; eng->bases_total.store(tb); eng->bases_left.store(tb); }
         s->eng = eng;
         if (getenv("MTR_PROFILE")) fprintf(stderr, "[mtr profile] batch %lld (%zu reads) starts on engine %d at %.3f s\n", batch_index - 1, s->reads.size(), (int)(eng == rt.engines[gpu * rt.per_gpu] ? 0 : 1), now_s() - t_file0);
         s->th = std::thread([eng, s, print_alignment] { s->out = eng->process(s->reads, print_alignment); });
