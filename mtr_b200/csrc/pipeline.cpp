@@ -89,21 +89,24 @@ void apply_dp(Rec &r, int qs, const mtr_wdp_result &d, int g, int m, int in)
 
 // ---------------------------------------------------------------- exact k-mer counts of one window
 // (init_inputString + generate_freqNode_*, consensus.c:37-253; the hash layout is unobservable)
+constexpr int kDirectK = 8;           // k <= 8: direct table of 4^k counters (256 KB at k = 8; 3 ns per position against 6-10 ns for the
+                                      // hash table, and cheaper look-ups in the walks); k = 9, 10 direct (1-4 MB) gained nothing in the
+                                      // pipeline; larger k: open addressing
 struct Counter {
     std::vector<int> codes;           // codes[i - qs] for i in [qs, qe]
-    std::vector<int> direct;          // k <= 6: 4^k counters
-    // k > 6: open addressing, one 8-byte slot per node (key + 1 in the high word so that 0 means empty); the slots
+    std::vector<int> direct;          // k <= kDirectK: 4^k counters
+    // k > kDirectK: open addressing, one 8-byte slot per node (key + 1 in the high word so that 0 means empty); the slots
     // a window touched are cleared again from `codes`, so a build costs O(window), not O(table)
     std::vector<uint64_t> slots;
     std::vector<uint32_t> touched;
-    std::vector<uint32_t> pos_slot;   // slot of every window position (k > 6): the listing pass needs no second probe
+    std::vector<uint32_t> pos_slot;   // slot of every window position (k > kDirectK): the listing pass needs no second probe
     uint32_t hmask = 0;
     int k = 0, maxf = -1;
 
     static inline uint32_t hash(uint32_t node) { return node * 2654435761u; }
     void build(const uint8_t *org, int L, int kk, int qs, int qe)
     {
-        if (k <= 6) { for (int c : codes) direct[c] = 0; }      // undo the previous window (O(window), not O(4^k))
+        if (k <= kDirectK) { for (int c : codes) direct[c] = 0; }      // undo the previous window (O(window), not O(4^k))
         else { for (uint32_t h : touched) slots[h] = 0; touched.clear(); }
         k = kk;
         const int n = qe - qs + 1;
@@ -123,8 +126,8 @@ struct Counter {
             }
         }
         maxf = -1;
-        if (k <= 6) {
-            if (direct.size() < 4096) direct.assign(4096, 0);
+        if (k <= kDirectK) {
+            if (direct.size() < (size_t)P4.v[kDirectK]) direct.assign((size_t)P4.v[kDirectK], 0);
             for (int c : codes) maxf = std::max(maxf, ++direct[c]);
         } else {
             uint32_t cap = 1024;
@@ -151,7 +154,7 @@ struct Counter {
     }
     int get(int node)                                          // freq_node, consensus.c:231-253
     {
-        if (k <= 6) return (node >= 0 && node < P4.v[k]) ? direct[node] : 0;
+        if (k <= kDirectK) return (node >= 0 && node < P4.v[k]) ? direct[node] : 0;
         const uint64_t key = ((uint64_t)(uint32_t)node + 1) << 32;
         uint32_t h = hash((uint32_t)node) & hmask;
         for (;;) {
@@ -163,7 +166,7 @@ struct Counter {
     }
     void decrement(int node)
     {
-        if (k <= 6) { direct[node]--; return; }
+        if (k <= kDirectK) { direct[node]--; return; }
         const uint64_t key = ((uint64_t)(uint32_t)node + 1) << 32;
         uint32_t h = hash((uint32_t)node) & hmask;
         while ((slots[h] & 0xffffffff00000000ull) != key) h = (h + 1) & hmask;
@@ -174,7 +177,7 @@ struct Counter {
     int list_max_nodes(int *list, int cap, int maxfreq)
     {
         int n = 0;
-        if (k <= 6) {
+        if (k <= kDirectK) {
             for (int c : codes)
                 if (direct[c] == maxfreq) { list[n++] = c; direct[c]--; if (cap <= n) break; }
         } else {
@@ -593,19 +596,21 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
         wk.n_chain++;
         return;
     }
-    double tp0 = now_s();
+    // the stage timers cost four clock reads per chain (8 M chains per 8192-read batch): only with MTR_PROFILE
+    static const bool prof = getenv("MTR_PROFILE") != nullptr;
+    double tp0 = prof ? now_s() : 0.0;
     wk.cnt.build(rs.org, rs.L, ch.k, qs, qe);
-    double tp1 = now_s();
+    double tp1 = prof ? now_s() : 0.0;
     wk.t_build += tp1 - tp0; wk.n_chain++;
     const int maxf = wk.cnt.max_freq();
     int nodes[100];
     // the listing decrements counts (Q8), which only the walks can observe: skip it when they do not run (:532)
     const int nn = 5 < maxf ? wk.cnt.list_max_nodes(nodes, 100, maxf) : 0;
-    tp0 = now_s();
+    tp0 = prof ? now_s() : 0.0;
     wk.t_list += tp0 - tp1;
     const int sb = size_bucket(qe - qs + 1);
-    wk.hb_n[sb]++; wk.hb_t[sb] += tp0 - (tp1 - (tp1 - tp0 > 0 ? 0 : 0));
-    struct WalkTimer { Worker &w; double t0; int sb; bool walked; ~WalkTimer() { const double d = now_s() - t0; w.t_walk += d; if (walked) { w.hw_n[sb]++; w.hw_t[sb] += d; if (d > w.hw_max[sb]) w.hw_max[sb] = d; } } } walk_timer{wk, tp0, sb, 5 < maxf};
+    wk.hb_n[sb]++;
+    struct WalkTimer { Worker &w; double t0; int sb; bool walked, on; ~WalkTimer() { if (!on) return; const double d = now_s() - t0; w.t_walk += d; if (walked) { w.hw_n[sb]++; w.hw_t[sb] += d; if (d > w.hw_max[sb]) w.hw_max[sb] = d; } } } walk_timer{wk, tp0, sb, 5 < maxf, prof};
     bool any = false;
     if (5 < maxf) {
         for (int d = 0; d < 2; d++) {
@@ -616,8 +621,8 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
                 const bool found = walk(wk.cnt, wk.memo, qs, qe, nodes[i], ch.k, d == 1, r);
                 ch.found_last = found;
                 if (!found) continue;
-                ch.dir[d] = r; ch.dir_found[d] = true;
                 ch.dir_job[d] = add_job(rs, qs, qe - qs + 1, r.unit, 2, kSearchParams, MTR_TB_COUNTS);
+                ch.dir[d] = std::move(r); ch.dir_found[d] = true;
                 any = true;
                 break;
             }
@@ -686,7 +691,8 @@ void advance_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk, const R
         const int coverage = ch.rr.repeat_len / ch.rr.period;
         if (!(5 <= coverage && coverage <= 20 && 5 < ch.rr.period)) { ch.stage = Chain::DONE; return; }
         // revise_representative_unit (consensus.c:1048-1087)
-        { const double tq = now_s(); polish(wk.cnt, rs.org, rs.L, ch.rr); wk.t_polish += now_s() - tq; }
+        { static const bool prof = getenv("MTR_PROFILE") != nullptr;
+          const double tq = prof ? now_s() : 0.0; polish(wk.cnt, rs.org, rs.L, ch.rr); if (prof) wk.t_polish += now_s() - tq; }
         ch.ratio0 = ch.rr.ratio();
         ch.pass = 0;
         emit_revise_cons(rs, ch);
@@ -1110,11 +1116,11 @@ struct Engine {
                     cur.uf = uf_result_of[idx]->res.data(); cur.uf_units = uf_result_of[idx]->units.data();
                     cur.uf_scores = uf_result_of[idx]->scores.data();
                 }
-                const double ts = now_s();
+                const double ts = prof ? now_s() : 0.0;
                 const int left0 = rs.L - rs.cursor;
                 step_read(rs, workers[tid], cur, print_alignment);
                 bases_left.fetch_sub(left0 - (rs.phase == ReadState::FINISHED ? 0 : rs.L - rs.cursor), std::memory_order_relaxed);
-                workers[tid].t_step += now_s() - ts;
+                if (prof) workers[tid].t_step += now_s() - ts;
                 result_of[idx].reset();
                 uf_result_of[idx].reset();
                 int max_rows = 0, lane = 0;
