@@ -602,6 +602,7 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
     wk.cnt.build(rs.org, rs.L, ch.k, qs, qe);
     double tp1 = prof ? now_s() : 0.0;
     wk.t_build += tp1 - tp0; wk.n_chain++;
+    const double t_build_this = tp1 - tp0;
     const int maxf = wk.cnt.max_freq();
     int nodes[100];
     // the listing decrements counts (Q8), which only the walks can observe: skip it when they do not run (:532)
@@ -609,7 +610,7 @@ void start_chain(ReadState &rs, int qs, int qe, Chain &ch, Worker &wk)
     tp0 = prof ? now_s() : 0.0;
     wk.t_list += tp0 - tp1;
     const int sb = size_bucket(qe - qs + 1);
-    wk.hb_n[sb]++;
+    wk.hb_n[sb]++; wk.hb_t[sb] += t_build_this;
     struct WalkTimer { Worker &w; double t0; int sb; bool walked, on; ~WalkTimer() { if (!on) return; const double d = now_s() - t0; w.t_walk += d; if (walked) { w.hw_n[sb]++; w.hw_t[sb] += d; if (d > w.hw_max[sb]) w.hw_max[sb] = d; } } } walk_timer{wk, tp0, sb, 5 < maxf, prof};
     bool any = false;
     if (5 < maxf) {
@@ -1348,9 +1349,9 @@ struct Engine {
             for (int b = 0; b < 12; b++)
                 fprintf(stderr, "[mtr profile]   DP jobs with rows <= %6d: %9lld jobs %8.2f Gcells | read-rounds whose longest job is in this bucket: %8lld\n", 32 << b, rows_hist_n[b], rows_hist_cells[b] / 1e9, readmax_hist[b]);
             for (int b = 0; b < 8; b++) {
-                long long bn = 0, wn = 0; double wt = 0, wm = 0;
-                for (Worker &k : workers) { bn += k.hb_n[b]; wn += k.hw_n[b]; wt += k.hw_t[b]; wm = std::max(wm, k.hw_max[b]); k.hb_n[b] = k.hw_n[b] = 0; k.hw_t[b] = k.hw_max[b] = 0; }
-                fprintf(stderr, "[mtr profile]   window <= %5d: chains %9lld  with walks %8lld  walk cpu-s %8.3f  max walk ms %8.2f\n", 64 << b, bn, wn, wt, wm * 1e3);
+                long long bn = 0, wn = 0; double wt = 0, wm = 0, bt = 0;
+                for (Worker &k : workers) { bn += k.hb_n[b]; bt += k.hb_t[b]; wn += k.hw_n[b]; wt += k.hw_t[b]; wm = std::max(wm, k.hw_max[b]); k.hb_n[b] = k.hw_n[b] = 0; k.hb_t[b] = k.hw_t[b] = k.hw_max[b] = 0; }
+                fprintf(stderr, "[mtr profile]   window <= %5d: chains %9lld  table cpu-s %8.3f  with walks %8lld  walk cpu-s %8.3f  max walk ms %8.2f\n", 64 << b, bn, bt, wn, wt, wm * 1e3);
             }
             {
                 std::vector<double> f = finish_at;
