@@ -304,7 +304,14 @@ def main():
     # the K timed batches, exactly as main.c calls it -- parse, stale-state tracking, 2-bit pack, H2D, directional index,
     # every per-round H2D / D2H, chaining, formatting, ordered stdout.  The entry point owns its engines (two per GPU:
     # the next batch starts when the running one is down to its last reads); the pipelines above are closed first.
-    shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    need = 2 * world * max(4, a.steps) * max(len(t) for t in texts)          # every rank writes its own file; 2x headroom
+    shm = tempfile.gettempdir()
+    try:
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize >= need:
+            shm = "/dev/shm"
+    except OSError:
+        pass
     e2e_path = os.path.join(shm, "mtr_bench_rank%d_%d.fa" % (rank, os.getpid()))
     os.environ.setdefault("MTR_DEVICE", str(local_rank))
     os.environ.setdefault("MTR_THREADS", str(threads))
