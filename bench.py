@@ -399,6 +399,26 @@ def main():
         dt, ref_out = run_reference_cli(binary, sample, cores)
         line["cpu_baseline"] = {"value": round(len(sample) / dt, 3), "unit": "reads/s", "cores": cores, "kind": kind,
                                 "sample": "%d reads of the step's workload (seed of step %d), %d processes, %.1f s" % (len(sample), a.warmup, cores, dt)}
+        # parity at bench time, against the reference itself: the first reads of the timed step through the reference
+        # sources (oracle/_ref/mTR_ref_det: the reference with its alignment set in insertion order; one
+        # process, fresh state) and through a fresh pipeline on this GPU -- the two texts must be byte-identical
+        try:
+            par_n = min(32, R)
+            par_reads = step_reads(par_n, 0, a.warmup)           # the generator is prefix-stable: these are the step's first reads
+            det = os.path.join(ROOT, "oracle", "_ref", "mTR_ref_det")
+            det = det if os.path.exists(det) else ORACLE_BIN
+            with tempfile.TemporaryDirectory() as tmp:
+                pth = os.path.join(tmp, "parity.fa")
+                synth.write_fasta(pth, par_reads, ids=list(range(par_n)))
+                want = subprocess.run([det, pth], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
+            pp = capi.Pipeline(local_rank, threads=threads)
+            pp.load_fasta(fasta_bytes(par_reads))
+            got = pp.run()
+            pp.close()
+            line["parity"] = {"reads": par_n, "against": os.path.relpath(det, ROOT), "identical": got == want, "records": want.count(b"\n"),
+                              "md5": hashlib.md5(got).hexdigest()}
+        except Exception as e:      # noqa: BLE001 -- the bench line must still be printed
+            line["parity"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

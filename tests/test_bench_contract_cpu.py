@@ -51,6 +51,8 @@ def test_bench_line_has_every_contract_key():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
     # both legs processed the same reads: the resident loop's digest and handle_one_file's are digests of the same text
     assert d["output_md5"] == d["e2e"]["output_md5"]
+    # ... and the bench-time parity sample against the reference sources is byte-identical
+    assert d["parity"].get("identical") is True and d["parity"]["reads"] == 5 and d["parity"]["records"] >= 1, d["parity"]
 
 
 def test_quick_mode_and_batches_in_flight():
