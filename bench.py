@@ -213,7 +213,7 @@ def main():
     R = a.reads
     total = a.warmup + a.steps
     keys = ("reads", "bases", "candidates", "rounds", "rounds_fast", "rounds_uf", "uf_tasks", "uf_kernel_ms", "uf_wall_ms", "jobs", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
-            "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "wdp_fill_ms",
+            "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "spec_cells", "wdp_fill_ms",
             "wdp_tb_ms", "di_kernel_ms", "di_wall_ms", "rounds_wall_ms", "host_step_ms", "wdp_wall_ms")
 
     # Batches in flight (--inflight, default 1; handle_one_file: MTR_INFLIGHT_PER_GPU): with more than one, each batch
@@ -335,6 +335,10 @@ def main():
     e2e_md5 = hashlib.md5(out_file).hexdigest()
     clk = clocks.stop()
 
+    # algorithmic cells = what the reference executes: cells spent on speculative candidates that were pruned after all
+    # (MTR_SPECULATE) are launched and timed but not counted
+    acc["wdp_cells_launched"] = acc["wdp_cells"]
+    acc["wdp_cells"] = acc["wdp_cells"] - acc["spec_cells"]
     reads_all = sum_over_ranks(R * a.steps)
     cells_all = sum_over_ranks(acc["wdp_cells"])
     kernel_ms = acc["wdp_fill_ms"] + acc["wdp_tb_ms"]
@@ -363,7 +367,8 @@ def main():
                 "output_md5": e2e_md5},
         "gpu_launches": int(acc["launches"]),
         "gcups": {"wrap_around_dp": round(gcups_rank, 2), "fill_only": round(fill_gcups, 2),
-                  "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3), "algorithmic_cells_per_step": int(acc["wdp_cells"] / a.steps)},
+                  "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3), "algorithmic_cells_per_step": int(acc["wdp_cells"] / a.steps),
+                  "speculative_cells_per_step": int(acc["spec_cells"] / a.steps)},
         "roofline": {"kernel": "wdp_fill_* (K3 wrap-around DP: fill with the traceback fused in), all launches of the timed steps", "bound": "int-alu", "achieved": round(fill_gcups, 2),
                      "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4),
                      "traffic": {"dram_bytes_per_cell_ncu": 0.289, "algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3),

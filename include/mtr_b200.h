@@ -196,6 +196,8 @@ typedef struct {
     int64_t di_position_passes, di_bytes_in, di_bytes_out;
     int64_t h2d_bytes, d2h_bytes;
     int64_t launches;                                      /* CUDA kernels launched by run() */
+    int64_t spec_cells;                                    /* part of wdp_cells run for speculative candidates that were pruned
+                                                              after all (MTR_SPECULATE; 0 by default): not algorithmic cells */
     double  wdp_fill_ms, wdp_tb_ms, di_kernel_ms, uf_kernel_ms;   /* CUDA-event time on the launching streams */
     double  di_wall_ms, rounds_wall_ms, host_step_ms, wdp_wall_ms, uf_wall_ms;
 } mtr_pipeline_stats;

@@ -57,7 +57,7 @@ class Stats(C.Structure):
 class PipelineStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "reads", "bases", "candidates", "rounds", "rounds_fast", "rounds_uf", "jobs", "uf_tasks", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
-        "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches")] + \
+        "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "spec_cells")] + \
         [(n, C.c_double) for n in ("wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms", "uf_kernel_ms", "di_wall_ms", "rounds_wall_ms",
                                    "host_step_ms", "wdp_wall_ms", "uf_wall_ms")]
 

@@ -518,7 +518,7 @@ struct ReadState {
     int L = 0, index = 0;
     int32_t *end = nullptr, *w = nullptr; // directional_index_end / _w of this read (views into the batch arrays); dead entries have end < 0
     int cursor = 0;
-    struct Cand { int qs = 0, qe = 0; std::vector<Chain> chains; };
+    struct Cand { int qs = 0, qe = 0; bool spec = false; long long cells = 0; std::vector<Chain> chains; };
     std::vector<Cand> cands;           // candidates in flight, in candidate order (front commits first)
     std::vector<ChainItem> accepted;
     std::vector<Rec> printing;         // -a: the chain waiting for its PATH jobs
@@ -532,6 +532,8 @@ struct ReadState {
     std::vector<long long> job_aux;    // byte offset in the round's aux buffer of each job of the previous round
     std::string out;
     long long candidates = 0;
+    int print_job0 = 0;                // index of the first PATH job of `printing` among the round's jobs
+    long long cells_total = 0, cells_wasted = 0;   // DP cells queued so far / by speculative candidates that were pruned after all
 };
 
 struct Worker { Counter cnt; WalkMemo memo; double t_build = 0, t_list = 0, t_walk = 0, t_polish = 0, t_step = 0; long long n_chain = 0, n_walk = 0;
@@ -547,6 +549,8 @@ struct RoundResults {
     const int32_t *uf_scores = nullptr;
 };
 
+int g_speculate = 8;                       // MTR_SPECULATE: candidates a read may evaluate ahead of ones that could still prune them
+                                           // (0: none, exactly the reference's order of evaluation; output identical either way)
 bool g_uf_on_gpu = false;                  // MTR_UNITFINDER=gpu runs the unit finder as K4 on the GPU
 int g_uf_gpu_min_window = 0;               // ... for candidate windows of at least this many bases (MTR_UF_GPU_MIN_WINDOW)
 
@@ -565,6 +569,7 @@ int add_job(ReadState &rs, int first, int rows, const std::vector<uint8_t> &unit
     j.aux_need = mode == MTR_TB_CONSENSUS ? (long long)(j.ulen + 1) * 9 : (mode == MTR_TB_PATH ? (long long)6 * rows + 64 : 0);
     rs.units.insert(rs.units.end(), unit.begin(), unit.end());
     rs.jobs.push_back(j);
+    rs.cells_total += (long long)rows * j.ulen * n_param;
     return (int)rs.jobs.size() - 1;
 }
 
@@ -731,6 +736,7 @@ void finish_read(ReadState &rs, int print_alignment)
     rs.printing.clear();
     for (const Rec *r : chain) rs.printing.push_back(*r);
     if (rs.printing.empty()) { rs.phase = ReadState::FINISHED; return; }
+    rs.print_job0 = (int)rs.jobs.size();                    // jobs of a speculative candidate dropped in this very round may precede
     for (const Rec &r : rs.printing) {
         const int p[1][3] = {{r.gain, r.mis, r.indel}};
         add_job(rs, r.rep_start - 1, r.rep_end - r.rep_start + 1, r.unit, 1, p, MTR_TB_PATH);
@@ -749,14 +755,17 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
         const mtr_wdp_result *res = rr.res + 2 * rs.job_base;
         for (size_t i = 0; i < rs.printing.size(); i++) {
             append_record(rs.out, rs.id, rs.printing[i]);
-            append_alignment(rs.out, rs.printing[i], rs.org, res[2 * i], rr.aux + rs.job_aux[i]);
+            append_alignment(rs.out, rs.printing[i], rs.org, res[2 * (rs.print_job0 + i)], rr.aux + rs.job_aux[rs.print_job0 + i]);
         }
         rs.phase = ReadState::FINISHED;
         return;
     }
-    for (ReadState::Cand &cd : rs.cands)
+    for (ReadState::Cand &cd : rs.cands) {
+        const long long before = rs.cells_total;
         for (Chain &ch : cd.chains)
             if (ch.stage != Chain::DONE) advance_chain(rs, cd.qs, cd.qe, ch, wk, rr);
+        cd.cells += rs.cells_total - before;
+    }
     for (;;) {
         // commit finished candidates in candidate order
         while (!rs.cands.empty()) {
@@ -780,6 +789,12 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
                 ChainItem it;
                 it.rec = pick; it.start = pick.rep_start; it.end = pick.rep_end; it.score = pick.nm; it.pred = nullptr;
                 rs.accepted.push_back(it);
+                // speculative candidates whose range this repeat has just pruned would never have been visited by the
+                // reference: drop them (results of their jobs still in flight are simply never looked at)
+                for (size_t c = 1; c < rs.cands.size();) {
+                    if (rs.end[rs.cands[c].qs] < 0) { rs.cells_wasted += rs.cands[c].cells; rs.cands.erase(rs.cands.begin() + c); }
+                    else c++;
+                }
             }
             rs.cands.erase(rs.cands.begin());
         }
@@ -793,17 +808,23 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
             return;
         }
         const int qs = rs.cursor, qe = rs.end[rs.cursor];
-        bool safe = (int)rs.cands.size() < kMaxInflightCands;
-        for (const ReadState::Cand &cd : rs.cands) if (cd.qe >= qe) { safe = false; break; }
-        if (!safe) return;                                  // wait for the in-flight candidates (they have jobs queued)
+        if ((int)rs.cands.size() >= kMaxInflightCands) return;
+        bool safe = true;
+        int n_spec = 0;
+        for (const ReadState::Cand &cd : rs.cands) { if (cd.qe >= qe) safe = false; n_spec += cd.spec; }
+        // A candidate that an in-flight one could still prune waits, exactly as in the reference -- or, with
+        // MTR_SPECULATE = S, up to S of them are evaluated ahead: if the earlier candidate does accept a repeat that
+        // prunes them they are dropped (wasted DP cells, counted apart), otherwise a dependent round has been saved.
+        if (!safe && n_spec >= g_speculate) return;         // wait for the in-flight candidates (they have jobs queued)
         const int cw = rs.w[rs.cursor];
         rs.cursor++;
         int min_k, max_k;                                   // handle_one_read.c:105-120
         if (cw < 100) { min_k = 2; max_k = 10; } else if (cw < 1000) { min_k = 2; max_k = 12; } else { min_k = 5; max_k = 15; }
         rs.cands.emplace_back();
         ReadState::Cand &cd = rs.cands.back();
-        cd.qs = qs; cd.qe = qe;
+        cd.qs = qs; cd.qe = qe; cd.spec = !safe;
         cd.chains.resize(max_k - min_k + 1);
+        const long long cells_before = rs.cells_total;
         // A k'-mer that occurs c times has a k-prefix (k < k') that occurs at least c times at the same coded
         // positions, so maxFreq(k') <= maxFreq(k) + (number of raw-base entries of the k' window, Q7).  Once that
         // bound is <= 5 the search cannot pass the maxFreq gate (consensus.c:532) for any larger k: those chains
@@ -821,6 +842,7 @@ void step_read(ReadState &rs, Worker &wk, const RoundResults &rr, int print_alig
             start_chain(rs, qs, qe, ch, wk);
             if (!g_uf_on_gpu) low_maxf = std::min(low_maxf, wk.cnt.max_freq());
         }
+        cd.cells += rs.cells_total - cells_before;
     }
 }
 
@@ -933,6 +955,7 @@ struct Engine {
         if (rc) die(nullptr, "mtr_cuda_init", rc);
         if (const char *e = getenv("MTR_UNITFINDER")) g_uf_on_gpu = strcmp(e, "gpu") == 0;
         if (const char *e = getenv("MTR_UF_GPU_MIN_WINDOW")) g_uf_gpu_min_window = atoi(e);
+        if (const char *e = getenv("MTR_SPECULATE")) g_speculate = std::max(0, atoi(e));
         int want_uf = g_uf_on_gpu ? 2 : 0;
         if (const char *e = getenv("MTR_UF_LANES")) want_uf = g_uf_on_gpu ? std::max(1, atoi(e)) : 0;
         // MTR_TIER_ROWS="128,1536": upper row bounds of all tiers but the last; MTR_TIER_LANES="2,2,2"; MTR_TIER_SPIN="0,0,0"
@@ -1329,7 +1352,7 @@ struct Engine {
         t_rounds += now_s() - t0;
         t_dp += wdp_ms / 1e3;
         ps.rounds_wall_ms = (now_s() - t0) * 1e3;
-        for (int r = 0; r < n; r++) { out += st[r].out; candidates += st[r].candidates; ps.candidates += st[r].candidates; }
+        for (int r = 0; r < n; r++) { out += st[r].out; candidates += st[r].candidates; ps.candidates += st[r].candidates; ps.spec_cells += st[r].cells_wasted; }
         ps.host_step_ms = host_ms; ps.wdp_wall_ms = wdp_ms; ps.uf_wall_ms = uf_ms;
         if (getenv("MTR_PROFILE")) {
             double b = 0, l = 0, w = 0, p = 0, t = 0; long long nc = 0, nw = 0;
@@ -1598,7 +1621,7 @@ struct Runtime {
         totals.rounds_fast += p.rounds_fast; totals.jobs += p.jobs; totals.wdp_calls += p.wdp_calls; totals.wdp_cells += p.wdp_cells;
         totals.wdp_slot_cells += p.wdp_slot_cells; totals.wdp_dir_bytes += p.wdp_dir_bytes; totals.di_position_passes += p.di_position_passes;
         totals.di_bytes_in += p.di_bytes_in; totals.di_bytes_out += p.di_bytes_out; totals.h2d_bytes += p.h2d_bytes; totals.d2h_bytes += p.d2h_bytes;
-        totals.launches += p.launches; totals.wdp_fill_ms += p.wdp_fill_ms; totals.wdp_tb_ms += p.wdp_tb_ms; totals.di_kernel_ms += p.di_kernel_ms;
+        totals.launches += p.launches; totals.spec_cells += p.spec_cells; totals.wdp_fill_ms += p.wdp_fill_ms; totals.wdp_tb_ms += p.wdp_tb_ms; totals.di_kernel_ms += p.di_kernel_ms;
         totals.di_wall_ms += p.di_wall_ms; totals.rounds_wall_ms += p.rounds_wall_ms; totals.host_step_ms += p.host_step_ms; totals.wdp_wall_ms += p.wdp_wall_ms;
     }
 

@@ -84,3 +84,18 @@ print(json.dumps({"n": n, "md5": hashlib.md5(out).hexdigest(), "reads": st["read
 ''' % (mixed, mixed), env)
     assert r["md5"] == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
     assert r["n"] == r["reads"] > 0 and r["jobs"] > 0 and r["same"]
+
+
+def test_speculative_cells_are_counted_apart(mixed):
+    """Cells spent on speculative candidates that were pruned after all are launched but are not algorithmic cells:
+    mtr_pipeline_stats.spec_cells reports them, and the text is the same with and without speculation."""
+    body = r'''
+text = open(%r, "rb").read()
+pipe = capi.Pipeline(0); pipe.load_fasta(text); out = pipe.run(); st = pipe.stats(); pipe.close()
+print(json.dumps({"md5": hashlib.md5(out).hexdigest(), "cells": st["wdp_cells"], "spec": st["spec_cells"], "jobs": st["jobs"]}))
+''' % mixed
+    a = child(body, {"MTR_SPECULATE": "0"})
+    b = child(body, {"MTR_SPECULATE": "24"})
+    assert a["md5"] == b["md5"] == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
+    assert b["jobs"] >= a["jobs"] and b["spec"] >= a["spec"] >= 0
+    assert b["cells"] - b["spec"] <= a["cells"]          # what is left after removing the waste is at most the reference's work

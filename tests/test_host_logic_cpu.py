@@ -70,3 +70,15 @@ def test_batching_threads_and_lanes_do_not_change_the_output(sim, synthetic_dir)
     for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_BATCH_READS": "3", "MTR_GPUS": "2"},
                 {"MTR_TIER_ROWS": "1536", "MTR_TIER_LANES": "1,1"}, {"MTR_TIER_ROWS": "40,100,400", "MTR_TIER_SPIN": "1,1,0,0", "MTR_THREADS": "3"}):
         assert hashlib.md5(run(sim, [], path, env)).hexdigest() == ref, env
+
+
+@pytest.mark.parametrize("spec", ["0", "1", "24"])
+def test_speculative_look_ahead_does_not_change_the_output(sim, synthetic_dir, shipped_dir, spec):
+    """MTR_SPECULATE (default 8): candidates evaluated ahead of ones that could still prune them are dropped when they
+    are pruned after all -- the reference would never have visited them.  Any depth, incl. none, gives the same bytes
+    in every mode (the -a path indexes its PATH jobs behind jobs a dropped candidate may have queued)."""
+    cases = [(os.path.join(synthetic_dir, n + ".fa"), DIGESTS["synthetic"][n]) for n in ("mixed", "single_TR_10", "pacbio_200_200", "long4")]
+    cases += [(os.path.join(shipped_dir, n), DIGESTS["shipped"][n]) for n in ("worm_chrII_1.fasta", "2_5_10_20_50_100_200_set.fasta")]
+    for path, want in cases:
+        for mode, flags in golden_cases.MODES.items():
+            assert hashlib.md5(run(sim, flags, path, {"MTR_SPECULATE": spec})).hexdigest() == want[mode]["md5"], (path, mode, spec)

@@ -164,3 +164,13 @@ print(json.dumps({"n": n, "md5": hashlib.md5(out).hexdigest(), "reads": st["read
         r = json.loads(p.stdout.decode().strip().splitlines()[-1])
         assert r["md5"] == DIGESTS["synthetic"]["mixed"]["default"]["md5"], env
         assert r["n"] == r["reads"] > 0 and r["launches"] > 0 and r["cells"] > 0 and r["d2h"] > 0
+
+
+@pytest.mark.parametrize("spec", ["0", "24"])
+def test_speculative_look_ahead_does_not_change_the_output(synthetic_dir, shipped_dir, spec):
+    """MTR_SPECULATE (default 8): any depth of speculative candidate look-ahead, incl. none, prints the same bytes."""
+    cases = [(os.path.join(synthetic_dir, "mixed.fa"), DIGESTS["synthetic"]["mixed"]), (os.path.join(shipped_dir, "worm_chrII_1.fasta"), DIGESTS["shipped"]["worm_chrII_1.fasta"])]
+    for path, want in cases:
+        for mode, flags in golden_cases.MODES.items():
+            out = run(MTR, flags, path, {"MTR_SPECULATE": spec})
+            assert hashlib.md5(out).hexdigest() == want[mode]["md5"], (path, mode, spec, explain(out, flags, path))
