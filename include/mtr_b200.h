@@ -163,6 +163,54 @@ typedef struct {
 int mtr_uf_run(mtr_ctx *ctx, const mtr_uf_task *tasks, int n_tasks, mtr_uf_result *results,
                uint8_t *units, int32_t *scores, int64_t out_cap, int64_t *out_used);
 
+/* ------------------------------------------------------------------ resident engine: the per-read path on the device */
+/* handle_one_TR (handle_one_read.c:190-261) for EVERY read of the resident batch, without the host in the loop:
+ * directional index (fill_directional_index_with_end), the candidate loop with its pruning (:227-246),
+ * find_tandem_repeat over the k range (:102-154), search_De_Bruijn_graph (consensus.c:507-582: k-mer counts, greedy
+ * walks, wrap_around_DP under both penalty sets), polish_repeat and revise_representative_unit (:584-704, 1048-1087).
+ * The reads advance in waves of kernels; the host only launches waves until every read is finished.
+ *
+ * The result is what the reference hands to insert_an_alignment_into_set (mTR.h:146-165, handle_one_read.c:156-176),
+ * one record per accepted repeat, ordered by (read, order of insertion); chaining and printing (chaining.cpp) remain
+ * with the caller.  Arrays returned through the out-pointers belong to the context and stay valid until the next
+ * call on it.  stale / stale_off: as for mtr_di_run. */
+typedef struct {
+    int32_t read;              /* index into the resident batch */
+    int32_t seq;               /* order of insertion within the read */
+    int32_t rep_start, rep_end, repeat_len, rep_period, num_freq_unit;
+    int32_t num_matches, num_mismatches, num_insertions, num_deletions;
+    int32_t kmer, match_gain, mismatch_penalty, indel_penalty;
+    int32_t pad_;
+    int64_t unit_off;          /* offset of the unit (rep_period bytes, values 0..3) in the units array */
+} mtr_repeat;
+
+typedef struct {
+    int64_t waves;             /* kernel waves launched for the group */
+    int64_t candidates;        /* query_counter: candidate ranges the reference would have visited */
+    int64_t dp_jobs, dp_tasks; /* wrap-around DP calls (a two-penalty call is one job) / fill tasks launched */
+    int64_t dp_cells;          /* sum rows * ulen over every DP launched (both penalty sets) */
+    int64_t dp_slot_cells, dp_dir_bytes;
+    int64_t spec_cells;        /* part of dp_cells run for look-ahead candidates that were pruned after all */
+    int64_t tables, table_positions, walks;   /* k-mer count tables built, positions counted, greedy walks run */
+    int64_t repeats;
+    int64_t wrapdp_messages;   /* "You need to increse the value of WrapDPsize." lines (handle_one_read.c:89-91) */
+    int64_t launches;          /* CUDA kernels launched */
+    int64_t h2d_bytes, d2h_bytes;
+    double  di_ms;             /* CUDA-event time of the directional-index kernels */
+    double  dp_ms;             /* CUDA-event time of the K3 fill + traceback kernels, summed over the waves */
+    double  uf_ms;             /* ... of the scheduler / unit-finder / polish kernels */
+    double  wall_ms;           /* host wall clock of the whole call */
+} mtr_engine_stats;
+
+int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio, const uint16_t *stale, const int64_t *stale_off,
+                   const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units, mtr_engine_stats *stats);
+/* MTR_SPECULATE-style knobs of the engine (defaults: 8 look-ahead candidates). */
+int mtr_engine_set_speculate(mtr_ctx *ctx, int depth);
+/* Union, over every engine call of the process since the last reset, of the time intervals in which K3 kernels of
+ * ANY context were running on `device` (milliseconds): the in-pipeline kernel time of the DP roofline when several
+ * groups share one GPU.  reset != 0 clears the record after reading it. */
+double mtr_engine_dp_busy_ms(int device, int reset);
+
 /* ------------------------------------------------------------------ counters for the roofline */
 typedef struct {
     double   wdp_fill_ms, wdp_tb_ms, di_ms;      /* CUDA-event time of the last launch of each stage */
@@ -185,21 +233,27 @@ int mtr_alu_probe(mtr_ctx *ctx, int kind, double *gops);
 /* ------------------------------------------------------------------ batch-level pipeline */
 /* The whole per-read path of handle_one_file (handle_one_file.c:271-293 -> handle_one_read.c:190-261) on FASTA
  * text that is already in host memory, split so that the host<->device boundary can be timed separately:
- *   load_fasta : parse + stale-state tracking + 2-bit pack + H2D   (afterwards the batch is resident in HBM)
- *   run        : directional index, candidate rounds (unit finder on the host cores, DP on the GPU), chaining;
+ *   load_fasta : parse + stale-state tracking + 2-bit pack + H2D, one group of reads per engine context
+ *                (MTR_GROUPS_PER_GPU contexts; afterwards the batch is resident in HBM)
+ *   run        : mtr_engine_run on every group concurrently, then chaining and formatting on the host;
  *                returns the text the reference would print for these reads (TSV records, alignments with -a)
  * Uses the globals Manhattan_Distance and min_match_ratio like the reference. */
 typedef struct mtr_pipeline mtr_pipeline;
 typedef struct {
-    int64_t reads, bases, candidates, rounds, rounds_fast, rounds_uf, jobs, uf_tasks, wdp_calls;
-    int64_t wdp_cells, wdp_slot_cells, wdp_dir_bytes;      /* algorithmic cells = sum rows * ulen over every DP run */
-    int64_t di_position_passes, di_bytes_in, di_bytes_out;
+    int64_t reads, bases, groups;
+    int64_t candidates;                                    /* query_counter */
+    int64_t waves;                                         /* engine waves, summed over the groups */
+    int64_t jobs, dp_tasks;                                /* wrap-around DP calls / K3 fill tasks */
+    int64_t wdp_cells, wdp_slot_cells, wdp_dir_bytes;      /* cells = sum rows * ulen over every DP launched */
+    int64_t spec_cells;                                    /* part of wdp_cells run for look-ahead candidates that were pruned
+                                                              after all (MTR_SPECULATE, default 8): not algorithmic cells */
+    int64_t tables, table_positions, walks, repeats;
     int64_t h2d_bytes, d2h_bytes;
-    int64_t launches;                                      /* CUDA kernels launched by run() */
-    int64_t spec_cells;                                    /* part of wdp_cells run for speculative candidates that were pruned
-                                                              after all (MTR_SPECULATE; 0 by default): not algorithmic cells */
-    double  wdp_fill_ms, wdp_tb_ms, di_kernel_ms, uf_kernel_ms;   /* CUDA-event time on the launching streams */
-    double  di_wall_ms, rounds_wall_ms, host_step_ms, wdp_wall_ms, uf_wall_ms;
+    int64_t launches;                                      /* CUDA kernels launched */
+    double  dp_ms, di_kernel_ms, uf_kernel_ms;             /* CUDA-event time on the launching streams, summed over groups */
+    double  engine_wall_ms;                                /* wall clock inside mtr_engine_run, summed over groups */
+    double  pack_ms, chain_ms;                             /* host: 2-bit pack + upload / chaining + formatting, summed */
+    double  wall_ms;                                       /* mtr_pipeline_run: wall clock of the call */
 } mtr_pipeline_stats;
 int  mtr_pipeline_open(int device, int threads, mtr_pipeline **out);
 void mtr_pipeline_close(mtr_pipeline *p);
@@ -209,11 +263,6 @@ int  mtr_pipeline_load_fasta(mtr_pipeline *p, const char *text, int64_t len);
 int  mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, int64_t len, int first, int count);
 int  mtr_pipeline_run(mtr_pipeline *p, int print_alignment, const char **out_text, int64_t *out_len);
 int  mtr_pipeline_get_stats(const mtr_pipeline *p, mtr_pipeline_stats *out);
-/* Measurement support: log every DP job run() sends to the GPU (as COUNTS jobs), read the log back, and get the
- * context that holds the resident reads so that the logged jobs can be replayed as ONE batch with mtr_wdp_upload /
- * mtr_wdp_launch -- K3 timed alone on exactly the step's jobs. */
-int  mtr_pipeline_log_jobs(mtr_pipeline *p, int on);
-int  mtr_pipeline_get_job_log(mtr_pipeline *p, const mtr_wdp_job **jobs, int64_t *n_jobs, const uint8_t **units, int64_t *units_len);
 mtr_ctx *mtr_pipeline_ctx(mtr_pipeline *p);
 
 /* ------------------------------------------------------------------ the reference's entry points */

@@ -93,6 +93,7 @@ extern "C" void mtr_cuda_shutdown(mtr_ctx *ctx)
     cudaDeviceSynchronize();
     di_state_free(ctx);
     uf_state_free(ctx);
+    eng_state_free(ctx);
     WdpState &w = ctx->wdp;
     w.d_tasks.release(); w.d_dirs.release(); w.d_results.release(); w.d_aux.release();
     w.d_counters.release(); w.h_tasks.release(); w.h_results.release();

@@ -379,13 +379,15 @@ extern "C" int mtr_di_run(mtr_ctx *ctx, int manhattan, const uint16_t *stale, co
 // Reads [first, first + count) of the resident batch only; stale_off / pos_off and the output arrays are indexed as
 // for the whole batch, so a caller can sweep the batch in slices and start working on a slice while the next one is
 // still on the GPU.
-extern "C" int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
-                                const int64_t *pos_off, double *di, int32_t *end, int32_t *w_out, int first, int count)
+// Runs the kernels for reads [first, first + count) and leaves directional_index / _end / _w in device memory
+// (di_device_outputs; read r of the range starts at pos_off[first + r] - pos_off[first]).  The resident engine consumes
+// them there; mtr_di_run_range copies them out.
+int di_compute(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off, const int64_t *pos_off, int first, int count)
 {
     if (!ctx) return MTR_EINVAL;
     if (first < 0 || count < 0 || first + count > ctx->n_reads) { mtr_set_error(ctx, "di_run: read range outside the resident batch"); return MTR_EINVAL; }
     if (count == 0) return MTR_OK;
-    if (!pos_off || !end || !w_out) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
+    if (!pos_off) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
     MTR_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->di) ctx->di = new DiState();
     DiState &d = *ctx->di;
@@ -510,19 +512,42 @@ extern "C" int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *sta
     MTR_CUDA(ctx, cudaGetLastError());
     launches++;
     MTR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-    // the copies are issued only when the kernels are done: a copy waiting for its stream at the head of a copy-engine
-    // queue would hold up the copies of every other context on the GPU
-    MTR_CUDA(ctx, mtr_sync(ctx));
-    if (di) MTR_CUDA(ctx, cudaMemcpyAsync(di + pos0, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
-    MTR_CUDA(ctx, cudaMemcpyAsync(end + pos0, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
-    MTR_CUDA(ctx, cudaMemcpyAsync(w_out + pos0, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, mtr_sync(ctx));
     float ms = 0;
     MTR_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
     ctx->stats.di_ms = ms;
     ctx->stats.di_position_passes = pp;
     ctx->stats.di_bytes_in = (ctx->word_off[first + n] - ctx->word_off[first]) * 4 + nstale_total * 2;
-    ctx->stats.di_bytes_out = total_pos * (di ? 16 : 8);
+    ctx->stats.di_bytes_out = 0;
     ctx->stats.launches = launches;
+    return MTR_OK;
+}
+
+void di_device_outputs(mtr_ctx *ctx, double **di, int **end, int **w)
+{
+    DiState &d = *ctx->di;
+    if (di) *di = (double *)d.d_di.p;
+    if (end) *end = (int *)d.d_end.p;
+    if (w) *w = (int *)d.d_w.p;
+}
+
+extern "C" int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off,
+                                const int64_t *pos_off, double *di, int32_t *end, int32_t *w_out, int first, int count)
+{
+    if (!ctx) return MTR_EINVAL;
+    if (count > 0 && (!pos_off || !end || !w_out)) { mtr_set_error(ctx, "di_run: null argument"); return MTR_EINVAL; }
+    const int rc = di_compute(ctx, manhattan, stale, stale_off, pos_off, first, count);
+    if (rc || count == 0) return rc;
+    DiState &d = *ctx->di;
+    cudaStream_t s = ctx->main_stream;
+    const int64_t pos0 = pos_off[first];
+    const long long total_pos = pos_off[first + count] - pos0;
+    // (di_compute has drained the stream: a copy waiting for its stream at the head of a copy-engine queue would hold
+    // up the copies of every other context on the GPU)
+    if (di) MTR_CUDA(ctx, cudaMemcpyAsync(di + pos0, d.d_di.p, (size_t)total_pos * 8, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(end + pos0, d.d_end.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, cudaMemcpyAsync(w_out + pos0, d.d_w.p, (size_t)total_pos * 4, cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, mtr_sync(ctx));
+    ctx->stats.di_bytes_out = total_pos * (di ? 16 : 8);
     return MTR_OK;
 }

@@ -1,0 +1,365 @@
+// eng.cu -- the resident engine on the GPU: kernel wrappers around eng_core.h and the host driver that launches waves.
+//
+// mtr_engine_run = handle_one_TR (/root/reference/handle_one_read.c:190-261) for every read of the resident batch.
+// One wave (see eng_core.h) is ~30 kernel launches on one stream (the K3 class kernels fan out over side streams);
+// nothing is copied between host and device inside the loop except a 64-byte status snapshot that the last kernel of
+// a wave writes into mapped host memory.  The host launches a few waves ahead and looks at the snapshot in between.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "eng_host.h"
+
+using namespace eng;
+
+// ---------------------------------------------------------------- kernels
+__global__ void eng_begin(Ptrs P) { if (threadIdx.x == 0 && blockIdx.x == 0) wave_begin(P); }
+
+__global__ void __launch_bounds__(128) eng_advance(Ptrs P)
+{
+    const int nw = gridDim.x * (blockDim.x >> 5);
+    const int n = P.ctr->n_advance;
+    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) advance_chain(P, P.wait_list[i]);
+}
+
+__global__ void __launch_bounds__(128) eng_polish(Ptrs P)
+{
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const Scratch S = scratch_of(P, warp);
+    const int n = P.ctr->n_polish;
+    for (;;) {
+        int i = 0;
+        if (lane() == 0) i = atomicAdd(&P.ctr->polish_head, 1);
+        i = bcast(i, 0);
+        if (i >= n) break;
+        polish_chain(P, P.polish_list[i], S);
+    }
+}
+
+__global__ void __launch_bounds__(64) eng_sched(Ptrs P)
+{
+    __shared__ unsigned long long tab[2][kInlineSlots];
+    const int read = blockIdx.x * 2 + (threadIdx.x >> 5);
+    if (read >= P.n_reads) return;
+    sched_read(P, read, tab[threadIdx.x >> 5], kInlineSlots);
+}
+
+__global__ void __launch_bounds__(128) eng_walk(Ptrs P)
+{
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const Scratch S = scratch_of(P, warp);
+    const int n = P.ctr->n_walk;
+    for (;;) {
+        int i = 0;
+        if (lane() == 0) i = atomicAdd(&P.ctr->walk_head, 1);
+        i = bcast(i, 0);
+        if (i >= n) break;
+        walk_chain(P, P.walk_list[i], S);
+    }
+}
+
+__global__ void __launch_bounds__(256) eng_emit(Ptrs P, int n_chains)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_chains) emit_chain(P, c);
+}
+
+__global__ void eng_plan(Ptrs P) { if (blockIdx.x == 0 && threadIdx.x < 32) plan_tasks(P); }
+
+__global__ void __launch_bounds__(256) eng_scatter(Ptrs P)
+{
+    const int n = min(P.ctr->n_tasks, P.task_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) scatter_task(P, i);
+}
+
+__global__ void __launch_bounds__(256) eng_zero_aux(Ptrs P)
+{
+    const long long n = min((long long)P.ctr->aux_used, P.aux_cap);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) P.aux[i] = 0;
+}
+
+struct EngSnapshot { int unfinished, error, error_read, deferred, waves, n_accepted, n_tasks, pad; unsigned long long tasks_total, candidates_started; };
+
+__global__ void eng_publish(Ptrs P, EngSnapshot *snap)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Counters &c = *P.ctr;
+    snap->error = c.error; snap->error_read = c.error_read; snap->deferred = c.deferred; snap->waves = c.waves;
+    snap->n_accepted = c.n_accepted; snap->n_tasks = c.n_tasks; snap->tasks_total = c.tasks_total; snap->candidates_started = c.tables + (unsigned long long)(unsigned)c.progress;
+    __threadfence_system();
+    snap->unfinished = c.unfinished;
+}
+
+// ---------------------------------------------------------------- per-context engine state
+struct EngState {
+    DevBuf d_main, d_dirs, d_scratch;
+    PinBuf h_snap, h_acc, h_ctr;
+    Config cfg;
+    Layout lay;
+    Ptrs P;
+    bool bound = false;
+    int speculate = 8;
+    cudaStream_t side[8] = {};
+    cudaEvent_t fork = nullptr, join[8] = {};
+    int n_side = 0;
+    static constexpr int kEv = 32;
+    cudaEvent_t ev_dp0[kEv] = {}, ev_dp1[kEv] = {}, ev_w0[kEv] = {};
+    std::vector<mtr_repeat> reps;
+    std::vector<uint8_t> units;
+};
+
+void eng_state_free(mtr_ctx *ctx)
+{
+    if (!ctx->eng) return;
+    EngState *e = ctx->eng;
+    e->d_main.release(); e->d_dirs.release(); e->d_scratch.release();
+    e->h_snap.release(); e->h_acc.release(); e->h_ctr.release();
+    for (int i = 0; i < 8; i++) { if (e->side[i]) cudaStreamDestroy(e->side[i]); if (e->join[i]) cudaEventDestroy(e->join[i]); }
+    if (e->fork) cudaEventDestroy(e->fork);
+    for (int i = 0; i < EngState::kEv; i++) {
+        if (e->ev_dp0[i]) cudaEventDestroy(e->ev_dp0[i]);
+        if (e->ev_dp1[i]) cudaEventDestroy(e->ev_dp1[i]);
+        if (e->ev_w0[i]) cudaEventDestroy(e->ev_w0[i]);
+    }
+    delete e;
+    ctx->eng = nullptr;
+}
+
+// ---------------------------------------------------------------- K3 busy intervals of the whole process (roofline)
+namespace {
+struct BusyLog {
+    std::mutex mu;
+    cudaEvent_t base[16] = {};
+    std::vector<std::pair<double, double>> iv[16];
+} g_busy;
+
+cudaEvent_t busy_base(int device)
+{
+    std::lock_guard<std::mutex> g(g_busy.mu);
+    if (device < 0 || device >= 16) return nullptr;
+    if (!g_busy.base[device]) {
+        cudaEventCreate(&g_busy.base[device]);
+        cudaEventRecord(g_busy.base[device], 0);
+        cudaEventSynchronize(g_busy.base[device]);
+    }
+    return g_busy.base[device];
+}
+}  // namespace
+
+extern "C" double mtr_engine_dp_busy_ms(int device, int reset)
+{
+    if (device < 0 || device >= 16) return 0;
+    std::lock_guard<std::mutex> g(g_busy.mu);
+    std::vector<std::pair<double, double>> &v = g_busy.iv[device];
+    std::sort(v.begin(), v.end());
+    double total = 0, hi = -1e300;
+    for (const auto &p : v) {
+        if (p.first > hi) { total += p.second - p.first; hi = p.second; }
+        else if (p.second > hi) { total += p.second - hi; hi = p.second; }
+    }
+    if (reset) v.clear();
+    return total;
+}
+
+extern "C" int mtr_engine_set_speculate(mtr_ctx *ctx, int depth)
+{
+    if (!ctx || depth < 0) return MTR_EINVAL;
+    if (!ctx->eng) ctx->eng = new EngState();
+    ctx->eng->speculate = depth;
+    return MTR_OK;
+}
+
+static double wall_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- the driver
+extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio, const uint16_t *stale, const int64_t *stale_off,
+                              const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units, mtr_engine_stats *stats)
+{
+    if (!ctx) return MTR_EINVAL;
+    if (repeats) *repeats = nullptr;
+    if (n_repeats) *n_repeats = 0;
+    if (units) *units = nullptr;
+    if (stats) memset(stats, 0, sizeof *stats);
+    const int n = ctx->n_reads;
+    if (n == 0) return MTR_OK;
+    const double t_wall0 = wall_ms();
+    MTR_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->eng) ctx->eng = new EngState();
+    EngState &E = *ctx->eng;
+    cudaStream_t s = ctx->main_stream;
+    static const bool prof = getenv("MTR_PROFILE") != nullptr;
+    if (E.n_side == 0) {
+        int want = 4;
+        if (const char *e = getenv("MTR_ENGINE_SIDE_STREAMS")) want = std::max(0, std::min(8, atoi(e)));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int i = 0; i < want; i++) {
+            MTR_CUDA(ctx, cudaStreamCreateWithFlags(&E.side[i], cudaStreamNonBlocking));
+            MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.join[i], cudaEventDisableTiming));
+        }
+        MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.fork, cudaEventDisableTiming));
+        for (int i = 0; i < EngState::kEv; i++) {
+            MTR_CUDA(ctx, cudaEventCreate(&E.ev_dp0[i]));
+            MTR_CUDA(ctx, cudaEventCreate(&E.ev_dp1[i]));
+            MTR_CUDA(ctx, cudaEventCreate(&E.ev_w0[i]));
+        }
+        E.n_side = want;
+        if (want == 0) E.n_side = -1;                        // "initialised, no side streams"
+    }
+    const int n_side = std::max(E.n_side, 0);
+
+    // ---- directional index, left in device memory
+    std::vector<int64_t> pos_off((size_t)n + 1, 0);
+    int max_len = 0;
+    for (int r = 0; r < n; r++) { pos_off[r + 1] = pos_off[r] + ctx->len[r]; max_len = std::max(max_len, (int)ctx->len[r]); }
+    int rc = di_compute(ctx, manhattan, stale, stale_off, pos_off.data(), 0, n);
+    if (rc) return rc;
+    const double di_ms = ctx->stats.di_ms;
+    const int di_launches = ctx->stats.launches;
+    const int64_t di_h2d = ctx->stats.di_bytes_in - (ctx->word_off[n] - ctx->word_off[0]) * 4;
+
+    // ---- buffers
+    Config cfg = default_config(n, pos_off[n], max_len, ctx->n_sm);
+    if (const char *e = getenv("MTR_ENGINE_DIR_MB")) cfg.dir_cap = std::max(64LL, atoll(e)) << 20;
+    Layout lay = make_layout(cfg);
+    MTR_CUDA(ctx, E.d_main.reserve(lay.total));
+    MTR_CUDA(ctx, E.d_scratch.reserve((size_t)lay.uf_stride * (size_t)cfg.uf_warps));
+    if ((size_t)cfg.dir_cap > E.d_dirs.cap) MTR_CUDA(ctx, E.d_dirs.reserve_exact((size_t)cfg.dir_cap));
+    cfg.dir_cap = (long long)E.d_dirs.cap;
+    MTR_CUDA(ctx, E.h_snap.reserve(sizeof(EngSnapshot)));
+    MTR_CUDA(ctx, E.h_ctr.reserve(sizeof(Counters)));
+    E.cfg = cfg; E.lay = lay;
+    Ptrs P = bind(E.d_main.p, lay, cfg);
+    P.packed = (const uint32_t *)ctx->d_packed.p;
+    int *d_end = nullptr, *d_w = nullptr;
+    di_device_outputs(ctx, nullptr, &d_end, &d_w);
+    P.end = d_end; P.w = d_w;
+    P.uf_scratch = (unsigned char *)E.d_scratch.p;
+    P.min_match_ratio = min_match_ratio;
+    P.speculate = E.speculate;
+    if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
+    E.P = P;
+
+    // zero: chain stages (ST_FREE), lists, counters, histograms, the scratch epochs; then the per-read state
+    MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.chains, 0, sizeof(Chain) * (size_t)lay.n_chains, s));
+    MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.ctr, 0, lay.total - lay.ctr, s));
+    MTR_CUDA(ctx, cudaMemsetAsync(E.d_scratch.p, 0, (size_t)lay.uf_stride * (size_t)cfg.uf_warps, s));
+    std::vector<Read> reads;
+    init_reads(reads, ctx->word_off.data(), ctx->len.data(), n);
+    MTR_CUDA(ctx, cudaMemcpyAsync(P.reads, reads.data(), sizeof(Read) * (size_t)n, cudaMemcpyHostToDevice, s));
+    {
+        Counters c0;
+        memset(&c0, 0, sizeof c0);
+        c0.unfinished = n;
+        MTR_CUDA(ctx, cudaMemcpyAsync(P.ctr, &c0, sizeof c0, cudaMemcpyHostToDevice, s));
+    }
+    EngSnapshot *snap = (EngSnapshot *)E.h_snap.p;
+    memset(snap, 0, sizeof *snap);
+    snap->unfinished = n;
+
+    WdpDevLaunch L;
+    memset(&L, 0, sizeof L);
+    L.tasks = P.tasks; L.class_begin = P.class_begin; L.counters = P.slot_counter; L.packed = P.packed;
+    L.units = P.units; L.dirs = (uint8_t *)E.d_dirs.p; L.results = P.results; L.aux = P.aux;
+    L.blocks = ctx->n_sm * 4;
+    for (int i = 0; i < n_side; i++) { L.side[i] = E.side[i]; L.join[i] = E.join[i]; }
+    L.fork = E.fork; L.n_side = n_side;
+
+    const int uf_blocks = cfg.uf_warps / 4;
+    const int launches_per_wave = 10 + 20 + 1;
+    cudaEvent_t base = busy_base(ctx->device);
+    double dp_ms = 0, uf_ms = 0;
+    long long launches = di_launches;
+    int burst = 4;
+    if (const char *e = getenv("MTR_ENGINE_BURST")) burst = std::max(1, std::min(EngState::kEv, atoi(e)));
+    unsigned long long last_tasks = ~0ull, last_started = ~0ull;
+    int last_accepted = -1, last_unfinished = -1, stalled = 0;
+    for (;;) {
+        for (int b = 0; b < burst; b++) {
+            MTR_CUDA(ctx, cudaEventRecord(E.ev_w0[b], s));
+            eng_begin<<<1, 32, 0, s>>>(P);
+            eng_advance<<<ctx->n_sm * 4, 128, 0, s>>>(P);
+            eng_polish<<<uf_blocks, 128, 0, s>>>(P);
+            eng_sched<<<(n + 1) / 2, 64, 0, s>>>(P);
+            eng_walk<<<uf_blocks, 128, 0, s>>>(P);
+            eng_emit<<<(lay.n_chains + 255) / 256, 256, 0, s>>>(P, lay.n_chains);
+            eng_plan<<<1, 32, 0, s>>>(P);
+            eng_scatter<<<ctx->n_sm * 2, 256, 0, s>>>(P);
+            eng_zero_aux<<<ctx->n_sm * 2, 256, 0, s>>>(P);
+            MTR_CUDA(ctx, cudaGetLastError());
+            MTR_CUDA(ctx, cudaEventRecord(E.ev_dp0[b], s));
+            MTR_CUDA(ctx, wdp_launch_dev(L, s));
+            MTR_CUDA(ctx, cudaEventRecord(E.ev_dp1[b], s));
+            eng_publish<<<1, 1, 0, s>>>(P, snap);
+            MTR_CUDA(ctx, cudaGetLastError());
+            launches += launches_per_wave;
+        }
+        MTR_CUDA(ctx, mtr_sync(ctx));
+        for (int b = 0; b < burst; b++) {
+            float f = 0, g = 0, t0 = 0, t1 = 0;
+            MTR_CUDA(ctx, cudaEventElapsedTime(&f, E.ev_dp0[b], E.ev_dp1[b]));
+            MTR_CUDA(ctx, cudaEventElapsedTime(&g, E.ev_w0[b], E.ev_dp0[b]));
+            dp_ms += f; uf_ms += g;
+            if (base && cudaEventElapsedTime(&t0, base, E.ev_dp0[b]) == cudaSuccess && cudaEventElapsedTime(&t1, base, E.ev_dp1[b]) == cudaSuccess) {
+                std::lock_guard<std::mutex> gl(g_busy.mu);
+                g_busy.iv[ctx->device].push_back(std::make_pair((double)t0, (double)t1));
+            }
+        }
+        if (prof) fprintf(stderr, "[mtr engine] ctx %p wave %d: unfinished %d accepted %d tasks(last wave) %d deferred %d\n", (void *)ctx, snap->waves, snap->unfinished, snap->n_accepted, snap->n_tasks, snap->deferred);
+        if (snap->error) break;
+        if (snap->unfinished <= 0) break;
+        // no progress at all during a whole burst: either the per-wave budgets are too small for a single task (grow
+        // them) or the engine is stuck (a bug: fail loudly instead of spinning)
+        if (snap->tasks_total == last_tasks && snap->candidates_started == last_started && snap->n_accepted == last_accepted && snap->unfinished == last_unfinished) {
+            if (snap->deferred > 0 && stalled < 6) {
+                const size_t want = E.d_dirs.cap * 2;
+                E.d_dirs.release();
+                MTR_CUDA(ctx, E.d_dirs.reserve_exact(want));
+                P.dir_cap = (long long)E.d_dirs.cap; E.P = P;
+                L.dirs = (uint8_t *)E.d_dirs.p;
+                stalled++;
+            } else {
+                mtr_set_error(ctx, "engine_run: no progress after wave %d (%d reads unfinished, %d tasks deferred)", snap->waves, snap->unfinished, snap->deferred);
+                return MTR_ECUDA;
+            }
+        }
+        last_tasks = snap->tasks_total; last_started = snap->candidates_started; last_accepted = snap->n_accepted; last_unfinished = snap->unfinished;
+    }
+    Counters *hc = (Counters *)E.h_ctr.p;
+    MTR_CUDA(ctx, cudaMemcpyAsync(hc, P.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    MTR_CUDA(ctx, mtr_sync(ctx));
+    if (hc->error) {
+        switch (hc->error) {
+        case ERR_WRAPCAP: mtr_set_error(ctx, "You need to increse the value of WrapDPsize."); return MTR_ERANGE;
+        case ERR_EMPTY_UNIT: mtr_set_error(ctx, "the revised repeat unit is empty (read %d)", hc->error_read); return MTR_ERANGE;
+        case ERR_ACCEPTED_FULL: mtr_set_error(ctx, "engine_run: more than %d accepted repeats in one group", cfg.acc_cap); return MTR_ENOMEM;
+        default: mtr_set_error(ctx, "engine_run: device error %d", hc->error); return MTR_ECUDA;
+        }
+    }
+    const int na = hc->n_accepted;
+    if (na > 0) {
+        MTR_CUDA(ctx, E.h_acc.reserve(sizeof(Accepted) * (size_t)na));
+        MTR_CUDA(ctx, cudaMemcpyAsync(E.h_acc.p, P.acc, sizeof(Accepted) * (size_t)na, cudaMemcpyDeviceToHost, s));
+        MTR_CUDA(ctx, mtr_sync(ctx));
+    }
+    export_repeats((const Accepted *)E.h_acc.p, na, E.reps, E.units);
+    if (repeats) *repeats = E.reps.data();
+    if (n_repeats) *n_repeats = na;
+    if (units) *units = E.units.data();
+    if (stats) {
+        export_stats(*hc, stats);
+        stats->launches = launches;
+        stats->di_ms = di_ms; stats->dp_ms = dp_ms; stats->uf_ms = uf_ms;
+        stats->h2d_bytes = di_h2d + (int64_t)sizeof(Read) * n + (int64_t)sizeof(Counters);
+        stats->d2h_bytes = (int64_t)sizeof(Accepted) * na + (int64_t)sizeof(Counters);
+        stats->wall_ms = wall_ms() - t_wall0;
+    }
+    ctx->stats.launches = (int32_t)std::min<long long>(launches, 0x7fffffff);
+    return MTR_OK;
+}

@@ -1,0 +1,1106 @@
+// eng_core.h -- the resident engine: mTR's per-read candidate loop, unit finder and revise chain as device code.
+//
+// Replaces, for a whole group of reads at once and without the host in the loop,
+//   handle_one_TR's candidate loop            /root/reference/handle_one_read.c:227-246  (eng::sched_read)
+//   find_tandem_repeat / _sub                 handle_one_read.c:77-154                   (sched_read, advance_chain)
+//   search_De_Bruijn_graph                    consensus.c:507-582                         (gate, walk_chain, advance_chain)
+//     init_inputString, generate_freqNode_return_list_maxNodes, freq_node   :37-60,132-253   (Table)
+//     search_De_Bruijn_graph_forward / _backward                            :269-505         (walk)
+//   polish_repeat                             consensus.c:584-704                         (polish_chain)
+//   revise_representative_unit (+ the vote of revise_representative_unit_sub)  :964-1013,1048-1087  (advance_chain, vote_unit)
+//   wrap_around_DP's pick between the two penalty sets   wrap_around_DP.c:357-429         (advance_chain)
+// The wrap-around DPs themselves are the K3 kernels of wdp.cu; this file only writes their task records (emit_chain,
+// plan_tasks, scatter_task) and reads their results.
+//
+// Execution model: a group of reads advances in WAVES.  One wave is the kernel sequence
+//     advance -> polish -> sched -> walk -> emit -> plan -> scatter -> K3 fill + traceback
+// and every kernel is a loop over independent work items (a chain, a read, a DP task) handled by one warp or one
+// thread.  All cross-kernel state (per-read cursor and candidate ring, chain records, work lists, counters) lives in
+// device memory, so the host only launches waves until the `unfinished` counter reaches zero.
+//
+// The code is written against simt.h: warp-uniform control flow, lane-strided data loops.  tests/hostsim compiles this
+// very header with one lane per warp and runs the waves on the CPU (DP and directional index answered by the oracle).
+#pragma once
+#include "simt.h"
+#include "mtr_internal.h"
+
+namespace eng {
+using namespace simt;
+
+// state shared by the lanes of a warp is written by lane 0 only, fenced on both sides: every lane has finished reading
+// the old value before it changes, and sees the new one afterwards
+#define ENG_LANE0(...) do { wsync(); if (lane() == 0) { __VA_ARGS__; } wsync(); } while (0)
+
+constexpr int kMaxPeriod = 500;              // MAX_PERIOD, mTR.h:34
+constexpr int kMaxTies = 1024;               // MAX_tiebreaks, mTR.h:46
+constexpr long long kWrapCap = 200000000LL;  // WrapDPsize, mTR.h:51
+constexpr int kUnitStride = 512;             // bytes reserved per stored unit / score string
+constexpr int kRing = 64;                    // candidates of one read in flight (most of them die at the maxFreq gate)
+constexpr int kSets = 16;                    // ... of which this many may hold chains (one chain per k)
+constexpr int kMaxK = 11;                    // k values per candidate: 2..10, 2..12 or 5..15 (handle_one_read.c:105-120)
+constexpr int kInlineWindow = 512;           // windows up to this many bases pass the maxFreq gate inside sched_read
+constexpr int kInlineSlots = 2048;           // count-table slots of a scheduler warp (>= 2 * (kInlineWindow + 2), power of two)
+constexpr int kMemoSlots = 8192;             // walk-memo entries per unit-finder warp
+constexpr int kSchedBudget = 96;             // candidates one sched_read call may start (bounds the latency of a wave)
+constexpr int kDpClasses = 20;               // 10 int32 + 10 paired int16x2 fill classes (wdp.cu)
+constexpr int kRowBuckets = 96;              // quarter-octave buckets of a task's row count (longest first)
+
+enum Stage : int {
+    ST_FREE = 0, ST_DONE, ST_WALK, ST_WALKING, ST_NEED_SEARCH, ST_WAIT_SEARCH, ST_NEED_POLISH, ST_NEED_CONS, ST_WAIT_CONS, ST_NEED_DP, ST_WAIT_DP
+};
+enum { U_RR = 0, U_TMP = 1, U_DIR0 = 2, U_DIR1 = 3 };       // unit strings of a chain
+enum { S_RR = 0, S_DIR0 = 1, S_DIR1 = 2 };                  // score strings (node counts clamped to 255: only ==1 and <2 are ever tested)
+enum { ERR_NONE = 0, ERR_WRAPCAP = 1, ERR_EMPTY_UNIT = 2, ERR_ACCEPTED_FULL = 3, ERR_TASKS_FULL = 4, ERR_STUCK = 5 };
+
+// the per-repeat feature record (mTR.h:99-119), without the strings
+struct Rec { int rep_start, rep_end, repeat_len, period, units, nm, nx, ni, nd, kmer, gain, mis, indel, pad[3]; };
+
+struct Chain {                     // one k of one candidate: find_tandem_repeat_sub (handle_one_read.c:77-100)
+    Rec rr, tmp;
+    int stage, k, pass, found_last;
+    float ratio0;
+    int read, qs, qe;
+    int dir_found[2], dir_period[2];
+    int fatal;                     // ERR_* to raise when (and only if) the candidate commits
+    int msg;                       // "You need to increse the value of WrapDPsize." lines to print when it commits
+    int ring;                      // ring position of its candidate (absolute), for the cell accounting
+    int aux_off;                   // CONSENSUS block of the wave (int32 offset into Ptrs::aux)
+};
+
+struct Cand { int qs, qe, set, spec, min_k, n_k; long long cells; };   // set < 0: no k passed the maxFreq gate
+
+struct Read {
+    long long word_off, pos_off;
+    int L, cursor, head, n_ring;   // ring entries head .. head + n_ring - 1 (mod kRing), in candidate order
+    int phase, n_accepted, candidates;
+    unsigned set_mask;             // chain sets in use
+    long long cells_wasted;
+    Cand ring[kRing];
+};
+
+struct Accepted { int read, seq; Rec rec; unsigned char unit[kUnitStride]; };   // insert_an_alignment, handle_one_read.c:156-176
+
+struct MemoEntry { unsigned key, epoch; int next, seen; };
+
+struct Counters {
+    int n_wait, n_polish, n_walk, n_tasks, n_advance, walk_head, polish_head, pad0;
+    int unfinished, error, error_read, n_accepted;
+    int deferred, msgs, waves, progress;
+    unsigned long long dir_used, aux_used;
+    unsigned long long cells, slot_cells, spec_cells, jobs, candidates, tables, walks, table_positions, dir_bytes, tasks_total;
+};
+
+struct Ptrs {
+    const uint32_t *packed;
+    Read *reads;
+    int n_reads;
+    int *end, *w;                  // directional_index_end / _w of every read (Read::pos_off)
+    Chain *chains;                 // [n_reads * kSets * kMaxK]
+    unsigned char *units;          // [chain][4][kUnitStride]
+    unsigned char *scores;         // [chain][3][kUnitStride]
+    mtr_wdp_result *results;       // [chain][4]: search: direction d, penalty set s at 2d + s; revise: slot 0
+    int *wait_list, *polish_list, *walk_list;
+    WdpTask *tasks_in, *tasks;     // as emitted / sorted by (class, rows descending)
+    int task_cap;
+    int *aux;                      // consensus histograms of the wave
+    long long aux_cap;             // in int32
+    long long dir_cap;             // bytes of direction matrices per wave
+    Accepted *acc;
+    int acc_cap;
+    Counters *ctr;
+    int *hist, *bucket_begin, *bucket_cursor;   // [kDpClasses * kRowBuckets (+1)]
+    int *class_begin;              // [WDP_NCLASS + 1] into tasks[]
+    int *slot_counter;             // [WDP_NCLASS] work-queue heads of the fill kernels
+    unsigned char *uf_scratch;     // per unit-finder warp: count table, memo, tie lists, node list, unit / score strings
+    long long uf_stride;
+    unsigned table_cap;            // slots of a unit-finder warp's table (power of two)
+    float min_match_ratio;
+    int speculate;
+};
+
+// ---------------------------------------------------------------- records
+MTR_DEV void rec_clear(Rec &r)                                  // clear_rr, fill_directional_index.c:40-60
+{
+    r.rep_start = r.rep_end = r.repeat_len = r.period = r.units = -1;
+    r.nm = r.nx = r.ni = r.nd = -1; r.kmer = r.gain = r.mis = r.indel = -1;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+}
+MTR_DEV float rec_ratio(const Rec &r) { return (float)r.nm / (float)(r.nm + r.nx + r.ni + r.nd); }   // e.g. wrap_around_DP.c:398
+
+// wrap_around_DP_sub's record update (wrap_around_DP.c:337-350)
+MTR_DEV void apply_dp(Rec &r, int qs, const mtr_wdp_result &d, int g, int m, int in)
+{
+    r.rep_start = qs + d.end_i + 1;
+    r.rep_end = qs + d.max_i;
+    r.repeat_len = d.max_i - d.end_i;
+    r.units = d.n_scanned / r.period;
+    r.nm = d.n_match; r.nx = d.n_mismatch; r.ni = d.n_ins; r.nd = d.n_del;
+    r.gain = g; r.mis = m; r.indel = in;
+}
+
+MTR_DEV unsigned char *unit_ptr(const Ptrs &P, int chain, int slot) { return P.units + ((size_t)chain * 4 + slot) * kUnitStride; }
+MTR_DEV unsigned char *score_ptr(const Ptrs &P, int chain, int slot) { return P.scores + ((size_t)chain * 3 + slot) * kUnitStride; }
+MTR_DEV void copy_bytes(unsigned char *dst, const unsigned char *src, int n)      // warp-cooperative
+{
+    for (int i = lane(); i < n; i += NL) dst[i] = src[i];
+    wsync();
+}
+
+// ---------------------------------------------------------------- packed reads
+MTR_DEV int base_at(const uint32_t *rd, int i) { return (int)((rd[i >> 4] >> ((i & 15) * 2)) & 3u); }
+
+// code of the k bases starting at i, first base most significant
+MTR_DEV unsigned kmer_at(const uint32_t *rd, int i, int k)
+{
+#ifdef __CUDA_ARCH__
+    const unsigned long long w = (unsigned long long)rd[i >> 4] | ((unsigned long long)rd[(i >> 4) + 1] << 32);
+    unsigned v = (unsigned)(w >> ((i & 15) * 2));
+    if (k < 16) v &= (1u << (2 * k)) - 1u;
+    v = __brev(v);
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);     // bit-reversed -> 2-bit groups reversed
+    return v >> (32 - 2 * k);
+#else
+    unsigned v = 0;
+    for (int t = 0; t < k; t++) v = v * 4u + (unsigned)base_at(rd, i + t);
+    return v;
+#endif
+}
+
+// ---------------------------------------------------------------- exact k-mer counts of one window
+// init_inputString + generate_freqNode_return_list_maxNodes + freq_node (consensus.c:37-60,132-253).  Open addressing,
+// one 64-bit slot per node: key + 1 in the high word (0 = empty), count in the low word.  The reference's own table
+// layout (direct for k <= 6, hashing modulo a prime above) is unobservable.
+struct Table { unsigned long long *slots; unsigned mask; int shift; };
+
+MTR_DEV Table table_make(unsigned long long *mem, unsigned cap_max, int n)
+{
+    unsigned cap = 64;
+    while (cap < 2u * (unsigned)(n + 2) && cap < cap_max) cap <<= 1;
+    Table t;
+    t.slots = mem; t.mask = cap - 1u; t.shift = clz(cap) + 1;    // hash -> top log2(cap) bits
+    return t;
+}
+MTR_DEV unsigned table_home(const Table &t, unsigned code) { return ((code + 0x9e3779b9u) * 2654435761u) >> t.shift; }
+MTR_DEV void table_clear(const Table &t)
+{
+    for (unsigned i = (unsigned)lane(); i <= t.mask; i += NL) t.slots[i] = 0ull;
+    wsync();
+}
+MTR_DEV int table_insert(const Table &t, unsigned code)         // count after the insert
+{
+    const unsigned long long key = ((unsigned long long)code + 1ull) << 32;
+    unsigned h = table_home(t, code);
+    for (;;) {
+        const unsigned long long old = atomic_cas(&t.slots[h], 0ull, key | 1ull);
+        if (old == 0ull) return 1;
+        if ((old & 0xffffffff00000000ull) == key) return (int)(unsigned)(atomic_add(&t.slots[h], 1ull) + 1ull);
+        h = (h + 1u) & t.mask;
+    }
+}
+MTR_DEV int table_find(const Table &t, unsigned code)           // slot or -1
+{
+    const unsigned long long key = ((unsigned long long)code + 1ull) << 32;
+    unsigned h = table_home(t, code);
+    for (;;) {
+        const unsigned long long sl = ldv(&t.slots[h]);
+        if ((sl & 0xffffffff00000000ull) == key) return (int)h;
+        if (sl == 0ull) return -1;
+        h = (h + 1u) & t.mask;
+    }
+}
+MTR_DEV int table_count(const Table &t, unsigned code)          // freq_node
+{
+    const int h = table_find(t, code);
+    return h < 0 ? 0 : (int)(unsigned)ldv(&t.slots[h]);
+}
+
+// codes of the window [qs, qe]: k-mer codes below min(qe, L-k+1), the raw base above (Q7); index >= L reads as 0
+// (the reference's value there depends on its whole call history, H4b)
+struct Window { const uint32_t *rd; int L, k, qs, qe, coded_end; };
+MTR_DEV Window window_make(const uint32_t *rd, int L, int k, int qs, int qe)
+{
+    Window w;
+    w.rd = rd; w.L = L; w.k = k; w.qs = qs; w.qe = qe;
+    w.coded_end = qe < L - k + 1 ? qe : L - k + 1;
+    return w;
+}
+MTR_DEV unsigned window_code(const Window &w, int i)
+{
+    if (i < w.coded_end) return kmer_at(w.rd, i, w.k);
+    return i < w.L ? (unsigned)base_at(w.rd, i) : 0u;
+}
+
+// builds the table of a window, returns maxFreq (counts only grow while building: the running maximum is the final one)
+MTR_DEV int table_build(const Table &t, const Window &w)
+{
+    table_clear(t);
+    int maxf = -1;
+    for (int i = w.qs + lane(); i <= w.qe; i += NL) {
+        const int c = table_insert(t, window_code(w, i));
+        maxf = c > maxf ? c : maxf;
+    }
+    maxf = wmax(maxf);
+    wsync();
+    return maxf;
+}
+
+// generate_freqNode_return_list_maxNodes (:132-229): nodes whose CURRENT count equals maxFreq, in order of first
+// occurrence, at most `cap`; a listed node loses one count (Q8).  NL positions per step; duplicates inside a step are
+// resolved with match_any so that the order is exactly the sequential one.
+MTR_DEV int table_list_max(const Table &t, const Window &w, int maxf, int *nodes, int cap)
+{
+    int nn = 0;
+    for (int p0 = w.qs; p0 <= w.qe && nn < cap; p0 += NL) {
+        const int p = p0 + lane();
+        unsigned code = 0x80000000u | (unsigned)lane();         // unique dummy for idle lanes
+        int h = -1;
+        bool ismax = false;
+        if (p <= w.qe) {
+            const unsigned c = window_code(w, p);
+            h = table_find(t, c);
+            ismax = h >= 0 && (int)(unsigned)ldv(&t.slots[h]) == maxf;
+            if (ismax) code = c;
+        }
+        const unsigned grp = match_any(code);
+        const bool lead = ismax && (ffs(grp) - 1) == lane();
+        const unsigned lst = wballot(lead);
+        const int at = nn + popc(lst & lanemask_lt());
+        if (lead && at < cap) { nodes[at] = (int)code; atomic_add(&t.slots[h], ~0ull); }   // count - 1 (the key is untouched: count >= 6)
+        nn += popc(lst);
+        if (nn > cap) nn = cap;
+        wsync();
+    }
+    return nn;
+}
+
+// ---------------------------------------------------------------- greedy de Bruijn walk (consensus.c:269-505)
+// From step 10 on the look-ahead depth is constant (k), so the next node is a pure function of the current node and of
+// the (now frozen) count table.  The memo caches that function across the <= 100 start nodes of one (window, k,
+// direction) and marks the nodes a walk has visited: coming back to a visited node means the walk is caught in a cycle
+// that does not contain its start node, i.e. it can only run out its step limit -- "no loop" is returned at once.
+// Both shortcuts leave every observable result unchanged; a full memo simply stops learning.
+struct Memo { MemoEntry *tab; unsigned epoch; int used, serial; };
+
+MTR_DEV void memo_reset(Memo &m)
+{
+    m.epoch++;
+    if (m.epoch == 0u) {                                       // (cannot happen within one task; kept for safety)
+        for (int i = lane(); i < kMemoSlots; i += NL) m.tab[i].epoch = 0u;
+        wsync();
+        m.epoch = 1u;
+    }
+    m.used = 0; m.serial = 0;
+}
+MTR_DEV int memo_slot(Memo &m, unsigned node)                  // entry index, or -1 when the memo is full
+{
+    unsigned h = ((node + 0x9e3779b9u) * 2654435761u) >> (32 - 13);
+    for (;;) {
+        const MemoEntry e = m.tab[h];
+        if (e.epoch != m.epoch) {
+            if (2 * m.used >= kMemoSlots) return -1;
+            ENG_LANE0(MemoEntry n; n.key = node; n.epoch = m.epoch; n.next = -1; n.seen = -1; m.tab[h] = n);
+            wsync();
+            m.used++;
+            return (int)h;
+        }
+        if (e.key == node) return (int)h;
+        h = (h + 1u) & (unsigned)(kMemoSlots - 1);
+    }
+}
+static_assert(kMemoSlots == 8192, "memo_slot hashes to 13 bits");
+
+// One walk.  Returns the period (0 = no loop).  ustr / uscore: the unit and its node counts (clamped to 255) in walk
+// order (the backward walk's strings are reversed by the caller).
+MTR_DEV int walk(const Table &tb, Memo &memo, int qs, int qe, unsigned start, int k, bool backward,
+                 unsigned char *ustr, unsigned char *uscore, int *ties, int *fresh)
+{
+    unsigned node = start;
+    int limit = (qe - qs) / 5;                                  // MIN_NUM_FREQ_UNIT
+    if (limit > kMaxPeriod) limit = kMaxPeriod;
+    const int serial = memo.serial++;
+    int period = 0;
+    for (int l = 0; l < limit; l++) {
+        if (!backward) {
+            const int sc = table_count(tb, node);
+            ENG_LANE0(ustr[l] = (unsigned char)(node >> (2 * (k - 1))); uscore[l] = (unsigned char)(sc > 255 ? 255 : sc));
+        }
+        int me = -1, next = -1;
+        if (l >= 10) {
+            me = memo_slot(memo, node);
+            if (me >= 0) {
+                if (memo.tab[me].seen == serial) return 0;     // cycle without the start node
+                wsync();
+                ENG_LANE0(memo.tab[me].seen = serial);
+                next = memo.tab[me].next;
+                wsync();
+            }
+        }
+        if (next < 0) {
+            const int depth = l < 10 ? 1 : k;
+            int nties = 1, pick = 0, m;
+            ENG_LANE0(ties[0] = 0);
+            wsync();
+            int *cur = ties, *nxt = fresh;
+            for (m = 1; m <= depth; m++) {
+                const int ncand = 4 * nties;
+                const unsigned keep = (1u << (2 * (k - m))) - 1u;
+                // pass 1: maximum count over all extensions
+                int best = -1;
+                for (int ci = lane(); ci < ncand; ci += NL) {
+                    const int t = cur[ci >> 2], b = ci & 3;
+                    const int digits = backward ? (b << (2 * (m - 1))) + t : 4 * t + b;
+                    const unsigned cand = backward ? ((unsigned)digits << (2 * (k - m))) + (node >> (2 * m))
+                                                   : ((node & keep) << (2 * m)) + (unsigned)digits;
+                    const int c = table_count(tb, cand);
+                    best = c > best ? c : best;
+                }
+                best = wmax(best);
+                // pass 2: the extensions that reach the maximum, in order (first wins, at most 1024)
+                int nf = 0;
+                bool have_pick = false;
+                for (int c0 = 0; c0 < ncand; c0 += NL) {
+                    const int ci = c0 + lane();
+                    int c = -2, digits = 0;
+                    if (ci < ncand) {
+                        const int t = cur[ci >> 2], b = ci & 3;
+                        digits = backward ? (b << (2 * (m - 1))) + t : 4 * t + b;
+                        const unsigned cand = backward ? ((unsigned)digits << (2 * (k - m))) + (node >> (2 * m))
+                                                       : ((node & keep) << (2 * m)) + (unsigned)digits;
+                        c = table_count(tb, cand);
+                    }
+                    const unsigned eq = wballot(c == best);
+                    if (eq) {
+                        if (!have_pick) { pick = bcast(digits, ffs(eq) - 1); have_pick = true; }
+                        const int at = nf + popc(eq & lanemask_lt());
+                        if (c == best && at < kMaxTies) nxt[at] = digits;
+                        nf += popc(eq);
+                        if (nf > kMaxTies) nf = kMaxTies;
+                    }
+                }
+                wsync();
+                if (backward ? nf <= 1 : nf == 1) break;
+                int *sw = cur; cur = nxt; nxt = sw;
+                nties = nf;
+            }
+            // m == depth + 1 when the ties were never resolved: the appended base is then pick / 4^depth == 0 ('A', :336)
+            next = backward ? (int)(((unsigned)(pick & 3) << (2 * (k - 1))) + (node >> 2))
+                            : (int)(((node & ((1u << (2 * (k - 1))) - 1u)) << 2) + ((unsigned)pick >> (2 * (m - 1))));
+            if (me >= 0) ENG_LANE0(memo.tab[me].next = next);
+        }
+        node = (unsigned)next;
+        if (backward) {
+            const int sc = table_count(tb, node);
+            ENG_LANE0(ustr[l] = (unsigned char)(node >> (2 * (k - 1))); uscore[l] = (unsigned char)(sc > 255 ? 255 : sc));
+        }
+        if (node == start) { period = l + 1; if (kMaxPeriod <= period) period = 0; break; }
+    }
+    wsync();
+    return period;
+}
+
+// ---------------------------------------------------------------- unit-finder scratch of one warp
+struct Scratch {
+    unsigned long long *table;
+    MemoEntry *memo;
+    int *ties, *fresh, *nodes;
+    unsigned *epoch;               // the warp's running memo epoch (survives from task to task and from wave to wave)
+    unsigned char *ustr, *uscore, *revised;
+};
+constexpr long long kScratchFixed = (long long)kMemoSlots * 16 + 2LL * kMaxTies * 4 + 128 * 4 + 3 * kUnitStride;
+MTR_DEV Scratch scratch_of(const Ptrs &P, int warp)
+{
+    unsigned char *b = P.uf_scratch + (size_t)warp * (size_t)P.uf_stride;
+    Scratch s;
+    s.table = (unsigned long long *)b; b += (size_t)P.table_cap * 8;
+    s.memo = (MemoEntry *)b; b += (size_t)kMemoSlots * 16;
+    s.ties = (int *)b; b += (size_t)kMaxTies * 4;
+    s.fresh = (int *)b; b += (size_t)kMaxTies * 4;
+    s.nodes = (int *)b; s.epoch = (unsigned *)b + 120; b += 128 * 4;
+    s.ustr = b; b += kUnitStride;
+    s.uscore = b; b += kUnitStride;
+    s.revised = b;
+    return s;
+}
+
+// ---------------------------------------------------------------- search_De_Bruijn_graph up to wrap_around_DP (consensus.c:507-549)
+// One chain in stage ST_WALK: counts, maxFreq gate, list of maximum-frequency nodes, forward walks over that list
+// until the first loop, backward walks likewise.
+MTR_DEV void walk_chain(const Ptrs &P, int chain, const Scratch &S)
+{
+    Chain &ch = P.chains[chain];
+    // A set freed and taken again inside one sched_read call leaves two entries for the same chain in the walk list
+    // (the first one from the dropped candidate): whoever claims the chain first does the work, the other one leaves.
+    int mine = 0;
+    ENG_LANE0(mine = atomic_cas(&ch.stage, (int)ST_WALK, (int)ST_WALKING) == (int)ST_WALK);
+    if (!bcast(mine, 0)) return;
+    const Read &rs = P.reads[ch.read];
+    const uint32_t *rd = P.packed + rs.word_off;
+    const int k = ch.k, qs = ch.qs, qe = ch.qe;
+    const Window win = window_make(rd, rs.L, k, qs, qe);
+    const Table tb = table_make(S.table, P.table_cap, qe - qs + 1);
+    const int maxf = table_build(tb, win);
+    if (lane() == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)(qe - qs + 1)); }
+    int found_last = 0, found[2] = {0, 0}, period[2] = {0, 0};
+    if (5 < maxf) {                                             // MIN_NUM_FREQ_UNIT < maxFreq, :532
+        const int nn = table_list_max(tb, win, maxf, S.nodes, 100);
+        Memo memo;
+        memo.tab = S.memo; memo.epoch = *S.epoch; memo.used = 0; memo.serial = 0;
+        int nwalks = 0;
+        for (int d = 0; d < 2; d++) {
+            memo_reset(memo);
+            for (int i = 0; i < nn; i++) {
+                nwalks++;
+                const int p = walk(tb, memo, qs, qe, (unsigned)S.nodes[i], k, d == 1, S.ustr, S.uscore, S.ties, S.fresh);
+                found_last = p > 0;
+                if (p == 0) continue;
+                unsigned char *du = unit_ptr(P, chain, U_DIR0 + d), *ds = score_ptr(P, chain, S_DIR0 + d);
+                for (int x = lane(); x < p; x += NL) {
+                    const int s = d == 1 ? p - 1 - x : x;      // the backward walk is reversed (:458-470)
+                    du[x] = S.ustr[s]; ds[x] = S.uscore[s];
+                }
+                wsync();
+                found[d] = 1; period[d] = p;
+                break;
+            }
+        }
+        ENG_LANE0(*S.epoch = memo.epoch);
+        if (lane() == 0) atomic_add(&P.ctr->walks, (unsigned long long)nwalks);
+    }
+    wsync();
+    if (lane() == 0) {
+        ch.found_last = found_last;
+        ch.dir_found[0] = found[0]; ch.dir_found[1] = found[1];
+        ch.dir_period[0] = period[0]; ch.dir_period[1] = period[1];
+        if (found[0] || found[1]) ch.stage = ST_NEED_SEARCH;
+        else { rec_clear(ch.rr); ch.stage = ST_DONE; }         // nothing found: find_tandem_repeat_sub clears (:86-88)
+    }
+    wsync();
+}
+
+// ---------------------------------------------------------------- polish_repeat (consensus.c:584-704)
+MTR_DEV int align_score(const Table &tb, int start, int k, int node, int period, const unsigned char *unit)
+{
+    int sum = 0;
+    for (int j = start; 0 <= j && start - k < j; j--) {
+        node = unit[j % period] * (1 << (2 * (k - 1))) + node / 4;
+        sum += table_count(tb, (unsigned)node);
+    }
+    return sum;
+}
+MTR_DEV bool suspicious(const unsigned char *score, int nscore, int kmer, int j)
+{
+    int c = 0;
+    for (int i = 0; i < kmer - 1 && 0 <= j - i; i++) {
+        const int sc = (j - i) < nscore ? score[j - i] : -1;
+        if (sc < 2) c++;
+    }
+    return (kmer - 1) * 0.8 < (double)c;
+}
+
+// polish rr of a chain in place (warp-uniform scalar code; the table build is the parallel part)
+MTR_DEV void polish_rr(const Ptrs &P, int chain, const Scratch &S)
+{
+    Chain &ch = P.chains[chain];
+    const Read &rs = P.reads[ch.read];
+    const int k = ch.rr.kmer, period = ch.rr.period;
+    if (period <= k) return;
+    const Window win = window_make(P.packed + rs.word_off, rs.L, k, ch.rr.rep_start, ch.rr.rep_end);
+    const Table tb = table_make(S.table, P.table_cap, ch.rr.rep_end - ch.rr.rep_start + 1);
+    table_build(tb, win);
+    if (lane() == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)(ch.rr.rep_end - ch.rr.rep_start + 1)); }
+    unsigned char *unit = unit_ptr(P, chain, U_RR);
+    const unsigned char *score = score_ptr(P, chain, S_RR);
+    const int nscore = period;                                  // the score string of the walk that produced the unit
+    const int p4 = 1 << (2 * (k - 1));
+    unsigned char *revised = S.revised;                         // filled from the back, kMaxPeriod entries
+    int jr = kMaxPeriod - 1;
+    int best = 0;
+    for (int i = 0; i < k; i++) best = unit[i] * (1 << (2 * (k - 1 - i))) + best;
+    for (int j = period - 1; 0 <= j;) {
+        const int ref = unit[j] * p4 + best / 4;
+        int best_freq = table_count(tb, (unsigned)ref);
+        best = ref;
+        const int sc = j < nscore ? score[j] : -1;
+        unsigned char out;
+        if (sc == 1 && suspicious(score, nscore, k, j)) {
+            for (int l = 0; l < 4; l++) {
+                const int alt = (ref + (l - unit[j]) * p4) % (4 * p4);
+                const int f = table_count(tb, (unsigned)alt);
+                if (best_freq < f) { best_freq = f; best = alt; }
+            }
+            if (best == ref) {
+                out = unit[j]; j--;
+            } else {
+                const int s_del = align_score(tb, j, k, best, period, unit);
+                const int s_sub = align_score(tb, j - 1, k, best, period, unit);
+                int s_ins = -1;
+                if (j >= 1 && best / p4 == unit[(j - 1) % period]) s_ins = align_score(tb, j - 2, k, best, period, unit);
+                out = (unsigned char)(best / p4);
+                int mx = s_del > s_sub ? s_del : s_sub;
+                if (s_ins > mx) mx = s_ins;
+                if (mx == s_del) {} else if (mx == s_sub) j -= 1; else j -= 2;
+            }
+        } else {
+            out = unit[j]; j--;
+        }
+        ENG_LANE0(revised[jr] = out);
+        jr--;
+        if (jr < 0) return;                                     // "fails to revise": record unchanged
+    }
+    wsync();
+    const int np = (kMaxPeriod - 1) - jr;
+    copy_bytes(unit, revised + jr + 1, np);
+    ENG_LANE0(ch.rr.period = np);
+    wsync();
+}
+
+// ---------------------------------------------------------------- min_missing (consensus.c:714-820)
+// each row of min_missing_bases[10][10][20] starts at 1 and steps by 0 or 1: stored as 19 step bits
+MTR_CONST unsigned kMissingSteps[10][10] = {
+    {0x21127,0x42227,0x08447,0x1084b,0x0108b,0x08113,0x40423,0x04043,0x00205,0x00041},
+    {0x21127,0x04227,0x0844b,0x2088b,0x0210b,0x08213,0x00823,0x04085,0x00409,0x00081},
+    {0x42227,0x0444b,0x1084b,0x4108b,0x04113,0x20413,0x01023,0x10085,0x00809,0x00101},
+    {0x0422b,0x0844b,0x2088b,0x0208b,0x08213,0x20423,0x02045,0x20105,0x01009,0x00201},
+    {0x0444b,0x1084b,0x4108b,0x04113,0x10213,0x00823,0x04045,0x40205,0x02011,0x00402},
+    {0x1084b,0x2108b,0x02113,0x08213,0x20423,0x01045,0x08085,0x00409,0x08021,0x01002},
+    {0x1088b,0x41113,0x04113,0x10423,0x40825,0x02085,0x10109,0x00809,0x10021,0x04002},
+    {0x42113,0x04213,0x10423,0x40845,0x02085,0x08109,0x00409,0x02011,0x00081,0x40004},
+    {0x04225,0x10425,0x40845,0x02085,0x08109,0x40209,0x01011,0x10041,0x00202,0x00010},
+    {0x20845,0x01085,0x04089,0x08209,0x40411,0x01021,0x08041,0x00102,0x01004,0x00040},
+};
+MTR_DEV int min_missing(int period, double error, int coverage)
+{
+    const int plim[9] = {200, 150, 100, 75, 50, 30, 20, 10, 5};
+    const double elim[9] = {0.25, 0.225, 0.2, 0.175, 0.15, 0.125, 0.1, 0.075, 0.05};
+    int i = 9, j = 9;
+    for (int t = 0; t < 9; t++) if (period > plim[t]) { i = t; break; }
+    for (int t = 0; t < 9; t++) if (error > elim[t]) { j = t; break; }
+    const int k = coverage <= 1 ? 0 : (coverage >= 20 ? 19 : coverage - 1);
+    return 1 + popc(kMissingSteps[i][j] & ((1u << k) - 1u));
+}
+
+// majority vote of revise_representative_unit_sub (consensus.c:964-1013) from the two histograms of the CONSENSUS
+// traceback: per unit column at most one consensus base (none if the gap wins) then at most one inserted base.
+// Columns are voted NL at a time; the output order is the column order (ballot compaction).  Writes at most
+// kUnitStride bases; the returned period may exceed that (the caller discards periods >= MAX_PERIOD).
+MTR_DEV int vote_unit(const Rec &r, const int *cons, const int *miss, unsigned char *out)
+{
+    const int ulen = r.period;
+    const int coverage = r.repeat_len / r.period;
+    const bool ins_ok = 5 <= coverage && coverage <= 20;
+    int need = 0;
+    if (ins_ok) {
+        const double mismatch_ratio = (double)(r.nx + r.ni + r.nd) / r.repeat_len;
+        need = min_missing(r.period, mismatch_ratio, coverage);
+    }
+    int n = 0;
+    for (int j0 = 1; j0 <= ulen; j0 += NL) {
+        const int j = j0 + lane();
+        int cb = -1, ib = -1;                                   // consensus base (0..3) / inserted base, -1 = none
+        if (j <= ulen) {
+            int mv = -1, mb = -1;
+            for (int q = 0; q < 5; q++) if (mv < cons[j * 5 + q]) { mv = cons[j * 5 + q]; mb = q; }
+            if (mb < 4) cb = mb;
+            mv = -1; int mm = -1;
+            for (int q = 0; q < 4; q++) if (mv < miss[j * 4 + q]) { mv = miss[j * 4 + q]; mm = q; }
+            if (ins_ok && need <= mv && 0 <= mm && mm <= 3) ib = mm;
+        }
+        const unsigned bc = wballot(cb >= 0), bi = wballot(ib >= 0);
+        const unsigned lt = lanemask_lt();
+        int at = n + popc(bc & lt) + popc(bi & lt);
+        if (cb >= 0) { if (at < kUnitStride) out[at] = (unsigned char)cb; at++; }
+        if (ib >= 0) { if (at < kUnitStride) out[at] = (unsigned char)ib; }
+        n += popc(bc) + popc(bi);
+    }
+    wsync();
+    return n;
+}
+
+// ---------------------------------------------------------------- chain state machine: consume DP results
+MTR_CONST int kSearchParams[2][3] = {{1, 1, 3}, {1, 3, 1}};    // wrap_around_DP.c:395,405
+MTR_CONST int kReviseParams[2][3] = {{5, 1, 1}, {1, 1, 3}};    // consensus.c:1062,1076
+
+MTR_DEV void start_revise_pass(const Ptrs &P, int chain)      // revise_representative_unit_sub's input: a copy of rr
+{
+    Chain &ch = P.chains[chain];
+    copy_bytes(unit_ptr(P, chain, U_TMP), unit_ptr(P, chain, U_RR), ch.rr.period < kUnitStride ? ch.rr.period : kUnitStride);
+    wsync();
+    if (lane() == 0) {
+        ch.tmp = ch.rr;
+        ch.tmp.gain = kReviseParams[ch.pass][0]; ch.tmp.mis = kReviseParams[ch.pass][1]; ch.tmp.indel = kReviseParams[ch.pass][2];
+        ch.stage = ST_NEED_CONS;
+    }
+    wsync();
+}
+
+MTR_DEV void next_pass_or_done(const Ptrs &P, int chain)
+{
+    Chain &ch = P.chains[chain];
+    if (ch.pass == 0) {
+        ENG_LANE0(ch.pass = 1);
+        wsync();
+        start_revise_pass(P, chain);
+    } else {
+        ENG_LANE0(ch.stage = ST_DONE);
+        wsync();
+    }
+}
+
+// one chain of the wait list (its DP results of the previous wave are in P.results)
+MTR_DEV void advance_chain(const Ptrs &P, int chain)
+{
+    Chain &ch = P.chains[chain];
+    const mtr_wdp_result *res = P.results + (size_t)chain * 4;
+    const int stage = ch.stage;
+    if (stage == ST_WAIT_SEARCH) {
+        // max_rr of search_De_Bruijn_graph starts cleared; wrap_around_DP (wrap_around_DP.c:357-429) keeps the strictly
+        // better of the two penalty sets of a direction (NaN never wins); a cleared record never qualifies
+        int best_d = -1, best_s = -1;
+        float best_ratio = -1;
+        for (int d = 0; d < 2; d++) {
+            if (!ch.dir_found[d]) continue;
+            int pick_s = -1;
+            float pick_ratio = -1;
+            for (int s = 0; s < 2; s++) {
+                const mtr_wdp_result &r = res[2 * d + s];
+                const float ratio = (float)r.n_match / (float)(r.n_match + r.n_mismatch + r.n_ins + r.n_del);
+                if (pick_ratio < ratio) { pick_s = s; pick_ratio = ratio; }
+            }
+            if (pick_s < 0) continue;
+            const int period = ch.dir_period[d];
+            const int units = res[2 * d + pick_s].n_scanned / period;
+            if (best_ratio < pick_ratio && P.min_match_ratio <= pick_ratio && 5 < units && 2 <= period && period < kMaxPeriod) {
+                best_ratio = pick_ratio; best_d = d; best_s = pick_s;
+            }
+        }
+        bool cleared = best_d < 0 || !ch.found_last;            // Q4: the LAST walk attempted must have found a loop
+        if (!cleared) {
+            copy_bytes(unit_ptr(P, chain, U_RR), unit_ptr(P, chain, U_DIR0 + best_d), ch.dir_period[best_d]);
+            copy_bytes(score_ptr(P, chain, S_RR), score_ptr(P, chain, S_DIR0 + best_d), ch.dir_period[best_d]);
+            Rec r = ch.rr;
+            r.period = ch.dir_period[best_d];
+            apply_dp(r, ch.qs, res[2 * best_d + best_s], kSearchParams[best_s][0], kSearchParams[best_s][1], kSearchParams[best_s][2]);
+            int msg = 0;
+            if ((long long)r.period * (ch.qe - ch.qs + 1) > kWrapCap) { msg = 1; cleared = true; }   // handle_one_read.c:89-91
+            ENG_LANE0(ch.rr = r; ch.msg += msg);
+            wsync();
+        }
+        if (cleared) {
+            ENG_LANE0(rec_clear(ch.rr); ch.stage = ST_DONE);
+            wsync();
+            return;
+        }
+        const int coverage = ch.rr.repeat_len / ch.rr.period;
+        if (!(5 <= coverage && coverage <= 20 && 5 < ch.rr.period)) {
+            ENG_LANE0(ch.stage = ST_DONE);
+            wsync();
+            return;
+        }
+        // revise_representative_unit (consensus.c:1048-1087), after polish_repeat
+        ENG_LANE0(ch.stage = ST_NEED_POLISH; P.polish_list[atomic_add(&P.ctr->n_polish, 1)] = chain);
+        return;
+    }
+    if (stage == ST_WAIT_CONS) {
+        const int *cons = P.aux + ch.aux_off;
+        const int np = vote_unit(ch.tmp, cons, cons + (size_t)(ch.tmp.period + 1) * 5, unit_ptr(P, chain, U_TMP));
+        ENG_LANE0(ch.tmp.period = np);
+        wsync();
+        if (np < kMaxPeriod) {
+            if (np <= 0) {                                      // the reference divides by zero here (H9)
+                ENG_LANE0(ch.fatal = ERR_EMPTY_UNIT; rec_clear(ch.rr); ch.stage = ST_DONE);
+                wsync();
+                return;
+            }
+            ENG_LANE0(ch.stage = ST_NEED_DP);
+            wsync();
+            return;
+        }
+        next_pass_or_done(P, chain);
+        return;
+    }
+    if (stage == ST_WAIT_DP) {
+        Rec t = ch.tmp;
+        apply_dp(t, ch.tmp.rep_start, res[0], kReviseParams[ch.pass][0], kReviseParams[ch.pass][1], kReviseParams[ch.pass][2]);
+        if (ch.ratio0 < rec_ratio(t)) {                         // ratio0 is never refreshed (Q10)
+            copy_bytes(unit_ptr(P, chain, U_RR), unit_ptr(P, chain, U_TMP), t.period);
+            ENG_LANE0(ch.rr = t);
+        }
+        ENG_LANE0(ch.tmp = t);
+        wsync();
+        next_pass_or_done(P, chain);
+        return;
+    }
+}
+
+// one chain of the polish list: polish_repeat, then the first revise pass
+MTR_DEV void polish_chain(const Ptrs &P, int chain, const Scratch &S)
+{
+    Chain &ch = P.chains[chain];
+    polish_rr(P, chain, S);
+    ENG_LANE0(ch.ratio0 = rec_ratio(ch.rr); ch.pass = 0);
+    wsync();
+    start_revise_pass(P, chain);
+}
+
+// ---------------------------------------------------------------- DP task emission (one thread per chain slot)
+MTR_CONST int kClassCap[10] = {16, 32, 48, 64, 96, 128, 192, 256, 384, 512};   // G * C of the throughput classes of wdp.cu
+MTR_DEV int dp_class_of(int ulen)
+{
+    for (int c = 0; c < 10; c++) if (ulen <= kClassCap[c]) return c;
+    return 9;
+}
+MTR_DEV int row_bucket(int rows)
+{
+    if (rows < 4) return rows < 0 ? 0 : rows;
+    const int lz = 31 - clz((unsigned)rows);
+    const int b = lz * 4 + ((rows >> (lz - 2)) & 3);
+    return b < kRowBuckets - 1 ? b : kRowBuckets - 1;
+}
+
+struct TaskSpec { int first, rows, ulen, uslot, n_param, mode, res_slot; const int *params; };
+
+// reserves direction space (+ consensus block) and task slots, then appends the tasks; false = no room in this wave
+// (the chain stays NEED_* and is emitted again by the next wave)
+MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
+{
+    Chain &ch = P.chains[chain];
+    const Read &rs = P.reads[ch.read];
+    long long dir_need = 0, aux_need = 0;
+    int slots = 0;
+    bool paired[2] = {false, false};
+    for (int i = 0; i < n; i++) {
+        const int cls = dp_class_of(sp[i].ulen);
+        dir_need += (((long long)sp[i].rows * (kClassCap[cls] / 4) + 15) & ~15LL) * sp[i].n_param;
+        if (sp[i].mode == MTR_TB_CONSENSUS) aux_need += ((long long)(sp[i].ulen + 1) * 9 + 3) & ~3LL;
+        int gmax = 0;
+        for (int p = 0; p < sp[i].n_param; p++) gmax = sp[i].params[3 * p] > gmax ? sp[i].params[3 * p] : gmax;
+        // both penalty sets in one int16x2 task while every score (x4, plus tag) fits 15 bits
+        paired[i] = sp[i].n_param == 2 && sp[i].mode == MTR_TB_COUNTS && 4LL * gmax * sp[i].rows <= 32760;
+        slots += (sp[i].n_param == 2 && !paired[i]) ? 2 : 1;
+    }
+    const long long d0 = (long long)atomic_add(&P.ctr->dir_used, (unsigned long long)dir_need);
+    const long long a0 = (long long)atomic_add(&P.ctr->aux_used, (unsigned long long)aux_need);
+    const int t0 = atomic_add(&P.ctr->n_tasks, slots);
+    if (d0 + dir_need > P.dir_cap || a0 + aux_need > P.aux_cap || t0 + slots > P.task_cap) {
+        // over budget: the slots it took in the task list are marked empty (the counters restart with the next wave)
+        for (int i = 0; i < slots && t0 + i < P.task_cap; i++) P.tasks_in[t0 + i].rows = -1;
+        atomic_add(&P.ctr->deferred, 1);
+        return false;
+    }
+    long long doff = d0, aoff = a0, cells = 0;
+    int at = t0;
+    for (int i = 0; i < n; i++) {
+        WdpTask t;
+        t.base0 = rs.word_off * 16 + sp[i].first;
+        t.rows = sp[i].rows; t.ulen = sp[i].ulen;
+        t.unit_off = (long long)((size_t)chain * 4 + sp[i].uslot) * kUnitStride;
+        const int cls = dp_class_of(sp[i].ulen);
+        t.dir_stride = kClassCap[cls] / 4;
+        t.dir_bytes = ((long long)t.rows * t.dir_stride + 15) & ~15LL;
+        t.dir_off = doff; doff += t.dir_bytes * sp[i].n_param;
+        t.aux_off = 0; t.aux_cap = 0;
+        if (sp[i].mode == MTR_TB_CONSENSUS) {
+            t.aux_off = aoff; aoff += ((long long)(sp[i].ulen + 1) * 9 + 3) & ~3LL;
+            ch.aux_off = (int)t.aux_off;
+        }
+        t.result_idx = chain * 4 + sp[i].res_slot;
+        t.n_param = (unsigned char)sp[i].n_param; t.mode = (unsigned char)sp[i].mode; t.pad_ = 0;
+        for (int p = 0; p < 2; p++) {
+            const int *q = sp[i].params + 3 * (p < sp[i].n_param ? p : 0);
+            t.gain[p] = (short)q[0]; t.mis[p] = (short)q[1]; t.indel[p] = (short)q[2];
+        }
+        t.cls = (unsigned char)(paired[i] ? 10 + cls : cls);
+        if (sp[i].n_param == 2 && !paired[i]) {                 // two int32 tasks
+            WdpTask u = t;
+            t.n_param = 1; u.n_param = 1;
+            u.gain[0] = t.gain[1]; u.mis[0] = t.mis[1]; u.indel[0] = t.indel[1];
+            u.dir_off = t.dir_off + t.dir_bytes; u.result_idx = t.result_idx + 1;
+            P.tasks_in[at++] = u;
+            atomic_add(&P.hist[(int)u.cls * kRowBuckets + row_bucket(u.rows)], 1);
+        }
+        P.tasks_in[at++] = t;
+        atomic_add(&P.hist[(int)t.cls * kRowBuckets + row_bucket(t.rows)], 1);
+        cells += (long long)t.rows * t.ulen * sp[i].n_param;
+        atomic_add(&P.ctr->slot_cells, (unsigned long long)((long long)t.rows * kClassCap[cls] * sp[i].n_param));
+    }
+    atomic_add(&P.ctr->cells, (unsigned long long)cells);
+    atomic_add(&P.ctr->jobs, (unsigned long long)n);
+    atomic_add(&P.ctr->dir_bytes, (unsigned long long)dir_need);
+    atomic_add((unsigned long long *)&P.reads[ch.read].ring[ch.ring % kRing].cells, (unsigned long long)cells);
+    P.wait_list[atomic_add(&P.ctr->n_wait, 1)] = chain;
+    return true;
+}
+
+MTR_DEV void emit_chain(const Ptrs &P, int chain)
+{
+    Chain &ch = P.chains[chain];
+    const int stage = ch.stage;
+    if (stage != ST_NEED_SEARCH && stage != ST_NEED_CONS && stage != ST_NEED_DP) return;
+    TaskSpec sp[2];
+    int n = 0;
+    if (stage == ST_NEED_SEARCH) {
+        for (int d = 0; d < 2; d++) {
+            if (!ch.dir_found[d]) continue;
+            sp[n].first = ch.qs; sp[n].rows = ch.qe - ch.qs + 1; sp[n].ulen = ch.dir_period[d]; sp[n].uslot = U_DIR0 + d;
+            sp[n].n_param = 2; sp[n].mode = MTR_TB_COUNTS; sp[n].res_slot = 2 * d; sp[n].params = &kSearchParams[0][0];
+            n++;
+        }
+    } else {
+        sp[0].first = ch.tmp.rep_start; sp[0].rows = ch.tmp.rep_end - ch.tmp.rep_start + 1; sp[0].ulen = ch.tmp.period; sp[0].uslot = U_TMP;
+        sp[0].n_param = 1; sp[0].mode = stage == ST_NEED_CONS ? MTR_TB_CONSENSUS : MTR_TB_COUNTS; sp[0].res_slot = 0;
+        sp[0].params = &kReviseParams[ch.pass][0];
+        n = 1;
+    }
+    for (int i = 0; i < n; i++) {
+        // wrap_around_DP.c:260-263: the reference aborts the whole run when (ulen + 1) * i + j reaches WrapDPsize
+        if ((long long)(sp[i].ulen + 1) * sp[i].rows + sp[i].ulen >= kWrapCap) {
+            ch.fatal = ERR_WRAPCAP; rec_clear(ch.rr); ch.stage = ST_DONE;
+            return;
+        }
+    }
+    if (!emit_tasks(P, chain, sp, n)) return;
+    ch.stage = stage == ST_NEED_SEARCH ? ST_WAIT_SEARCH : (stage == ST_NEED_CONS ? ST_WAIT_CONS : ST_WAIT_DP);
+}
+
+// single thread, first thing in a wave: the chains emitted by the previous wave become this wave's advance list, and the
+// per-wave reservations start from zero
+MTR_DEV void wave_begin(const Ptrs &P)
+{
+    Counters &c = *P.ctr;
+    c.n_advance = c.n_wait; c.n_wait = 0;
+    c.n_polish = 0; c.n_walk = 0; c.n_tasks = 0; c.deferred = 0; c.walk_head = 0; c.polish_head = 0;
+    c.dir_used = 0; c.aux_used = 0;
+    c.waves++;
+}
+
+// one warp: bucket offsets (class ascending, rows descending), class boundaries for the fill kernels, and the reset of
+// the histogram for the next wave
+MTR_DEV void plan_tasks(const Ptrs &P)
+{
+    int at = 0;
+    for (int c = 0; c < kDpClasses; c++) {
+        const int wc = c < 10 ? c : 16 + (c - 10);             // class index of wdp.cu (10..15 are its latency classes)
+        const int begin = at;
+        for (int j0 = 0; j0 < kRowBuckets; j0 += NL) {
+            const int j = j0 + lane();
+            const int i = c * kRowBuckets + (kRowBuckets - 1 - j);
+            const int h = j < kRowBuckets ? P.hist[i] : 0;
+            const int off = wscan_excl(h);
+            if (j < kRowBuckets) { P.bucket_begin[i] = at + off; P.hist[i] = 0; P.bucket_cursor[i] = 0; }
+            at += wsum(h);
+        }
+        ENG_LANE0(P.class_begin[wc] = begin; P.class_begin[wc + 1] = at; if (c == 9) for (int q = 10; q <= 16; q++) P.class_begin[q] = at);
+    }
+    for (int q = lane(); q < WDP_NCLASS; q += NL) P.slot_counter[q] = 0;
+    ENG_LANE0(P.ctr->tasks_total += (unsigned long long)at);
+}
+
+MTR_DEV void scatter_task(const Ptrs &P, int i)
+{
+    const WdpTask t = P.tasks_in[i];
+    if (t.rows < 0) return;                                    // slot of a deferred emission
+    const int b = (int)t.cls * kRowBuckets + row_bucket(t.rows);
+    P.tasks[P.bucket_begin[b] + atomic_add(&P.bucket_cursor[b], 1)] = t;
+}
+
+// ---------------------------------------------------------------- per-read scheduler: handle_one_TR's candidate loop
+// (handle_one_read.c:227-246) with candidate look-ahead.  An accepted repeat found from candidate (qs', qe') prunes
+// only ranges that start inside it and end before its rep_end (:178-188): a later candidate whose range ends beyond
+// every in-flight qe' can (almost) never be pruned by them and is evaluated concurrently; up to `speculate` further
+// candidates are evaluated ahead of ones that could still prune them.  Results are committed in candidate order; when
+// a commit accepts a repeat, every in-flight candidate whose start it has just pruned is dropped -- the reference
+// would never have visited it.  Same bytes for any depth.
+MTR_DEV void free_set(const Ptrs &P, Read &rs, int read, int set)
+{
+    if (set < 0) return;
+    for (int c = lane(); c < kMaxK; c += NL) P.chains[((size_t)read * kSets + set) * kMaxK + c].stage = ST_FREE;
+    wsync();
+    ENG_LANE0(rs.set_mask &= ~(1u << set));
+    wsync();
+}
+
+MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, unsigned table_cap)
+{
+    Read &rs = P.reads[read];
+    if (rs.phase != 0) return;
+    const uint32_t *rd = P.packed + rs.word_off;
+    int *END = P.end + rs.pos_off, *WW = P.w + rs.pos_off;
+    const int L = rs.L;
+    int started = 0;
+    for (;;) {
+        // ---- commit finished candidates in candidate order
+        while (rs.n_ring > 0) {
+            Cand &cd = rs.ring[rs.head % kRing];
+            int best_c = -1;
+            bool done = true;
+            int fatal = 0, msgs = 0;
+            if (cd.set >= 0) {
+                const size_t c0 = ((size_t)read * kSets + cd.set) * kMaxK;
+                for (int c = 0; c < cd.n_k; c++) if (P.chains[c0 + c].stage != ST_DONE) { done = false; break; }
+                if (!done) break;
+                // find_tandem_repeat's pick over k (handle_one_read.c:135-146)
+                float best_ratio = -1;
+                for (int c = 0; c < cd.n_k; c++) {
+                    const Chain &ch = P.chains[c0 + c];
+                    if (ch.fatal && !fatal) fatal = ch.fatal;
+                    msgs += ch.msg;
+                    const float ratio = rec_ratio(ch.rr);
+                    if (best_ratio < ratio && P.min_match_ratio <= ratio && 5 < ch.rr.units && 2 <= ch.rr.period) { best_ratio = ratio; best_c = c; }
+                }
+            }
+            if (fatal) {
+                ENG_LANE0(if (atomic_max(&P.ctr->error, fatal) < fatal) P.ctr->error_read = read; rs.phase = 1; atomic_add(&P.ctr->unfinished, -1));
+                wsync();
+                return;
+            }
+            ENG_LANE0(rs.candidates++; atomic_add(&P.ctr->progress, 1); if (msgs) atomic_add(&P.ctr->msgs, msgs));
+            bool accepted = false;
+            Rec pick;
+            rec_clear(pick);
+            if (best_c >= 0) {
+                const int chain = (int)(((size_t)read * kSets + cd.set) * kMaxK + best_c);
+                pick = P.chains[chain].rr;
+                if (pick.repeat_len > 0 && pick.rep_start + 10 < pick.rep_end) {        // handle_one_TR's accept (:236-243)
+                    accepted = true;
+                    int slot = 0;
+                    ENG_LANE0(slot = atomic_add(&P.ctr->n_accepted, 1));
+                    slot = bcast(slot, 0);
+                    if (slot >= P.acc_cap) {
+                        ENG_LANE0(atomic_max(&P.ctr->error, ERR_ACCEPTED_FULL); rs.phase = 1; atomic_add(&P.ctr->unfinished, -1));
+                        wsync();
+                        return;
+                    }
+                    Accepted &a = P.acc[slot];
+                    copy_bytes(a.unit, unit_ptr(P, chain, U_RR), pick.period < kUnitStride ? pick.period : kUnitStride);
+                    ENG_LANE0(a.read = read; a.seq = rs.n_accepted; a.rec = pick; rs.n_accepted++);
+                    // remove_redundant_ranges_from_directional_index (:178-188)
+                    const int hi = pick.rep_end < L ? pick.rep_end : L;
+                    for (int i = pick.rep_start + lane(); i < hi; i += NL)
+                        if (END[i] >= 0 && END[i] < pick.rep_end) { END[i] = -1; WW[i] = -1; }
+                    wsync();
+                }
+            }
+            const int front_set = cd.set;
+            ENG_LANE0(rs.head = (rs.head + 1) % kRing; rs.n_ring--);
+            wsync();
+            free_set(P, rs, read, front_set);
+            if (accepted) {
+                // in-flight candidates whose range this repeat has just pruned would never have been visited: drop them
+                int keep = 0;
+                const int n = rs.n_ring;
+                for (int c = 0; c < n; c++) {
+                    const Cand cc = rs.ring[(rs.head + c) % kRing];
+                    if (END[cc.qs] < 0) {
+                        ENG_LANE0(rs.cells_wasted += cc.cells; atomic_add(&P.ctr->spec_cells, (unsigned long long)cc.cells));
+                        free_set(P, rs, read, cc.set);
+                    } else {
+                        if (keep != c) {
+                            ENG_LANE0(rs.ring[(rs.head + keep) % kRing] = cc);
+                            if (cc.set >= 0)
+                                for (int q = lane(); q < cc.n_k; q += NL) P.chains[((size_t)read * kSets + cc.set) * kMaxK + q].ring = rs.head + keep;
+                            wsync();
+                        }
+                        keep++;
+                    }
+                }
+                ENG_LANE0(rs.n_ring = keep);
+                wsync();
+            }
+        }
+        // ---- start further candidates
+        int cur = rs.cursor;
+        for (;;) {                                              // next live range: -1 < END[qs] < L (:228-229)
+            const int i = cur + lane();
+            const bool live = i < L && END[i] > -1 && END[i] < L;
+            const unsigned m = wballot(live || i >= L);
+            if (m) { cur += ffs(m) - 1; break; }
+            cur += NL;
+        }
+        if (cur > L) cur = L;
+        ENG_LANE0(rs.cursor = cur);
+        wsync();
+        if (cur >= L) {
+            if (rs.n_ring == 0) {
+                ENG_LANE0(rs.phase = 1; atomic_add(&P.ctr->unfinished, -1); atomic_add(&P.ctr->candidates, (unsigned long long)rs.candidates));
+                wsync();
+            }
+            return;
+        }
+        const int qs = cur, qe = END[cur];
+        if (rs.n_ring >= kRing || started >= kSchedBudget) return;
+        bool safe = true;
+        int n_spec = 0;
+        for (int c = 0; c < rs.n_ring; c++) {
+            const Cand &cc = rs.ring[(rs.head + c) % kRing];
+            if (cc.set < 0) continue;                           // died at the gate: can never accept, never prunes
+            if (cc.qe >= qe) safe = false;
+            n_spec += cc.spec;
+        }
+        if (!safe && n_spec >= P.speculate) return;
+        const int cw = WW[cur];
+        int min_k, max_k;                                       // handle_one_read.c:105-120
+        if (cw < 100) { min_k = 2; max_k = 10; } else if (cw < 1000) { min_k = 2; max_k = 12; } else { min_k = 5; max_k = 15; }
+        const int n_k = max_k - min_k + 1;
+        // The maxFreq gate (consensus.c:532).  A k'-mer that occurs c times has a k-prefix (k < k') that occurs at
+        // least c times at the same coded positions, so maxFreq(k') <= maxFreq(k) + (raw-base entries of the k'
+        // window, Q7): once that bound is <= 5 no larger k can pass.  Small windows are counted right here; for large
+        // ones every k goes to the walk kernel, which applies the gate itself.
+        const int width = qe - qs + 1;
+        unsigned pass_mask = 0;
+        if (width <= kInlineWindow) {
+            int low_maxf = 1 << 30;
+            for (int k = min_k; k <= max_k; k++) {
+                const int coded_end = qe < L - k + 1 ? qe : L - k + 1;
+                const int raw = qe - coded_end + 1;
+                if (low_maxf + raw <= 5) continue;
+                const Window win = window_make(rd, L, k, qs, qe);
+                const Table tb = table_make(table_mem, table_cap, width);
+                const int maxf = table_build(tb, win);
+                if (lane() == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)width); }
+                if (maxf < low_maxf) low_maxf = maxf;
+                if (5 < maxf) pass_mask |= 1u << (k - min_k);
+            }
+        } else {
+            pass_mask = (1u << n_k) - 1u;
+        }
+        int set = -1;
+        if (pass_mask) {
+            const unsigned free_mask = ~rs.set_mask & ((1u << kSets) - 1u);
+            if (!free_mask) return;                             // every chain set is busy: wait for a commit
+            set = ffs(free_mask) - 1;
+        }
+        const int pos = rs.head + rs.n_ring;
+        wsync();
+        if (lane() == 0) {
+            Cand &cd = rs.ring[pos % kRing];
+            cd.qs = qs; cd.qe = qe; cd.set = set; cd.spec = safe ? 0 : 1; cd.min_k = min_k; cd.n_k = n_k; cd.cells = 0;
+            rs.n_ring++;
+            rs.cursor = cur + 1;
+            if (set >= 0) rs.set_mask |= 1u << set;
+        }
+        wsync();
+        started++;
+        if (set >= 0) {
+            for (int c = lane(); c < n_k; c += NL) {
+                const int chain = (int)(((size_t)read * kSets + set) * kMaxK + c);
+                Chain &ch = P.chains[chain];
+                rec_clear(ch.rr); rec_clear(ch.tmp);
+                ch.rr.kmer = min_k + c;
+                ch.k = min_k + c; ch.pass = 0; ch.found_last = 0; ch.ratio0 = 0;
+                ch.read = read; ch.qs = qs; ch.qe = qe;
+                ch.dir_found[0] = ch.dir_found[1] = 0; ch.dir_period[0] = ch.dir_period[1] = 0;
+                ch.fatal = 0; ch.msg = 0; ch.ring = pos; ch.aux_off = 0;
+                if (pass_mask & (1u << c)) {
+                    ch.stage = ST_WALK;
+                    P.walk_list[atomic_add(&P.ctr->n_walk, 1)] = chain;
+                } else {
+                    rec_clear(ch.rr);
+                    ch.stage = ST_DONE;
+                }
+            }
+            wsync();
+        }
+    }
+}
+
+}  // namespace eng

@@ -1,0 +1,146 @@
+// eng_host.h -- host-side layout of one engine group (shared by eng.cu and by the CPU twin in tests/hostsim).
+// Everything the waves touch is carved out of ONE allocation (plus the direction matrices and the unit-finder scratch,
+// which are sized separately), so binding eng::Ptrs is pointer arithmetic on a base address -- device or host.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include "eng_core.h"
+
+namespace eng {
+
+struct Config {
+    int n_reads = 0;
+    long long total_bases = 0;
+    int max_len = 0;
+    int uf_warps = 0;            // persistent unit-finder warps (each owns a scratch slice)
+    int task_cap = 0;            // DP tasks per wave
+    int acc_cap = 0;             // accepted repeats of the whole group
+    long long aux_cap = 0;       // int32 of consensus histograms per wave
+    long long dir_cap = 0;       // bytes of direction matrices per wave
+    int walk_cap = 0;
+};
+
+struct Layout {
+    size_t reads, chains, units, scores, results, wait_list, polish_list, walk_list, tasks_in, tasks, aux, acc, ctr, hist,
+        bucket_begin, bucket_cursor, class_begin, slot_counter, total;
+    int n_chains;
+    unsigned table_cap;
+    long long uf_stride;
+};
+
+inline Config default_config(int n_reads, long long total_bases, int max_len, int n_sm)
+{
+    Config c;
+    c.n_reads = n_reads; c.total_bases = total_bases; c.max_len = max_len;
+    c.uf_warps = std::max(64, n_sm * 8);
+    const long long n_chains = (long long)n_reads * kSets * kMaxK;
+    c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains), 1 << 20);
+    c.acc_cap = (int)std::min<long long>((long long)n_reads * 64 + total_bases / 16 + 64, 1 << 24);
+    c.aux_cap = std::max<long long>((long long)c.task_cap / 8 * 512, 2 * 4500) ;
+    c.dir_cap = 2LL << 30;
+    c.walk_cap = (int)std::min<long long>((long long)n_reads * kSchedBudget * kMaxK, 1 << 26);
+    return c;
+}
+
+inline Layout make_layout(const Config &c)
+{
+    Layout l;
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
+    l.n_chains = c.n_reads * kSets * kMaxK;
+    l.reads = take(sizeof(Read) * (size_t)std::max(c.n_reads, 1));
+    l.chains = take(sizeof(Chain) * (size_t)std::max(l.n_chains, 1));
+    l.units = take((size_t)std::max(l.n_chains, 1) * 4 * kUnitStride);
+    l.scores = take((size_t)std::max(l.n_chains, 1) * 3 * kUnitStride);
+    l.results = take(sizeof(mtr_wdp_result) * (size_t)std::max(l.n_chains, 1) * 4);
+    l.wait_list = take(4 * (size_t)std::max(l.n_chains, 1));
+    l.polish_list = take(4 * (size_t)std::max(l.n_chains, 1));
+    l.walk_list = take(4 * (size_t)std::max(c.walk_cap, 1));
+    l.tasks_in = take(sizeof(WdpTask) * (size_t)c.task_cap);
+    l.tasks = take(sizeof(WdpTask) * (size_t)c.task_cap);
+    l.aux = take(4 * (size_t)c.aux_cap);
+    l.acc = take(sizeof(Accepted) * (size_t)c.acc_cap);
+    l.ctr = take(sizeof(Counters));
+    l.hist = take(4 * (size_t)kDpClasses * kRowBuckets);
+    l.bucket_begin = take(4 * (size_t)(kDpClasses * kRowBuckets + 1));
+    l.bucket_cursor = take(4 * (size_t)kDpClasses * kRowBuckets);
+    l.class_begin = take(4 * (size_t)(WDP_NCLASS + 1));
+    l.slot_counter = take(4 * (size_t)WDP_NCLASS);
+    l.total = at;
+    unsigned cap = 64;
+    while (cap < 2u * (unsigned)(c.max_len + 8)) cap <<= 1;
+    l.table_cap = cap;
+    l.uf_stride = (((long long)cap * 8 + kScratchFixed) + 255) & ~255LL;
+    return l;
+}
+
+inline Ptrs bind(void *base, const Layout &l, const Config &c)
+{
+    unsigned char *b = (unsigned char *)base;
+    Ptrs P;
+    memset(&P, 0, sizeof P);
+    P.reads = (Read *)(b + l.reads); P.n_reads = c.n_reads;
+    P.chains = (Chain *)(b + l.chains);
+    P.units = b + l.units; P.scores = b + l.scores;
+    P.results = (mtr_wdp_result *)(b + l.results);
+    P.wait_list = (int *)(b + l.wait_list); P.polish_list = (int *)(b + l.polish_list); P.walk_list = (int *)(b + l.walk_list);
+    P.tasks_in = (WdpTask *)(b + l.tasks_in); P.tasks = (WdpTask *)(b + l.tasks);
+    P.task_cap = c.task_cap;
+    P.aux = (int *)(b + l.aux); P.aux_cap = c.aux_cap;
+    P.dir_cap = c.dir_cap;
+    P.acc = (Accepted *)(b + l.acc); P.acc_cap = c.acc_cap;
+    P.ctr = (Counters *)(b + l.ctr);
+    P.hist = (int *)(b + l.hist); P.bucket_begin = (int *)(b + l.bucket_begin); P.bucket_cursor = (int *)(b + l.bucket_cursor);
+    P.class_begin = (int *)(b + l.class_begin); P.slot_counter = (int *)(b + l.slot_counter);
+    P.table_cap = l.table_cap; P.uf_stride = l.uf_stride;
+    return P;
+}
+
+// initial per-read state (host side; copied into the group's buffer)
+inline void init_reads(std::vector<Read> &out, const int64_t *word_off, const int32_t *len, int n)
+{
+    out.assign((size_t)n, Read());
+    long long pos = 0;
+    for (int r = 0; r < n; r++) {
+        Read &rs = out[r];
+        memset(&rs, 0, sizeof rs);
+        rs.word_off = word_off[r]; rs.pos_off = pos; rs.L = len[r];
+        pos += len[r];
+    }
+}
+
+// converts the accepted list into the ABI records, ordered by (read, insertion order)
+inline void export_repeats(const Accepted *acc, int n, std::vector<mtr_repeat> &reps, std::vector<uint8_t> &units)
+{
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) {
+        if (acc[a].read != acc[b].read) return acc[a].read < acc[b].read;
+        return acc[a].seq < acc[b].seq;
+    });
+    reps.resize(n);
+    units.clear();
+    for (int i = 0; i < n; i++) {
+        const Accepted &a = acc[order[i]];
+        mtr_repeat &r = reps[i];
+        r.read = a.read; r.seq = a.seq;
+        r.rep_start = a.rec.rep_start; r.rep_end = a.rec.rep_end; r.repeat_len = a.rec.repeat_len; r.rep_period = a.rec.period;
+        r.num_freq_unit = a.rec.units; r.num_matches = a.rec.nm; r.num_mismatches = a.rec.nx; r.num_insertions = a.rec.ni;
+        r.num_deletions = a.rec.nd; r.kmer = a.rec.kmer; r.match_gain = a.rec.gain; r.mismatch_penalty = a.rec.mis;
+        r.indel_penalty = a.rec.indel;
+        r.unit_off = (int64_t)units.size();
+        units.insert(units.end(), a.unit, a.unit + std::min(a.rec.period, kUnitStride));
+    }
+}
+
+inline void export_stats(const Counters &c, mtr_engine_stats *s)
+{
+    if (!s) return;
+    s->waves = c.waves; s->candidates = (int64_t)c.candidates; s->dp_jobs = (int64_t)c.jobs; s->dp_tasks = (int64_t)c.tasks_total;
+    s->dp_cells = (int64_t)c.cells; s->dp_slot_cells = (int64_t)c.slot_cells; s->dp_dir_bytes = (int64_t)c.dir_bytes;
+    s->spec_cells = (int64_t)c.spec_cells; s->tables = (int64_t)c.tables; s->table_positions = (int64_t)c.table_positions;
+    s->walks = (int64_t)c.walks; s->repeats = c.n_accepted; s->wrapdp_messages = c.msgs;
+}
+
+}  // namespace eng

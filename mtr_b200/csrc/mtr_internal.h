@@ -69,12 +69,14 @@ struct WdpTask {
     long long dir_bytes;  // bytes of one direction matrix = rows * dir_stride
     long long aux_off;    // CONSENSUS: int32 offset, PATH: byte offset
     long long aux_cap;
-    int rows, ulen, unit_off;
+    long long unit_off;   // offset of the unit (one byte per base) in the units array
+    int rows, ulen;
     int dir_stride;       // bytes per row of the direction matrix (= slots / 4)
     int result_idx;       // results[result_idx (+1 for the second set of a paired task)]
     short gain[2], mis[2], indel[2];
     unsigned char n_param, mode;
-    unsigned char pad_[2];
+    unsigned char cls;    // resident engine: fill class 0..9 (int32) / 10..19 (paired int16x2), see eng_core.h
+    unsigned char pad_;
 };
 
 constexpr int WDP_NCLASS = 26;
@@ -116,6 +118,7 @@ struct mtr_ctx {
     WdpState wdp;
     struct DiState *di = nullptr;
     struct UfState *uf = nullptr;
+    struct EngState *eng = nullptr;
     mtr_stats stats = {};
     double prof_s[3] = {0, 0, 0};           // MTR_PROFILE: host seconds in upload / launch / download+wait of mtr_wdp_run
     long long prof_n = 0;
@@ -136,6 +139,25 @@ inline cudaError_t mtr_sync(mtr_ctx *ctx)
     if (e != cudaSuccess) return e;
     return cudaEventSynchronize(ctx->sync_ev);
 }
+// launch description of the K3 kernels over a task list that lives in device memory (resident engine, wdp.cu)
+struct WdpDevLaunch {
+    const WdpTask *tasks;
+    const int *class_begin;       // [WDP_NCLASS + 1]
+    int *counters;                // [WDP_NCLASS] slot-queue heads, zero at launch
+    const uint32_t *packed;
+    const uint8_t *units;
+    uint8_t *dirs;
+    mtr_wdp_result *results;
+    void *aux;
+    int blocks;                   // persistent grid of every kernel
+    cudaStream_t side[8];
+    cudaEvent_t fork, join[8];
+    int n_side;
+};
+cudaError_t wdp_launch_dev(const WdpDevLaunch &L, cudaStream_t s);
+int  di_compute(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off, const int64_t *pos_off, int first, int count);
+void di_device_outputs(mtr_ctx *ctx, double **di, int **end, int **w);
 void di_state_free(mtr_ctx *ctx);
 void uf_state_free(mtr_ctx *ctx);
+void eng_state_free(mtr_ctx *ctx);
 long long wdp_dir_bytes(int ulen, int rows);   // bytes of one direction matrix (per penalty set)

@@ -78,7 +78,8 @@ __device__ __forceinline__ void traceback_one(const WdpTask &t, const int p, con
                                               const uint8_t *dirs, mtr_wdp_result *res, void *aux)
 {
     const int G = t.gain[p], MM = t.mis[p], IN = t.indel[p];
-    const int ulen = t.ulen, dstride = t.dir_stride, unit_off = t.unit_off;
+    const int ulen = t.ulen, dstride = t.dir_stride;
+    const long long unit_off = t.unit_off;
     const long long base0 = t.base0, aux_cap = t.aux_cap;
     const uint8_t *d = dirs + t.dir_off + (size_t)p * t.dir_bytes;
     int i = max_i, j = max_j, run = best;
@@ -381,10 +382,9 @@ wdp_fill_multi(const WdpTask *__restrict__ tasks, const WdpMultiParams mp, const
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 
 template <int G, int C, bool FUSED>
-__global__ void __launch_bounds__(128)
-wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
-             const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counter,
-             void *aux)
+__device__ __forceinline__ void fill_slot_p16(const WdpTask *__restrict__ tasks, const int ntasks, const int slot,
+                                              const uint32_t *__restrict__ packed, const uint8_t *__restrict__ units,
+                                              uint8_t *dirs, mtr_wdp_result *results, void *aux)
 {
     constexpr int JPW = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
@@ -392,13 +392,7 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int grp = lane / G;
-    const int nslots = (ntasks + JPW - 1) / JPW;
-
-    for (;;) {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(counter, 1);
-        slot = __shfl_sync(FULL, slot, 0);
-        if (slot >= nslots) break;
+    {
         const int tidx = slot * JPW + grp;
         const bool have = tidx < ntasks;
         const WdpTask *tp = tasks + (have ? tidx : 0);
@@ -552,6 +546,109 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
             res->best = my_v; res->max_i = my_i; res->max_j = my_j;
         }
     }
+}
+
+template <int G, int C, bool FUSED>
+__global__ void __launch_bounds__(128)
+wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__restrict__ packed,
+             const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counter,
+             void *aux)
+{
+    constexpr int JPW = 32 / G;
+    const int nslots = (ntasks + JPW - 1) / JPW;
+    for (;;) {
+        int slot = 0;
+        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counter, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= nslots) break;
+        fill_slot_p16<G, C, FUSED>(tasks, ntasks, slot, packed, units, dirs, results, aux);
+    }
+}
+
+// ---------------------------------------------------------------- resident engine: task lists built on the device
+// The engine (eng_core.h) writes the sorted task array and the class boundaries in device memory; the host cannot know
+// the counts, so these kernels are launched with a fixed persistent grid and read their range from class_begin[].
+// Split traceback: the fill stores the argmax into results[], wdp_traceback_dev finishes the record in place.
+template <int G, int C, bool P16>
+__global__ void __launch_bounds__(128)
+wdp_fill_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const int cls,
+             const uint32_t *__restrict__ packed, const uint8_t *__restrict__ units, uint8_t *dirs,
+             mtr_wdp_result *results, int *__restrict__ counters)
+{
+    constexpr int JPW = 32 / G;
+    const int b = class_begin[cls], n = class_begin[cls + 1] - b;
+    const int nslots = (n + JPW - 1) / JPW;
+    for (;;) {
+        int slot = 0;
+        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counters + cls, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= nslots) break;
+        if (P16) fill_slot_p16<G, C, false>(tasks + b, n, slot, packed, units, dirs, results, nullptr);
+        else fill_slot_i32<G, C, false>(tasks + b, n, slot, packed, units, dirs, results, nullptr);
+    }
+}
+
+// one thread per (task, penalty set)
+__global__ void __launch_bounds__(128)
+wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const uint32_t *__restrict__ packed,
+                  const uint8_t *__restrict__ units, const uint8_t *dirs, mtr_wdp_result *results, void *aux)
+{
+    const int total = 2 * class_begin[WDP_NCLASS];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const WdpTask &t = tasks[idx >> 1];
+        const int p = idx & 1;
+        if (p >= (int)t.n_param) continue;
+        const mtr_wdp_result in = results[t.result_idx + p];
+        traceback_one(t, p, in.best, in.max_i, in.max_j, packed, units, dirs, results + t.result_idx + p, aux);
+    }
+}
+
+template <int G, int C, bool P16>
+static void launch_fill_dev(const WdpDevLaunch &L, int cls, cudaStream_t s)
+{
+    wdp_fill_dev<G, C, P16><<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, cls, L.packed, L.units, L.dirs, L.results, L.counters);
+}
+
+// enqueues the fill kernels of every engine class and the traceback on `s` (class kernels fan out over L.side streams)
+cudaError_t wdp_launch_dev(const WdpDevLaunch &L, cudaStream_t s)
+{
+    cudaError_t e;
+    if ((e = cudaEventRecord(L.fork, s)) != cudaSuccess) return e;
+    for (int k = 0; k < WDP_NCLASS; k++) {
+        if (k >= 10 && k < 16) continue;                    // latency classes: never used by the engine
+        cudaStream_t cs = L.n_side > 0 ? L.side[k % L.n_side] : s;
+        if (L.n_side > 0 && (e = cudaStreamWaitEvent(cs, L.fork, 0)) != cudaSuccess) return e;
+        switch (k) {
+        case 0: launch_fill_dev<4, 4, false>(L, k, cs); break;
+        case 1: launch_fill_dev<4, 8, false>(L, k, cs); break;
+        case 2: launch_fill_dev<4, 12, false>(L, k, cs); break;
+        case 3: launch_fill_dev<8, 8, false>(L, k, cs); break;
+        case 4: launch_fill_dev<8, 12, false>(L, k, cs); break;
+        case 5: launch_fill_dev<8, 16, false>(L, k, cs); break;
+        case 6: launch_fill_dev<16, 12, false>(L, k, cs); break;
+        case 7: launch_fill_dev<16, 16, false>(L, k, cs); break;
+        case 8: launch_fill_dev<32, 12, false>(L, k, cs); break;
+        case 9: launch_fill_dev<32, 16, false>(L, k, cs); break;
+        case 16: launch_fill_dev<4, 4, true>(L, k, cs); break;
+        case 17: launch_fill_dev<4, 8, true>(L, k, cs); break;
+        case 18: launch_fill_dev<4, 12, true>(L, k, cs); break;
+        case 19: launch_fill_dev<8, 8, true>(L, k, cs); break;
+        case 20: launch_fill_dev<8, 12, true>(L, k, cs); break;
+        case 21: launch_fill_dev<8, 16, true>(L, k, cs); break;
+        case 22: launch_fill_dev<16, 12, true>(L, k, cs); break;
+        case 23: launch_fill_dev<16, 16, true>(L, k, cs); break;
+        case 24: launch_fill_dev<32, 12, true>(L, k, cs); break;
+        default: launch_fill_dev<32, 16, true>(L, k, cs); break;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (L.n_side > 0)
+        for (int i = 0; i < L.n_side; i++) {
+            if ((e = cudaEventRecord(L.join[i], L.side[i])) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(s, L.join[i], 0)) != cudaSuccess) return e;
+        }
+    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------- host side

@@ -3,9 +3,9 @@
 // A stand-in for the kernel-level layer of include/mtr_b200.h (mtr_cuda_init, mtr_reads_upload, mtr_di_run,
 // mtr_wdp_run, ...) that answers every device call with the CPU oracle (oracle/mtr_oracle.c).  It is linked, together
 // with the UNMODIFIED product source mtr_b200/csrc/pipeline.cpp, into tests/hostsim/_build/ only, so that the host
-// side of the drop-in -- FASTA reader, stale-state tracker, per-read state machines, unit finder (k-mer counts, de
-// Bruijn walks, polish, vote), candidate look-ahead, chaining, TSV / alignment formatting, the handle_one_file /
-// handle_one_read entry points -- can be checked against the golden digests on a machine without a GPU
+// side of the drop-in -- FASTA reader, stale-state tracker, group dispatcher, chaining, TSV / alignment formatting,
+// the handle_one_file / handle_one_read entry points -- and, through sim_engine.cpp, the resident engine's own code
+// (eng_core.h) can be checked against the golden digests on a machine without a GPU
 // (`-m "not gpu"`), and profiled there.
 //
 // Nothing here is built by mtr_b200/csrc/Makefile, shipped in libmtr_b200.so or reachable from the product: the
@@ -60,6 +60,9 @@ void mtr_set_error(mtr_ctx *ctx, const char *fmt, ...)
 long long wdp_dir_bytes(int ulen, int rows) { return (long long)rows * ((ulen + 15) / 16 * 4); }
 void di_state_free(mtr_ctx *ctx) { if (ctx->di) { if (ctx->di->oracle) mtro_free(ctx->di->oracle); delete ctx->di; ctx->di = nullptr; } }
 void uf_state_free(mtr_ctx *) {}
+// the engine twin (sim_engine.cpp) reads the resident reads and shares the context's oracle
+const uint32_t *sim_packed(mtr_ctx *ctx) { return ctx->di->reads->packed.data(); }
+mtro_ctx *sim_oracle(mtr_ctx *ctx, int manhattan) { return ctx->di->get(manhattan ? 1 : 0); }
 
 extern "C" {
 
@@ -84,6 +87,7 @@ void mtr_cuda_shutdown(mtr_ctx *ctx)
 {
     if (!ctx) return;
     di_state_free(ctx);
+    eng_state_free(ctx);
     delete ctx;
 }
 

@@ -1,0 +1,145 @@
+// tests/hostsim/sim_engine.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// The CPU twin of mtr_b200/csrc/eng.cu: the SAME engine code (mtr_b200/csrc/eng_core.h, compiled here by g++ with one
+// lane per warp, see simt.h) driven wave by wave on host memory.  What is a kernel launch on the GPU is a plain loop
+// over the work items here; the wrap-around DP tasks the engine emits are answered by the oracle's DP, the directional
+// index by the oracle's (sim_device.cpp).  So the per-read scheduler with its look-ahead and pruning, the maxFreq
+// gate, count tables, greedy walks with memo and cycle cut, polish, the revise chain with its vote, the two-penalty
+// pick, the DP task emission / bucket sort and the accepted-repeat list are all checked against the reference's
+// digests on a machine without a GPU.  Never linked into libmtr_b200.so.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <vector>
+#include "../../mtr_b200/csrc/eng_host.h"
+#include "../../oracle/mtr_oracle.h"
+
+using namespace eng;
+
+struct EngState {
+    std::vector<unsigned char> main_buf, scratch;
+    std::vector<int> end, w;
+    std::vector<mtr_repeat> reps;
+    std::vector<uint8_t> units;
+    int speculate = 8;
+};
+
+void eng_state_free(mtr_ctx *ctx) { delete ctx->eng; ctx->eng = nullptr; }
+
+// provided by sim_device.cpp
+const uint32_t *sim_packed(mtr_ctx *ctx);
+mtro_ctx *sim_oracle(mtr_ctx *ctx, int manhattan);
+
+extern "C" int mtr_engine_set_speculate(mtr_ctx *ctx, int depth)
+{
+    if (!ctx || depth < 0) return MTR_EINVAL;
+    if (!ctx->eng) ctx->eng = new EngState();
+    ctx->eng->speculate = depth;
+    return MTR_OK;
+}
+
+extern "C" double mtr_engine_dp_busy_ms(int, int) { return 0.0; }
+
+static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, mtro_ctx *o)
+{
+    const int total = P.class_begin[WDP_NCLASS];
+    std::vector<int> x, u;
+    for (int i = 0; i < total; i++) {
+        const WdpTask &t = P.tasks[i];
+        x.assign((size_t)t.rows + 2, 0);
+        for (int r = 1; r <= t.rows; r++) { const long long b = t.base0 + r; x[r] = (int)((P.packed[b >> 4] >> ((b & 15) * 2)) & 3u); }
+        u.assign((size_t)t.ulen + 2, 0);
+        for (int j = 1; j <= t.ulen; j++) u[j] = P.units[t.unit_off + j - 1];
+        for (int p = 0; p < (int)t.n_param; p++) {
+            mtro_dp_result r;
+            int *cons = nullptr, *miss = nullptr;
+            if (t.mode == MTR_TB_CONSENSUS) { cons = P.aux + t.aux_off; miss = cons + (size_t)(t.ulen + 1) * 5; }
+            mtro_wrap_dp(o, x.data(), t.rows, u.data(), t.ulen, t.gain[p], t.mis[p], t.indel[p], t.mode, &r, cons, miss, nullptr, nullptr);
+            mtr_wdp_result &d = P.results[t.result_idx + p];
+            d.best = r.best; d.max_i = r.max_i; d.max_j = r.max_j; d.end_i = r.end_i; d.end_j = r.end_j;
+            d.n_match = r.n_match; d.n_mismatch = r.n_mismatch; d.n_ins = r.n_ins; d.n_del = r.n_del; d.n_scanned = r.n_scanned;
+            d.path_len = r.path_len; d.flags = 0;
+        }
+    }
+    (void)ctx;
+}
+
+extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio, const uint16_t *stale, const int64_t *stale_off,
+                              const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units, mtr_engine_stats *stats)
+{
+    if (!ctx) return MTR_EINVAL;
+    if (repeats) *repeats = nullptr;
+    if (n_repeats) *n_repeats = 0;
+    if (units) *units = nullptr;
+    if (stats) memset(stats, 0, sizeof *stats);
+    const int n = ctx->n_reads;
+    if (n == 0) return MTR_OK;
+    if (!ctx->eng) ctx->eng = new EngState();
+    EngState &E = *ctx->eng;
+    std::vector<int64_t> pos_off((size_t)n + 1, 0);
+    int max_len = 0;
+    for (int r = 0; r < n; r++) { pos_off[r + 1] = pos_off[r] + ctx->len[r]; max_len = std::max(max_len, (int)ctx->len[r]); }
+    E.end.assign((size_t)pos_off[n] + 1, -1); E.w.assign((size_t)pos_off[n] + 1, -1);
+    int rc = mtr_di_run(ctx, manhattan, stale, stale_off, pos_off.data(), nullptr, E.end.data(), E.w.data());
+    if (rc) return rc;
+
+    Config cfg = default_config(n, pos_off[n], max_len, 1);
+    cfg.uf_warps = 1;
+    // small per-wave budgets on request, to exercise the deferral path on the CPU
+    if (const char *e = getenv("MTR_ENGINE_DIR_KB")) cfg.dir_cap = std::max(1LL, atoll(e)) << 10;
+    if (const char *e = getenv("MTR_ENGINE_TASK_CAP")) cfg.task_cap = std::max(4, atoi(e));
+    const Layout lay = make_layout(cfg);
+    E.main_buf.assign(lay.total, 0);
+    E.scratch.assign((size_t)lay.uf_stride, 0);
+    Ptrs P = bind(E.main_buf.data(), lay, cfg);
+    P.packed = sim_packed(ctx);
+    P.end = E.end.data(); P.w = E.w.data();
+    P.uf_scratch = E.scratch.data();
+    P.min_match_ratio = min_match_ratio;
+    P.speculate = E.speculate;
+    if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
+    std::vector<Read> reads;
+    init_reads(reads, ctx->word_off.data(), ctx->len.data(), n);
+    memcpy(P.reads, reads.data(), sizeof(Read) * (size_t)n);
+    P.ctr->unfinished = n;
+    mtro_ctx *o = sim_oracle(ctx, manhattan);
+    std::vector<unsigned long long> inline_tab(kInlineSlots);
+    const Scratch S = scratch_of(P, 0);
+    unsigned long long last_sig = ~0ull;
+    int idle = 0;
+    while (P.ctr->unfinished > 0 && !P.ctr->error) {
+        wave_begin(P);
+        for (int i = 0; i < P.ctr->n_advance; i++) advance_chain(P, P.wait_list[i]);
+        for (int i = 0; i < P.ctr->n_polish; i++) polish_chain(P, P.polish_list[i], S);
+        for (int r = 0; r < n; r++) sched_read(P, r, inline_tab.data(), kInlineSlots);
+        for (int i = 0; i < P.ctr->n_walk; i++) walk_chain(P, P.walk_list[i], S);
+        for (int c = 0; c < lay.n_chains; c++) emit_chain(P, c);
+        plan_tasks(P);
+        const int nt = std::min(P.ctr->n_tasks, P.task_cap);
+        for (int i = 0; i < nt; i++) scatter_task(P, i);
+        const long long na = std::min<long long>((long long)P.ctr->aux_used, P.aux_cap);
+        for (long long i = 0; i < na; i++) P.aux[i] = 0;
+        run_dp_tasks(ctx, P, o);
+        const unsigned long long sig = P.ctr->tasks_total * 1315423911ull + P.ctr->tables * 2654435761ull + (unsigned)P.ctr->progress * 97ull + (unsigned)P.ctr->unfinished;
+        if (sig == last_sig) {
+            if (++idle > 8) { mtr_set_error(ctx, "hostsim engine_run: no progress (wave %d, %d tasks deferred)", P.ctr->waves, P.ctr->deferred); return MTR_ECUDA; }
+        } else idle = 0;
+        last_sig = sig;
+    }
+    const Counters &c = *P.ctr;
+    if (c.error) {
+        switch (c.error) {
+        case ERR_WRAPCAP: mtr_set_error(ctx, "You need to increse the value of WrapDPsize."); return MTR_ERANGE;
+        case ERR_EMPTY_UNIT: mtr_set_error(ctx, "the revised repeat unit is empty (read %d)", c.error_read); return MTR_ERANGE;
+        case ERR_ACCEPTED_FULL: mtr_set_error(ctx, "engine_run: more than %d accepted repeats in one group", cfg.acc_cap); return MTR_ENOMEM;
+        default: mtr_set_error(ctx, "engine_run: device error %d", c.error); return MTR_ECUDA;
+        }
+    }
+    export_repeats(P.acc, c.n_accepted, E.reps, E.units);
+    if (repeats) *repeats = E.reps.data();
+    if (n_repeats) *n_repeats = c.n_accepted;
+    if (units) *units = E.units.data();
+    export_stats(c, stats);
+    return MTR_OK;
+}

@@ -1,8 +1,10 @@
-"""Host logic on the CPU: the product's pipeline.cpp + main.c (unmodified) linked against tests/hostsim/sim_device.cpp,
-a TEST-ONLY stand-in that answers the kernel-level ABI (mtr_di_run, mtr_wdp_run, ...) with the oracle.  Everything the
-host does -- FASTA reader, stale-state tracker, per-read state machines with candidate look-ahead, k-mer count tables,
-de Bruijn walks, polish / vote, chaining, TSV and alignment formatting, batch splitting -- must reproduce the digests
-taken from the reference binary (tests/golden/digests.json).  The GPU twins of these tests are in
+"""Host logic and engine logic on the CPU: the product's pipeline.cpp + main.c (unmodified) linked against
+tests/hostsim/sim_device.cpp, a TEST-ONLY stand-in that answers the kernel-level ABI (mtr_di_run, mtr_wdp_run) with the
+oracle, and against tests/hostsim/sim_engine.cpp, which runs the resident engine's own code (mtr_b200/csrc/eng_core.h,
+one lane per warp) wave by wave on host memory.  Everything but the DP cells and the directional index -- FASTA reader,
+stale-state tracker, group dispatcher, per-read scheduler with candidate look-ahead, k-mer count tables, de Bruijn
+walks, polish / vote, DP task emission, chaining, TSV and alignment formatting -- must reproduce the digests taken from
+the reference binary (tests/golden/digests.json).  The GPU twins of these tests are in
 tests/test_pipeline_gpu.py; the simulator is never part of the product (tests/test_abi_cpu.py)."""
 import hashlib
 import json
@@ -62,13 +64,15 @@ def test_host_logic_on_synthetic_cases(sim, synthetic_dir, name):
         assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
 
 
-def test_batching_threads_and_lanes_do_not_change_the_output(sim, synthetic_dir):
-    """Batch boundaries (stale state crosses them), worker count, dispatch lanes and the two-device round-robin are
-    scheduling only: not a byte may change."""
+def test_grouping_contexts_and_budgets_do_not_change_the_output(sim, synthetic_dir):
+    """Group boundaries (the stale state crosses them), the number of engine contexts, the two-device round-robin and
+    the per-wave budgets of the engine (direction-matrix bytes, task slots: a chain that does not fit is emitted again
+    by the next wave) are scheduling only: not a byte may change."""
     path = os.path.join(synthetic_dir, "mixed.fa")
     ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
-    for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_BATCH_READS": "3", "MTR_GPUS": "2"},
-                {"MTR_TIER_ROWS": "1536", "MTR_TIER_LANES": "1,1"}, {"MTR_TIER_ROWS": "40,100,400", "MTR_TIER_SPIN": "1,1,0,0", "MTR_THREADS": "3"}):
+    for env in ({"MTR_GROUP_READS": "1"}, {"MTR_GROUP_READS": "5", "MTR_GROUPS_PER_GPU": "1"}, {"MTR_GROUP_READS": "3", "MTR_GPUS": "2"},
+                {"MTR_GROUP_READS": "7", "MTR_GROUPS_PER_GPU": "3", "MTR_GPUS": "2"}, {"MTR_ENGINE_DIR_KB": "600"},
+                {"MTR_ENGINE_TASK_CAP": "6", "MTR_GROUP_READS": "4"}):
         assert hashlib.md5(run(sim, [], path, env)).hexdigest() == ref, env
 
 
