@@ -21,7 +21,7 @@ ABI_FUNCTIONS = [
     "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_set_priority", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_wdp_set_fused_traceback", "mtr_di_run", "mtr_di_run_range", "mtr_get_stats",
     "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_load_fasta_shard",
-    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_log_jobs", "mtr_pipeline_get_job_log", "mtr_pipeline_ctx", "handle_one_file", "handle_one_read", "mtr_flush", "mtr_file_stats",
+    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_ctx", "mtr_engine_run", "mtr_engine_set_speculate", "mtr_engine_dp_busy_ms", "handle_one_file", "handle_one_read", "mtr_flush", "mtr_file_stats",
 ]
 ABI_GLOBALS = [
     "Manhattan_Distance", "min_match_ratio", "orgInputString", "time_all", "time_memory", "time_range",
@@ -56,10 +56,21 @@ class Stats(C.Structure):
 
 class PipelineStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
-        "reads", "bases", "candidates", "rounds", "rounds_fast", "rounds_uf", "jobs", "uf_tasks", "wdp_calls", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
-        "di_position_passes", "di_bytes_in", "di_bytes_out", "h2d_bytes", "d2h_bytes", "launches", "spec_cells")] + \
-        [(n, C.c_double) for n in ("wdp_fill_ms", "wdp_tb_ms", "di_kernel_ms", "uf_kernel_ms", "di_wall_ms", "rounds_wall_ms",
-                                   "host_step_ms", "wdp_wall_ms", "uf_wall_ms")]
+        "reads", "bases", "groups", "candidates", "waves", "jobs", "dp_tasks", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
+        "spec_cells", "tables", "table_positions", "walks", "repeats", "h2d_bytes", "d2h_bytes", "launches")] + \
+        [(n, C.c_double) for n in ("dp_ms", "di_kernel_ms", "uf_kernel_ms", "engine_wall_ms", "pack_ms", "chain_ms", "wall_ms")]
+
+
+class EngineStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "waves", "candidates", "dp_jobs", "dp_tasks", "dp_cells", "dp_slot_cells", "dp_dir_bytes", "spec_cells", "tables",
+        "table_positions", "walks", "repeats", "wrapdp_messages", "launches", "h2d_bytes", "d2h_bytes")] + \
+        [(n, C.c_double) for n in ("di_ms", "dp_ms", "uf_ms", "wall_ms")]
+
+
+REPEAT_DTYPE = np.dtype([(n, "<i4") for n in (
+    "read", "seq", "rep_start", "rep_end", "repeat_len", "rep_period", "num_freq_unit", "num_matches", "num_mismatches",
+    "num_insertions", "num_deletions", "kmer", "match_gain", "mismatch_penalty", "indel_penalty", "pad_")] + [("unit_off", "<i8")])
 
 
 UF_TASK_DTYPE = np.dtype([("read", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("k", "<i4")])
@@ -116,8 +127,11 @@ def load_library() -> C.CDLL:
     lib.mtr_pipeline_load_fasta_shard.restype = C.c_int
     lib.mtr_pipeline_run.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(i64)]
     lib.mtr_pipeline_get_stats.argtypes = [vp, C.POINTER(PipelineStats)]
-    lib.mtr_pipeline_log_jobs.argtypes = [vp, C.c_int]
-    lib.mtr_pipeline_get_job_log.argtypes = [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(i64)]
+    lib.mtr_engine_run.argtypes = [vp, C.c_int, C.c_float, vp, vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(vp), C.POINTER(EngineStats)]
+    lib.mtr_engine_run.restype = C.c_int
+    lib.mtr_engine_set_speculate.argtypes = [vp, C.c_int]
+    lib.mtr_engine_dp_busy_ms.argtypes = [C.c_int, C.c_int]
+    lib.mtr_engine_dp_busy_ms.restype = C.c_double
     lib.mtr_pipeline_ctx.argtypes = [vp]
     lib.mtr_pipeline_ctx.restype = vp
     lib.mtr_file_stats.argtypes = [C.POINTER(PipelineStats)]
@@ -262,6 +276,23 @@ class Context:
                                         C.byref(used)), "mtr_uf_run")
         return res, units[:used.value], scores[:used.value]
 
+    def engine_run(self, manhattan: bool = True, min_match_ratio: float = 0.6, stale: Optional[np.ndarray] = None,
+                   stale_off: Optional[np.ndarray] = None):
+        """handle_one_TR (handle_one_read.c:190-261) for every resident read on the device.  Returns (repeats as a
+        REPEAT_DTYPE array ordered by (read, insertion order), units bytes, stats dict)."""
+        reps, n, units, st = C.c_void_p(), C.c_int64(), C.c_void_p(), EngineStats()
+        rc = self.lib.mtr_engine_run(self.h, 1 if manhattan else 0, min_match_ratio, _ptr(stale), _ptr(stale_off),
+                                     C.byref(reps), C.byref(n), C.byref(units), C.byref(st))
+        self._check(rc, "mtr_engine_run")
+        k = int(n.value)
+        if k == 0:
+            arr, ub = np.zeros(0, REPEAT_DTYPE), np.zeros(0, np.uint8)
+        else:
+            arr = np.frombuffer((C.c_char * (k * REPEAT_DTYPE.itemsize)).from_address(reps.value), dtype=REPEAT_DTYPE).copy()
+            total = int(arr["unit_off"][-1] + arr["rep_period"][-1])
+            ub = np.frombuffer((C.c_char * total).from_address(units.value), dtype=np.uint8).copy()
+        return arr, ub, {k2: getattr(st, k2) for k2, _ in EngineStats._fields_}
+
     def alu_probe(self, kind: int) -> float:
         """Giga lane-ops/s of the integer pipe (0: VIADDMNMX.RELU s32, 1: LOP3+IADD, 2: VIADDMNMX s16x2)."""
         g = C.c_double()
@@ -304,36 +335,6 @@ class Pipeline:
             raise MtrError("mtr_pipeline_run failed (%d)" % rc)
         return C.string_at(out, n.value)
 
-    def log_jobs(self, on: bool = True):
-        self.lib.mtr_pipeline_log_jobs(self.h, 1 if on else 0)
-
-    def replay_logged_jobs(self, iters: int = 2, fused: bool = True, max_jobs: int = 1_500_000) -> dict:
-        """Replays the DP jobs logged by the last run() as ONE batch on the pipeline's own context (K3 alone,
-        operands resident); returns the library's kernel statistics of the last replay.  fused=False: fill kernels
-        and traceback kernel launched separately, so wdp_fill_ms is the fill alone."""
-        jobs, n, units, ul = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int64()
-        rc = self.lib.mtr_pipeline_get_job_log(self.h, C.byref(jobs), C.byref(n), C.byref(units), C.byref(ul))
-        if rc != 0 or n.value == 0:
-            raise MtrError("no logged jobs")
-        ctx = self.lib.mtr_pipeline_ctx(self.h)
-        self.lib.mtr_wdp_set_fused_traceback(ctx, 1 if fused else 0)
-        if n.value > max_jobs:        # bounded (the direction matrices of the replay must fit HBM): every stride-th job
-            stride = -(-int(n.value) // max_jobs)
-            all_jobs = np.frombuffer((C.c_char * (int(n.value) * JOB_DTYPE.itemsize)).from_address(jobs.value), dtype=JOB_DTYPE)
-            self._replay_subset = np.ascontiguousarray(all_jobs[::stride])
-            jobs, n = C.c_void_p(self._replay_subset.ctypes.data), C.c_int64(len(self._replay_subset))
-        rc = self.lib.mtr_wdp_upload(ctx, jobs, int(n.value), units, ul.value, 0)
-        if rc != 0:
-            raise MtrError("replay upload failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))
-        st = Stats()
-        for _ in range(iters):
-            rc = self.lib.mtr_wdp_launch(ctx)
-            if rc != 0:
-                raise MtrError("replay launch failed (%d): %s" % (rc, self.lib.mtr_last_error(ctx).decode()))
-        self.lib.mtr_get_stats(ctx, C.byref(st))
-        self.lib.mtr_wdp_set_fused_traceback(ctx, 1)
-        return {k: getattr(st, k) for k, _ in Stats._fields_} | {"jobs": int(n.value)}
-
     def stats(self) -> dict:
         s = PipelineStats()
         self.lib.mtr_pipeline_get_stats(self.h, C.byref(s))
@@ -344,7 +345,7 @@ def run_file(path: str, print_alignment: bool = False, manhattan: bool = True, m
     """handle_one_file (mTR.h:126) on a FASTA file, exactly as main.c calls it; what the library prints to stdout is
     captured through a temporary file.  Returns (number of reads, stdout bytes, counters of the call).  The process-wide
     runtime behind the entry point is configured by the MTR_* environment at its first use (MTR_DEVICE, MTR_GPUS,
-    MTR_THREADS, MTR_BATCH_READS ...)."""
+    MTR_GROUPS_PER_GPU, MTR_GROUP_READS ...)."""
     import sys
     import tempfile
     lib = load_library()

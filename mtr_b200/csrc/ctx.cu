@@ -42,6 +42,9 @@ extern "C" int mtr_cuda_init(int device, mtr_ctx **out)
 {
     if (!out) return MTR_EINVAL;
     *out = nullptr;
+    // many engine contexts share one GPU, each with its own streams: ask for the maximum number of hardware work queues
+    // (the default of 8 makes kernels of unrelated streams wait for each other); only effective before CUDA starts
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {

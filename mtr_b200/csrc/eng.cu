@@ -25,40 +25,55 @@ __global__ void __launch_bounds__(128) eng_advance(Ptrs P)
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) advance_chain(P, P.wait_list[i]);
 }
 
-__global__ void __launch_bounds__(128) eng_polish(Ptrs P)
+// walk / polish kernels: one block (four warps) per task, persistent blocks pulling from a list; shared memory = 16 ints
+// of cta scratch + 32 KB for the count table (DIRECT / COMPACT) or for the probe cache of a WIDE table
+template <int WHICH>      // 0: walks (queue entries below the tail seen at the start), 1: polish
+__global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0)
 {
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const Scratch S = scratch_of(P, warp);
-    const int n = P.ctr->n_polish;
+    __shared__ int sh[16];
+    extern __shared__ __align__(16) unsigned char uf_dyn[];     // kUfDynSmem bytes: count table | near tie lists | walk memos
+    unsigned *tab = (unsigned *)uf_dyn;
+    int *near = (int *)(uf_dyn + kUfSmemWords * 4);
+    MemoEntry *memos = (MemoEntry *)(uf_dyn + kUfSmemWords * 4 + 4 * kTiesNear * 4);   // zeroed once: epoch 0 is never current
+    if (WHICH == 0) { for (int i = threadIdx.x; i < 2 * kMemoSlots; i += blockDim.x) memos[i].epoch = 0u; __syncthreads(); }
+    const Cta c = cta_of_block(sh);
+    const Scratch S = scratch_of(P, slice0 + blockIdx.x);
+    if (WHICH == 1) {
+        const int n = P.ctr->n_polish;
+        for (;;) {
+            int i = 0;
+            if (c.tid == 0) i = atomicAdd(&P.ctr->polish_head, 1);
+            i = cta_bcast(c, i, 7);
+            if (i >= n) break;
+            polish_chain(P, P.polish_list[i], S, c, tab);
+        }
+        return;
+    }
+    // every entry below `limit` was written before this instance was launched (later ones belong to later instances)
+    const unsigned limit = *(volatile unsigned *)&P.ctr->walk_tail;
     for (;;) {
-        int i = 0;
-        if (lane() == 0) i = atomicAdd(&P.ctr->polish_head, 1);
-        i = bcast(i, 0);
-        if (i >= n) break;
-        polish_chain(P, P.polish_list[i], S);
+        int chain = -1;
+        if (c.tid == 0) {
+            unsigned h = *(volatile unsigned *)&P.ctr->walk_head;
+            while ((int)(limit - h) > 0) {
+                const unsigned seen = atomicCAS(&P.ctr->walk_head, h, h + 1u);
+                if (seen == h) { chain = P.walk_ring[h & P.walk_ring_mask]; break; }
+                h = seen;
+            }
+        }
+        chain = cta_bcast(c, chain, 7);
+        if (chain < 0) break;
+        walk_chain(P, chain, S, c, tab, near, memos);
     }
 }
 
 __global__ void __launch_bounds__(64) eng_sched(Ptrs P)
 {
     __shared__ unsigned long long tab[2][kInlineSlots];
+    __shared__ int sh[2][16];
     const int read = blockIdx.x * 2 + (threadIdx.x >> 5);
     if (read >= P.n_reads) return;
-    sched_read(P, read, tab[threadIdx.x >> 5], kInlineSlots);
-}
-
-__global__ void __launch_bounds__(128) eng_walk(Ptrs P)
-{
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const Scratch S = scratch_of(P, warp);
-    const int n = P.ctr->n_walk;
-    for (;;) {
-        int i = 0;
-        if (lane() == 0) i = atomicAdd(&P.ctr->walk_head, 1);
-        i = bcast(i, 0);
-        if (i >= n) break;
-        walk_chain(P, P.walk_list[i], S);
-    }
+    sched_read(P, read, tab[threadIdx.x >> 5], kInlineSlots, sh[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(256) eng_emit(Ptrs P, int n_chains)
@@ -88,14 +103,14 @@ __global__ void eng_publish(Ptrs P, EngSnapshot *snap)
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const Counters &c = *P.ctr;
     snap->error = c.error; snap->error_read = c.error_read; snap->deferred = c.deferred; snap->waves = c.waves;
-    snap->n_accepted = c.n_accepted; snap->n_tasks = c.n_tasks; snap->tasks_total = c.tasks_total; snap->candidates_started = c.tables + (unsigned long long)(unsigned)c.progress;
+    snap->n_accepted = c.n_accepted; snap->n_tasks = c.n_tasks; snap->pad = (int)(c.walk_tail - c.walk_head) + c.walks_running; snap->tasks_total = c.tasks_total; snap->candidates_started = c.tables + (unsigned long long)(unsigned)c.progress + ((unsigned long long)(unsigned)c.walks_done << 32);
     __threadfence_system();
     snap->unfinished = c.unfinished;
 }
 
 // ---------------------------------------------------------------- per-context engine state
 struct EngState {
-    DevBuf d_main, d_dirs, d_scratch;
+    DevBuf d_main, d_dirs, d_scratch, d_wide;
     PinBuf h_snap, h_acc, h_ctr;
     Config cfg;
     Layout lay;
@@ -104,6 +119,8 @@ struct EngState {
     int speculate = 8;
     cudaStream_t side[8] = {};
     cudaEvent_t fork = nullptr, join[8] = {};
+    cudaStream_t walk_stream[4] = {};      // walk kernel instances run here, beside everything else
+    cudaEvent_t sched_done[4] = {};
     int n_side = 0;
     static constexpr int kEv = 32;
     cudaEvent_t ev_dp0[kEv] = {}, ev_dp1[kEv] = {}, ev_w0[kEv] = {};
@@ -115,10 +132,11 @@ void eng_state_free(mtr_ctx *ctx)
 {
     if (!ctx->eng) return;
     EngState *e = ctx->eng;
-    e->d_main.release(); e->d_dirs.release(); e->d_scratch.release();
+    e->d_main.release(); e->d_dirs.release(); e->d_scratch.release(); e->d_wide.release();
     e->h_snap.release(); e->h_acc.release(); e->h_ctr.release();
     for (int i = 0; i < 8; i++) { if (e->side[i]) cudaStreamDestroy(e->side[i]); if (e->join[i]) cudaEventDestroy(e->join[i]); }
     if (e->fork) cudaEventDestroy(e->fork);
+    for (int i = 0; i < 4; i++) { if (e->walk_stream[i]) cudaStreamDestroy(e->walk_stream[i]); if (e->sched_done[i]) cudaEventDestroy(e->sched_done[i]); }
     for (int i = 0; i < EngState::kEv; i++) {
         if (e->ev_dp0[i]) cudaEventDestroy(e->ev_dp0[i]);
         if (e->ev_dp1[i]) cudaEventDestroy(e->ev_dp1[i]);
@@ -195,8 +213,8 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     cudaStream_t s = ctx->main_stream;
     static const bool prof = getenv("MTR_PROFILE") != nullptr;
     if (E.n_side == 0) {
-        int want = 4;
-        if (const char *e = getenv("MTR_ENGINE_SIDE_STREAMS")) want = std::max(0, std::min(8, atoi(e)));
+        int want = 1;
+        if (const char *e = getenv("MTR_ENGINE_SIDE_STREAMS")) want = std::max(0, std::min(1, atoi(e)));
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         for (int i = 0; i < want; i++) {
@@ -204,6 +222,10 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
             MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.join[i], cudaEventDisableTiming));
         }
         MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.fork, cudaEventDisableTiming));
+        for (int i = 0; i < 4; i++) {
+            MTR_CUDA(ctx, cudaStreamCreateWithFlags(&E.walk_stream[i], cudaStreamNonBlocking));
+            MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.sched_done[i], cudaEventDisableTiming));
+        }
         for (int i = 0; i < EngState::kEv; i++) {
             MTR_CUDA(ctx, cudaEventCreate(&E.ev_dp0[i]));
             MTR_CUDA(ctx, cudaEventCreate(&E.ev_dp1[i]));
@@ -229,7 +251,9 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     if (const char *e = getenv("MTR_ENGINE_DIR_MB")) cfg.dir_cap = std::max(64LL, atoll(e)) << 20;
     Layout lay = make_layout(cfg);
     MTR_CUDA(ctx, E.d_main.reserve(lay.total));
-    MTR_CUDA(ctx, E.d_scratch.reserve((size_t)lay.uf_stride * (size_t)cfg.uf_warps));
+    const size_t n_slices = (size_t)cfg.uf_ctas * (size_t)cfg.walk_streams + (size_t)cfg.polish_ctas;
+    MTR_CUDA(ctx, E.d_scratch.reserve((size_t)lay.uf_stride * n_slices));
+    MTR_CUDA(ctx, E.d_wide.reserve((size_t)lay.table_cap * 8 * n_slices));
     if ((size_t)cfg.dir_cap > E.d_dirs.cap) MTR_CUDA(ctx, E.d_dirs.reserve_exact((size_t)cfg.dir_cap));
     cfg.dir_cap = (long long)E.d_dirs.cap;
     MTR_CUDA(ctx, E.h_snap.reserve(sizeof(EngSnapshot)));
@@ -241,6 +265,7 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     di_device_outputs(ctx, nullptr, &d_end, &d_w);
     P.end = d_end; P.w = d_w;
     P.uf_scratch = (unsigned char *)E.d_scratch.p;
+    P.uf_wide = (unsigned char *)E.d_wide.p;
     P.min_match_ratio = min_match_ratio;
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
@@ -249,7 +274,7 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     // zero: chain stages (ST_FREE), lists, counters, histograms, the scratch epochs; then the per-read state
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.chains, 0, sizeof(Chain) * (size_t)lay.n_chains, s));
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.ctr, 0, lay.total - lay.ctr, s));
-    MTR_CUDA(ctx, cudaMemsetAsync(E.d_scratch.p, 0, (size_t)lay.uf_stride * (size_t)cfg.uf_warps, s));
+    MTR_CUDA(ctx, cudaMemsetAsync(E.d_scratch.p, 0, (size_t)lay.uf_stride * n_slices, s));
     std::vector<Read> reads;
     init_reads(reads, ctx->word_off.data(), ctx->len.data(), n);
     MTR_CUDA(ctx, cudaMemcpyAsync(P.reads, reads.data(), sizeof(Read) * (size_t)n, cudaMemcpyHostToDevice, s));
@@ -265,29 +290,37 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
 
     WdpDevLaunch L;
     memset(&L, 0, sizeof L);
-    L.tasks = P.tasks; L.class_begin = P.class_begin; L.counters = P.slot_counter; L.packed = P.packed;
+    L.tasks = P.tasks; L.class_begin = P.class_begin; L.seg_task = P.seg_task; L.seg_slot = P.seg_slot; L.nseg_family = kSegs / 2; L.counters = P.slot_counter; L.packed = P.packed;
     L.units = P.units; L.dirs = (uint8_t *)E.d_dirs.p; L.results = P.results; L.aux = P.aux;
-    L.blocks = ctx->n_sm * 4;
+    L.blocks = ctx->n_sm;
     for (int i = 0; i < n_side; i++) { L.side[i] = E.side[i]; L.join[i] = E.join[i]; }
     L.fork = E.fork; L.n_side = n_side;
 
-    const int uf_blocks = cfg.uf_warps / 4;
-    const int launches_per_wave = 10 + 20 + 1;
+    // (the attribute belongs to the function, not to the launch: every context sets the same constant)
+    MTR_CUDA(ctx, cudaFuncSetAttribute(eng_unitfinder<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUfDynSmem));
+    MTR_CUDA(ctx, cudaFuncSetAttribute(eng_unitfinder<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUfDynSmem));
+    const int launches_per_wave = 10 + 2 + 1;
     cudaEvent_t base = busy_base(ctx->device);
     double dp_ms = 0, uf_ms = 0;
     long long launches = di_launches;
-    int burst = 4;
+    int burst = 4, wave_no = 0;
     if (const char *e = getenv("MTR_ENGINE_BURST")) burst = std::max(1, std::min(EngState::kEv, atoi(e)));
     unsigned long long last_tasks = ~0ull, last_started = ~0ull;
-    int last_accepted = -1, last_unfinished = -1, stalled = 0;
+    int last_accepted = -1, last_unfinished = -1, stalled = 0, quiet = 0;
     for (;;) {
         for (int b = 0; b < burst; b++) {
             MTR_CUDA(ctx, cudaEventRecord(E.ev_w0[b], s));
             eng_begin<<<1, 32, 0, s>>>(P);
             eng_advance<<<ctx->n_sm * 4, 128, 0, s>>>(P);
-            eng_polish<<<uf_blocks, 128, 0, s>>>(P);
+            eng_unitfinder<1><<<cfg.polish_ctas, 128, kUfDynSmem, s>>>(P, cfg.uf_ctas * cfg.walk_streams);
             eng_sched<<<(n + 1) / 2, 64, 0, s>>>(P);
-            eng_walk<<<uf_blocks, 128, 0, s>>>(P);
+            {
+                // the walk kernel of this wave: on the next walk stream, behind the scheduler pass, beside everything else
+                const int ws = wave_no++ % cfg.walk_streams;
+                MTR_CUDA(ctx, cudaEventRecord(E.sched_done[ws], s));
+                MTR_CUDA(ctx, cudaStreamWaitEvent(E.walk_stream[ws], E.sched_done[ws], 0));
+                eng_unitfinder<0><<<cfg.uf_ctas, 128, kUfDynSmem, E.walk_stream[ws]>>>(P, ws * cfg.uf_ctas);
+            }
             eng_emit<<<(lay.n_chains + 255) / 256, 256, 0, s>>>(P, lay.n_chains);
             eng_plan<<<1, 32, 0, s>>>(P);
             eng_scatter<<<ctx->n_sm * 2, 256, 0, s>>>(P);
@@ -311,13 +344,16 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
                 g_busy.iv[ctx->device].push_back(std::make_pair((double)t0, (double)t1));
             }
         }
-        if (prof) fprintf(stderr, "[mtr engine] ctx %p wave %d: unfinished %d accepted %d tasks(last wave) %d deferred %d\n", (void *)ctx, snap->waves, snap->unfinished, snap->n_accepted, snap->n_tasks, snap->deferred);
+        if (prof) fprintf(stderr, "[mtr engine] ctx %p wave %d: unfinished %d accepted %d tasks(last wave) %d deferred %d walks queued or running %d\n", (void *)ctx, snap->waves, snap->unfinished, snap->n_accepted, snap->n_tasks, snap->deferred, snap->pad);
         if (snap->error) break;
         if (snap->unfinished <= 0) break;
         // no progress at all during a whole burst: either the per-wave budgets are too small for a single task (grow
         // them) or the engine is stuck (a bug: fail loudly instead of spinning)
-        if (snap->tasks_total == last_tasks && snap->candidates_started == last_started && snap->n_accepted == last_accepted && snap->unfinished == last_unfinished) {
-            if (snap->deferred > 0 && stalled < 6) {
+        if (snap->pad == 0 && snap->tasks_total == last_tasks && snap->candidates_started == last_started && snap->n_accepted == last_accepted && snap->unfinished == last_unfinished) {
+            if (snap->deferred == 0 && ++quiet < 3) {
+                // (a walk may have published its result after the last emission pass of the burst: look again)
+            } else if (snap->deferred > 0 && stalled < 6) {
+                quiet = 0;
                 const size_t want = E.d_dirs.cap * 2;
                 E.d_dirs.release();
                 MTR_CUDA(ctx, E.d_dirs.reserve_exact(want));
@@ -329,11 +365,17 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
                 return MTR_ECUDA;
             }
         }
+        else quiet = 0;
         last_tasks = snap->tasks_total; last_started = snap->candidates_started; last_accepted = snap->n_accepted; last_unfinished = snap->unfinished;
     }
+    for (int i = 0; i < cfg.walk_streams; i++) MTR_CUDA(ctx, cudaStreamSynchronize(E.walk_stream[i]));   // walks nobody waits for any more
     Counters *hc = (Counters *)E.h_ctr.p;
     MTR_CUDA(ctx, cudaMemcpyAsync(hc, P.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, mtr_sync(ctx));
+    if (prof)
+        fprintf(stderr, "[mtr engine] ctx %p: %d reads, %d waves | unit finder: %llu tables (direct %llu compact %llu wide %llu), %llu with walks, %llu walks | Mticks: build %.1f list %.1f walk fwd %.1f bwd %.1f, slowest task %.3f, slowest walk %.3f | walk steps %llu (memo hits %llu, steps reaching level 4 %llu), probe rounds %llu, failed walks %llu | dp %.1f ms uf %.1f ms\n", (void *)ctx, n, hc->waves,
+                hc->tables, hc->prof_kind[2], hc->prof_kind[1], hc->prof_kind[0], hc->prof_walk_tasks, hc->walks, hc->prof_build / 1e6, hc->prof_list / 1e6, hc->prof_walk[0] / 1e6, hc->prof_walk[1] / 1e6,
+                hc->prof_max_task / 1e6, hc->prof_max_walk / 1e6, hc->prof_steps, hc->prof_memo_hits, hc->prof_deep_steps, hc->prof_probe_rounds, hc->prof_fail_walks, dp_ms, uf_ms);
     if (hc->error) {
         switch (hc->error) {
         case ERR_WRAPCAP: mtr_set_error(ctx, "You need to increse the value of WrapDPsize."); return MTR_ERANGE;

@@ -40,13 +40,14 @@ constexpr int kSets = 16;                    // ... of which this many may hold 
 constexpr int kMaxK = 11;                    // k values per candidate: 2..10, 2..12 or 5..15 (handle_one_read.c:105-120)
 constexpr int kInlineWindow = 512;           // windows up to this many bases pass the maxFreq gate inside sched_read
 constexpr int kInlineSlots = 2048;           // count-table slots of a scheduler warp (>= 2 * (kInlineWindow + 2), power of two)
-constexpr int kMemoSlots = 8192;             // walk-memo entries per unit-finder warp
+constexpr int kMemoSlots = 512;              // walk-memo entries per direction (shared memory, 16 bytes each)
 constexpr int kSchedBudget = 96;             // candidates one sched_read call may start (bounds the latency of a wave)
 constexpr int kDpClasses = 20;               // 10 int32 + 10 paired int16x2 fill classes (wdp.cu)
 constexpr int kRowBuckets = 96;              // quarter-octave buckets of a task's row count (longest first)
+constexpr int kSegs = 2 * kRowBuckets * 10;  // (family, rows bucket, class) segments of the sorted task list
 
 enum Stage : int {
-    ST_FREE = 0, ST_DONE, ST_WALK, ST_WALKING, ST_NEED_SEARCH, ST_WAIT_SEARCH, ST_NEED_POLISH, ST_NEED_CONS, ST_WAIT_CONS, ST_NEED_DP, ST_WAIT_DP
+    ST_FREE = 0, ST_DONE, ST_WALK, ST_WALKING, ST_ZOMBIE_WALKING, ST_NEED_SEARCH, ST_WAIT_SEARCH, ST_NEED_POLISH, ST_NEED_CONS, ST_WAIT_CONS, ST_NEED_DP, ST_WAIT_DP
 };
 enum { U_RR = 0, U_TMP = 1, U_DIR0 = 2, U_DIR1 = 3 };       // unit strings of a chain
 enum { S_RR = 0, S_DIR0 = 1, S_DIR1 = 2 };                  // score strings (node counts clamped to 255: only ==1 and <2 are ever tested)
@@ -72,22 +73,31 @@ struct Cand { int qs, qe, set, spec, min_k, n_k; long long cells; };   // set < 
 struct Read {
     long long word_off, pos_off;
     int L, cursor, head, n_ring;   // ring entries head .. head + n_ring - 1 (mod kRing), in candidate order
-    int phase, n_accepted, candidates;
+    int phase, n_accepted, candidates, pad0;
     unsigned set_mask;             // chain sets in use
+    unsigned zombie_mask;          // ... by dropped candidates whose walks have not finished yet
     long long cells_wasted;
     Cand ring[kRing];
 };
 
 struct Accepted { int read, seq; Rec rec; unsigned char unit[kUnitStride]; };   // insert_an_alignment, handle_one_read.c:156-176
 
-struct MemoEntry { unsigned key, epoch; int next, seen; };
+struct MemoEntry { unsigned key, epoch; int next; unsigned short seen; unsigned char self1, next1; };   // scores: min(count, 254) + 1, 0 = not known yet
 
 struct Counters {
-    int n_wait, n_polish, n_walk, n_tasks, n_advance, walk_head, polish_head, pad0;
+    int n_wait, n_polish, n_tasks, n_advance, polish_head, pad0;
+    // Walks run beside everything else (a pathological walk takes tens of milliseconds: it must delay its own candidate,
+    // not the group): sched_read pushes chains at walk_tail, the walk kernel instance launched after a scheduler pass pops
+    // below the tail it saw at its start.  Both counters only grow.
+    unsigned walk_tail, walk_head;
+    int walks_running, walks_done; // chains a walk kernel is working on right now / has finished so far
     int unfinished, error, error_read, n_accepted;
     int deferred, msgs, waves, progress;
     unsigned long long dir_used, aux_used;
     unsigned long long cells, slot_cells, spec_cells, jobs, candidates, tables, walks, table_positions, dir_bytes, tasks_total;
+    // profile (clock64 ticks, thread 0 / lane 0 of the walking warps): table build, node list, walks per direction; walk steps; tasks per table layout
+    unsigned long long prof_build, prof_list, prof_walk[2], prof_steps, prof_kind[3], prof_walk_tasks, prof_max_task;
+    unsigned long long prof_probe_rounds, prof_memo_hits, prof_deep_steps, prof_fail_walks, prof_max_walk;
 };
 
 struct Ptrs {
@@ -99,7 +109,9 @@ struct Ptrs {
     unsigned char *units;          // [chain][4][kUnitStride]
     unsigned char *scores;         // [chain][3][kUnitStride]
     mtr_wdp_result *results;       // [chain][4]: search: direction d, penalty set s at 2d + s; revise: slot 0
-    int *wait_list, *polish_list, *walk_list;
+    int *wait_list, *polish_list;
+    int *walk_ring;                // queue of chains in ST_WALK (Counters::walk_tail / walk_head, never reset)
+    unsigned walk_ring_mask;
     WdpTask *tasks_in, *tasks;     // as emitted / sorted by (class, rows descending)
     int task_cap;
     int *aux;                      // consensus histograms of the wave
@@ -108,12 +120,17 @@ struct Ptrs {
     Accepted *acc;
     int acc_cap;
     Counters *ctr;
-    int *hist, *bucket_begin, *bucket_cursor;   // [kDpClasses * kRowBuckets (+1)]
-    int *class_begin;              // [WDP_NCLASS + 1] into tasks[]
-    int *slot_counter;             // [WDP_NCLASS] work-queue heads of the fill kernels
-    unsigned char *uf_scratch;     // per unit-finder warp: count table, memo, tie lists, node list, unit / score strings
+    // DP tasks are sorted by segment = (family: int32 | paired int16x2, rows bucket descending, fill class): hist counts
+    // the tasks of a segment while they are emitted, seg_task / seg_slot are the prefix sums (tasks, warp slots)
+    int *hist, *seg_task, *seg_slot, *bucket_cursor;   // [kSegs (+1)]
+    int *class_begin;              // [WDP_NCLASS + 1]: only the last entry (total number of tasks) is used
+    int *slot_counter;             // [WDP_NCLASS] work-queue heads of the fill / traceback kernels
+    unsigned char *uf_scratch;     // per unit-finder cta: memos, tie lists, node list, unit / score strings
     long long uf_stride;
-    unsigned table_cap;            // slots of a unit-finder warp's table (power of two)
+    unsigned char *uf_wide;        // WIDE count tables, one per unit-finder cta
+    unsigned table_cap;            // slots of one WIDE table (power of two)
+    unsigned compact_cap;          // slots of a COMPACT table (kCompactCap; tests lower it to reach the WIDE path)
+    int direct_max_k;              // largest k that gets a DIRECT table (7)
     float min_match_ratio;
     int speculate;
 };
@@ -166,30 +183,100 @@ MTR_DEV unsigned kmer_at(const uint32_t *rd, int i, int k)
 #endif
 }
 
-// ---------------------------------------------------------------- exact k-mer counts of one window
-// init_inputString + generate_freqNode_return_list_maxNodes + freq_node (consensus.c:37-60,132-253).  Open addressing,
-// one 64-bit slot per node: key + 1 in the high word (0 = empty), count in the low word.  The reference's own table
-// layout (direct for k <= 6, hashing modulo a prime above) is unobservable.
-struct Table { unsigned long long *slots; unsigned mask; int shift; };
+// ---------------------------------------------------------------- cooperating threads
+// A "cta" is the set of threads that work on one task together: a whole thread block (walk / polish kernels: four
+// warps build the count table, then warp d walks direction d) or a single warp (the scheduler's inline gate, and every
+// cta of the CPU twin).  sh: a few ints of memory all its threads see (shared memory on the GPU).
+struct Cta { int tid, size, warp, nwarps; int *sh; bool block; };
+MTR_DEV void cta_sync(const Cta &c) { if (c.block) block_sync(); else wsync(); }
+MTR_DEV Cta cta_of_warp(int *sh) { Cta c; c.tid = lane(); c.size = NL; c.warp = 0; c.nwarps = 1; c.sh = sh; c.block = false; return c; }
+MTR_DEV Cta cta_of_block(int *sh) { Cta c; c.tid = block_tid(); c.size = block_size(); c.warp = block_tid() / NL; c.nwarps = block_size() / NL; c.sh = sh; c.block = true; return c; }
+MTR_DEV int cta_bcast(const Cta &c, int v, int slot)           // value of thread 0, to everybody
+{
+    cta_sync(c);
+    if (c.tid == 0) c.sh[slot] = v;
+    cta_sync(c);
+    return c.sh[slot];
+}
 
-MTR_DEV Table table_make(unsigned long long *mem, unsigned cap_max, int n)
+// ---------------------------------------------------------------- exact k-mer counts of one window
+// init_inputString + generate_freqNode_return_list_maxNodes + freq_node (consensus.c:37-60,132-253).  The reference's own
+// table layout (direct for k <= 6, hashing modulo a prime above) is unobservable.  Three layouts, chosen per task so that
+// a unit-finder cta never needs more than kUfSmemBytes of shared memory (several ctas of several groups share an SM):
+//   DIRECT   k <= 7: one 16-bit counter per k-mer code (4^7 x 2 B = 32 KB), in shared memory; no keys, no probing
+//   COMPACT  small windows: open addressing in shared memory, keys (key + 1, 32 bit) and 16-bit counters apart, 6 B / slot
+//   WIDE     everything else: open addressing, one 64-bit slot per node (key + 1 high, count low) in global memory (or,
+//            for the scheduler's inline gate, in a warp's shared memory); the walks, which are chains of dependent
+//            probes into the by then frozen table, go through a direct-mapped (node -> count) CACHE in shared memory
+//            (an L2 round trip costs ~700 cycles, a shared-memory hit ~30)
+enum { TB_WIDE = 0, TB_COMPACT = 1, TB_DIRECT = 2 };
+constexpr int kUfSmemWords = 8192;                       // 32 KB of table / cache per unit-finder cta
+constexpr unsigned kCompactCap = 4096;                   // slots of a COMPACT table: 4096 * 6 B = 24 KB
+constexpr unsigned kCacheSlots = 4096;                   // 64-bit entries of the probe cache
+struct Table {
+    unsigned long long *slots;      // WIDE
+    unsigned *keys, *cnt;           // COMPACT (keys + counters) / DIRECT (counters)
+    unsigned long long *cache;      // WIDE: probe cache, nullptr while the counts still change
+    unsigned mask;
+    int shift, kind;
+};
+
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int compact_max_n(unsigned cap) { const unsigned m = cap / 4u * 3u; return (int)(m < 65000u ? m : 65000u) - 2; }
+
+MTR_DEV Table table_wide(unsigned long long *mem, unsigned cap_max, int n)
 {
     unsigned cap = 64;
     while (cap < 2u * (unsigned)(n + 2) && cap < cap_max) cap <<= 1;
     Table t;
-    t.slots = mem; t.mask = cap - 1u; t.shift = clz(cap) + 1;    // hash -> top log2(cap) bits
+    t.slots = mem; t.keys = nullptr; t.cnt = nullptr; t.cache = nullptr; t.mask = cap - 1u; t.shift = clz(cap) + 1; t.kind = TB_WIDE;
+    return t;
+}
+MTR_DEV Table table_compact(unsigned *mem, unsigned cap_max, int n)
+{
+    unsigned cap = 64;
+    while (cap < 2u * (unsigned)(n + 2) && cap < cap_max) cap <<= 1;
+    Table t;
+    t.slots = nullptr; t.keys = mem; t.cnt = mem + cap; t.cache = nullptr; t.mask = cap - 1u; t.shift = clz(cap) + 1; t.kind = TB_COMPACT;
+    return t;
+}
+MTR_DEV Table table_direct(unsigned *mem, int k)
+{
+    Table t;
+    t.slots = nullptr; t.keys = nullptr; t.cnt = mem; t.cache = nullptr; t.mask = (1u << (2 * k)) - 1u; t.shift = 0; t.kind = TB_DIRECT;
     return t;
 }
 MTR_DEV unsigned table_home(const Table &t, unsigned code) { return ((code + 0x9e3779b9u) * 2654435761u) >> t.shift; }
-MTR_DEV void table_clear(const Table &t)
+MTR_DEV void table_clear(const Table &t, const Cta &c)
 {
-    for (unsigned i = (unsigned)lane(); i <= t.mask; i += NL) t.slots[i] = 0ull;
-    wsync();
+    if (t.kind == TB_WIDE) {
+        for (unsigned i = (unsigned)c.tid; i <= t.mask; i += (unsigned)c.size) t.slots[i] = 0ull;
+    } else {
+        if (t.kind == TB_COMPACT) for (unsigned i = (unsigned)c.tid; i <= t.mask; i += (unsigned)c.size) t.keys[i] = 0u;
+        for (unsigned i = (unsigned)c.tid; i <= t.mask / 2u; i += (unsigned)c.size) t.cnt[i] = 0u;
+    }
+    cta_sync(c);
+}
+MTR_DEV int half_add(unsigned *cnt, unsigned h, unsigned delta)        // 16-bit counter h: returns the old value
+{
+    const int sh = (int)(h & 1u) * 16;
+    return (int)((atomic_add(&cnt[h >> 1], delta << sh) >> sh) & 0xffffu);
 }
 MTR_DEV int table_insert(const Table &t, unsigned code)         // count after the insert
 {
-    const unsigned long long key = ((unsigned long long)code + 1ull) << 32;
+    if (t.kind == TB_DIRECT) return half_add(t.cnt, code, 1u) + 1;
     unsigned h = table_home(t, code);
+    if (t.kind == TB_COMPACT) {
+        const unsigned key = code + 1u;
+        for (;;) {
+            const unsigned old = atomic_cas(&t.keys[h], 0u, key);
+            if (old == 0u || old == key) return half_add(t.cnt, h, 1u) + 1;
+            h = (h + 1u) & t.mask;
+        }
+    }
+    const unsigned long long key = ((unsigned long long)code + 1ull) << 32;
     for (;;) {
         const unsigned long long old = atomic_cas(&t.slots[h], 0ull, key | 1ull);
         if (old == 0ull) return 1;
@@ -199,8 +286,18 @@ MTR_DEV int table_insert(const Table &t, unsigned code)         // count after t
 }
 MTR_DEV int table_find(const Table &t, unsigned code)           // slot or -1
 {
-    const unsigned long long key = ((unsigned long long)code + 1ull) << 32;
+    if (t.kind == TB_DIRECT) return code <= t.mask ? (int)code : -1;
     unsigned h = table_home(t, code);
+    if (t.kind == TB_COMPACT) {
+        const unsigned key = code + 1u;
+        for (;;) {
+            const unsigned k = ldv(&t.keys[h]);
+            if (k == key) return (int)h;
+            if (k == 0u) return -1;
+            h = (h + 1u) & t.mask;
+        }
+    }
+    const unsigned long long key = ((unsigned long long)code + 1ull) << 32;
     for (;;) {
         const unsigned long long sl = ldv(&t.slots[h]);
         if ((sl & 0xffffffff00000000ull) == key) return (int)h;
@@ -208,10 +305,39 @@ MTR_DEV int table_find(const Table &t, unsigned code)           // slot or -1
         h = (h + 1u) & t.mask;
     }
 }
+MTR_DEV int table_count_at(const Table &t, int h)
+{
+    if (t.kind == TB_WIDE) return (int)(unsigned)ldv(&t.slots[h]);
+    return (int)((ldv(&t.cnt[h >> 1]) >> ((h & 1) * 16)) & 0xffffu);
+}
+MTR_DEV void table_decrement_at(const Table &t, int h)          // the count is >= 6 here: no borrow into the neighbour / the key
+{
+    if (t.kind == TB_WIDE) atomic_add(&t.slots[h], ~0ull);
+    else atomic_add(&t.cnt[h >> 1], 0u - (1u << ((h & 1) * 16)));
+}
 MTR_DEV int table_count(const Table &t, unsigned code)          // freq_node
 {
+    if (t.cache) {
+        // frozen WIDE table: (node + 1, count) pairs in shared memory, direct-mapped, absent nodes cached as count 0
+        const unsigned cs = ((code + 0x9e3779b9u) * 2654435761u) >> 20 & (kCacheSlots - 1u);
+        const unsigned long long e = ldv(&t.cache[cs]);
+        if ((unsigned)(e >> 32) == code + 1u) return (int)(unsigned)e;
+        const int h = table_find(t, code);
+        const int n = h < 0 ? 0 : table_count_at(t, h);
+        t.cache[cs] = ((unsigned long long)(code + 1u) << 32) | (unsigned)n;
+        return n;
+    }
     const int h = table_find(t, code);
-    return h < 0 ? 0 : (int)(unsigned)ldv(&t.slots[h]);
+    return h < 0 ? 0 : table_count_at(t, h);
+}
+// after the counts are final: route the probes of a WIDE table through the cache in `smem` (kCacheSlots entries)
+MTR_DEV void table_freeze(Table &t, unsigned *smem, const Cta &c)
+{
+    if (t.kind != TB_WIDE || !smem) return;
+    unsigned long long *cache = (unsigned long long *)smem;
+    for (unsigned i = (unsigned)c.tid; i < kCacheSlots; i += (unsigned)c.size) cache[i] = 0ull;
+    cta_sync(c);
+    t.cache = cache;
 }
 
 // codes of the window [qs, qe]: k-mer codes below min(qe, L-k+1), the raw base above (Q7); index >= L reads as 0
@@ -230,25 +356,34 @@ MTR_DEV unsigned window_code(const Window &w, int i)
     return i < w.L ? (unsigned)base_at(w.rd, i) : 0u;
 }
 
-// builds the table of a window, returns maxFreq (counts only grow while building: the running maximum is the final one)
-MTR_DEV int table_build(const Table &t, const Window &w)
+// builds the table of a window with every thread of the cta, returns maxFreq to all of them (counts only grow while
+// building: the running maximum is the final one)
+MTR_DEV int table_build(const Table &t, const Window &w, const Cta &c)
 {
-    table_clear(t);
+    table_clear(t, c);
+    if (c.tid == 0) c.sh[0] = -1;
+    cta_sync(c);
     int maxf = -1;
-    for (int i = w.qs + lane(); i <= w.qe; i += NL) {
-        const int c = table_insert(t, window_code(w, i));
-        maxf = c > maxf ? c : maxf;
+    for (int i = w.qs + c.tid; i <= w.qe; i += c.size) {
+        const int n = table_insert(t, window_code(w, i));
+        maxf = n > maxf ? n : maxf;
     }
     maxf = wmax(maxf);
-    wsync();
+    if (lane() == 0) atomic_max(&c.sh[0], maxf);
+    cta_sync(c);
+    maxf = c.sh[0];
+    cta_sync(c);
     return maxf;
 }
 
 // generate_freqNode_return_list_maxNodes (:132-229): nodes whose CURRENT count equals maxFreq, in order of first
 // occurrence, at most `cap`; a listed node loses one count (Q8).  NL positions per step; duplicates inside a step are
 // resolved with match_any so that the order is exactly the sequential one.
-MTR_DEV int table_list_max(const Table &t, const Window &w, int maxf, int *nodes, int cap)
+MTR_DEV int table_list_max(const Table &t, const Window &w, int maxf, int *nodes, int cap, int n_max)
 {
+    // n_max: number of distinct nodes whose count is maxFreq (table_count_max): once all of them are listed the rest of
+    // the window cannot add anything, and the nodes of a repeat show up within its first copies
+    if (n_max < cap) cap = n_max;
     int nn = 0;
     for (int p0 = w.qs; p0 <= w.qe && nn < cap; p0 += NL) {
         const int p = p0 + lane();
@@ -258,19 +393,35 @@ MTR_DEV int table_list_max(const Table &t, const Window &w, int maxf, int *nodes
         if (p <= w.qe) {
             const unsigned c = window_code(w, p);
             h = table_find(t, c);
-            ismax = h >= 0 && (int)(unsigned)ldv(&t.slots[h]) == maxf;
+            ismax = h >= 0 && table_count_at(t, h) == maxf;
             if (ismax) code = c;
         }
         const unsigned grp = match_any(code);
         const bool lead = ismax && (ffs(grp) - 1) == lane();
         const unsigned lst = wballot(lead);
         const int at = nn + popc(lst & lanemask_lt());
-        if (lead && at < cap) { nodes[at] = (int)code; atomic_add(&t.slots[h], ~0ull); }   // count - 1 (the key is untouched: count >= 6)
+        if (lead && at < cap) { nodes[at] = (int)code; table_decrement_at(t, h); }
         nn += popc(lst);
         if (nn > cap) nn = cap;
         wsync();
     }
     return nn;
+}
+
+// number of table entries whose count equals maxf (every thread of the cta gets the result); the table is final
+MTR_DEV int table_count_max(const Table &t, int maxf, const Cta &c)
+{
+    if (c.tid == 0) c.sh[0] = 0;
+    cta_sync(c);
+    int mine = 0;
+    if (t.kind == TB_WIDE) { for (unsigned i = (unsigned)c.tid; i <= t.mask; i += (unsigned)c.size) mine += (int)(unsigned)t.slots[i] == maxf && t.slots[i] != 0ull; }
+    else for (unsigned i = (unsigned)c.tid; i <= t.mask / 2u; i += (unsigned)c.size) { const unsigned v = t.cnt[i]; mine += (int)(v & 0xffffu) == maxf; mine += (int)(v >> 16) == maxf; }
+    mine = wsum(mine);
+    if (lane() == 0 && mine) atomic_add(&c.sh[0], mine);
+    cta_sync(c);
+    const int r = c.sh[0];
+    cta_sync(c);
+    return r;
 }
 
 // ---------------------------------------------------------------- greedy de Bruijn walk (consensus.c:269-505)
@@ -291,190 +442,268 @@ MTR_DEV void memo_reset(Memo &m)
     }
     m.used = 0; m.serial = 0;
 }
-MTR_DEV int memo_slot(Memo &m, unsigned node)                  // entry index, or -1 when the memo is full
+// slot of `node`: a window of four consecutive slots starting at its home; *e receives the entry and *fresh = false if
+// the node is there, else *fresh = true and the slot returned is the one to (over)write: the first free one of the
+// window, or -- all four taken by other nodes -- the home slot itself.  Forgetting an entry only costs time: its
+// look-ahead is redone, and a walk caught in a cycle goes round until it meets a node it still remembers.  No lane
+// writes here: every lane sees the same table.
+MTR_DEV int memo_find(const Memo &m, unsigned node, MemoEntry *e, bool *fresh)
 {
-    unsigned h = ((node + 0x9e3779b9u) * 2654435761u) >> (32 - 13);
-    for (;;) {
-        const MemoEntry e = m.tab[h];
-        if (e.epoch != m.epoch) {
-            if (2 * m.used >= kMemoSlots) return -1;
-            ENG_LANE0(MemoEntry n; n.key = node; n.epoch = m.epoch; n.next = -1; n.seen = -1; m.tab[h] = n);
-            wsync();
-            m.used++;
-            return (int)h;
-        }
-        if (e.key == node) return (int)h;
-        h = (h + 1u) & (unsigned)(kMemoSlots - 1);
+    const unsigned home = (((node + 0x9e3779b9u) * 2654435761u) >> 16) & (unsigned)(kMemoSlots - 4);   // windows do not wrap
+    int free_slot = -1;
+    for (unsigned w = 0; w < 4u; w++) {
+        const unsigned h = home + w;
+        *e = m.tab[h];
+        if (e->epoch != m.epoch) { if (free_slot < 0) free_slot = (int)h; continue; }
+        if (e->key == node) { *fresh = false; return (int)h; }
     }
+    *fresh = true;
+    return free_slot >= 0 ? free_slot : (int)home;
 }
-static_assert(kMemoSlots == 8192, "memo_slot hashes to 13 bits");
+MTR_DEV int score_byte(int count) { return count > 254 ? 254 : count; }
 
-// One walk.  Returns the period (0 = no loop).  ustr / uscore: the unit and its node counts (clamped to 255) in walk
-// order (the backward walk's strings are reversed by the caller).
+// A tie list: the first kTiesNear entries live in shared memory (`near`), the rest in global memory (`far`).  A list is
+// written by one look-ahead level and read by the next; almost all lists are a handful of entries long, and a store to
+// global memory followed by a load of the same address costs an L2 round trip.
+constexpr int kTiesNear = 64;
+struct TieList { int *near, *far; };
+constexpr int kUfDynSmem = kUfSmemWords * 4 + 4 * kTiesNear * 4 + 2 * kMemoSlots * 16;   // dynamic shared memory of a unit-finder cta
+MTR_DEV int tie_get(const TieList &t, int i) { return i < kTiesNear ? t.near[i] : t.far[i]; }
+MTR_DEV void tie_put(const TieList &t, int i, int v) { if (i < kTiesNear) t.near[i] = v; else t.far[i] = v; }
+
+// One walk.  Returns the period (0 = no loop).  ustr / uscore: the unit and its node counts (clamped to 254) in walk
+// order (the backward walk's strings are reversed by the caller).  Per step: every lane reads the memo entry of the
+// node, the warp computes what the entry does not know yet (look-ahead, counts), lane 0 writes entry and strings, one
+// fence on each side of the write.  near-lists: 4 * kTiesNear ints of shared memory per cta (two lists per direction).
 MTR_DEV int walk(const Table &tb, Memo &memo, int qs, int qe, unsigned start, int k, bool backward,
-                 unsigned char *ustr, unsigned char *uscore, int *ties, int *fresh)
+                 unsigned char *ustr, unsigned char *uscore, TieList ties, TieList fresh, Counters *prof)
 {
     unsigned node = start;
+    long long p_steps = 0, p_rounds = 0, p_hits = 0, p_deep = 0;
+    const long long p_t0 = clock_now();
     int limit = (qe - qs) / 5;                                  // MIN_NUM_FREQ_UNIT
     if (limit > kMaxPeriod) limit = kMaxPeriod;
-    const int serial = memo.serial++;
+    const int serial = ++memo.serial;                           // 1, 2, ... within one (window, k, direction)
     int period = 0;
     for (int l = 0; l < limit; l++) {
-        if (!backward) {
-            const int sc = table_count(tb, node);
-            ENG_LANE0(ustr[l] = (unsigned char)(node >> (2 * (k - 1))); uscore[l] = (unsigned char)(sc > 255 ? 255 : sc));
-        }
-        int me = -1, next = -1;
+        MemoEntry e;
+        e.key = node; e.epoch = memo.epoch; e.next = -1; e.seen = 0; e.self1 = 0; e.next1 = 0;
+        int me = -1;
+        bool is_fresh = true;
         if (l >= 10) {
-            me = memo_slot(memo, node);
-            if (me >= 0) {
-                if (memo.tab[me].seen == serial) return 0;     // cycle without the start node
-                wsync();
-                ENG_LANE0(memo.tab[me].seen = serial);
-                next = memo.tab[me].next;
-                wsync();
+            MemoEntry got;
+            me = memo_find(memo, node, &got, &is_fresh);
+            if (me >= 0 && !is_fresh) {
+                e = got;
+                if (e.seen == serial) { period = 0; break; }   // cycle without the start node
             }
         }
+        int self_sc = e.self1 ? e.self1 - 1 : -1, next_sc = e.next1 ? e.next1 - 1 : -1;
+        if (!backward && self_sc < 0) self_sc = score_byte(table_count(tb, node));
+        int next = e.next;
+        p_steps++;
+        if (next >= 0) p_hits++;
         if (next < 0) {
             const int depth = l < 10 ? 1 : k;
             int nties = 1, pick = 0, m;
-            ENG_LANE0(ties[0] = 0);
             wsync();
-            int *cur = ties, *nxt = fresh;
+            if (lane() == 0) tie_put(ties, 0, 0);
+            wsync();
+            TieList cur = ties, nxt = fresh;
             for (m = 1; m <= depth; m++) {
                 const int ncand = 4 * nties;
+                p_rounds += (ncand + NL - 1) / NL;
+                if (m == 4) p_deep++;
                 const unsigned keep = (1u << (2 * (k - m))) - 1u;
-                // pass 1: maximum count over all extensions
-                int best = -1;
-                for (int ci = lane(); ci < ncand; ci += NL) {
-                    const int t = cur[ci >> 2], b = ci & 3;
-                    const int digits = backward ? (b << (2 * (m - 1))) + t : 4 * t + b;
-                    const unsigned cand = backward ? ((unsigned)digits << (2 * (k - m))) + (node >> (2 * m))
-                                                   : ((node & keep) << (2 * m)) + (unsigned)digits;
-                    const int c = table_count(tb, cand);
-                    best = c > best ? c : best;
-                }
-                best = wmax(best);
-                // pass 2: the extensions that reach the maximum, in order (first wins, at most 1024)
-                int nf = 0;
-                bool have_pick = false;
+                // one pass in candidate order: the running maximum, and the list of the extensions that reach it (a new
+                // maximum restarts the list; first wins, at most 1024) -- the reference's own loop, 32 candidates a time
+                int best = -1, nf = 0;
                 for (int c0 = 0; c0 < ncand; c0 += NL) {
                     const int ci = c0 + lane();
                     int c = -2, digits = 0;
                     if (ci < ncand) {
-                        const int t = cur[ci >> 2], b = ci & 3;
+                        const int t = tie_get(cur, ci >> 2), b = ci & 3;
                         digits = backward ? (b << (2 * (m - 1))) + t : 4 * t + b;
                         const unsigned cand = backward ? ((unsigned)digits << (2 * (k - m))) + (node >> (2 * m))
                                                        : ((node & keep) << (2 * m)) + (unsigned)digits;
                         c = table_count(tb, cand);
                     }
+                    const int cmax = wmax(c);
+                    if (cmax > best) { best = cmax; nf = 0; }
                     const unsigned eq = wballot(c == best);
                     if (eq) {
-                        if (!have_pick) { pick = bcast(digits, ffs(eq) - 1); have_pick = true; }
+                        if (nf == 0) pick = bcast(digits, ffs(eq) - 1);
                         const int at = nf + popc(eq & lanemask_lt());
-                        if (c == best && at < kMaxTies) nxt[at] = digits;
+                        if (c == best && at < kMaxTies) tie_put(nxt, at, digits);
                         nf += popc(eq);
                         if (nf > kMaxTies) nf = kMaxTies;
                     }
                 }
                 wsync();
                 if (backward ? nf <= 1 : nf == 1) break;
-                int *sw = cur; cur = nxt; nxt = sw;
+                const TieList sw = cur; cur = nxt; nxt = sw;
                 nties = nf;
             }
             // m == depth + 1 when the ties were never resolved: the appended base is then pick / 4^depth == 0 ('A', :336)
             next = backward ? (int)(((unsigned)(pick & 3) << (2 * (k - 1))) + (node >> 2))
                             : (int)(((node & ((1u << (2 * (k - 1))) - 1u)) << 2) + ((unsigned)pick >> (2 * (m - 1))));
-            if (me >= 0) ENG_LANE0(memo.tab[me].next = next);
         }
+        if (backward && next_sc < 0) next_sc = score_byte(table_count(tb, (unsigned)next));
+        const unsigned strnode = backward ? (unsigned)next : node;
+        wsync();                                                // every lane has read the entry
+        if (lane() == 0) {
+            ustr[l] = (unsigned char)(strnode >> (2 * (k - 1)));
+            uscore[l] = (unsigned char)(backward ? next_sc : self_sc);
+            if (me >= 0) {
+                e.seen = (unsigned short)serial;
+                e.next = next;                                  // (only entries of steps >= 10 exist: full look-ahead depth)
+                if (!backward) e.self1 = (unsigned char)(self_sc + 1); else e.next1 = (unsigned char)(next_sc + 1);
+                memo.tab[me] = e;
+            }
+        }
+        wsync();
         node = (unsigned)next;
-        if (backward) {
-            const int sc = table_count(tb, node);
-            ENG_LANE0(ustr[l] = (unsigned char)(node >> (2 * (k - 1))); uscore[l] = (unsigned char)(sc > 255 ? 255 : sc));
-        }
         if (node == start) { period = l + 1; if (kMaxPeriod <= period) period = 0; break; }
     }
     wsync();
+    if (prof && lane() == 0) {
+        atomic_add(&prof->prof_steps, (unsigned long long)p_steps); atomic_add(&prof->prof_probe_rounds, (unsigned long long)p_rounds);
+        atomic_add(&prof->prof_memo_hits, (unsigned long long)p_hits); atomic_add(&prof->prof_deep_steps, (unsigned long long)p_deep);
+        if (period == 0) atomic_add(&prof->prof_fail_walks, 1ull);
+        const unsigned long long dt = (unsigned long long)(clock_now() - p_t0);
+        unsigned long long old = prof->prof_max_walk;
+        while (dt > old) { const unsigned long long seen = atomic_cas(&prof->prof_max_walk, old, dt); if (seen == old) break; old = seen; }
+    }
     return period;
 }
 
-// ---------------------------------------------------------------- unit-finder scratch of one warp
+// ---------------------------------------------------------------- unit-finder scratch of one cta (global memory)
+// Per direction (= walking warp): the far parts of the two tie lists, unit / score strings.  Shared: the list of start nodes, the
+// polish output and the WIDE count table.
 struct Scratch {
-    unsigned long long *table;
-    MemoEntry *memo;
-    int *ties, *fresh, *nodes;
-    unsigned *epoch;               // the warp's running memo epoch (survives from task to task and from wave to wave)
-    unsigned char *ustr, *uscore, *revised;
+    int *ties[2], *fresh[2];       // far parts of the tie lists
+    unsigned char *ustr[2], *uscore[2];
+    unsigned *epoch[2];            // running memo epochs (survive from task to task and from wave to wave)
+    int *nodes;
+    unsigned char *revised;
+    unsigned long long *wide;      // this cta's WIDE table
 };
-constexpr long long kScratchFixed = (long long)kMemoSlots * 16 + 2LL * kMaxTies * 4 + 128 * 4 + 3 * kUnitStride;
-MTR_DEV Scratch scratch_of(const Ptrs &P, int warp)
+constexpr long long kScratchFixed = 4LL * kMaxTies * 4 + 4LL * kUnitStride + 128 * 4 + kUnitStride + 256;
+MTR_DEV Scratch scratch_of(const Ptrs &P, int cta)
 {
-    unsigned char *b = P.uf_scratch + (size_t)warp * (size_t)P.uf_stride;
+    unsigned char *b = P.uf_scratch + (size_t)cta * (size_t)P.uf_stride;
     Scratch s;
-    s.table = (unsigned long long *)b; b += (size_t)P.table_cap * 8;
-    s.memo = (MemoEntry *)b; b += (size_t)kMemoSlots * 16;
-    s.ties = (int *)b; b += (size_t)kMaxTies * 4;
-    s.fresh = (int *)b; b += (size_t)kMaxTies * 4;
-    s.nodes = (int *)b; s.epoch = (unsigned *)b + 120; b += 128 * 4;
-    s.ustr = b; b += kUnitStride;
-    s.uscore = b; b += kUnitStride;
-    s.revised = b;
+    for (int d = 0; d < 2; d++) { s.ties[d] = (int *)b; b += (size_t)kMaxTies * 4; s.fresh[d] = (int *)b; b += (size_t)kMaxTies * 4; }
+    for (int d = 0; d < 2; d++) { s.ustr[d] = b; b += kUnitStride; s.uscore[d] = b; b += kUnitStride; }
+    s.nodes = (int *)b; s.epoch[0] = (unsigned *)b + 120; s.epoch[1] = (unsigned *)b + 121; b += 128 * 4;
+    s.revised = b; b += kUnitStride + 256;
+    s.wide = (unsigned long long *)(P.uf_wide + (size_t)cta * (size_t)P.table_cap * 8);
     return s;
 }
 
+// the count table of a window of n positions and k-mer length k for this cta (smem: kUfSmemWords words)
+MTR_DEV Table table_for(const Scratch &S, const Ptrs &P, unsigned *smem, int n, int k)
+{
+    if (k <= P.direct_max_k && n <= 65000) return table_direct(smem, k);
+    if (n <= compact_max_n(P.compact_cap)) return table_compact(smem, P.compact_cap, n);
+    return table_wide(S.wide, P.table_cap, n);
+}
+
 // ---------------------------------------------------------------- search_De_Bruijn_graph up to wrap_around_DP (consensus.c:507-549)
-// One chain in stage ST_WALK: counts, maxFreq gate, list of maximum-frequency nodes, forward walks over that list
-// until the first loop, backward walks likewise.
-MTR_DEV void walk_chain(const Ptrs &P, int chain, const Scratch &S)
+// One chain in stage ST_WALK, one cta: counts (all threads), maxFreq gate, list of maximum-frequency nodes (warp 0), then
+// the forward walks over that list until the first loop on warp 0 and the backward walks likewise on warp 1 (both on
+// the same warp, one after the other, when the cta has only one).
+// counts, gate, node list and walks of one window on one cta.  Results: c.sh[8] = maxFreq, c.sh[2 + d] = direction d found
+// a loop, c.sh[4 + d] = its period, unit / score strings in S.ustr[d] / S.uscore[d] in WALK order (the caller reverses
+// the backward one, :458-470).  walks_ctr: optional counter of walks run.
+MTR_DEV void unit_walks(Table tb, const Window &win, const Scratch &S, const Cta &c, unsigned *smem, int *near, MemoEntry *memos, Counters *ctr)
+{
+    const long long t0 = clock_now();
+    const int maxf = table_build(tb, win, c);
+    const long long t1 = clock_now();
+    if (c.tid == 0) { c.sh[2] = 0; c.sh[3] = 0; c.sh[4] = 0; c.sh[5] = 0; c.sh[6] = 0; c.sh[8] = maxf; }
+    cta_sync(c);
+    long long t2 = t1;
+    if (5 < maxf) {                                             // MIN_NUM_FREQ_UNIT < maxFreq, :532
+        const int n_max = table_count_max(tb, maxf, c);
+        if (c.warp == 0) {
+            const int nn = table_list_max(tb, win, maxf, S.nodes, 100, n_max);
+            if (lane() == 0) c.sh[6] = nn;
+        }
+        cta_sync(c);
+        const int nn = c.sh[6];
+        table_freeze(tb, smem, c);
+        t2 = clock_now();
+        for (int d = 0; d < 2; d++) {
+            if (c.warp != d % c.nwarps) continue;
+            const long long tw0 = clock_now();
+            Memo memo;
+            memo.tab = memos + (size_t)d * kMemoSlots; memo.epoch = *S.epoch[d]; memo.used = 0; memo.serial = 0;
+            memo_reset(memo);
+            int nwalks = 0;
+            for (int i = 0; i < nn; i++) {
+                nwalks++;
+                TieList ta, tf;
+                ta.near = near + (2 * d) * kTiesNear; ta.far = S.ties[d]; tf.near = near + (2 * d + 1) * kTiesNear; tf.far = S.fresh[d];
+                const int p = walk(tb, memo, win.qs, win.qe, (unsigned)S.nodes[i], win.k, d == 1, S.ustr[d], S.uscore[d], ta, tf, ctr);
+                if (p == 0) continue;
+                if (lane() == 0) { c.sh[2 + d] = 1; c.sh[4 + d] = p; }
+                break;
+            }
+            ENG_LANE0(*S.epoch[d] = memo.epoch; if (ctr) { atomic_add(&ctr->walks, (unsigned long long)nwalks); atomic_add(&ctr->prof_walk[d], (unsigned long long)(clock_now() - tw0)); });
+        }
+    }
+    cta_sync(c);
+    if (ctr && c.tid == 0) {
+        const long long t3 = clock_now();
+        atomic_add(&ctr->prof_build, (unsigned long long)(t1 - t0)); atomic_add(&ctr->prof_list, (unsigned long long)(t2 - t1));
+        atomic_add(&ctr->prof_kind[tb.kind], 1ull); atomic_add(&ctr->prof_walk_tasks, 5 < maxf ? 1ull : 0ull);
+        unsigned long long old = ctr->prof_max_task;
+        const unsigned long long mine = (unsigned long long)(t3 - t0);
+        while (mine > old) { const unsigned long long seen = atomic_cas(&ctr->prof_max_task, old, mine); if (seen == old) break; old = seen; }
+    }
+}
+
+MTR_DEV void walk_chain(const Ptrs &P, int chain, const Scratch &S, const Cta &c, unsigned *smem, int *near, MemoEntry *memos)
 {
     Chain &ch = P.chains[chain];
     // A set freed and taken again inside one sched_read call leaves two entries for the same chain in the walk list
     // (the first one from the dropped candidate): whoever claims the chain first does the work, the other one leaves.
     int mine = 0;
-    ENG_LANE0(mine = atomic_cas(&ch.stage, (int)ST_WALK, (int)ST_WALKING) == (int)ST_WALK);
-    if (!bcast(mine, 0)) return;
+    if (c.tid == 0) { mine = atomic_cas(&ch.stage, (int)ST_WALK, (int)ST_WALKING) == (int)ST_WALK; if (mine) atomic_add(&P.ctr->walks_running, 1); }
+    if (!cta_bcast(c, mine, 1)) return;
+    fence();                                                   // the scheduler wrote the chain's fields before it set ST_WALK
     const Read &rs = P.reads[ch.read];
-    const uint32_t *rd = P.packed + rs.word_off;
     const int k = ch.k, qs = ch.qs, qe = ch.qe;
-    const Window win = window_make(rd, rs.L, k, qs, qe);
-    const Table tb = table_make(S.table, P.table_cap, qe - qs + 1);
-    const int maxf = table_build(tb, win);
-    if (lane() == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)(qe - qs + 1)); }
-    int found_last = 0, found[2] = {0, 0}, period[2] = {0, 0};
-    if (5 < maxf) {                                             // MIN_NUM_FREQ_UNIT < maxFreq, :532
-        const int nn = table_list_max(tb, win, maxf, S.nodes, 100);
-        Memo memo;
-        memo.tab = S.memo; memo.epoch = *S.epoch; memo.used = 0; memo.serial = 0;
-        int nwalks = 0;
-        for (int d = 0; d < 2; d++) {
-            memo_reset(memo);
-            for (int i = 0; i < nn; i++) {
-                nwalks++;
-                const int p = walk(tb, memo, qs, qe, (unsigned)S.nodes[i], k, d == 1, S.ustr, S.uscore, S.ties, S.fresh);
-                found_last = p > 0;
-                if (p == 0) continue;
-                unsigned char *du = unit_ptr(P, chain, U_DIR0 + d), *ds = score_ptr(P, chain, S_DIR0 + d);
-                for (int x = lane(); x < p; x += NL) {
-                    const int s = d == 1 ? p - 1 - x : x;      // the backward walk is reversed (:458-470)
-                    du[x] = S.ustr[s]; ds[x] = S.uscore[s];
-                }
-                wsync();
-                found[d] = 1; period[d] = p;
-                break;
-            }
+    const Window win = window_make(P.packed + rs.word_off, rs.L, k, qs, qe);
+    const Table tb = table_for(S, P, smem, qe - qs + 1, k);
+    if (c.tid == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)(qe - qs + 1)); }
+    unit_walks(tb, win, S, c, smem, near, memos, P.ctr);
+    for (int d = 0; d < 2; d++) {
+        if (c.warp != d % c.nwarps || !c.sh[2 + d]) continue;
+        const int p = c.sh[4 + d];
+        unsigned char *du = unit_ptr(P, chain, U_DIR0 + d), *ds = score_ptr(P, chain, S_DIR0 + d);
+        for (int x = lane(); x < p; x += NL) {
+            const int sx = d == 1 ? p - 1 - x : x;             // the backward walk is reversed (:458-470)
+            du[x] = S.ustr[d][sx]; ds[x] = S.uscore[d][sx];
         }
-        ENG_LANE0(*S.epoch = memo.epoch);
-        if (lane() == 0) atomic_add(&P.ctr->walks, (unsigned long long)nwalks);
     }
-    wsync();
-    if (lane() == 0) {
-        ch.found_last = found_last;
-        ch.dir_found[0] = found[0]; ch.dir_found[1] = found[1];
-        ch.dir_period[0] = period[0]; ch.dir_period[1] = period[1];
-        if (found[0] || found[1]) ch.stage = ST_NEED_SEARCH;
-        else { rec_clear(ch.rr); ch.stage = ST_DONE; }         // nothing found: find_tandem_repeat_sub clears (:86-88)
+    cta_sync(c);
+    if (c.tid == 0) {
+        // foundLoop of the LAST walk attempted (Q4): the backward pass tries the start nodes until its first loop, so its
+        // last attempt found one iff the pass did
+        ch.found_last = c.sh[3];
+        ch.dir_found[0] = c.sh[2]; ch.dir_found[1] = c.sh[3];
+        ch.dir_period[0] = c.sh[4]; ch.dir_period[1] = c.sh[5];
+        if (!(c.sh[2] || c.sh[3])) rec_clear(ch.rr);           // nothing found: find_tandem_repeat_sub clears (:86-88)
+        // the walk kernel of a wave runs beside the wave's emission / DP kernels: publish the stage last, behind a fence
+        fence();
+        const int done = (c.sh[2] || c.sh[3]) ? (int)ST_NEED_SEARCH : (int)ST_DONE;
+        if (atomic_cas(&ch.stage, (int)ST_WALKING, done) != (int)ST_WALKING) atomic_exch(&ch.stage, (int)ST_DONE);   // dropped meanwhile
+        atomic_add(&P.ctr->walks_done, 1);
+        atomic_add(&P.ctr->walks_running, -1);
     }
-    wsync();
+    cta_sync(c);
 }
 
 // ---------------------------------------------------------------- polish_repeat (consensus.c:584-704)
@@ -497,17 +726,20 @@ MTR_DEV bool suspicious(const unsigned char *score, int nscore, int kmer, int j)
     return (kmer - 1) * 0.8 < (double)c;
 }
 
-// polish rr of a chain in place (warp-uniform scalar code; the table build is the parallel part)
-MTR_DEV void polish_rr(const Ptrs &P, int chain, const Scratch &S)
+// polish rr of a chain in place: the table build uses the whole cta, the polish itself is warp-uniform scalar code on
+// warp 0
+MTR_DEV void polish_rr(const Ptrs &P, int chain, const Scratch &S, const Cta &c, unsigned *smem)
 {
     Chain &ch = P.chains[chain];
     const Read &rs = P.reads[ch.read];
     const int k = ch.rr.kmer, period = ch.rr.period;
     if (period <= k) return;
     const Window win = window_make(P.packed + rs.word_off, rs.L, k, ch.rr.rep_start, ch.rr.rep_end);
-    const Table tb = table_make(S.table, P.table_cap, ch.rr.rep_end - ch.rr.rep_start + 1);
-    table_build(tb, win);
-    if (lane() == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)(ch.rr.rep_end - ch.rr.rep_start + 1)); }
+    Table tb = table_for(S, P, smem, ch.rr.rep_end - ch.rr.rep_start + 1, k);
+    table_build(tb, win, c);
+    table_freeze(tb, smem, c);
+    if (c.tid == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)(ch.rr.rep_end - ch.rr.rep_start + 1)); }
+    if (c.warp != 0) return;
     unsigned char *unit = unit_ptr(P, chain, U_RR);
     const unsigned char *score = score_ptr(P, chain, S_RR);
     const int nscore = period;                                  // the score string of the walk that produced the unit
@@ -543,7 +775,7 @@ MTR_DEV void polish_rr(const Ptrs &P, int chain, const Scratch &S)
         } else {
             out = unit[j]; j--;
         }
-        ENG_LANE0(revised[jr] = out);
+        if (lane() == 0) revised[jr] = out;
         jr--;
         if (jr < 0) return;                                     // "fails to revise": record unchanged
     }
@@ -551,7 +783,6 @@ MTR_DEV void polish_rr(const Ptrs &P, int chain, const Scratch &S)
     const int np = (kMaxPeriod - 1) - jr;
     copy_bytes(unit, revised + jr + 1, np);
     ENG_LANE0(ch.rr.period = np);
-    wsync();
 }
 
 // ---------------------------------------------------------------- min_missing (consensus.c:714-820)
@@ -733,13 +964,15 @@ MTR_DEV void advance_chain(const Ptrs &P, int chain)
 }
 
 // one chain of the polish list: polish_repeat, then the first revise pass
-MTR_DEV void polish_chain(const Ptrs &P, int chain, const Scratch &S)
+MTR_DEV void polish_chain(const Ptrs &P, int chain, const Scratch &S, const Cta &c, unsigned *smem)
 {
     Chain &ch = P.chains[chain];
-    polish_rr(P, chain, S);
-    ENG_LANE0(ch.ratio0 = rec_ratio(ch.rr); ch.pass = 0);
-    wsync();
-    start_revise_pass(P, chain);
+    polish_rr(P, chain, S, c, smem);
+    if (c.warp == 0) {
+        ENG_LANE0(ch.ratio0 = rec_ratio(ch.rr); ch.pass = 0);
+        start_revise_pass(P, chain);
+    }
+    cta_sync(c);
 }
 
 // ---------------------------------------------------------------- DP task emission (one thread per chain slot)
@@ -749,12 +982,20 @@ MTR_DEV int dp_class_of(int ulen)
     for (int c = 0; c < 10; c++) if (ulen <= kClassCap[c]) return c;
     return 9;
 }
+MTR_DEV int seg_of(int cls20, int rows);
 MTR_DEV int row_bucket(int rows)
 {
     if (rows < 4) return rows < 0 ? 0 : rows;
     const int lz = 31 - clz((unsigned)rows);
     const int b = lz * 4 + ((rows >> (lz - 2)) & 3);
     return b < kRowBuckets - 1 ? b : kRowBuckets - 1;
+}
+
+// segment of a task: family-major, longest rows first, then class
+MTR_DEV int seg_of(int cls20, int rows)
+{
+    const int fam = cls20 >= 10 ? 1 : 0, c = cls20 - 10 * fam;
+    return (fam * kRowBuckets + (kRowBuckets - 1 - row_bucket(rows))) * 10 + c;
 }
 
 struct TaskSpec { int first, rows, ulen, uslot, n_param, mode, res_slot; const int *params; };
@@ -816,10 +1057,10 @@ MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
             u.gain[0] = t.gain[1]; u.mis[0] = t.mis[1]; u.indel[0] = t.indel[1];
             u.dir_off = t.dir_off + t.dir_bytes; u.result_idx = t.result_idx + 1;
             P.tasks_in[at++] = u;
-            atomic_add(&P.hist[(int)u.cls * kRowBuckets + row_bucket(u.rows)], 1);
+            atomic_add(&P.hist[seg_of(u.cls, u.rows)], 1);
         }
         P.tasks_in[at++] = t;
-        atomic_add(&P.hist[(int)t.cls * kRowBuckets + row_bucket(t.rows)], 1);
+        atomic_add(&P.hist[seg_of(t.cls, t.rows)], 1);
         cells += (long long)t.rows * t.ulen * sp[i].n_param;
         atomic_add(&P.ctr->slot_cells, (unsigned long long)((long long)t.rows * kClassCap[cls] * sp[i].n_param));
     }
@@ -834,8 +1075,9 @@ MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
 MTR_DEV void emit_chain(const Ptrs &P, int chain)
 {
     Chain &ch = P.chains[chain];
-    const int stage = ch.stage;
+    const int stage = ldv(&ch.stage);
     if (stage != ST_NEED_SEARCH && stage != ST_NEED_CONS && stage != ST_NEED_DP) return;
+    fence();                                                   // (a walk may have published NEED_SEARCH a moment ago: read its data after the stage)
     TaskSpec sp[2];
     int n = 0;
     if (stage == ST_NEED_SEARCH) {
@@ -868,39 +1110,36 @@ MTR_DEV void wave_begin(const Ptrs &P)
 {
     Counters &c = *P.ctr;
     c.n_advance = c.n_wait; c.n_wait = 0;
-    c.n_polish = 0; c.n_walk = 0; c.n_tasks = 0; c.deferred = 0; c.walk_head = 0; c.polish_head = 0;
+    c.n_polish = 0; c.n_tasks = 0; c.deferred = 0; c.polish_head = 0;
     c.dir_used = 0; c.aux_used = 0;
     c.waves++;
 }
 
-// one warp: bucket offsets (class ascending, rows descending), class boundaries for the fill kernels, and the reset of
-// the histogram for the next wave
+// one warp: prefix sums over the segments (tasks and warp slots), and the reset of the histogram for the next wave
+MTR_CONST int kClassJpw[10] = {8, 8, 8, 4, 4, 4, 2, 2, 1, 1};  // tasks per warp slot = 32 / G of the fill classes of wdp.cu
 MTR_DEV void plan_tasks(const Ptrs &P)
 {
-    int at = 0;
-    for (int c = 0; c < kDpClasses; c++) {
-        const int wc = c < 10 ? c : 16 + (c - 10);             // class index of wdp.cu (10..15 are its latency classes)
-        const int begin = at;
-        for (int j0 = 0; j0 < kRowBuckets; j0 += NL) {
-            const int j = j0 + lane();
-            const int i = c * kRowBuckets + (kRowBuckets - 1 - j);
-            const int h = j < kRowBuckets ? P.hist[i] : 0;
-            const int off = wscan_excl(h);
-            if (j < kRowBuckets) { P.bucket_begin[i] = at + off; P.hist[i] = 0; P.bucket_cursor[i] = 0; }
-            at += wsum(h);
-        }
-        ENG_LANE0(P.class_begin[wc] = begin; P.class_begin[wc + 1] = at; if (c == 9) for (int q = 10; q <= 16; q++) P.class_begin[q] = at);
+    int at = 0, slots = 0;
+    for (int s0 = 0; s0 < kSegs; s0 += NL) {
+        const int sg = s0 + lane();
+        const int h = sg < kSegs ? P.hist[sg] : 0;
+        const int jpw = kClassJpw[(sg < kSegs ? sg : 0) % 10];
+        const int sl = (h + jpw - 1) / jpw;
+        const int off = wscan_excl(h), soff = wscan_excl(sl);
+        if (sg < kSegs) { P.seg_task[sg] = at + off; P.seg_slot[sg] = slots + soff; P.hist[sg] = 0; P.bucket_cursor[sg] = 0; }
+        at += wsum(h); slots += wsum(sl);
     }
+    ENG_LANE0(P.seg_task[kSegs] = at; P.seg_slot[kSegs] = slots; P.class_begin[WDP_NCLASS] = at; P.ctr->tasks_total += (unsigned long long)at);
     for (int q = lane(); q < WDP_NCLASS; q += NL) P.slot_counter[q] = 0;
-    ENG_LANE0(P.ctr->tasks_total += (unsigned long long)at);
+    wsync();
 }
 
 MTR_DEV void scatter_task(const Ptrs &P, int i)
 {
     const WdpTask t = P.tasks_in[i];
     if (t.rows < 0) return;                                    // slot of a deferred emission
-    const int b = (int)t.cls * kRowBuckets + row_bucket(t.rows);
-    P.tasks[P.bucket_begin[b] + atomic_add(&P.bucket_cursor[b], 1)] = t;
+    const int sg = seg_of(t.cls, t.rows);
+    P.tasks[P.seg_task[sg] + atomic_add(&P.bucket_cursor[sg], 1)] = t;
 }
 
 // ---------------------------------------------------------------- per-read scheduler: handle_one_TR's candidate loop
@@ -919,7 +1158,25 @@ MTR_DEV void free_set(const Ptrs &P, Read &rs, int read, int set)
     wsync();
 }
 
-MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, unsigned table_cap)
+// chain set of a candidate that is dropped while its chains may still be with the walk kernel: queued walks are cancelled,
+// running ones are told that nobody waits for them (their set is freed by a later scheduler pass)
+MTR_DEV void drop_set(const Ptrs &P, Read &rs, int read, int set)
+{
+    if (set < 0) return;
+    int walking = 0;
+    for (int c = lane(); c < kMaxK; c += NL) {
+        Chain &ch = P.chains[((size_t)read * kSets + set) * kMaxK + c];
+        int st = ldv(&ch.stage);
+        if (st == ST_WALK) st = atomic_cas(&ch.stage, (int)ST_WALK, (int)ST_DONE) == (int)ST_WALK ? (int)ST_DONE : ldv(&ch.stage);
+        if (st == ST_WALKING) st = atomic_cas(&ch.stage, (int)ST_WALKING, (int)ST_ZOMBIE_WALKING) == (int)ST_WALKING ? (int)ST_ZOMBIE_WALKING : ldv(&ch.stage);
+        if (st == ST_ZOMBIE_WALKING) walking = 1;
+    }
+    walking = wmax(walking);
+    if (walking) ENG_LANE0(rs.zombie_mask |= 1u << set);
+    else free_set(P, rs, read, set);
+}
+
+MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, unsigned table_cap, int *sh)
 {
     Read &rs = P.reads[read];
     if (rs.phase != 0) return;
@@ -927,6 +1184,16 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
     int *END = P.end + rs.pos_off, *WW = P.w + rs.pos_off;
     const int L = rs.L;
     int started = 0;
+    // chain sets of dropped candidates whose walks were still running: free them once the walks have let go
+    for (unsigned zm = rs.zombie_mask; zm; zm &= zm - 1u) {
+        const int set = ffs(zm) - 1;
+        bool busy = false;
+        for (int c = 0; c < kMaxK; c++) {
+            const int st = ldv(&P.chains[((size_t)read * kSets + set) * kMaxK + c].stage);
+            if (st == ST_WALK || st == ST_WALKING || st == ST_ZOMBIE_WALKING) busy = true;
+        }
+        if (!busy) { ENG_LANE0(rs.zombie_mask &= ~(1u << set)); free_set(P, rs, read, set); }
+    }
     for (;;) {
         // ---- commit finished candidates in candidate order
         while (rs.n_ring > 0) {
@@ -992,7 +1259,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                     const Cand cc = rs.ring[(rs.head + c) % kRing];
                     if (END[cc.qs] < 0) {
                         ENG_LANE0(rs.cells_wasted += cc.cells; atomic_add(&P.ctr->spec_cells, (unsigned long long)cc.cells));
-                        free_set(P, rs, read, cc.set);
+                        drop_set(P, rs, read, cc.set);
                     } else {
                         if (keep != c) {
                             ENG_LANE0(rs.ring[(rs.head + keep) % kRing] = cc);
@@ -1054,8 +1321,8 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                 const int raw = qe - coded_end + 1;
                 if (low_maxf + raw <= 5) continue;
                 const Window win = window_make(rd, L, k, qs, qe);
-                const Table tb = table_make(table_mem, table_cap, width);
-                const int maxf = table_build(tb, win);
+                const Table tb = table_wide(table_mem, table_cap, width);
+                const int maxf = table_build(tb, win, cta_of_warp(sh));
                 if (lane() == 0) { atomic_add(&P.ctr->tables, 1ull); atomic_add(&P.ctr->table_positions, (unsigned long long)width); }
                 if (maxf < low_maxf) low_maxf = maxf;
                 if (5 < maxf) pass_mask |= 1u << (k - min_k);
@@ -1091,8 +1358,11 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                 ch.dir_found[0] = ch.dir_found[1] = 0; ch.dir_period[0] = ch.dir_period[1] = 0;
                 ch.fatal = 0; ch.msg = 0; ch.ring = pos; ch.aux_off = 0;
                 if (pass_mask & (1u << c)) {
-                    ch.stage = ST_WALK;
-                    P.walk_list[atomic_add(&P.ctr->n_walk, 1)] = chain;
+                    // a walk kernel may be running right now and may hold a stale queue entry for this very chain (a
+                    // cancelled walk of the set's previous owner): the fields first, then the stage
+                    fence();
+                    atomic_exch(&ch.stage, (int)ST_WALK);
+                    P.walk_ring[atomic_add(&P.ctr->walk_tail, 1u) & P.walk_ring_mask] = chain;
                 } else {
                     rec_clear(ch.rr);
                     ch.stage = ST_DONE;

@@ -13,7 +13,11 @@ struct Config {
     int n_reads = 0;
     long long total_bases = 0;
     int max_len = 0;
-    int uf_warps = 0;            // persistent unit-finder warps (each owns a scratch slice)
+    int uf_ctas = 0;             // persistent ctas of the walk kernel (each owns a scratch slice and a WIDE table)
+    int walk_streams = 4;        // walk kernel instances in flight (one scratch bank of uf_ctas slices each)
+    int polish_ctas = 0;         // ... of the polish kernel (scratch slices behind the walk banks: it runs beside the walks)
+    unsigned compact_cap = kCompactCap;
+    int direct_max_k = 7;
     int task_cap = 0;            // DP tasks per wave
     int acc_cap = 0;             // accepted repeats of the whole group
     long long aux_cap = 0;       // int32 of consensus histograms per wave
@@ -22,8 +26,8 @@ struct Config {
 };
 
 struct Layout {
-    size_t reads, chains, units, scores, results, wait_list, polish_list, walk_list, tasks_in, tasks, aux, acc, ctr, hist,
-        bucket_begin, bucket_cursor, class_begin, slot_counter, total;
+    size_t reads, chains, units, scores, results, wait_list, polish_list, walk_ring, tasks_in, tasks, aux, acc, ctr, hist,
+        seg_task, seg_slot, bucket_cursor, class_begin, slot_counter, total;
     int n_chains;
     unsigned table_cap;
     long long uf_stride;
@@ -33,13 +37,20 @@ inline Config default_config(int n_reads, long long total_bases, int max_len, in
 {
     Config c;
     c.n_reads = n_reads; c.total_bases = total_bases; c.max_len = max_len;
-    c.uf_warps = std::max(64, n_sm * 8);
+    // every cta owns a WIDE table sized for the longest read: at most 1 GB of them per group
+    unsigned cap = 64;
+    while (cap < 2u * (unsigned)(max_len + 8)) cap <<= 1;
+    c.uf_ctas = (int)std::max<long long>(4, std::min<long long>(n_sm, (1LL << 28) / ((long long)cap * 8)));
+    c.polish_ctas = c.uf_ctas;
     const long long n_chains = (long long)n_reads * kSets * kMaxK;
     c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains), 1 << 20);
-    c.acc_cap = (int)std::min<long long>((long long)n_reads * 64 + total_bases / 16 + 64, 1 << 24);
-    c.aux_cap = std::max<long long>((long long)c.task_cap / 8 * 512, 2 * 4500) ;
-    c.dir_cap = 2LL << 30;
-    c.walk_cap = (int)std::min<long long>((long long)n_reads * kSchedBudget * kMaxK, 1 << 26);
+    c.acc_cap = (int)std::min<long long>((long long)n_reads * 32 + total_bases / 48 + 64, 1 << 24);
+    c.aux_cap = std::max<long long>((long long)c.task_cap / 8 * 512, 2 * 4500);
+    c.dir_cap = std::min<long long>(2LL << 30, std::max<long long>(256LL << 20, total_bases * 64));
+    // walk queue: a power of two well above the chains that can be queued at once (entries of cancelled walks linger
+    // until a walk kernel pops them)
+    c.walk_cap = 4096;
+    while (c.walk_cap < 8 * n_chains && c.walk_cap < (1 << 28)) c.walk_cap <<= 1;
     return c;
 }
 
@@ -56,22 +67,23 @@ inline Layout make_layout(const Config &c)
     l.results = take(sizeof(mtr_wdp_result) * (size_t)std::max(l.n_chains, 1) * 4);
     l.wait_list = take(4 * (size_t)std::max(l.n_chains, 1));
     l.polish_list = take(4 * (size_t)std::max(l.n_chains, 1));
-    l.walk_list = take(4 * (size_t)std::max(c.walk_cap, 1));
+    l.walk_ring = take(4 * (size_t)c.walk_cap);
     l.tasks_in = take(sizeof(WdpTask) * (size_t)c.task_cap);
     l.tasks = take(sizeof(WdpTask) * (size_t)c.task_cap);
     l.aux = take(4 * (size_t)c.aux_cap);
     l.acc = take(sizeof(Accepted) * (size_t)c.acc_cap);
     l.ctr = take(sizeof(Counters));
-    l.hist = take(4 * (size_t)kDpClasses * kRowBuckets);
-    l.bucket_begin = take(4 * (size_t)(kDpClasses * kRowBuckets + 1));
-    l.bucket_cursor = take(4 * (size_t)kDpClasses * kRowBuckets);
+    l.hist = take(4 * (size_t)kSegs);
+    l.seg_task = take(4 * (size_t)(kSegs + 1));
+    l.seg_slot = take(4 * (size_t)(kSegs + 1));
+    l.bucket_cursor = take(4 * (size_t)kSegs);
     l.class_begin = take(4 * (size_t)(WDP_NCLASS + 1));
     l.slot_counter = take(4 * (size_t)WDP_NCLASS);
     l.total = at;
     unsigned cap = 64;
     while (cap < 2u * (unsigned)(c.max_len + 8)) cap <<= 1;
     l.table_cap = cap;
-    l.uf_stride = (((long long)cap * 8 + kScratchFixed) + 255) & ~255LL;
+    l.uf_stride = (kScratchFixed + 255) & ~255LL;
     return l;
 }
 
@@ -84,16 +96,17 @@ inline Ptrs bind(void *base, const Layout &l, const Config &c)
     P.chains = (Chain *)(b + l.chains);
     P.units = b + l.units; P.scores = b + l.scores;
     P.results = (mtr_wdp_result *)(b + l.results);
-    P.wait_list = (int *)(b + l.wait_list); P.polish_list = (int *)(b + l.polish_list); P.walk_list = (int *)(b + l.walk_list);
+    P.wait_list = (int *)(b + l.wait_list); P.polish_list = (int *)(b + l.polish_list); P.walk_ring = (int *)(b + l.walk_ring); P.walk_ring_mask = (unsigned)c.walk_cap - 1u;
     P.tasks_in = (WdpTask *)(b + l.tasks_in); P.tasks = (WdpTask *)(b + l.tasks);
     P.task_cap = c.task_cap;
     P.aux = (int *)(b + l.aux); P.aux_cap = c.aux_cap;
     P.dir_cap = c.dir_cap;
     P.acc = (Accepted *)(b + l.acc); P.acc_cap = c.acc_cap;
     P.ctr = (Counters *)(b + l.ctr);
-    P.hist = (int *)(b + l.hist); P.bucket_begin = (int *)(b + l.bucket_begin); P.bucket_cursor = (int *)(b + l.bucket_cursor);
+    P.hist = (int *)(b + l.hist); P.seg_task = (int *)(b + l.seg_task); P.seg_slot = (int *)(b + l.seg_slot); P.bucket_cursor = (int *)(b + l.bucket_cursor);
     P.class_begin = (int *)(b + l.class_begin); P.slot_counter = (int *)(b + l.slot_counter);
     P.table_cap = l.table_cap; P.uf_stride = l.uf_stride;
+    P.compact_cap = c.compact_cap; P.direct_max_k = c.direct_max_k;
     return P;
 }
 

@@ -142,7 +142,9 @@ inline cudaError_t mtr_sync(mtr_ctx *ctx)
 // launch description of the K3 kernels over a task list that lives in device memory (resident engine, wdp.cu)
 struct WdpDevLaunch {
     const WdpTask *tasks;
-    const int *class_begin;       // [WDP_NCLASS + 1]
+    const int *class_begin;       // [WDP_NCLASS + 1]: the last entry is the number of tasks
+    const int *seg_task, *seg_slot;   // prefix sums over the 2 * nseg_family segments (+1) of the sorted task list
+    int nseg_family;
     int *counters;                // [WDP_NCLASS] slot-queue heads, zero at launch
     const uint32_t *packed;
     const uint8_t *units;

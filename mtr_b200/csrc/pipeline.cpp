@@ -530,8 +530,8 @@ void add_stats(mtr_pipeline_stats &t, const mtr_pipeline_stats &p)
 // ---------------------------------------------------------------- process-wide state behind the C entry points
 struct Runtime {
     std::vector<mtr_ctx *> ctxs;       // groups_per_gpu engine contexts on each GPU, GPU-major
-    int n_gpu = 1, groups_per_gpu = 8;
-    int group_reads = 1024;            // reads per group (MTR_GROUP_READS) ...
+    int n_gpu = 1, groups_per_gpu = 16;
+    int group_reads = 512;            // reads per group (MTR_GROUP_READS) ...
     long long group_bases = 24LL << 20;   // ... or bases per group (MTR_GROUP_MBASES), whichever fills first
     StaleTracker stale;
     std::vector<ReadInput> pending;    // handle_one_read: reads enqueued since the last flush
@@ -778,7 +778,7 @@ extern "C" int mtr_pipeline_open(int device, int threads, mtr_pipeline **out)
 {
     if (!out) return MTR_EINVAL;
     *out = nullptr;
-    int k = 8;
+    int k = 16;
     if (const char *e = getenv("MTR_GROUPS_PER_GPU")) k = std::max(1, atoi(e));
     mtr_pipeline *p = new mtr_pipeline();
     for (int i = 0; i < k; i++) {

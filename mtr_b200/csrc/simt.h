@@ -60,6 +60,13 @@ MTR_DEV int wscan_excl(int v)                   // exclusive prefix sum over the
     return x - v;
 }
 MTR_DEV int atomic_cas(int *p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+MTR_DEV unsigned atomic_cas(unsigned *p, unsigned cmp, unsigned v) { return atomicCAS(p, cmp, v); }
+MTR_DEV unsigned atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+MTR_DEV unsigned ldv(const unsigned *p) { return *(const volatile unsigned *)p; }
+MTR_DEV void block_sync() { __syncthreads(); }
+MTR_DEV int block_tid() { return (int)threadIdx.x; }
+MTR_DEV int block_size() { return (int)blockDim.x; }
+MTR_DEV long long clock_now() { return clock64(); }
 MTR_DEV int atomic_add(int *p, int v) { return atomicAdd(p, v); }
 MTR_DEV unsigned long long atomic_add(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 MTR_DEV unsigned long long atomic_cas(unsigned long long *p, unsigned long long cmp, unsigned long long v) { return atomicCAS(p, cmp, v); }
@@ -93,6 +100,13 @@ inline int wsum(int v) { return v; }
 inline long long wsum(long long v) { return v; }
 inline int wscan_excl(int) { return 0; }
 inline int atomic_cas(int *p, int cmp, int v) { const int o = *p; if (o == cmp) *p = v; return o; }
+inline unsigned atomic_cas(unsigned *p, unsigned cmp, unsigned v) { const unsigned o = *p; if (o == cmp) *p = v; return o; }
+inline unsigned atomic_add(unsigned *p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline unsigned ldv(const unsigned *p) { return *p; }
+inline void block_sync() {}
+inline int block_tid() { return 0; }
+inline int block_size() { return 1; }
+inline long long clock_now() { return 0; }
 inline int atomic_add(int *p, int v) { const int o = *p; *p = o + v; return o; }
 inline unsigned long long atomic_add(unsigned long long *p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
 inline unsigned long long atomic_cas(unsigned long long *p, unsigned long long cmp, unsigned long long v) { const unsigned long long o = *p; if (o == cmp) *p = v; return o; }

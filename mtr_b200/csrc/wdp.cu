@@ -569,85 +569,179 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
 // The engine (eng_core.h) writes the sorted task array and the class boundaries in device memory; the host cannot know
 // the counts, so these kernels are launched with a fixed persistent grid and read their range from class_begin[].
 // Split traceback: the fill stores the argmax into results[], wdp_traceback_dev finishes the record in place.
-template <int G, int C, bool P16>
-__global__ void __launch_bounds__(128)
-wdp_fill_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const int cls,
-             const uint32_t *__restrict__ packed, const uint8_t *__restrict__ units, uint8_t *dirs,
-             mtr_wdp_result *results, int *__restrict__ counters)
+// One kernel per score family (int32 | paired int16x2) covers all ten fill classes: the task list is sorted by segment =
+// (family, rows bucket descending, class), a warp pulls the next slot of the family's queue, finds its segment by binary
+// search in the slot prefix sums and runs that class's fill.  Longest tasks first across ALL classes, two launches per
+// wave instead of twenty.
+struct WdpSegs { const int *task; const int *slot; int nseg_family; };   // prefix sums over 2 * nseg_family segments (+1)
+
+template <bool P16>
+__global__ void __launch_bounds__(128, 4)
+wdp_fill_family(const WdpTask *__restrict__ tasks, const WdpSegs sg, const uint32_t *__restrict__ packed,
+                const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counters)
 {
-    constexpr int JPW = 32 / G;
-    const int b = class_begin[cls], n = class_begin[cls + 1] - b;
-    const int nslots = (n + JPW - 1) / JPW;
+    const int seg0 = P16 ? sg.nseg_family : 0;
+    const int slot0 = sg.slot[seg0], slot1 = sg.slot[seg0 + sg.nseg_family];
     for (;;) {
         int slot = 0;
-        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counters + cls, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        if (slot >= nslots) break;
-        if (P16) fill_slot_p16<G, C, false>(tasks + b, n, slot, packed, units, dirs, results, nullptr);
-        else fill_slot_i32<G, C, false>(tasks + b, n, slot, packed, units, dirs, results, nullptr);
+        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counters + (P16 ? 1 : 0), 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0) + slot0;
+        if (slot >= slot1) break;
+        int lo = seg0, hi = seg0 + sg.nseg_family;          // largest segment with slot[seg] <= slot (empty segments share a value)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sg.slot[mid] <= slot) lo = mid; else hi = mid;
+        }
+        const WdpTask *ct = tasks + sg.task[lo];
+        const int cn = sg.task[lo + 1] - sg.task[lo];
+        const int ls = slot - sg.slot[lo];
+        const int cls = (lo - seg0) % 10;
+        if (P16) {
+            switch (cls) {
+            case 0: fill_slot_p16<4, 4, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 1: fill_slot_p16<4, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 2: fill_slot_p16<4, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 3: fill_slot_p16<8, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 4: fill_slot_p16<8, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 5: fill_slot_p16<8, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 6: fill_slot_p16<16, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 7: fill_slot_p16<16, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 8: fill_slot_p16<32, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            default: fill_slot_p16<32, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            }
+        } else {
+            switch (cls) {
+            case 0: fill_slot_i32<4, 4, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 1: fill_slot_i32<4, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 2: fill_slot_i32<4, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 3: fill_slot_i32<8, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 4: fill_slot_i32<8, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 5: fill_slot_i32<8, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 6: fill_slot_i32<16, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 7: fill_slot_i32<16, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            case 8: fill_slot_i32<32, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            default: fill_slot_i32<32, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+            }
+        }
     }
 }
 
-// one thread per (task, penalty set)
+// Warp-cooperative traceback of one (task, penalty set): wrap_around_DP.c:288-333 (counts) and consensus.c:919-962
+// (histograms).  The walk itself is sequential, but one thread chasing it pays an L2 round trip per step (read base,
+// direction byte): here the 32 lanes fetch the next 32 rows at once -- lane q the read base of row i - q and 64 direction
+// slots of that row around the column the diagonal will reach (the whole row when it has at most 64 slots) -- and the
+// warp then walks through registers (one shuffle per step) until the path leaves the fetched rows or columns.
+__device__ __forceinline__ void traceback_warp(const WdpTask &t, const int p, const int best, const int max_i, const int max_j,
+                                               const uint32_t *__restrict__ packed, const uint8_t *__restrict__ units,
+                                               const uint8_t *dirs, mtr_wdp_result *res, void *aux)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int G = t.gain[p], MM = t.mis[p], IN = t.indel[p];
+    const int ulen = t.ulen, dstride = t.dir_stride, nslots = t.dir_stride * 4;
+    const uint8_t *un = units + t.unit_off;
+    const long long base0 = t.base0;
+    const uint8_t *d = dirs + t.dir_off + (size_t)p * t.dir_bytes;
+    int i = max_i, j = max_j, run = best;
+    if (j == 0) j = ulen;                                   // wrap_around_DP.c:296
+    int nm = 0, nx = 0, ni = 0, nd = 0, steps = 0, flags = 0;
+    int *cons = nullptr, *miss = nullptr;
+    if (t.mode == MTR_TB_CONSENSUS) {
+        cons = (int *)aux + t.aux_off;
+        miss = cons + (size_t)(ulen + 1) * 5;
+    }
+    while (i > 0 && run > 0) {
+        // fetch rows i, i-1, ..., i-31
+        const int top = i;
+        const int rq = top - lane;
+        int jq = j - lane;                                  // column the diagonal reaches in my row
+        if (jq < 1) { jq = ulen - ((-jq) % ulen); }
+        int c0 = 0;                                         // first slot of my 64-slot window
+        if (nslots > 64) { c0 = ((jq - 1) - 32) & ~15; c0 = max(0, min(c0, nslots - 64)); }
+        int xq = 0;
+        unsigned w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+        if (rq >= 1) {
+            xq = read_base(packed, base0 + rq);
+            const unsigned *row = reinterpret_cast<const unsigned *>(d + (size_t)(rq - 1) * dstride + (c0 >> 2));
+            w0 = row[0];
+            if (nslots > 16) w1 = row[1];
+            if (nslots > 32) w2 = row[2];
+            if (nslots > 48) w3 = row[3];
+        }
+        while (i > 0 && run > 0 && i > top - 32) {
+            const int q = top - i;
+            const int xi = __shfl_sync(FULL, xq, q);
+            const int uj = un[j - 1];
+            int op;
+            if (xi == uj) {
+                op = 0;
+            } else {
+                const int s = j - 1 - __shfl_sync(FULL, c0, q);
+                if (s < 0 || s >= 64) break;                   // the path left the fetched columns: fetch again from here
+                const int wi = s >> 4;
+                const unsigned mine = wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
+                const unsigned v = __shfl_sync(FULL, mine, q);
+                const int code = (int)((v >> ((s & 15) * 2)) & 3u);
+                if (code == 0) { flags |= 2; run = 0; break; }  // cannot happen: run > 0 means W[i][j] > 0
+                op = code == 3 ? 1 : (code == 2 ? 2 : 3);
+            }
+            steps++;
+            if (op == 0)      { if (cons && lane == 0) atomicAdd(&cons[j * 5 + xi], 1); run -= G;  i--; j--; nm++; }
+            else if (op == 1) { if (cons && lane == 0) atomicAdd(&cons[j * 5 + xi], 1); run += MM; i--; j--; nx++; }
+            else if (op == 2) { if (cons && lane == 0) atomicAdd(&cons[j * 5 + 4], 1);  run += IN; j--;      nd++; }
+            else              { if (miss && lane == 0) atomicAdd(&miss[j * 4 + xi], 1); run += IN; i--;      ni++; }
+            if (j == 0) j = ulen;
+        }
+    }
+    if (lane == 0) {
+        int4 *o = reinterpret_cast<int4 *>(res);
+        o[0] = make_int4(best, max_i, max_j, i);
+        o[1] = make_int4(j, nm, nx, ni);
+        o[2] = make_int4(nd, nm + nx + nd, steps, flags);
+    }
+}
+
+// one warp per (task, penalty set), pulled from a queue in task order (longest tasks of every class first)
 __global__ void __launch_bounds__(128)
 wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const uint32_t *__restrict__ packed,
-                  const uint8_t *__restrict__ units, const uint8_t *dirs, mtr_wdp_result *results, void *aux)
+                  const uint8_t *__restrict__ units, const uint8_t *dirs, mtr_wdp_result *results, void *aux, int *__restrict__ head)
 {
     const int total = 2 * class_begin[WDP_NCLASS];
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    for (;;) {
+        int idx = 0;
+        if ((threadIdx.x & 31) == 0) idx = atomicAdd(head, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= total) break;
         const WdpTask &t = tasks[idx >> 1];
         const int p = idx & 1;
         if (p >= (int)t.n_param) continue;
         const mtr_wdp_result in = results[t.result_idx + p];
-        traceback_one(t, p, in.best, in.max_i, in.max_j, packed, units, dirs, results + t.result_idx + p, aux);
+        __syncwarp();
+        traceback_warp(t, p, in.best, in.max_i, in.max_j, packed, units, dirs, results + t.result_idx + p, aux);
+        __syncwarp();
     }
 }
 
-template <int G, int C, bool P16>
-static void launch_fill_dev(const WdpDevLaunch &L, int cls, cudaStream_t s)
-{
-    wdp_fill_dev<G, C, P16><<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, cls, L.packed, L.units, L.dirs, L.results, L.counters);
-}
-
-// enqueues the fill kernels of every engine class and the traceback on `s` (class kernels fan out over L.side streams)
+// enqueues the two family fill kernels (the paired one on the side stream) and the traceback on `s`
 cudaError_t wdp_launch_dev(const WdpDevLaunch &L, cudaStream_t s)
 {
     cudaError_t e;
-    if ((e = cudaEventRecord(L.fork, s)) != cudaSuccess) return e;
-    for (int k = 0; k < WDP_NCLASS; k++) {
-        if (k >= 10 && k < 16) continue;                    // latency classes: never used by the engine
-        cudaStream_t cs = L.n_side > 0 ? L.side[k % L.n_side] : s;
-        if (L.n_side > 0 && (e = cudaStreamWaitEvent(cs, L.fork, 0)) != cudaSuccess) return e;
-        switch (k) {
-        case 0: launch_fill_dev<4, 4, false>(L, k, cs); break;
-        case 1: launch_fill_dev<4, 8, false>(L, k, cs); break;
-        case 2: launch_fill_dev<4, 12, false>(L, k, cs); break;
-        case 3: launch_fill_dev<8, 8, false>(L, k, cs); break;
-        case 4: launch_fill_dev<8, 12, false>(L, k, cs); break;
-        case 5: launch_fill_dev<8, 16, false>(L, k, cs); break;
-        case 6: launch_fill_dev<16, 12, false>(L, k, cs); break;
-        case 7: launch_fill_dev<16, 16, false>(L, k, cs); break;
-        case 8: launch_fill_dev<32, 12, false>(L, k, cs); break;
-        case 9: launch_fill_dev<32, 16, false>(L, k, cs); break;
-        case 16: launch_fill_dev<4, 4, true>(L, k, cs); break;
-        case 17: launch_fill_dev<4, 8, true>(L, k, cs); break;
-        case 18: launch_fill_dev<4, 12, true>(L, k, cs); break;
-        case 19: launch_fill_dev<8, 8, true>(L, k, cs); break;
-        case 20: launch_fill_dev<8, 12, true>(L, k, cs); break;
-        case 21: launch_fill_dev<8, 16, true>(L, k, cs); break;
-        case 22: launch_fill_dev<16, 12, true>(L, k, cs); break;
-        case 23: launch_fill_dev<16, 16, true>(L, k, cs); break;
-        case 24: launch_fill_dev<32, 12, true>(L, k, cs); break;
-        default: launch_fill_dev<32, 16, true>(L, k, cs); break;
-        }
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    WdpSegs sg;
+    sg.task = L.seg_task; sg.slot = L.seg_slot; sg.nseg_family = L.nseg_family;
+    cudaStream_t ps = L.n_side > 0 ? L.side[0] : s;
+    if (L.n_side > 0) {
+        if ((e = cudaEventRecord(L.fork, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(ps, L.fork, 0)) != cudaSuccess) return e;
     }
-    if (L.n_side > 0)
-        for (int i = 0; i < L.n_side; i++) {
-            if ((e = cudaEventRecord(L.join[i], L.side[i])) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(s, L.join[i], 0)) != cudaSuccess) return e;
-        }
-    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux);
+    wdp_fill_family<false><<<L.blocks, 128, 0, s>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    wdp_fill_family<true><<<L.blocks, 128, 0, ps>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (L.n_side > 0) {
+        if ((e = cudaEventRecord(L.join[0], ps)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(s, L.join[0], 0)) != cudaSuccess) return e;
+    }
+    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 10);
     return cudaGetLastError();
 }
 

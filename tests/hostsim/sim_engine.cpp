@@ -18,7 +18,7 @@
 using namespace eng;
 
 struct EngState {
-    std::vector<unsigned char> main_buf, scratch;
+    std::vector<unsigned char> main_buf, scratch, wide;
     std::vector<int> end, w;
     std::vector<mtr_repeat> reps;
     std::vector<uint8_t> units;
@@ -85,17 +85,28 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     if (rc) return rc;
 
     Config cfg = default_config(n, pos_off[n], max_len, 1);
-    cfg.uf_warps = 1;
+    cfg.uf_ctas = 1;
+    // MTR_SIM_COMPACT_CAP / MTR_SIM_DIRECT_K: shrink the shared-memory table layouts so that small test windows reach
+    // the COMPACT and the WIDE (+ probe cache) paths too
+    if (const char *e = getenv("MTR_SIM_COMPACT_CAP")) cfg.compact_cap = (unsigned)std::max(64, std::min(4096, atoi(e)));
+    if (const char *e = getenv("MTR_SIM_DIRECT_K")) cfg.direct_max_k = std::max(0, std::min(7, atoi(e)));
     // small per-wave budgets on request, to exercise the deferral path on the CPU
     if (const char *e = getenv("MTR_ENGINE_DIR_KB")) cfg.dir_cap = std::max(1LL, atoll(e)) << 10;
     if (const char *e = getenv("MTR_ENGINE_TASK_CAP")) cfg.task_cap = std::max(4, atoi(e));
     const Layout lay = make_layout(cfg);
     E.main_buf.assign(lay.total, 0);
     E.scratch.assign((size_t)lay.uf_stride, 0);
+    E.wide.assign((size_t)lay.table_cap * 8, 0);
+    std::vector<unsigned> smem((size_t)kUfSmemWords, 0u);
+    int sh[16] = {0}, near[4 * kTiesNear] = {0};
+    std::vector<MemoEntry> memos(2 * kMemoSlots);
+    memset(memos.data(), 0, sizeof(MemoEntry) * memos.size());
+    const Cta cta = cta_of_warp(sh);
     Ptrs P = bind(E.main_buf.data(), lay, cfg);
     P.packed = sim_packed(ctx);
     P.end = E.end.data(); P.w = E.w.data();
     P.uf_scratch = E.scratch.data();
+    P.uf_wide = E.wide.data();
     P.min_match_ratio = min_match_ratio;
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
@@ -108,12 +119,20 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     const Scratch S = scratch_of(P, 0);
     unsigned long long last_sig = ~0ull;
     int idle = 0;
+    std::vector<unsigned> tails;
     while (P.ctr->unfinished > 0 && !P.ctr->error) {
         wave_begin(P);
         for (int i = 0; i < P.ctr->n_advance; i++) advance_chain(P, P.wait_list[i]);
-        for (int i = 0; i < P.ctr->n_polish; i++) polish_chain(P, P.polish_list[i], S);
-        for (int r = 0; r < n; r++) sched_read(P, r, inline_tab.data(), kInlineSlots);
-        for (int i = 0; i < P.ctr->n_walk; i++) walk_chain(P, P.walk_list[i], S);
+        for (int i = 0; i < P.ctr->n_polish; i++) polish_chain(P, P.polish_list[i], S, cta, smem.data());
+        for (int r = 0; r < n; r++) sched_read(P, r, inline_tab.data(), kInlineSlots, sh);
+        // the walk queue: with MTR_SIM_WALK_LAG = n the entries pushed by a scheduler pass are only walked n waves later,
+        // like walks that are still running when the next passes start (dropped candidates then meet chains in ST_WALK)
+        {
+            static const int lag = getenv("MTR_SIM_WALK_LAG") ? std::min(5, atoi(getenv("MTR_SIM_WALK_LAG"))) : 0;
+            tails.push_back(P.ctr->walk_tail);
+            const unsigned limit = (int)tails.size() > lag ? tails[tails.size() - 1 - (size_t)lag] : 0u;
+            while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(P, P.walk_ring[P.ctr->walk_head++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
+        }
         for (int c = 0; c < lay.n_chains; c++) emit_chain(P, c);
         plan_tasks(P);
         const int nt = std::min(P.ctr->n_tasks, P.task_cap);

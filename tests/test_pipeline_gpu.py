@@ -66,11 +66,13 @@ def test_synthetic_cases(synthetic_dir, name):
         assert hashlib.md5(out).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode, explain(out, flags, path))
 
 
-def test_small_batches_give_identical_output(synthetic_dir):
-    """Batch boundaries (and with them the round structure) must not change a byte."""
+def test_small_groups_give_identical_output(synthetic_dir):
+    """Group boundaries, the number of engine contexts and the per-wave direction-matrix budget (a chain that does not
+    fit is emitted again by the next wave) must not change a byte."""
     path = os.path.join(synthetic_dir, "mixed.fa")
     ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
-    for env in ({"MTR_BATCH_READS": "1"}, {"MTR_BATCH_READS": "5", "MTR_THREADS": "1"}, {"MTR_DIR_BUDGET_MB": "1"}):
+    for env in ({"MTR_GROUP_READS": "1"}, {"MTR_GROUP_READS": "5", "MTR_GROUPS_PER_GPU": "1"}, {"MTR_ENGINE_DIR_MB": "64", "MTR_ENGINE_SIDE_STREAMS": "0"},
+                {"MTR_GROUP_READS": "7", "MTR_GROUPS_PER_GPU": "3", "MTR_ENGINE_BURST": "1"}):
         assert hashlib.md5(run(MTR, [], path, env)).hexdigest() == ref, env
 
 
@@ -103,12 +105,12 @@ def test_pipeline_abi_alignment_and_pearson_modes(synthetic_dir):
 
 
 def test_cli_on_two_gpus_matches_digest(synthetic_dir):
-    """handle_one_file with MTR_GPUS=2: batches alternate between the GPUs, output is merged in input order."""
+    """handle_one_file with MTR_GPUS=2: groups of reads are pulled by the engine contexts of both GPUs, output is merged in input order."""
     from mtr_b200 import capi
     if capi.load_library().mtr_device_count() < 2:
         pytest.skip("needs two GPUs")
     path = os.path.join(synthetic_dir, "mixed.fa")
-    out = run(MTR, [], path, {"MTR_GPUS": "2", "MTR_BATCH_READS": "5"})
+    out = run(MTR, [], path, {"MTR_GPUS": "2", "MTR_GROUP_READS": "5", "MTR_GROUPS_PER_GPU": "2"})
     assert hashlib.md5(out).hexdigest() == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
 
 
@@ -157,7 +159,7 @@ from mtr_b200 import capi
 n, out, st = capi.run_file(%r)
 print(json.dumps({"n": n, "md5": hashlib.md5(out).hexdigest(), "reads": st["reads"], "launches": st["launches"], "cells": st["wdp_cells"], "d2h": st["d2h_bytes"]}))
 ''' % (ROOT, path)
-    for env in ({"MTR_BATCH_READS": "4"}, {"MTR_BATCH_READS": "3", "MTR_STAGGER_FRAC": "0.9", "MTR_TIER_PRIO": "0"}):
+    for env in ({"MTR_GROUP_READS": "4"}, {"MTR_GROUP_READS": "3", "MTR_GROUPS_PER_GPU": "2"}):
         e = dict(os.environ); e.update(env)
         p = subprocess.run([sys.executable, "-c", script], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
         assert p.returncode == 0, p.stderr.decode()[-1500:]

@@ -50,6 +50,6 @@ def test_unit_finder_matches_oracle(gpu_ctx):
                 assert int(got["period"][d]) == p, (i, d, tasks[i])
                 off = int(got["unit_off"][d])
                 assert np.array_equal(units[off:off + p], exp["units"][d]), (i, d, tasks[i])
-                assert np.array_equal(scores[off:off + p], exp["scores"][d]), (i, d, tasks[i])
+                assert np.array_equal(scores[off:off + p], np.minimum(exp["scores"][d], 254)), (i, d, tasks[i])   # counts are kept clamped to a byte
     o.close()
     assert n_found > 200
