@@ -204,6 +204,12 @@ typedef struct {
 
 int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio, const uint16_t *stale, const int64_t *stale_off,
                    const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units, mtr_engine_stats *stats);
+/* The same for reads [first, first + count) of the resident batch only (mtr_repeat::read stays an index into the whole
+ * batch; stale_off is indexed like the whole batch): several groups of reads can be resident in one context and run one
+ * after the other. */
+int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manhattan, float min_match_ratio, const uint16_t *stale,
+                         const int64_t *stale_off, const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units,
+                         mtr_engine_stats *stats);
 /* MTR_SPECULATE-style knobs of the engine (defaults: 8 look-ahead candidates). */
 int mtr_engine_set_speculate(mtr_ctx *ctx, int depth);
 /* Union, over every engine call of the process since the last reset, of the time intervals in which K3 kernels of

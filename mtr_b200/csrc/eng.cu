@@ -16,10 +16,24 @@
 using namespace eng;
 
 // ---------------------------------------------------------------- kernels
-__global__ void eng_begin(Ptrs P) { if (threadIdx.x == 0 && blockIdx.x == 0) wave_begin(P); }
+// MTR_TIMELINE: every kernel of a wave stamps %globaltimer when its first thread starts (and publish when it ends), so the
+// waves of concurrent groups can be laid side by side afterwards
+__device__ __forceinline__ void stamp(const Ptrs &P, int id)
+{
+    if (!P.stamps) return;
+    const int w = P.ctr->waves;
+    if (w >= P.stamp_waves) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.stamps[(size_t)w * 16 + id] = t;
+}
+#define STAMP0(id) do { if (blockIdx.x == 0 && threadIdx.x == 0) stamp(P, id); } while (0)
+
+__global__ void eng_begin(Ptrs P) { if (threadIdx.x == 0 && blockIdx.x == 0) { wave_begin(P); stamp(P, 0); } }
 
 __global__ void __launch_bounds__(128) eng_advance(Ptrs P)
 {
+    STAMP0(1);
     const int nw = gridDim.x * (blockDim.x >> 5);
     const int n = P.ctr->n_advance;
     for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) advance_chain(P, P.wait_list[i]);
@@ -38,6 +52,7 @@ __global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0)
     if (WHICH == 0) { for (int i = threadIdx.x; i < 2 * kMemoSlots; i += blockDim.x) memos[i].epoch = 0u; __syncthreads(); }
     const Cta c = cta_of_block(sh);
     const Scratch S = scratch_of(P, slice0 + blockIdx.x);
+    STAMP0(WHICH == 1 ? 2 : 4);
     if (WHICH == 1) {
         const int n = P.ctr->n_polish;
         for (;;) {
@@ -67,31 +82,36 @@ __global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0)
     }
 }
 
-__global__ void __launch_bounds__(64) eng_sched(Ptrs P)
+// one warp per read, one warp per block: 16.5 KB of shared memory fit beside the unit-finder ctas of other groups
+__global__ void __launch_bounds__(32) eng_sched(Ptrs P)
 {
-    __shared__ unsigned long long tab[2][kInlineSlots];
-    __shared__ int sh[2][16];
-    const int read = blockIdx.x * 2 + (threadIdx.x >> 5);
+    __shared__ unsigned long long tab[kInlineSlots];
+    __shared__ int sh[16];
+    const int read = blockIdx.x;
+    STAMP0(3);
     if (read >= P.n_reads) return;
-    sched_read(P, read, tab[threadIdx.x >> 5], kInlineSlots, sh[threadIdx.x >> 5]);
+    sched_read(P, read, tab, kInlineSlots, sh);
 }
 
 __global__ void __launch_bounds__(256) eng_emit(Ptrs P, int n_chains)
 {
+    STAMP0(5);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n_chains) emit_chain(P, c);
 }
 
-__global__ void eng_plan(Ptrs P) { if (blockIdx.x == 0 && threadIdx.x < 32) plan_tasks(P); }
+__global__ void eng_plan(Ptrs P) { STAMP0(6); if (blockIdx.x == 0 && threadIdx.x < 32) plan_tasks(P); }
 
 __global__ void __launch_bounds__(256) eng_scatter(Ptrs P)
 {
+    STAMP0(7);
     const int n = min(P.ctr->n_tasks, P.task_cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) scatter_task(P, i);
 }
 
 __global__ void __launch_bounds__(256) eng_zero_aux(Ptrs P)
 {
+    STAMP0(8);
     const long long n = min((long long)P.ctr->aux_used, P.aux_cap);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) P.aux[i] = 0;
 }
@@ -101,6 +121,7 @@ struct EngSnapshot { int unfinished, error, error_read, deferred, waves, n_accep
 __global__ void eng_publish(Ptrs P, EngSnapshot *snap)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    stamp(P, 10);
     const Counters &c = *P.ctr;
     snap->error = c.error; snap->error_read = c.error_read; snap->deferred = c.deferred; snap->waves = c.waves;
     snap->n_accepted = c.n_accepted; snap->n_tasks = c.n_tasks; snap->pad = (int)(c.walk_tail - c.walk_head) + c.walks_running; snap->tasks_total = c.tasks_total; snap->candidates_started = c.tables + (unsigned long long)(unsigned)c.progress + ((unsigned long long)(unsigned)c.walks_done << 32);
@@ -110,7 +131,7 @@ __global__ void eng_publish(Ptrs P, EngSnapshot *snap)
 
 // ---------------------------------------------------------------- per-context engine state
 struct EngState {
-    DevBuf d_main, d_dirs, d_scratch, d_wide;
+    DevBuf d_main, d_dirs, d_scratch, d_wide, d_stamps;
     PinBuf h_snap, h_acc, h_ctr;
     Config cfg;
     Layout lay;
@@ -200,11 +221,20 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
                               const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units, mtr_engine_stats *stats)
 {
     if (!ctx) return MTR_EINVAL;
+    return mtr_engine_run_range(ctx, 0, ctx->n_reads, manhattan, min_match_ratio, stale, stale_off, repeats, n_repeats, units, stats);
+}
+
+extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manhattan, float min_match_ratio, const uint16_t *stale,
+                                    const int64_t *stale_off, const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units,
+                                    mtr_engine_stats *stats)
+{
+    if (!ctx) return MTR_EINVAL;
     if (repeats) *repeats = nullptr;
     if (n_repeats) *n_repeats = 0;
     if (units) *units = nullptr;
     if (stats) memset(stats, 0, sizeof *stats);
-    const int n = ctx->n_reads;
+    if (first < 0 || count < 0 || first + count > ctx->n_reads) { mtr_set_error(ctx, "engine_run: read range outside the resident batch"); return MTR_EINVAL; }
+    const int n = count;
     if (n == 0) return MTR_OK;
     const double t_wall0 = wall_ms();
     MTR_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -237,17 +267,20 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     const int n_side = std::max(E.n_side, 0);
 
     // ---- directional index, left in device memory
-    std::vector<int64_t> pos_off((size_t)n + 1, 0);
+    // (pos_off is indexed like the resident batch; only the entries of the range matter)
+    std::vector<int64_t> pos_off((size_t)first + n + 1, 0);
     int max_len = 0;
-    for (int r = 0; r < n; r++) { pos_off[r + 1] = pos_off[r] + ctx->len[r]; max_len = std::max(max_len, (int)ctx->len[r]); }
-    int rc = di_compute(ctx, manhattan, stale, stale_off, pos_off.data(), 0, n);
+    for (int r = 0; r < n; r++) { pos_off[first + r + 1] = pos_off[first + r] + ctx->len[first + r]; max_len = std::max(max_len, (int)ctx->len[first + r]); }
+    int rc = di_compute(ctx, manhattan, stale, stale_off, pos_off.data(), first, n);
     if (rc) return rc;
     const double di_ms = ctx->stats.di_ms;
     const int di_launches = ctx->stats.launches;
-    const int64_t di_h2d = ctx->stats.di_bytes_in - (ctx->word_off[n] - ctx->word_off[0]) * 4;
+    const int64_t di_h2d = ctx->stats.di_bytes_in - (ctx->word_off[first + n] - ctx->word_off[first]) * 4;
 
     // ---- buffers
-    Config cfg = default_config(n, pos_off[n], max_len, ctx->n_sm);
+    Config cfg = default_config(n, pos_off[first + n], max_len, ctx->n_sm);
+    if (const char *e = getenv("MTR_ENGINE_WALK_STREAMS")) cfg.walk_streams = std::max(1, std::min(4, atoi(e)));
+    if (const char *e = getenv("MTR_ENGINE_WALK_CTAS")) cfg.uf_ctas = cfg.polish_ctas = std::max(1, atoi(e));
     if (const char *e = getenv("MTR_ENGINE_DIR_MB")) cfg.dir_cap = std::max(64LL, atoll(e)) << 20;
     Layout lay = make_layout(cfg);
     MTR_CUDA(ctx, E.d_main.reserve(lay.total));
@@ -269,6 +302,13 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     P.min_match_ratio = min_match_ratio;
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
+    static const bool timeline = getenv("MTR_TIMELINE") != nullptr;
+    if (timeline) {
+        P.stamp_waves = 1024;
+        MTR_CUDA(ctx, E.d_stamps.reserve((size_t)P.stamp_waves * 16 * 8));
+        MTR_CUDA(ctx, cudaMemsetAsync(E.d_stamps.p, 0, (size_t)P.stamp_waves * 16 * 8, s));
+        P.stamps = (unsigned long long *)E.d_stamps.p;
+    }
     E.P = P;
 
     // zero: chain stages (ST_FREE), lists, counters, histograms, the scratch epochs; then the per-read state
@@ -276,7 +316,7 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.ctr, 0, lay.total - lay.ctr, s));
     MTR_CUDA(ctx, cudaMemsetAsync(E.d_scratch.p, 0, (size_t)lay.uf_stride * n_slices, s));
     std::vector<Read> reads;
-    init_reads(reads, ctx->word_off.data(), ctx->len.data(), n);
+    init_reads(reads, ctx->word_off.data() + first, ctx->len.data() + first, n);
     MTR_CUDA(ctx, cudaMemcpyAsync(P.reads, reads.data(), sizeof(Read) * (size_t)n, cudaMemcpyHostToDevice, s));
     {
         Counters c0;
@@ -292,7 +332,7 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     memset(&L, 0, sizeof L);
     L.tasks = P.tasks; L.class_begin = P.class_begin; L.seg_task = P.seg_task; L.seg_slot = P.seg_slot; L.nseg_family = kSegs / 2; L.counters = P.slot_counter; L.packed = P.packed;
     L.units = P.units; L.dirs = (uint8_t *)E.d_dirs.p; L.results = P.results; L.aux = P.aux;
-    L.blocks = ctx->n_sm;
+    L.blocks = ctx->n_sm * 2;
     for (int i = 0; i < n_side; i++) { L.side[i] = E.side[i]; L.join[i] = E.join[i]; }
     L.fork = E.fork; L.n_side = n_side;
 
@@ -307,13 +347,15 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     if (const char *e = getenv("MTR_ENGINE_BURST")) burst = std::max(1, std::min(EngState::kEv, atoi(e)));
     unsigned long long last_tasks = ~0ull, last_started = ~0ull;
     int last_accepted = -1, last_unfinished = -1, stalled = 0, quiet = 0;
+    double t_launch = 0, t_wait = 0;
     for (;;) {
+        const double tl0 = wall_ms();
         for (int b = 0; b < burst; b++) {
             MTR_CUDA(ctx, cudaEventRecord(E.ev_w0[b], s));
             eng_begin<<<1, 32, 0, s>>>(P);
             eng_advance<<<ctx->n_sm * 4, 128, 0, s>>>(P);
             eng_unitfinder<1><<<cfg.polish_ctas, 128, kUfDynSmem, s>>>(P, cfg.uf_ctas * cfg.walk_streams);
-            eng_sched<<<(n + 1) / 2, 64, 0, s>>>(P);
+            eng_sched<<<n, 32, 0, s>>>(P);
             {
                 // the walk kernel of this wave: on the next walk stream, behind the scheduler pass, beside everything else
                 const int ws = wave_no++ % cfg.walk_streams;
@@ -333,7 +375,9 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
             MTR_CUDA(ctx, cudaGetLastError());
             launches += launches_per_wave;
         }
+        const double tl1 = wall_ms();
         MTR_CUDA(ctx, mtr_sync(ctx));
+        t_launch += tl1 - tl0; t_wait += wall_ms() - tl1;
         for (int b = 0; b < burst; b++) {
             float f = 0, g = 0, t0 = 0, t1 = 0;
             MTR_CUDA(ctx, cudaEventElapsedTime(&f, E.ev_dp0[b], E.ev_dp1[b]));
@@ -372,6 +416,19 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     Counters *hc = (Counters *)E.h_ctr.p;
     MTR_CUDA(ctx, cudaMemcpyAsync(hc, P.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, mtr_sync(ctx));
+    if (timeline) {
+        std::vector<unsigned long long> st((size_t)P.stamp_waves * 16);
+        MTR_CUDA(ctx, cudaMemcpy(st.data(), E.d_stamps.p, st.size() * 8, cudaMemcpyDeviceToHost));
+        static std::mutex tm;
+        std::lock_guard<std::mutex> g(tm);
+        for (int w = 1; w < P.stamp_waves && w <= hc->waves; w++) {
+            fprintf(stderr, "[timeline] %p %d", (void *)ctx, w);
+            for (int k = 0; k < 11; k++) fprintf(stderr, " %llu", st[(size_t)w * 16 + k]);
+            fprintf(stderr, "\n");
+        }
+    }
+    if (prof)
+        fprintf(stderr, "[mtr engine] ctx %p: host ms: launching %.1f, waiting %.1f, whole call so far %.1f (di %.1f)\n", (void *)ctx, t_launch, t_wait, wall_ms() - t_wall0, di_ms);
     if (prof)
         fprintf(stderr, "[mtr engine] ctx %p: %d reads, %d waves | unit finder: %llu tables (direct %llu compact %llu wide %llu), %llu with walks, %llu walks | Mticks: build %.1f list %.1f walk fwd %.1f bwd %.1f, slowest task %.3f, slowest walk %.3f | walk steps %llu (memo hits %llu, steps reaching level 4 %llu), probe rounds %llu, failed walks %llu | dp %.1f ms uf %.1f ms\n", (void *)ctx, n, hc->waves,
                 hc->tables, hc->prof_kind[2], hc->prof_kind[1], hc->prof_kind[0], hc->prof_walk_tasks, hc->walks, hc->prof_build / 1e6, hc->prof_list / 1e6, hc->prof_walk[0] / 1e6, hc->prof_walk[1] / 1e6,
@@ -390,7 +447,7 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
         MTR_CUDA(ctx, cudaMemcpyAsync(E.h_acc.p, P.acc, sizeof(Accepted) * (size_t)na, cudaMemcpyDeviceToHost, s));
         MTR_CUDA(ctx, mtr_sync(ctx));
     }
-    export_repeats((const Accepted *)E.h_acc.p, na, E.reps, E.units);
+    export_repeats((const Accepted *)E.h_acc.p, na, E.reps, E.units, first);
     if (repeats) *repeats = E.reps.data();
     if (n_repeats) *n_repeats = na;
     if (units) *units = E.units.data();

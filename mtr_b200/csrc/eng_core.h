@@ -133,6 +133,8 @@ struct Ptrs {
     int direct_max_k;              // largest k that gets a DIRECT table (7)
     float min_match_ratio;
     int speculate;
+    unsigned long long *stamps;    // MTR_TIMELINE: [wave][16] %globaltimer values written by the wave's kernels (nullptr: off)
+    int stamp_waves;
 };
 
 // ---------------------------------------------------------------- records

@@ -40,7 +40,7 @@ inline Config default_config(int n_reads, long long total_bases, int max_len, in
     // every cta owns a WIDE table sized for the longest read: at most 1 GB of them per group
     unsigned cap = 64;
     while (cap < 2u * (unsigned)(max_len + 8)) cap <<= 1;
-    c.uf_ctas = (int)std::max<long long>(4, std::min<long long>(n_sm, (1LL << 28) / ((long long)cap * 8)));
+    c.uf_ctas = (int)std::max<long long>(4, std::min<long long>(n_sm / 2, (1LL << 28) / ((long long)cap * 8)));
     c.polish_ctas = c.uf_ctas;
     const long long n_chains = (long long)n_reads * kSets * kMaxK;
     c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains), 1 << 20);
@@ -124,7 +124,7 @@ inline void init_reads(std::vector<Read> &out, const int64_t *word_off, const in
 }
 
 // converts the accepted list into the ABI records, ordered by (read, insertion order)
-inline void export_repeats(const Accepted *acc, int n, std::vector<mtr_repeat> &reps, std::vector<uint8_t> &units)
+inline void export_repeats(const Accepted *acc, int n, std::vector<mtr_repeat> &reps, std::vector<uint8_t> &units, int first_read = 0)
 {
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
@@ -137,7 +137,7 @@ inline void export_repeats(const Accepted *acc, int n, std::vector<mtr_repeat> &
     for (int i = 0; i < n; i++) {
         const Accepted &a = acc[order[i]];
         mtr_repeat &r = reps[i];
-        r.read = a.read; r.seq = a.seq;
+        r.read = a.read + first_read; r.seq = a.seq;
         r.rep_start = a.rec.rep_start; r.rep_end = a.rec.rep_end; r.repeat_len = a.rec.repeat_len; r.rep_period = a.rec.period;
         r.num_freq_unit = a.rec.units; r.num_matches = a.rec.nm; r.num_mismatches = a.rec.nx; r.num_insertions = a.rec.ni;
         r.num_deletions = a.rec.nd; r.kmer = a.rec.kmer; r.match_gain = a.rec.gain; r.mismatch_penalty = a.rec.mis;

@@ -388,50 +388,74 @@ int parse_fasta_text(const char *text, int64_t len, int first, int count, int th
     return MTR_OK;
 }
 
-// ---------------------------------------------------------------- one group of reads on one engine context
+// ---------------------------------------------------------------- groups of reads on one engine context
+struct Resident {                      // what stays on the host for the reads resident in one context
+    std::vector<int64_t> stale_off;    // indexed like the resident batch
+    std::vector<uint16_t> stale;
+};
+
 struct Group {
     std::vector<ReadInput> reads;      // in input order
     long long index = 0;               // position in the output order
     std::string out;
     mtr_pipeline_stats ps = {};
-    // resident form (after upload)
-    std::vector<int64_t> stale_off;
-    std::vector<uint16_t> stale;
-    bool resident = false;
+    // resident form (after upload): reads [first, first + reads.size()) of the context's batch
+    std::shared_ptr<Resident> res;
+    int first = 0;
 };
 
-// 2-bit packs the group's reads and uploads them: afterwards the group is resident in the context's HBM
-void upload_group(mtr_ctx *ctx, Group &g)
+// 2-bit packs the reads of the groups (in this order) and uploads them as ONE batch: afterwards they are resident in the
+// context's HBM and every group is a range of that batch
+void upload_groups(mtr_ctx *ctx, const std::vector<Group *> &groups)
 {
     const double t0 = now_s();
-    const int n = (int)g.reads.size();
+    int n = 0;
+    for (Group *g : groups) n += (int)g->reads.size();
     std::vector<int64_t> word_off((size_t)n + 1, 0);
     std::vector<int32_t> lens((size_t)n);
-    g.stale_off.assign((size_t)n + 1, 0);
-    long long bases = 0;
-    for (int r = 0; r < n; r++) {
-        lens[r] = g.reads[r].len;
-        const int64_t words = (g.reads[r].len + 2 + 15) / 16;
-        word_off[r + 1] = word_off[r] + ((words + 3) / 4) * 4;
-        g.stale_off[r + 1] = g.stale_off[r] + (int64_t)g.reads[r].stale.size();
-        bases += g.reads[r].len;
+    std::shared_ptr<Resident> res(new Resident());
+    res->stale_off.assign((size_t)n + 1, 0);
+    int r = 0;
+    for (Group *g : groups) {
+        g->first = r;
+        g->res = res;
+        long long bases = 0;
+        for (const ReadInput &in : g->reads) {
+            lens[r] = in.len;
+            const int64_t words = (in.len + 2 + 15) / 16;
+            word_off[r + 1] = word_off[r] + ((words + 3) / 4) * 4;
+            res->stale_off[r + 1] = res->stale_off[r] + (int64_t)in.stale.size();
+            bases += in.len;
+            r++;
+        }
+        memset(&g->ps, 0, sizeof g->ps);
+        g->ps.reads = (int64_t)g->reads.size(); g->ps.bases = bases; g->ps.groups = 1;
     }
     std::vector<uint32_t> packed((size_t)word_off[n], 0u);
-    g.stale.assign((size_t)g.stale_off[n], 0);
-    for (int r = 0; r < n; r++) {
-        uint32_t *dst = packed.data() + word_off[r];
-        const uint8_t *b = g.reads[r].bases.data();
-        const int nb = g.reads[r].len + 2;
-        for (int i = 0; i < nb; i++) dst[i >> 4] |= (uint32_t)b[i] << ((i & 15) * 2);
-        if (!g.reads[r].stale.empty()) memcpy(g.stale.data() + g.stale_off[r], g.reads[r].stale.data(), g.reads[r].stale.size() * 2);
-    }
+    res->stale.assign((size_t)res->stale_off[n], 0);
+    r = 0;
+    for (Group *g : groups)
+        for (const ReadInput &in : g->reads) {
+            uint32_t *dst = packed.data() + word_off[r];
+            const uint8_t *b = in.bases.data();
+            const int nb = in.len + 2;
+            for (int i = 0; i < nb; i++) dst[i >> 4] |= (uint32_t)b[i] << ((i & 15) * 2);
+            if (!in.stale.empty()) memcpy(res->stale.data() + res->stale_off[r], in.stale.data(), in.stale.size() * 2);
+            r++;
+        }
     const int rc = mtr_reads_upload(ctx, packed.data(), word_off.data(), lens.data(), n);
     if (rc) die(ctx, "mtr_reads_upload", rc);
-    memset(&g.ps, 0, sizeof g.ps);
-    g.ps.reads = n; g.ps.bases = bases; g.ps.groups = 1;
-    g.ps.h2d_bytes = (int64_t)packed.size() * 4 + (int64_t)(n + 1) * 12;
-    g.ps.pack_ms = (now_s() - t0) * 1e3;
-    g.resident = true;
+    const double ms = (now_s() - t0) * 1e3;
+    for (Group *g : groups) {
+        g->ps.h2d_bytes = (word_off[g->first + (int)g->reads.size()] - word_off[g->first]) * 4 + (int64_t)(g->reads.size() + 1) * 12;
+        g->ps.pack_ms = ms * (double)g->reads.size() / std::max(n, 1);
+    }
+}
+
+void upload_group(mtr_ctx *ctx, Group &g)
+{
+    std::vector<Group *> one(1, &g);
+    upload_groups(ctx, one);
 }
 
 // handle_one_TR for every read of the resident group on the GPU, then chaining + printing on the host
@@ -444,7 +468,7 @@ void run_group(mtr_ctx *ctx, Group &g, int print_alignment, int manhattan, float
     int64_t n_reps = 0;
     const uint8_t *units = nullptr;
     mtr_engine_stats es;
-    const int rc = mtr_engine_run(ctx, manhattan, ratio, g.stale.data(), g.stale_off.data(), &reps, &n_reps, &units, &es);
+    const int rc = mtr_engine_run_range(ctx, g.first, n, manhattan, ratio, g.res->stale.data(), g.res->stale_off.data(), &reps, &n_reps, &units, &es);
     if (rc) { fflush(stdout); die(ctx, "mtr_engine_run", rc); }
     for (int64_t i = 0; i < es.wrapdp_messages; i++) fprintf(stderr, "You need to increse the value of WrapDPsize.\n");
     const double tc0 = now_s();
@@ -455,7 +479,7 @@ void run_group(mtr_ctx *ctx, Group &g, int print_alignment, int manhattan, float
     long long n_printed = 0;
     for (int r = 0; r < n; r++) {
         items.clear();
-        for (; at < n_reps && reps[at].read == r; at++) {
+        for (; at < n_reps && reps[at].read == g.first + r; at++) {
             const mtr_repeat &q = reps[at];
             ChainItem it;
             it.rec.inputLen = g.reads[r].len; it.rec.rep_start = q.rep_start; it.rec.rep_end = q.rep_end; it.rec.repeat_len = q.repeat_len;
@@ -482,7 +506,7 @@ void run_group(mtr_ctx *ctx, Group &g, int print_alignment, int manhattan, float
             for (const Rec &q : printed[r]) {
                 mtr_wdp_job j;
                 memset(&j, 0, sizeof j);
-                j.read = r; j.first = q.rep_start - 1; j.rows = q.rep_end - q.rep_start + 1; j.ulen = q.period;
+                j.read = g.first + r; j.first = q.rep_start - 1; j.rows = q.rep_end - q.rep_start + 1; j.ulen = q.period;
                 j.unit_off = (int32_t)junits.size();
                 j.gain[0] = (int8_t)q.gain; j.mis[0] = (int8_t)q.mis; j.indel[0] = (int8_t)q.indel;
                 j.n_param = 1; j.mode = MTR_TB_PATH;
@@ -767,11 +791,13 @@ extern "C" int mtr_file_stats(mtr_pipeline_stats *out)
 // ================================================================ batch-level pipeline ABI (bench, tests, embedding)
 struct mtr_pipeline {
     std::vector<mtr_ctx *> ctxs;
-    std::vector<std::unique_ptr<Group>> groups;        // group i is resident in ctxs[i]
+    std::vector<std::unique_ptr<Group>> groups;        // in input order; group i is resident in ctxs[i % ctxs.size()]
     StaleTracker *stale = nullptr;
     std::string out;
     mtr_pipeline_stats ps = {};
     int threads = 1;
+    int group_reads = 512;
+    long long group_bases = 24LL << 20;
 };
 
 extern "C" int mtr_pipeline_open(int device, int threads, mtr_pipeline **out)
@@ -789,6 +815,8 @@ extern "C" int mtr_pipeline_open(int device, int threads, mtr_pipeline **out)
         p->ctxs.push_back(c);
     }
     p->threads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("MTR_GROUP_READS")) p->group_reads = std::max(1, atoi(e));
+    if (const char *e = getenv("MTR_GROUP_MBASES")) p->group_bases = std::max(1LL, atoll(e)) << 20;
     p->stale = new StaleTracker();
     *out = p;
     return MTR_OK;
@@ -825,28 +853,27 @@ extern "C" int mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, 
     p->stale->visit_batch(reads, 0, reads.size(), p->threads, nullptr);
     if (first > 0) reads.erase(reads.begin(), reads.begin() + std::min<size_t>((size_t)first, reads.size()));
     const int n = (int)reads.size();
-    // contiguous groups of (nearly) equal base counts, one per context
-    const int k = (int)p->ctxs.size();
-    long long total = 0;
-    for (const ReadInput &r : reads) total += r.len;
-    for (int gi = 0; gi < std::min(k, std::max(n, 1)); gi++) {
+    // the same groups handle_one_file would cut (MTR_GROUP_READS / MTR_GROUP_MBASES), dealt round-robin to the contexts;
+    // all groups of a context are uploaded as one resident batch
+    for (size_t a = 0; a < reads.size();) {
         std::unique_ptr<Group> g(new Group());
-        g->index = gi;
+        long long bases = 0;
+        while (a < reads.size() && (int)g->reads.size() < p->group_reads && bases < p->group_bases) {
+            bases += reads[a].len;
+            g->reads.push_back(std::move(reads[a++]));
+        }
+        g->index = (long long)p->groups.size();
         p->groups.push_back(std::move(g));
     }
-    // distribute by the running base count
-    {
-        long long run = 0;
-        size_t gi = 0;
-        for (size_t i = 0; i < reads.size(); i++) {
-            while (gi + 1 < p->groups.size() && run >= (total * (long long)(gi + 1)) / (long long)p->groups.size()) gi++;
-            run += reads[i].len;
-            p->groups[gi]->reads.push_back(std::move(reads[i]));
-        }
-    }
+    const size_t k = p->ctxs.size();
     std::vector<std::thread> th;
-    for (size_t gi = 0; gi < p->groups.size(); gi++)
-        th.emplace_back([p, gi] { cudaSetDevice(p->ctxs[gi]->device); upload_group(p->ctxs[gi], *p->groups[gi]); });
+    for (size_t c = 0; c < k && c < p->groups.size(); c++)
+        th.emplace_back([p, c, k] {
+            cudaSetDevice(p->ctxs[c]->device);
+            std::vector<Group *> mine;
+            for (size_t gi = c; gi < p->groups.size(); gi += k) mine.push_back(p->groups[gi].get());
+            upload_groups(p->ctxs[c], mine);
+        });
     for (std::thread &t : th) t.join();
     return n;
 }
@@ -858,17 +885,19 @@ extern "C" int mtr_pipeline_run(mtr_pipeline *p, int print_alignment, const char
     const int manhattan = Manhattan_Distance;
     const float ratio = min_match_ratio;
     const double t0 = now_s();
+    const size_t k = p->ctxs.size();
     std::vector<std::thread> th;
-    for (size_t gi = 0; gi < p->groups.size(); gi++)
-        th.emplace_back([p, gi, print_alignment, manhattan, ratio] {
-            cudaSetDevice(p->ctxs[gi]->device);
-            Group &g = *p->groups[gi];
-            const int64_t h2d = g.ps.h2d_bytes;
-            const double pack = g.ps.pack_ms;
-            const int64_t reads = g.ps.reads, bases = g.ps.bases;
-            memset(&g.ps, 0, sizeof g.ps);
-            g.ps.h2d_bytes = h2d; g.ps.pack_ms = pack; g.ps.reads = reads; g.ps.bases = bases; g.ps.groups = 1;
-            run_group(p->ctxs[gi], g, print_alignment, manhattan, ratio);
+    for (size_t c = 0; c < k && c < p->groups.size(); c++)
+        th.emplace_back([p, c, k, print_alignment, manhattan, ratio] {
+            cudaSetDevice(p->ctxs[c]->device);
+            for (size_t gi = c; gi < p->groups.size(); gi += k) {
+                Group &g = *p->groups[gi];
+                const int64_t h2d = g.ps.h2d_bytes, reads = g.ps.reads, bases = g.ps.bases;
+                const double pack = g.ps.pack_ms;
+                memset(&g.ps, 0, sizeof g.ps);
+                g.ps.h2d_bytes = h2d; g.ps.pack_ms = pack; g.ps.reads = reads; g.ps.bases = bases; g.ps.groups = 1;
+                run_group(p->ctxs[c], g, print_alignment, manhattan, ratio);
+            }
         });
     for (std::thread &t : th) t.join();
     p->out.clear();

@@ -576,7 +576,7 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
 struct WdpSegs { const int *task; const int *slot; int nseg_family; };   // prefix sums over 2 * nseg_family segments (+1)
 
 template <bool P16>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(64, 8)
 wdp_fill_family(const WdpTask *__restrict__ tasks, const WdpSegs sg, const uint32_t *__restrict__ packed,
                 const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counters)
 {
@@ -704,8 +704,10 @@ __device__ __forceinline__ void traceback_warp(const WdpTask &t, const int p, co
 // one warp per (task, penalty set), pulled from a queue in task order (longest tasks of every class first)
 __global__ void __launch_bounds__(128)
 wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const uint32_t *__restrict__ packed,
-                  const uint8_t *__restrict__ units, const uint8_t *dirs, mtr_wdp_result *results, void *aux, int *__restrict__ head)
+                  const uint8_t *__restrict__ units, const uint8_t *dirs, mtr_wdp_result *results, void *aux, int *__restrict__ head,
+                  unsigned long long *stamp)
 {
+    if (stamp && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); *stamp = t; }
     const int total = 2 * class_begin[WDP_NCLASS];
     for (;;) {
         int idx = 0;
@@ -733,15 +735,15 @@ cudaError_t wdp_launch_dev(const WdpDevLaunch &L, cudaStream_t s)
         if ((e = cudaEventRecord(L.fork, s)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ps, L.fork, 0)) != cudaSuccess) return e;
     }
-    wdp_fill_family<false><<<L.blocks, 128, 0, s>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
+    wdp_fill_family<false><<<L.blocks, 64, 0, s>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    wdp_fill_family<true><<<L.blocks, 128, 0, ps>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
+    wdp_fill_family<true><<<L.blocks, 64, 0, ps>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (L.n_side > 0) {
         if ((e = cudaEventRecord(L.join[0], ps)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(s, L.join[0], 0)) != cudaSuccess) return e;
     }
-    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 10);
+    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 10, nullptr);
     return cudaGetLastError();
 }
 

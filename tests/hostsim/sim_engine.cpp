@@ -27,6 +27,8 @@ struct EngState {
 
 void eng_state_free(mtr_ctx *ctx) { delete ctx->eng; ctx->eng = nullptr; }
 
+extern "C" int mtr_di_run_range(mtr_ctx *ctx, int manhattan, const uint16_t *stale, const int64_t *stale_off, const int64_t *pos_off,
+                                double *di, int32_t *end, int32_t *w, int first, int count);
 // provided by sim_device.cpp
 const uint32_t *sim_packed(mtr_ctx *ctx);
 mtro_ctx *sim_oracle(mtr_ctx *ctx, int manhattan);
@@ -65,26 +67,38 @@ static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, mtro_ctx *o)
     (void)ctx;
 }
 
+extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manhattan, float min_match_ratio, const uint16_t *stale,
+                                    const int64_t *stale_off, const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units,
+                                    mtr_engine_stats *stats);
 extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio, const uint16_t *stale, const int64_t *stale_off,
                               const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units, mtr_engine_stats *stats)
+{
+    if (!ctx) return MTR_EINVAL;
+    return mtr_engine_run_range(ctx, 0, ctx->n_reads, manhattan, min_match_ratio, stale, stale_off, repeats, n_repeats, units, stats);
+}
+
+extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manhattan, float min_match_ratio, const uint16_t *stale,
+                                    const int64_t *stale_off, const mtr_repeat **repeats, int64_t *n_repeats, const uint8_t **units,
+                                    mtr_engine_stats *stats)
 {
     if (!ctx) return MTR_EINVAL;
     if (repeats) *repeats = nullptr;
     if (n_repeats) *n_repeats = 0;
     if (units) *units = nullptr;
     if (stats) memset(stats, 0, sizeof *stats);
-    const int n = ctx->n_reads;
+    if (first < 0 || count < 0 || first + count > ctx->n_reads) return MTR_EINVAL;
+    const int n = count;
     if (n == 0) return MTR_OK;
     if (!ctx->eng) ctx->eng = new EngState();
     EngState &E = *ctx->eng;
-    std::vector<int64_t> pos_off((size_t)n + 1, 0);
+    std::vector<int64_t> pos_off((size_t)first + n + 1, 0);
     int max_len = 0;
-    for (int r = 0; r < n; r++) { pos_off[r + 1] = pos_off[r] + ctx->len[r]; max_len = std::max(max_len, (int)ctx->len[r]); }
-    E.end.assign((size_t)pos_off[n] + 1, -1); E.w.assign((size_t)pos_off[n] + 1, -1);
-    int rc = mtr_di_run(ctx, manhattan, stale, stale_off, pos_off.data(), nullptr, E.end.data(), E.w.data());
+    for (int r = 0; r < n; r++) { pos_off[first + r + 1] = pos_off[first + r] + ctx->len[first + r]; max_len = std::max(max_len, (int)ctx->len[first + r]); }
+    E.end.assign((size_t)pos_off[first + n] + 1, -1); E.w.assign((size_t)pos_off[first + n] + 1, -1);
+    int rc = mtr_di_run_range(ctx, manhattan, stale, stale_off, pos_off.data(), nullptr, E.end.data(), E.w.data(), first, n);
     if (rc) return rc;
 
-    Config cfg = default_config(n, pos_off[n], max_len, 1);
+    Config cfg = default_config(n, pos_off[first + n], max_len, 1);
     cfg.uf_ctas = 1;
     // MTR_SIM_COMPACT_CAP / MTR_SIM_DIRECT_K: shrink the shared-memory table layouts so that small test windows reach
     // the COMPACT and the WIDE (+ probe cache) paths too
@@ -111,7 +125,7 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
     std::vector<Read> reads;
-    init_reads(reads, ctx->word_off.data(), ctx->len.data(), n);
+    init_reads(reads, ctx->word_off.data() + first, ctx->len.data() + first, n);
     memcpy(P.reads, reads.data(), sizeof(Read) * (size_t)n);
     P.ctr->unfinished = n;
     mtro_ctx *o = sim_oracle(ctx, manhattan);
@@ -155,10 +169,14 @@ extern "C" int mtr_engine_run(mtr_ctx *ctx, int manhattan, float min_match_ratio
         default: mtr_set_error(ctx, "engine_run: device error %d", c.error); return MTR_ECUDA;
         }
     }
-    export_repeats(P.acc, c.n_accepted, E.reps, E.units);
+    export_repeats(P.acc, c.n_accepted, E.reps, E.units, first);
     if (repeats) *repeats = E.reps.data();
     if (n_repeats) *n_repeats = c.n_accepted;
     if (units) *units = E.units.data();
     export_stats(c, stats);
+    if (stats) {                                                // what the real engine would move over PCIe
+        stats->h2d_bytes = (int64_t)sizeof(Read) * n + (int64_t)sizeof(Counters);
+        stats->d2h_bytes = (int64_t)sizeof(Accepted) * c.n_accepted + (int64_t)sizeof(Counters);
+    }
     return MTR_OK;
 }

@@ -72,11 +72,11 @@ print(json.dumps({"md5": hashlib.md5(shard.merge_outputs(parts)).hexdigest()}))
     assert r["md5"] == DIGESTS["synthetic"]["mixed"]["default"]["md5"]
 
 
-@pytest.mark.parametrize("env", [{}, {"MTR_BATCH_READS": "4", "MTR_INFLIGHT_PER_GPU": "1"}, {"MTR_BATCH_READS": "3", "MTR_STAGGER_FRAC": "0.9", "MTR_DI_SLICE": "2"},
-                                 {"MTR_BATCH_READS": "2", "MTR_GPUS": "2", "MTR_TIER_PRIO": "0"}])
+@pytest.mark.parametrize("env", [{}, {"MTR_GROUP_READS": "4", "MTR_GROUPS_PER_GPU": "1"}, {"MTR_GROUP_READS": "3", "MTR_GROUPS_PER_GPU": "3"},
+                                 {"MTR_GROUP_READS": "2", "MTR_GPUS": "2", "MTR_GROUPS_PER_GPU": "2"}])
 def test_handle_one_file_through_ctypes(mixed, env):
-    """capi.run_file = handle_one_file as main.c calls it (stdout captured) + mtr_file_stats; staggered engines, batch
-    size, slices and the two-device round-robin must not change a byte, and the counters must cover every read."""
+    """capi.run_file = handle_one_file as main.c calls it (stdout captured) + mtr_file_stats; group size, number of
+    engine contexts and the two-device round-robin must not change a byte, and the counters must cover every read."""
     r = child(r'''
 n, out, st = capi.run_file(%r)
 n2, out2, st2 = capi.run_file(%r)                                        # counters reset between calls
