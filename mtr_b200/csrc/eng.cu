@@ -29,14 +29,22 @@ __device__ __forceinline__ void stamp(const Ptrs &P, int id)
 }
 #define STAMP0(id) do { if (blockIdx.x == 0 && threadIdx.x == 0) stamp(P, id); } while (0)
 
-__global__ void eng_begin(Ptrs P) { if (threadIdx.x == 0 && blockIdx.x == 0) { wave_begin(P); stamp(P, 0); } }
+__global__ void eng_begin(Ptrs P, DpQueue QL) { if (threadIdx.x == 0 && blockIdx.x == 0) { wave_begin(P, QL); stamp(P, 0); } }
 
-__global__ void __launch_bounds__(128) eng_advance(Ptrs P)
+// every chain in WAIT_* whose results have all arrived; 32 chain slots per warp step, the ready ones one after the other
+__global__ void __launch_bounds__(128) eng_advance(Ptrs P, int n_chains)
 {
     STAMP0(1);
     const int nw = gridDim.x * (blockDim.x >> 5);
-    const int n = P.ctr->n_advance;
-    for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nw) advance_chain(P, P.wait_list[i]);
+    for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_chains; base += nw * 32) {
+        const int mine = base + lane();
+        unsigned m = wballot(mine < n_chains && chain_ready(P, mine));
+        while (m) {
+            const int c = base + ffs(m) - 1;
+            m &= m - 1u;
+            advance_chain(P, c);
+        }
+    }
 }
 
 // walk / polish kernels: one block (four warps) per task, persistent blocks pulling from a list; shared memory = 16 ints
@@ -93,27 +101,27 @@ __global__ void __launch_bounds__(32) eng_sched(Ptrs P)
     sched_read(P, read, tab, kInlineSlots, sh);
 }
 
-__global__ void __launch_bounds__(256) eng_emit(Ptrs P, int n_chains)
+__global__ void __launch_bounds__(256) eng_emit(Ptrs P, DpQueue QL, int n_chains)
 {
     STAMP0(5);
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n_chains) emit_chain(P, c);
+    if (c < n_chains) emit_chain(P, QL, c);
 }
 
-__global__ void eng_plan(Ptrs P) { STAMP0(6); if (blockIdx.x == 0 && threadIdx.x < 32) plan_tasks(P); }
+__global__ void eng_plan(Ptrs P, DpQueue Q) { if (Q.id == 0) STAMP0(6); if (blockIdx.x == 0 && threadIdx.x < 32) plan_tasks(P, Q); }
 
-__global__ void __launch_bounds__(256) eng_scatter(Ptrs P)
+__global__ void __launch_bounds__(256) eng_scatter(Ptrs P, DpQueue Q)
 {
-    STAMP0(7);
-    const int n = min(P.ctr->n_tasks, P.task_cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) scatter_task(P, i);
+    if (Q.id == 0) STAMP0(7);
+    const int n = min(Q.qc->n_tasks, Q.task_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) scatter_task(Q, i);
 }
 
-__global__ void __launch_bounds__(256) eng_zero_aux(Ptrs P)
+__global__ void __launch_bounds__(256) eng_zero_aux(Ptrs P, DpQueue Q)
 {
-    STAMP0(8);
-    const long long n = min((long long)P.ctr->aux_used, P.aux_cap);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) P.aux[i] = 0;
+    if (Q.id == 0) STAMP0(8);
+    const long long n = min((long long)Q.qc->aux_used, Q.aux_cap);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) Q.aux[i] = 0;
 }
 
 struct EngSnapshot { int unfinished, error, error_read, deferred, waves, n_accepted, n_tasks, pad; unsigned long long tasks_total, candidates_started; };
@@ -124,14 +132,17 @@ __global__ void eng_publish(Ptrs P, EngSnapshot *snap)
     stamp(P, 10);
     const Counters &c = *P.ctr;
     snap->error = c.error; snap->error_read = c.error_read; snap->deferred = c.deferred; snap->waves = c.waves;
-    snap->n_accepted = c.n_accepted; snap->n_tasks = c.n_tasks; snap->pad = (int)(c.walk_tail - c.walk_head) + c.walks_running; snap->tasks_total = c.tasks_total; snap->candidates_started = c.tables + (unsigned long long)(unsigned)c.progress + ((unsigned long long)(unsigned)c.walks_done << 32);
+    snap->n_accepted = c.n_accepted; snap->n_tasks = P.q.qc->n_tasks; snap->pad = (int)(c.walk_tail - c.walk_head) + c.walks_running + c.dp_pending; snap->tasks_total = c.tasks_total; snap->candidates_started = c.tables + (unsigned long long)(unsigned)c.progress + ((unsigned long long)(unsigned)c.walks_done << 32);
     __threadfence_system();
     snap->unfinished = c.unfinished;
 }
 
 // ---------------------------------------------------------------- per-context engine state
 struct EngState {
-    DevBuf d_main, d_dirs, d_scratch, d_wide, d_stamps;
+    DevBuf d_main, d_dirs, d_scratch, d_wide, d_stamps, d_dirs_long[kLongInst];
+    cudaStream_t long_stream[kLongInst] = {};  // long DP queues run here, beside the waves
+    cudaEvent_t long_done[kLongInst] = {}, long_ev0[kLongInst] = {}, long_ev1[kLongInst] = {}, emit_done = nullptr;
+    bool long_busy[kLongInst] = {};
     PinBuf h_snap, h_acc, h_ctr;
     Config cfg;
     Layout lay;
@@ -153,7 +164,15 @@ void eng_state_free(mtr_ctx *ctx)
 {
     if (!ctx->eng) return;
     EngState *e = ctx->eng;
-    e->d_main.release(); e->d_dirs.release(); e->d_scratch.release(); e->d_wide.release();
+    e->d_main.release(); e->d_dirs.release(); e->d_scratch.release(); e->d_wide.release(); e->d_stamps.release();
+    for (int i = 0; i < kLongInst; i++) {
+        e->d_dirs_long[i].release();
+        if (e->long_stream[i]) cudaStreamDestroy(e->long_stream[i]);
+        if (e->long_done[i]) cudaEventDestroy(e->long_done[i]);
+        if (e->long_ev0[i]) cudaEventDestroy(e->long_ev0[i]);
+        if (e->long_ev1[i]) cudaEventDestroy(e->long_ev1[i]);
+    }
+    if (e->emit_done) cudaEventDestroy(e->emit_done);
     e->h_snap.release(); e->h_acc.release(); e->h_ctr.release();
     for (int i = 0; i < 8; i++) { if (e->side[i]) cudaStreamDestroy(e->side[i]); if (e->join[i]) cudaEventDestroy(e->join[i]); }
     if (e->fork) cudaEventDestroy(e->fork);
@@ -252,6 +271,13 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.join[i], cudaEventDisableTiming));
         }
         MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.fork, cudaEventDisableTiming));
+        for (int i = 0; i < kLongInst; i++) {
+            MTR_CUDA(ctx, cudaStreamCreateWithFlags(&E.long_stream[i], cudaStreamNonBlocking));
+            MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.long_done[i], cudaEventDisableTiming));
+            MTR_CUDA(ctx, cudaEventCreate(&E.long_ev0[i]));
+            MTR_CUDA(ctx, cudaEventCreate(&E.long_ev1[i]));
+        }
+        MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.emit_done, cudaEventDisableTiming));
         for (int i = 0; i < 4; i++) {
             MTR_CUDA(ctx, cudaStreamCreateWithFlags(&E.walk_stream[i], cudaStreamNonBlocking));
             MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.sched_done[i], cudaEventDisableTiming));
@@ -289,6 +315,13 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     MTR_CUDA(ctx, E.d_wide.reserve((size_t)lay.table_cap * 8 * n_slices));
     if ((size_t)cfg.dir_cap > E.d_dirs.cap) MTR_CUDA(ctx, E.d_dirs.reserve_exact((size_t)cfg.dir_cap));
     cfg.dir_cap = (long long)E.d_dirs.cap;
+    if (const char *e = getenv("MTR_ENGINE_LONG_ROWS")) cfg.long_rows = std::max(1, atoi(e));
+    for (int i = 0; i < kLongInst; i++) {
+        if ((size_t)cfg.long_dir_cap > E.d_dirs_long[i].cap) MTR_CUDA(ctx, E.d_dirs_long[i].reserve_exact((size_t)cfg.long_dir_cap));
+        E.long_busy[i] = false;
+    }
+    cfg.long_dir_cap = (long long)E.d_dirs_long[0].cap;
+    for (int i = 1; i < kLongInst; i++) cfg.long_dir_cap = std::min<long long>(cfg.long_dir_cap, (long long)E.d_dirs_long[i].cap);
     MTR_CUDA(ctx, E.h_snap.reserve(sizeof(EngSnapshot)));
     MTR_CUDA(ctx, E.h_ctr.reserve(sizeof(Counters)));
     E.cfg = cfg; E.lay = lay;
@@ -313,7 +346,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
 
     // zero: chain stages (ST_FREE), lists, counters, histograms, the scratch epochs; then the per-read state
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.chains, 0, sizeof(Chain) * (size_t)lay.n_chains, s));
-    MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.ctr, 0, lay.total - lay.ctr, s));
+    MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.zero_begin, 0, lay.total - lay.zero_begin, s));
     MTR_CUDA(ctx, cudaMemsetAsync(E.d_scratch.p, 0, (size_t)lay.uf_stride * n_slices, s));
     std::vector<Read> reads;
     init_reads(reads, ctx->word_off.data() + first, ctx->len.data() + first, n);
@@ -328,22 +361,33 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     memset(snap, 0, sizeof *snap);
     snap->unfinished = n;
 
-    WdpDevLaunch L;
-    memset(&L, 0, sizeof L);
-    L.tasks = P.tasks; L.class_begin = P.class_begin; L.seg_task = P.seg_task; L.seg_slot = P.seg_slot; L.nseg_family = kSegs / 2; L.counters = P.slot_counter; L.packed = P.packed;
-    L.units = P.units; L.dirs = (uint8_t *)E.d_dirs.p; L.results = P.results; L.aux = P.aux;
-    L.blocks = ctx->n_sm * 2;
+    // launch descriptions of K3 over the wave's queue and over the long queues
+    auto describe = [&](const DpQueue &Q, uint8_t *dirs) {
+        WdpDevLaunch L;
+        memset(&L, 0, sizeof L);
+        L.tasks = Q.tasks; L.class_begin = Q.class_begin; L.seg_task = Q.seg_task; L.seg_slot = Q.seg_slot; L.nseg_family = kSegs / 2;
+        L.counters = Q.slot_counter; L.packed = P.packed; L.units = P.units; L.dirs = dirs; L.results = P.results; L.aux = Q.aux;
+        L.pending0 = (char *)&P.chains[0].pending; L.pending_stride = (int)sizeof(Chain); L.pending_total = &P.ctr->dp_pending;
+        L.blocks = ctx->n_sm * 2;
+        return L;
+    };
+    WdpDevLaunch L = describe(P.q, (uint8_t *)E.d_dirs.p);
     for (int i = 0; i < n_side; i++) { L.side[i] = E.side[i]; L.join[i] = E.join[i]; }
     L.fork = E.fork; L.n_side = n_side;
+    DpQueue QLs[kLongInst];
+    WdpDevLaunch LL[kLongInst];
+    for (int i = 0; i < kLongInst; i++) { QLs[i] = bind_queue(E.d_main.p, lay, cfg, 1 + i); LL[i] = describe(QLs[i], (uint8_t *)E.d_dirs_long[i].p); }
+    const DpQueue none = no_queue();
 
     // (the attribute belongs to the function, not to the launch: every context sets the same constant)
     MTR_CUDA(ctx, cudaFuncSetAttribute(eng_unitfinder<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUfDynSmem));
     MTR_CUDA(ctx, cudaFuncSetAttribute(eng_unitfinder<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUfDynSmem));
-    const int launches_per_wave = 10 + 2 + 1;
+    const int launches_per_wave = 10 + 2 + 1, launches_per_long = 3 + 2 + 1;
     cudaEvent_t base = busy_base(ctx->device);
     double dp_ms = 0, uf_ms = 0;
     long long launches = di_launches;
-    int burst = 4, wave_no = 0;
+    int burst = 4, wave_no = 0, long_next = 0;
+    double dp_long_ms = 0;
     if (const char *e = getenv("MTR_ENGINE_BURST")) burst = std::max(1, std::min(EngState::kEv, atoi(e)));
     unsigned long long last_tasks = ~0ull, last_started = ~0ull;
     int last_accepted = -1, last_unfinished = -1, stalled = 0, quiet = 0;
@@ -352,8 +396,26 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         const double tl0 = wall_ms();
         for (int b = 0; b < burst; b++) {
             MTR_CUDA(ctx, cudaEventRecord(E.ev_w0[b], s));
-            eng_begin<<<1, 32, 0, s>>>(P);
-            eng_advance<<<ctx->n_sm * 4, 128, 0, s>>>(P);
+            // the long queue of this wave: the next one whose previous use has ended (none: long tasks wait a wave)
+            int li = -1;
+            for (int t = 0; t < kLongInst && li < 0; t++) {
+                const int i = (long_next + t) % kLongInst;
+                if (E.long_busy[i] && cudaEventQuery(E.long_done[i]) == cudaSuccess) {
+                    E.long_busy[i] = false;
+                    float t0 = 0, t1 = 0;
+                    if (base && cudaEventElapsedTime(&t0, base, E.long_ev0[i]) == cudaSuccess && cudaEventElapsedTime(&t1, base, E.long_ev1[i]) == cudaSuccess) {
+                        std::lock_guard<std::mutex> gl(g_busy.mu);
+                        g_busy.iv[ctx->device].push_back(std::make_pair((double)t0, (double)t1));
+                        dp_long_ms += t1 - t0;
+                    }
+                }
+                if (!E.long_busy[i]) li = i;
+            }
+            cudaGetLastError();                                 // (cudaErrorNotReady of the queries)
+            if (li >= 0) long_next = (li + 1) % kLongInst;
+            const DpQueue &QL = li >= 0 ? QLs[li] : none;
+            eng_begin<<<1, 32, 0, s>>>(P, QL);
+            eng_advance<<<ctx->n_sm * 4, 128, 0, s>>>(P, lay.n_chains);
             eng_unitfinder<1><<<cfg.polish_ctas, 128, kUfDynSmem, s>>>(P, cfg.uf_ctas * cfg.walk_streams);
             eng_sched<<<n, 32, 0, s>>>(P);
             {
@@ -363,10 +425,25 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
                 MTR_CUDA(ctx, cudaStreamWaitEvent(E.walk_stream[ws], E.sched_done[ws], 0));
                 eng_unitfinder<0><<<cfg.uf_ctas, 128, kUfDynSmem, E.walk_stream[ws]>>>(P, ws * cfg.uf_ctas);
             }
-            eng_emit<<<(lay.n_chains + 255) / 256, 256, 0, s>>>(P, lay.n_chains);
-            eng_plan<<<1, 32, 0, s>>>(P);
-            eng_scatter<<<ctx->n_sm * 2, 256, 0, s>>>(P);
-            eng_zero_aux<<<ctx->n_sm * 2, 256, 0, s>>>(P);
+            eng_emit<<<(lay.n_chains + 255) / 256, 256, 0, s>>>(P, QL, lay.n_chains);
+            if (li >= 0) {
+                // K3 over the long queue, on its own stream behind this wave's emission
+                cudaStream_t ls = E.long_stream[li];
+                MTR_CUDA(ctx, cudaEventRecord(E.emit_done, s));
+                MTR_CUDA(ctx, cudaStreamWaitEvent(ls, E.emit_done, 0));
+                eng_plan<<<1, 32, 0, ls>>>(P, QL);
+                eng_scatter<<<ctx->n_sm, 256, 0, ls>>>(P, QL);
+                eng_zero_aux<<<ctx->n_sm, 256, 0, ls>>>(P, QL);
+                MTR_CUDA(ctx, cudaEventRecord(E.long_ev0[li], ls));
+                MTR_CUDA(ctx, wdp_launch_dev(LL[li], ls));
+                MTR_CUDA(ctx, cudaEventRecord(E.long_ev1[li], ls));
+                MTR_CUDA(ctx, cudaEventRecord(E.long_done[li], ls));
+                E.long_busy[li] = true;
+                launches += launches_per_long;
+            }
+            eng_plan<<<1, 32, 0, s>>>(P, P.q);
+            eng_scatter<<<ctx->n_sm * 2, 256, 0, s>>>(P, P.q);
+            eng_zero_aux<<<ctx->n_sm * 2, 256, 0, s>>>(P, P.q);
             MTR_CUDA(ctx, cudaGetLastError());
             MTR_CUDA(ctx, cudaEventRecord(E.ev_dp0[b], s));
             MTR_CUDA(ctx, wdp_launch_dev(L, s));
@@ -401,7 +478,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
                 const size_t want = E.d_dirs.cap * 2;
                 E.d_dirs.release();
                 MTR_CUDA(ctx, E.d_dirs.reserve_exact(want));
-                P.dir_cap = (long long)E.d_dirs.cap; E.P = P;
+                P.q.dir_cap = (long long)E.d_dirs.cap; E.P = P;
                 L.dirs = (uint8_t *)E.d_dirs.p;
                 stalled++;
             } else {
@@ -413,6 +490,16 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         last_tasks = snap->tasks_total; last_started = snap->candidates_started; last_accepted = snap->n_accepted; last_unfinished = snap->unfinished;
     }
     for (int i = 0; i < cfg.walk_streams; i++) MTR_CUDA(ctx, cudaStreamSynchronize(E.walk_stream[i]));   // walks nobody waits for any more
+    for (int i = 0; i < kLongInst; i++) {
+        MTR_CUDA(ctx, cudaStreamSynchronize(E.long_stream[i]));
+        float t0 = 0, t1 = 0;
+        if (E.long_busy[i] && base && cudaEventElapsedTime(&t0, base, E.long_ev0[i]) == cudaSuccess && cudaEventElapsedTime(&t1, base, E.long_ev1[i]) == cudaSuccess) {
+            std::lock_guard<std::mutex> gl(g_busy.mu);
+            g_busy.iv[ctx->device].push_back(std::make_pair((double)t0, (double)t1));
+            dp_long_ms += t1 - t0;
+        }
+        E.long_busy[i] = false;
+    }
     Counters *hc = (Counters *)E.h_ctr.p;
     MTR_CUDA(ctx, cudaMemcpyAsync(hc, P.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     MTR_CUDA(ctx, mtr_sync(ctx));
@@ -454,7 +541,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     if (stats) {
         export_stats(*hc, stats);
         stats->launches = launches;
-        stats->di_ms = di_ms; stats->dp_ms = dp_ms; stats->uf_ms = uf_ms;
+        stats->di_ms = di_ms; stats->dp_ms = dp_ms + dp_long_ms; stats->uf_ms = uf_ms;
         stats->h2d_bytes = di_h2d + (int64_t)sizeof(Read) * n + (int64_t)sizeof(Counters);
         stats->d2h_bytes = (int64_t)sizeof(Accepted) * na + (int64_t)sizeof(Counters);
         stats->wall_ms = wall_ms() - t_wall0;

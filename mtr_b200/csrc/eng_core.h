@@ -45,6 +45,7 @@ constexpr int kSchedBudget = 96;             // candidates one sched_read call m
 constexpr int kDpClasses = 20;               // 10 int32 + 10 paired int16x2 fill classes (wdp.cu)
 constexpr int kRowBuckets = 96;              // quarter-octave buckets of a task's row count (longest first)
 constexpr int kSegs = 2 * kRowBuckets * 10;  // (family, rows bucket, class) segments of the sorted task list
+constexpr int kLongInst = 4;                 // long-task queues of a group (each with its own stream, task list and direction arena)
 
 enum Stage : int {
     ST_FREE = 0, ST_DONE, ST_WALK, ST_WALKING, ST_ZOMBIE_WALKING, ST_NEED_SEARCH, ST_WAIT_SEARCH, ST_NEED_POLISH, ST_NEED_CONS, ST_WAIT_CONS, ST_NEED_DP, ST_WAIT_DP
@@ -65,7 +66,10 @@ struct Chain {                     // one k of one candidate: find_tandem_repeat
     int fatal;                     // ERR_* to raise when (and only if) the candidate commits
     int msg;                       // "You need to increse the value of WrapDPsize." lines to print when it commits
     int ring;                      // ring position of its candidate (absolute), for the cell accounting
-    int aux_off;                   // CONSENSUS block of the wave (int32 offset into Ptrs::aux)
+    int aux_off;                   // CONSENSUS block (int32 offset into the aux pool of queue aux_q)
+    int pending;                   // DP results this chain is still waiting for (the traceback kernels count it down)
+    int aux_q;                     // 0: the wave's queue, 1 + i: long queue i
+    int pad_[2];
 };
 
 struct Cand { int qs, qe, set, spec, min_k, n_k; long long cells; };   // set < 0: no k passed the maxFreq gate
@@ -85,7 +89,9 @@ struct Accepted { int read, seq; Rec rec; unsigned char unit[kUnitStride]; };   
 struct MemoEntry { unsigned key, epoch; int next; unsigned short seen; unsigned char self1, next1; };   // scores: min(count, 254) + 1, 0 = not known yet
 
 struct Counters {
-    int n_wait, n_polish, n_tasks, n_advance, polish_head, pad0;
+    int n_polish, polish_head;
+    int dp_pending;                // (task, penalty set) results outstanding in any queue
+    int pad0;
     // Walks run beside everything else (a pathological walk takes tens of milliseconds: it must delay its own candidate,
     // not the group): sched_read pushes chains at walk_tail, the walk kernel instance launched after a scheduler pass pops
     // below the tail it saw at its start.  Both counters only grow.
@@ -93,11 +99,30 @@ struct Counters {
     int walks_running, walks_done; // chains a walk kernel is working on right now / has finished so far
     int unfinished, error, error_read, n_accepted;
     int deferred, msgs, waves, progress;
-    unsigned long long dir_used, aux_used;
     unsigned long long cells, slot_cells, spec_cells, jobs, candidates, tables, walks, table_positions, dir_bytes, tasks_total;
     // profile (clock64 ticks, thread 0 / lane 0 of the walking warps): table build, node list, walks per direction; walk steps; tasks per table layout
     unsigned long long prof_build, prof_list, prof_walk[2], prof_steps, prof_kind[3], prof_walk_tasks, prof_max_task;
     unsigned long long prof_probe_rounds, prof_memo_hits, prof_deep_steps, prof_fail_walks, prof_max_walk;
+};
+
+// One queue of wrap-around DP tasks: the list as emitted, the list sorted by segment, the sort's work arrays, and the
+// per-use reservations (task slots, direction-matrix bytes, consensus-histogram ints).  The wave's own queue is filled,
+// run and drained inside one wave (the wave waits for it: rows < Ptrs::long_rows only).  Tasks with more rows go to one
+// of kLongInst long queues that run beside the waves on their own streams -- a 20 k-row DP takes milliseconds, and the
+// 500 other reads of the group must not wait for it; the chain that owns it simply stays in WAIT_* until its `pending`
+// count reaches zero.
+struct QueueCtr { int n_tasks, deferred; unsigned long long dir_used, aux_used; };
+struct DpQueue {
+    WdpTask *tasks_in, *tasks;     // as emitted / sorted by (family, rows descending, class)
+    int task_cap;
+    int *hist, *seg_task, *seg_slot, *bucket_cursor;   // [kSegs (+1)]
+    int *class_begin;              // [WDP_NCLASS + 1]: only the last entry (total number of tasks) is used
+    int *slot_counter;             // [WDP_NCLASS] work-queue heads of the fill / traceback kernels
+    int *aux;                      // consensus histograms
+    long long aux_cap;             // in int32
+    long long dir_cap;             // bytes of direction matrices
+    QueueCtr *qc;
+    int id;                        // 0: the wave's queue, 1 + i: long queue i
 };
 
 struct Ptrs {
@@ -109,22 +134,15 @@ struct Ptrs {
     unsigned char *units;          // [chain][4][kUnitStride]
     unsigned char *scores;         // [chain][3][kUnitStride]
     mtr_wdp_result *results;       // [chain][4]: search: direction d, penalty set s at 2d + s; revise: slot 0
-    int *wait_list, *polish_list;
+    int *polish_list;
     int *walk_ring;                // queue of chains in ST_WALK (Counters::walk_tail / walk_head, never reset)
     unsigned walk_ring_mask;
-    WdpTask *tasks_in, *tasks;     // as emitted / sorted by (class, rows descending)
-    int task_cap;
-    int *aux;                      // consensus histograms of the wave
-    long long aux_cap;             // in int32
-    long long dir_cap;             // bytes of direction matrices per wave
+    DpQueue q;                     // the wave's DP queue
+    int *aux_of[1 + kLongInst];    // aux pools by Chain::aux_q
+    int long_rows;                 // tasks with at least this many rows go to a long queue
     Accepted *acc;
     int acc_cap;
     Counters *ctr;
-    // DP tasks are sorted by segment = (family: int32 | paired int16x2, rows bucket descending, fill class): hist counts
-    // the tasks of a segment while they are emitted, seg_task / seg_slot are the prefix sums (tasks, warp slots)
-    int *hist, *seg_task, *seg_slot, *bucket_cursor;   // [kSegs (+1)]
-    int *class_begin;              // [WDP_NCLASS + 1]: only the last entry (total number of tasks) is used
-    int *slot_counter;             // [WDP_NCLASS] work-queue heads of the fill / traceback kernels
     unsigned char *uf_scratch;     // per unit-finder cta: memos, tie lists, node list, unit / score strings
     long long uf_stride;
     unsigned char *uf_wide;        // WIDE count tables, one per unit-finder cta
@@ -879,10 +897,17 @@ MTR_DEV void next_pass_or_done(const Ptrs &P, int chain)
     }
 }
 
-// one chain of the wait list (its DP results of the previous wave are in P.results)
+// a chain in WAIT_* whose DP results have all arrived (pending == 0) and are in P.results
+MTR_DEV bool chain_ready(const Ptrs &P, int chain)
+{
+    const Chain &ch = P.chains[chain];
+    const int st = ch.stage;
+    return (st == ST_WAIT_SEARCH || st == ST_WAIT_CONS || st == ST_WAIT_DP) && ldv(&ch.pending) == 0;
+}
 MTR_DEV void advance_chain(const Ptrs &P, int chain)
 {
     Chain &ch = P.chains[chain];
+    fence();                                                   // (pending reached zero: the results are behind the fence)
     const mtr_wdp_result *res = P.results + (size_t)chain * 4;
     const int stage = ch.stage;
     if (stage == ST_WAIT_SEARCH) {
@@ -934,7 +959,7 @@ MTR_DEV void advance_chain(const Ptrs &P, int chain)
         return;
     }
     if (stage == ST_WAIT_CONS) {
-        const int *cons = P.aux + ch.aux_off;
+        const int *cons = P.aux_of[ch.aux_q] + ch.aux_off;
         const int np = vote_unit(ch.tmp, cons, cons + (size_t)(ch.tmp.period + 1) * 5, unit_ptr(P, chain, U_TMP));
         ENG_LANE0(ch.tmp.period = np);
         wsync();
@@ -1004,7 +1029,7 @@ struct TaskSpec { int first, rows, ulen, uslot, n_param, mode, res_slot; const i
 
 // reserves direction space (+ consensus block) and task slots, then appends the tasks; false = no room in this wave
 // (the chain stays NEED_* and is emitted again by the next wave)
-MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
+MTR_DEV bool emit_tasks(const Ptrs &P, const DpQueue &Q, int chain, const TaskSpec *sp, int n)
 {
     Chain &ch = P.chains[chain];
     const Read &rs = P.reads[ch.read];
@@ -1021,17 +1046,18 @@ MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
         paired[i] = sp[i].n_param == 2 && sp[i].mode == MTR_TB_COUNTS && 4LL * gmax * sp[i].rows <= 32760;
         slots += (sp[i].n_param == 2 && !paired[i]) ? 2 : 1;
     }
-    const long long d0 = (long long)atomic_add(&P.ctr->dir_used, (unsigned long long)dir_need);
-    const long long a0 = (long long)atomic_add(&P.ctr->aux_used, (unsigned long long)aux_need);
-    const int t0 = atomic_add(&P.ctr->n_tasks, slots);
-    if (d0 + dir_need > P.dir_cap || a0 + aux_need > P.aux_cap || t0 + slots > P.task_cap) {
-        // over budget: the slots it took in the task list are marked empty (the counters restart with the next wave)
-        for (int i = 0; i < slots && t0 + i < P.task_cap; i++) P.tasks_in[t0 + i].rows = -1;
+    const long long d0 = (long long)atomic_add(&Q.qc->dir_used, (unsigned long long)dir_need);
+    const long long a0 = (long long)atomic_add(&Q.qc->aux_used, (unsigned long long)aux_need);
+    const int t0 = atomic_add(&Q.qc->n_tasks, slots);
+    if (d0 + dir_need > Q.dir_cap || a0 + aux_need > Q.aux_cap || t0 + slots > Q.task_cap) {
+        // over budget: the slots it took in the task list are marked empty (the counters restart with the queue's next use)
+        for (int i = 0; i < slots && t0 + i < Q.task_cap; i++) Q.tasks_in[t0 + i].rows = -1;
+        atomic_add(&Q.qc->deferred, 1);
         atomic_add(&P.ctr->deferred, 1);
         return false;
     }
     long long doff = d0, aoff = a0, cells = 0;
-    int at = t0;
+    int at = t0, results = 0;
     for (int i = 0; i < n; i++) {
         WdpTask t;
         t.base0 = rs.word_off * 16 + sp[i].first;
@@ -1044,7 +1070,7 @@ MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
         t.aux_off = 0; t.aux_cap = 0;
         if (sp[i].mode == MTR_TB_CONSENSUS) {
             t.aux_off = aoff; aoff += ((long long)(sp[i].ulen + 1) * 9 + 3) & ~3LL;
-            ch.aux_off = (int)t.aux_off;
+            ch.aux_off = (int)t.aux_off; ch.aux_q = Q.id;
         }
         t.result_idx = chain * 4 + sp[i].res_slot;
         t.n_param = (unsigned char)sp[i].n_param; t.mode = (unsigned char)sp[i].mode; t.pad_ = 0;
@@ -1058,11 +1084,12 @@ MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
             t.n_param = 1; u.n_param = 1;
             u.gain[0] = t.gain[1]; u.mis[0] = t.mis[1]; u.indel[0] = t.indel[1];
             u.dir_off = t.dir_off + t.dir_bytes; u.result_idx = t.result_idx + 1;
-            P.tasks_in[at++] = u;
-            atomic_add(&P.hist[seg_of(u.cls, u.rows)], 1);
+            Q.tasks_in[at++] = u;
+            atomic_add(&Q.hist[seg_of(u.cls, u.rows)], 1);
         }
-        P.tasks_in[at++] = t;
-        atomic_add(&P.hist[seg_of(t.cls, t.rows)], 1);
+        Q.tasks_in[at++] = t;
+        atomic_add(&Q.hist[seg_of(t.cls, t.rows)], 1);
+        results += sp[i].n_param;
         cells += (long long)t.rows * t.ulen * sp[i].n_param;
         atomic_add(&P.ctr->slot_cells, (unsigned long long)((long long)t.rows * kClassCap[cls] * sp[i].n_param));
     }
@@ -1070,11 +1097,13 @@ MTR_DEV bool emit_tasks(const Ptrs &P, int chain, const TaskSpec *sp, int n)
     atomic_add(&P.ctr->jobs, (unsigned long long)n);
     atomic_add(&P.ctr->dir_bytes, (unsigned long long)dir_need);
     atomic_add((unsigned long long *)&P.reads[ch.read].ring[ch.ring % kRing].cells, (unsigned long long)cells);
-    P.wait_list[atomic_add(&P.ctr->n_wait, 1)] = chain;
+    ch.pending = results;                                      // (the traceback kernels of the queue count it down)
+    atomic_add(&P.ctr->dp_pending, results);
     return true;
 }
 
-MTR_DEV void emit_chain(const Ptrs &P, int chain)
+// QL: the long queue that takes this wave's long tasks (QL.tasks_in == nullptr: none is free, they wait for the next wave)
+MTR_DEV void emit_chain(const Ptrs &P, const DpQueue &QL, int chain)
 {
     Chain &ch = P.chains[chain];
     const int stage = ldv(&ch.stage);
@@ -1102,46 +1131,51 @@ MTR_DEV void emit_chain(const Ptrs &P, int chain)
             return;
         }
     }
-    if (!emit_tasks(P, chain, sp, n)) return;
+    const bool is_long = sp[0].rows >= P.long_rows;
+    if (is_long && !QL.tasks_in) { atomic_add(&P.ctr->deferred, 1); return; }
+    if (!emit_tasks(P, is_long ? QL : P.q, chain, sp, n)) return;
     ch.stage = stage == ST_NEED_SEARCH ? ST_WAIT_SEARCH : (stage == ST_NEED_CONS ? ST_WAIT_CONS : ST_WAIT_DP);
 }
 
-// single thread, first thing in a wave: the chains emitted by the previous wave become this wave's advance list, and the
-// per-wave reservations start from zero
-MTR_DEV void wave_begin(const Ptrs &P)
+// single thread, first thing in a wave: the reservations of the queues this wave fills start from zero
+MTR_DEV void queue_reset(const DpQueue &Q)
+{
+    Q.qc->n_tasks = 0; Q.qc->deferred = 0; Q.qc->dir_used = 0; Q.qc->aux_used = 0;
+}
+MTR_DEV void wave_begin(const Ptrs &P, const DpQueue &QL)
 {
     Counters &c = *P.ctr;
-    c.n_advance = c.n_wait; c.n_wait = 0;
-    c.n_polish = 0; c.n_tasks = 0; c.deferred = 0; c.polish_head = 0;
-    c.dir_used = 0; c.aux_used = 0;
+    c.n_polish = 0; c.polish_head = 0; c.deferred = 0;
+    queue_reset(P.q);
+    if (QL.tasks_in) queue_reset(QL);
     c.waves++;
 }
 
 // one warp: prefix sums over the segments (tasks and warp slots), and the reset of the histogram for the next wave
 MTR_CONST int kClassJpw[10] = {8, 8, 8, 4, 4, 4, 2, 2, 1, 1};  // tasks per warp slot = 32 / G of the fill classes of wdp.cu
-MTR_DEV void plan_tasks(const Ptrs &P)
+MTR_DEV void plan_tasks(const Ptrs &P, const DpQueue &Q)
 {
     int at = 0, slots = 0;
     for (int s0 = 0; s0 < kSegs; s0 += NL) {
         const int sg = s0 + lane();
-        const int h = sg < kSegs ? P.hist[sg] : 0;
+        const int h = sg < kSegs ? Q.hist[sg] : 0;
         const int jpw = kClassJpw[(sg < kSegs ? sg : 0) % 10];
         const int sl = (h + jpw - 1) / jpw;
         const int off = wscan_excl(h), soff = wscan_excl(sl);
-        if (sg < kSegs) { P.seg_task[sg] = at + off; P.seg_slot[sg] = slots + soff; P.hist[sg] = 0; P.bucket_cursor[sg] = 0; }
+        if (sg < kSegs) { Q.seg_task[sg] = at + off; Q.seg_slot[sg] = slots + soff; Q.hist[sg] = 0; Q.bucket_cursor[sg] = 0; }
         at += wsum(h); slots += wsum(sl);
     }
-    ENG_LANE0(P.seg_task[kSegs] = at; P.seg_slot[kSegs] = slots; P.class_begin[WDP_NCLASS] = at; P.ctr->tasks_total += (unsigned long long)at);
-    for (int q = lane(); q < WDP_NCLASS; q += NL) P.slot_counter[q] = 0;
+    ENG_LANE0(Q.seg_task[kSegs] = at; Q.seg_slot[kSegs] = slots; Q.class_begin[WDP_NCLASS] = at; atomic_add(&P.ctr->tasks_total, (unsigned long long)at));
+    for (int q = lane(); q < WDP_NCLASS; q += NL) Q.slot_counter[q] = 0;
     wsync();
 }
 
-MTR_DEV void scatter_task(const Ptrs &P, int i)
+MTR_DEV void scatter_task(const DpQueue &Q, int i)
 {
-    const WdpTask t = P.tasks_in[i];
+    const WdpTask t = Q.tasks_in[i];
     if (t.rows < 0) return;                                    // slot of a deferred emission
     const int sg = seg_of(t.cls, t.rows);
-    P.tasks[P.seg_task[sg] + atomic_add(&P.bucket_cursor[sg], 1)] = t;
+    Q.tasks[Q.seg_task[sg] + atomic_add(&Q.bucket_cursor[sg], 1)] = t;
 }
 
 // ---------------------------------------------------------------- per-read scheduler: handle_one_TR's candidate loop
@@ -1160,21 +1194,25 @@ MTR_DEV void free_set(const Ptrs &P, Read &rs, int read, int set)
     wsync();
 }
 
-// chain set of a candidate that is dropped while its chains may still be with the walk kernel: queued walks are cancelled,
-// running ones are told that nobody waits for them (their set is freed by a later scheduler pass)
+// chain set of a candidate that is dropped while its chains may still be with the walk kernel or a long DP queue: queued
+// walks are cancelled, running ones are told that nobody waits for them, DP results in flight are left to arrive; the set is
+// freed by a later scheduler pass once all of that has ended
 MTR_DEV void drop_set(const Ptrs &P, Read &rs, int read, int set)
 {
     if (set < 0) return;
-    int walking = 0;
+    int busy = 0;
     for (int c = lane(); c < kMaxK; c += NL) {
         Chain &ch = P.chains[((size_t)read * kSets + set) * kMaxK + c];
         int st = ldv(&ch.stage);
         if (st == ST_WALK) st = atomic_cas(&ch.stage, (int)ST_WALK, (int)ST_DONE) == (int)ST_WALK ? (int)ST_DONE : ldv(&ch.stage);
         if (st == ST_WALKING) st = atomic_cas(&ch.stage, (int)ST_WALKING, (int)ST_ZOMBIE_WALKING) == (int)ST_WALKING ? (int)ST_ZOMBIE_WALKING : ldv(&ch.stage);
-        if (st == ST_ZOMBIE_WALKING) walking = 1;
+        if (st == ST_ZOMBIE_WALKING) busy = 1;
+        else if (st != ST_FREE) ch.stage = ST_DONE;            // nothing of this chain is emitted or advanced any more ...
+        if (ldv(&ch.pending) > 0) busy = 1;                    // ... but DP tasks of a long queue may still write into it
     }
-    walking = wmax(walking);
-    if (walking) ENG_LANE0(rs.zombie_mask |= 1u << set);
+    busy = wmax(busy);
+    wsync();
+    if (busy) ENG_LANE0(rs.zombie_mask |= 1u << set);
     else free_set(P, rs, read, set);
 }
 
@@ -1193,6 +1231,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
         for (int c = 0; c < kMaxK; c++) {
             const int st = ldv(&P.chains[((size_t)read * kSets + set) * kMaxK + c].stage);
             if (st == ST_WALK || st == ST_WALKING || st == ST_ZOMBIE_WALKING) busy = true;
+            if (ldv(&P.chains[((size_t)read * kSets + set) * kMaxK + c].pending) > 0) busy = true;
         }
         if (!busy) { ENG_LANE0(rs.zombie_mask &= ~(1u << set)); free_set(P, rs, read, set); }
     }
@@ -1358,7 +1397,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                 ch.k = min_k + c; ch.pass = 0; ch.found_last = 0; ch.ratio0 = 0;
                 ch.read = read; ch.qs = qs; ch.qe = qe;
                 ch.dir_found[0] = ch.dir_found[1] = 0; ch.dir_period[0] = ch.dir_period[1] = 0;
-                ch.fatal = 0; ch.msg = 0; ch.ring = pos; ch.aux_off = 0;
+                ch.fatal = 0; ch.msg = 0; ch.ring = pos; ch.aux_off = 0; ch.pending = 0; ch.aux_q = 0;
                 if (pass_mask & (1u << c)) {
                     // a walk kernel may be running right now and may hold a stale queue entry for this very chain (a
                     // cancelled walk of the set's previous owner): the fields first, then the stage

@@ -22,12 +22,15 @@ struct Config {
     int acc_cap = 0;             // accepted repeats of the whole group
     long long aux_cap = 0;       // int32 of consensus histograms per wave
     long long dir_cap = 0;       // bytes of direction matrices per wave
+    int long_rows = 2048;        // DP tasks with at least this many rows run in a long queue, beside the waves
+    int long_task_cap = 0;       // tasks per use of a long queue
+    long long long_dir_cap = 0, long_aux_cap = 0;   // its direction arena (bytes) and consensus pool (int32)
     int walk_cap = 0;
 };
 
 struct Layout {
-    size_t reads, chains, units, scores, results, wait_list, polish_list, walk_ring, tasks_in, tasks, aux, acc, ctr, hist,
-        seg_task, seg_slot, bucket_cursor, class_begin, slot_counter, total;
+    size_t reads, chains, units, scores, results, polish_list, walk_ring, acc, ctr, zero_begin, total;
+    struct Q { size_t tasks_in, tasks, aux, hist, seg_task, seg_slot, bucket_cursor, class_begin, slot_counter, qc; } q[1 + kLongInst];
     int n_chains;
     unsigned table_cap;
     long long uf_stride;
@@ -47,6 +50,9 @@ inline Config default_config(int n_reads, long long total_bases, int max_len, in
     c.acc_cap = (int)std::min<long long>((long long)n_reads * 32 + total_bases / 48 + 64, 1 << 24);
     c.aux_cap = std::max<long long>((long long)c.task_cap / 8 * 512, 2 * 4500);
     c.dir_cap = std::min<long long>(2LL << 30, std::max<long long>(256LL << 20, total_bases * 64));
+    c.long_task_cap = (int)std::min<long long>(std::max<long long>(1024, 8LL * n_reads), 1 << 18);
+    c.long_dir_cap = std::min<long long>(1LL << 30, std::max<long long>(256LL << 20, total_bases * 64));
+    c.long_aux_cap = std::max<long long>((long long)c.long_task_cap / 8 * 512, 2 * 4500);
     // walk queue: a power of two well above the chains that can be queued at once (entries of cancelled walks linger
     // until a walk kernel pops them)
     c.walk_cap = 4096;
@@ -65,20 +71,27 @@ inline Layout make_layout(const Config &c)
     l.units = take((size_t)std::max(l.n_chains, 1) * 4 * kUnitStride);
     l.scores = take((size_t)std::max(l.n_chains, 1) * 3 * kUnitStride);
     l.results = take(sizeof(mtr_wdp_result) * (size_t)std::max(l.n_chains, 1) * 4);
-    l.wait_list = take(4 * (size_t)std::max(l.n_chains, 1));
     l.polish_list = take(4 * (size_t)std::max(l.n_chains, 1));
     l.walk_ring = take(4 * (size_t)c.walk_cap);
-    l.tasks_in = take(sizeof(WdpTask) * (size_t)c.task_cap);
-    l.tasks = take(sizeof(WdpTask) * (size_t)c.task_cap);
-    l.aux = take(4 * (size_t)c.aux_cap);
     l.acc = take(sizeof(Accepted) * (size_t)c.acc_cap);
+    for (int i = 0; i <= kLongInst; i++) {
+        const int cap = i == 0 ? c.task_cap : c.long_task_cap;
+        l.q[i].tasks_in = take(sizeof(WdpTask) * (size_t)cap);
+        l.q[i].tasks = take(sizeof(WdpTask) * (size_t)cap);
+        l.q[i].aux = take(4 * (size_t)(i == 0 ? c.aux_cap : c.long_aux_cap));
+    }
+    // everything from here on starts as zero
+    l.zero_begin = at;
     l.ctr = take(sizeof(Counters));
-    l.hist = take(4 * (size_t)kSegs);
-    l.seg_task = take(4 * (size_t)(kSegs + 1));
-    l.seg_slot = take(4 * (size_t)(kSegs + 1));
-    l.bucket_cursor = take(4 * (size_t)kSegs);
-    l.class_begin = take(4 * (size_t)(WDP_NCLASS + 1));
-    l.slot_counter = take(4 * (size_t)WDP_NCLASS);
+    for (int i = 0; i <= kLongInst; i++) {
+        l.q[i].hist = take(4 * (size_t)kSegs);
+        l.q[i].seg_task = take(4 * (size_t)(kSegs + 1));
+        l.q[i].seg_slot = take(4 * (size_t)(kSegs + 1));
+        l.q[i].bucket_cursor = take(4 * (size_t)kSegs);
+        l.q[i].class_begin = take(4 * (size_t)(WDP_NCLASS + 1));
+        l.q[i].slot_counter = take(4 * (size_t)WDP_NCLASS);
+        l.q[i].qc = take(sizeof(QueueCtr));
+    }
     l.total = at;
     unsigned cap = 64;
     while (cap < 2u * (unsigned)(c.max_len + 8)) cap <<= 1;
@@ -86,6 +99,23 @@ inline Layout make_layout(const Config &c)
     l.uf_stride = (kScratchFixed + 255) & ~255LL;
     return l;
 }
+
+inline DpQueue bind_queue(void *base, const Layout &l, const Config &c, int i)
+{
+    unsigned char *b = (unsigned char *)base;
+    DpQueue q;
+    q.tasks_in = (WdpTask *)(b + l.q[i].tasks_in); q.tasks = (WdpTask *)(b + l.q[i].tasks);
+    q.task_cap = i == 0 ? c.task_cap : c.long_task_cap;
+    q.hist = (int *)(b + l.q[i].hist); q.seg_task = (int *)(b + l.q[i].seg_task); q.seg_slot = (int *)(b + l.q[i].seg_slot);
+    q.bucket_cursor = (int *)(b + l.q[i].bucket_cursor); q.class_begin = (int *)(b + l.q[i].class_begin);
+    q.slot_counter = (int *)(b + l.q[i].slot_counter);
+    q.aux = (int *)(b + l.q[i].aux); q.aux_cap = i == 0 ? c.aux_cap : c.long_aux_cap;
+    q.dir_cap = i == 0 ? c.dir_cap : c.long_dir_cap;
+    q.qc = (QueueCtr *)(b + l.q[i].qc);
+    q.id = i;
+    return q;
+}
+inline DpQueue no_queue() { DpQueue q; memset(&q, 0, sizeof q); return q; }
 
 inline Ptrs bind(void *base, const Layout &l, const Config &c)
 {
@@ -96,15 +126,13 @@ inline Ptrs bind(void *base, const Layout &l, const Config &c)
     P.chains = (Chain *)(b + l.chains);
     P.units = b + l.units; P.scores = b + l.scores;
     P.results = (mtr_wdp_result *)(b + l.results);
-    P.wait_list = (int *)(b + l.wait_list); P.polish_list = (int *)(b + l.polish_list); P.walk_ring = (int *)(b + l.walk_ring); P.walk_ring_mask = (unsigned)c.walk_cap - 1u;
-    P.tasks_in = (WdpTask *)(b + l.tasks_in); P.tasks = (WdpTask *)(b + l.tasks);
-    P.task_cap = c.task_cap;
-    P.aux = (int *)(b + l.aux); P.aux_cap = c.aux_cap;
-    P.dir_cap = c.dir_cap;
+    P.polish_list = (int *)(b + l.polish_list);
+    P.walk_ring = (int *)(b + l.walk_ring); P.walk_ring_mask = (unsigned)c.walk_cap - 1u;
+    P.q = bind_queue(base, l, c, 0);
+    for (int i = 0; i <= kLongInst; i++) P.aux_of[i] = (int *)(b + l.q[i].aux);
+    P.long_rows = c.long_rows;
     P.acc = (Accepted *)(b + l.acc); P.acc_cap = c.acc_cap;
     P.ctr = (Counters *)(b + l.ctr);
-    P.hist = (int *)(b + l.hist); P.seg_task = (int *)(b + l.seg_task); P.seg_slot = (int *)(b + l.seg_slot); P.bucket_cursor = (int *)(b + l.bucket_cursor);
-    P.class_begin = (int *)(b + l.class_begin); P.slot_counter = (int *)(b + l.slot_counter);
     P.table_cap = l.table_cap; P.uf_stride = l.uf_stride;
     P.compact_cap = c.compact_cap; P.direct_max_k = c.direct_max_k;
     return P;

@@ -151,6 +151,9 @@ struct WdpDevLaunch {
     uint8_t *dirs;
     mtr_wdp_result *results;
     void *aux;
+    char *pending0;               // &owner[0].pending; owner of result r is r / 4 (nullptr: nobody counts)
+    int pending_stride;           // sizeof(owner)
+    int *pending_total;
     int blocks;                   // persistent grid of every kernel
     cudaStream_t side[8];
     cudaEvent_t fork, join[8];

@@ -705,9 +705,8 @@ __device__ __forceinline__ void traceback_warp(const WdpTask &t, const int p, co
 __global__ void __launch_bounds__(128)
 wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const uint32_t *__restrict__ packed,
                   const uint8_t *__restrict__ units, const uint8_t *dirs, mtr_wdp_result *results, void *aux, int *__restrict__ head,
-                  unsigned long long *stamp)
+                  char *pending0, int pending_stride, int *pending_total)
 {
-    if (stamp && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); *stamp = t; }
     const int total = 2 * class_begin[WDP_NCLASS];
     for (;;) {
         int idx = 0;
@@ -721,6 +720,12 @@ wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ cla
         __syncwarp();
         traceback_warp(t, p, in.best, in.max_i, in.max_j, packed, units, dirs, results + t.result_idx + p, aux);
         __syncwarp();
+        // the owner of the result (an engine chain: four result slots each) counts its outstanding results down
+        if (pending0 && (threadIdx.x & 31) == 0) {
+            __threadfence();
+            atomicSub(reinterpret_cast<int *>(pending0 + (size_t)(t.result_idx >> 2) * pending_stride), 1);
+            atomicSub(pending_total, 1);
+        }
     }
 }
 
@@ -743,7 +748,7 @@ cudaError_t wdp_launch_dev(const WdpDevLaunch &L, cudaStream_t s)
         if ((e = cudaEventRecord(L.join[0], ps)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(s, L.join[0], 0)) != cudaSuccess) return e;
     }
-    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 10, nullptr);
+    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 10, L.pending0, L.pending_stride, L.pending_total);
     return cudaGetLastError();
 }
 

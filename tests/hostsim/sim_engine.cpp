@@ -43,12 +43,12 @@ extern "C" int mtr_engine_set_speculate(mtr_ctx *ctx, int depth)
 
 extern "C" double mtr_engine_dp_busy_ms(int, int) { return 0.0; }
 
-static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, mtro_ctx *o)
+static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, const DpQueue &Q, mtro_ctx *o)
 {
-    const int total = P.class_begin[WDP_NCLASS];
+    const int total = Q.class_begin[WDP_NCLASS];
     std::vector<int> x, u;
     for (int i = 0; i < total; i++) {
-        const WdpTask &t = P.tasks[i];
+        const WdpTask &t = Q.tasks[i];
         x.assign((size_t)t.rows + 2, 0);
         for (int r = 1; r <= t.rows; r++) { const long long b = t.base0 + r; x[r] = (int)((P.packed[b >> 4] >> ((b & 15) * 2)) & 3u); }
         u.assign((size_t)t.ulen + 2, 0);
@@ -56,12 +56,14 @@ static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, mtro_ctx *o)
         for (int p = 0; p < (int)t.n_param; p++) {
             mtro_dp_result r;
             int *cons = nullptr, *miss = nullptr;
-            if (t.mode == MTR_TB_CONSENSUS) { cons = P.aux + t.aux_off; miss = cons + (size_t)(t.ulen + 1) * 5; }
+            if (t.mode == MTR_TB_CONSENSUS) { cons = Q.aux + t.aux_off; miss = cons + (size_t)(t.ulen + 1) * 5; }
             mtro_wrap_dp(o, x.data(), t.rows, u.data(), t.ulen, t.gain[p], t.mis[p], t.indel[p], t.mode, &r, cons, miss, nullptr, nullptr);
             mtr_wdp_result &d = P.results[t.result_idx + p];
             d.best = r.best; d.max_i = r.max_i; d.max_j = r.max_j; d.end_i = r.end_i; d.end_j = r.end_j;
             d.n_match = r.n_match; d.n_mismatch = r.n_mismatch; d.n_ins = r.n_ins; d.n_del = r.n_del; d.n_scanned = r.n_scanned;
             d.path_len = r.path_len; d.flags = 0;
+            P.chains[t.result_idx >> 2].pending--;              // what wdp_traceback_dev does on the GPU
+            P.ctr->dp_pending--;
         }
     }
     (void)ctx;
@@ -107,6 +109,11 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     // small per-wave budgets on request, to exercise the deferral path on the CPU
     if (const char *e = getenv("MTR_ENGINE_DIR_KB")) cfg.dir_cap = std::max(1LL, atoll(e)) << 10;
     if (const char *e = getenv("MTR_ENGINE_TASK_CAP")) cfg.task_cap = std::max(4, atoi(e));
+    // MTR_ENGINE_LONG_ROWS: tasks with at least this many rows take the long queues; MTR_SIM_LONG_EVERY = n: a long queue is
+    // free only every n-th wave and its results arrive n - 1 waves late (chains wait in WAIT_*, dropped candidates leave
+    // zombie sets behind)
+    if (const char *e = getenv("MTR_ENGINE_LONG_ROWS")) cfg.long_rows = std::max(1, atoi(e));
+    const int long_every = getenv("MTR_SIM_LONG_EVERY") ? std::max(1, std::min(5, atoi(getenv("MTR_SIM_LONG_EVERY")))) : 1;
     const Layout lay = make_layout(cfg);
     E.main_buf.assign(lay.total, 0);
     E.scratch.assign((size_t)lay.uf_stride, 0);
@@ -134,9 +141,18 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     unsigned long long last_sig = ~0ull;
     int idle = 0;
     std::vector<unsigned> tails;
+    DpQueue QLs[kLongInst];
+    for (int i = 0; i < kLongInst; i++) QLs[i] = bind_queue(E.main_buf.data(), lay, cfg, 1 + i);
+    const DpQueue none = no_queue();
+    int long_pending = -1, long_due = 0;                        // long queue in flight and the wave its results arrive
+    int wave = 0;
     while (P.ctr->unfinished > 0 && !P.ctr->error) {
-        wave_begin(P);
-        for (int i = 0; i < P.ctr->n_advance; i++) advance_chain(P, P.wait_list[i]);
+        wave++;
+        if (long_pending >= 0 && wave >= long_due) { run_dp_tasks(ctx, P, QLs[long_pending], o); long_pending = -1; }
+        const int li = long_pending < 0 ? wave % kLongInst : -1;
+        const DpQueue &QL = li >= 0 ? QLs[li] : none;
+        wave_begin(P, QL);
+        for (int c = 0; c < lay.n_chains; c++) if (chain_ready(P, c)) advance_chain(P, c);
         for (int i = 0; i < P.ctr->n_polish; i++) polish_chain(P, P.polish_list[i], S, cta, smem.data());
         for (int r = 0; r < n; r++) sched_read(P, r, inline_tab.data(), kInlineSlots, sh);
         // the walk queue: with MTR_SIM_WALK_LAG = n the entries pushed by a scheduler pass are only walked n waves later,
@@ -147,14 +163,22 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             const unsigned limit = (int)tails.size() > lag ? tails[tails.size() - 1 - (size_t)lag] : 0u;
             while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(P, P.walk_ring[P.ctr->walk_head++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
         }
-        for (int c = 0; c < lay.n_chains; c++) emit_chain(P, c);
-        plan_tasks(P);
-        const int nt = std::min(P.ctr->n_tasks, P.task_cap);
-        for (int i = 0; i < nt; i++) scatter_task(P, i);
-        const long long na = std::min<long long>((long long)P.ctr->aux_used, P.aux_cap);
-        for (long long i = 0; i < na; i++) P.aux[i] = 0;
-        run_dp_tasks(ctx, P, o);
-        const unsigned long long sig = P.ctr->tasks_total * 1315423911ull + P.ctr->tables * 2654435761ull + (unsigned)P.ctr->progress * 97ull + (unsigned)P.ctr->unfinished;
+        for (int c = 0; c < lay.n_chains; c++) emit_chain(P, QL, c);
+        for (int qi = 0; qi < 2; qi++) {
+            const DpQueue &Q = qi == 0 ? P.q : QL;
+            if (!Q.tasks_in) continue;
+            plan_tasks(P, Q);
+            const int nt = std::min(Q.qc->n_tasks, Q.task_cap);
+            for (int i = 0; i < nt; i++) scatter_task(Q, i);
+            const long long na = std::min<long long>((long long)Q.qc->aux_used, Q.aux_cap);
+            for (long long i = 0; i < na; i++) Q.aux[i] = 0;
+        }
+        run_dp_tasks(ctx, P, P.q, o);
+        if (li >= 0) {
+            if (long_every <= 1) run_dp_tasks(ctx, P, QL, o);
+            else { long_pending = li; long_due = wave + long_every - 1; }
+        }
+        const unsigned long long sig = (unsigned long long)(unsigned)P.ctr->dp_pending * 7919ull + P.ctr->tasks_total * 1315423911ull + P.ctr->tables * 2654435761ull + (unsigned)P.ctr->progress * 97ull + (unsigned)P.ctr->unfinished;
         if (sig == last_sig) {
             if (++idle > 8) { mtr_set_error(ctx, "hostsim engine_run: no progress (wave %d, %d tasks deferred)", P.ctr->waves, P.ctr->deferred); return MTR_ECUDA; }
         } else idle = 0;
