@@ -42,10 +42,14 @@ constexpr int kInlineWindow = 512;           // windows up to this many bases pa
 constexpr int kInlineSlots = 2048;           // count-table slots of a scheduler warp (>= 2 * (kInlineWindow + 2), power of two)
 constexpr int kMemoSlots = 512;              // walk-memo entries per direction (shared memory, 16 bytes each)
 constexpr int kSchedBudget = 96;             // candidates one sched_read call may start (bounds the latency of a wave)
+constexpr int kResSlots = 1 << kWdpOwnerShift; // DP result slots of a chain: search direction d, penalty set s at 2d + s; revise at kResRevise
+constexpr int kResRevise = 4;
 constexpr int kDpClasses = 20;               // 10 int32 + 10 paired int16x2 fill classes (wdp.cu)
-constexpr int kRowBuckets = 96;              // quarter-octave buckets of a task's row count (longest first)
-constexpr int kSegs = 2 * kRowBuckets * 10;  // (family, rows bucket, class) segments of the sorted task list
-constexpr int kLongInst = 4;                 // long-task queues of a group (each with its own stream, task list and direction arena)
+constexpr int kRowBuckets = kWdpRowBuckets;  // quarter-octave buckets of a task's row count (longest first)
+constexpr int kSegs = 2 * kRowBuckets * 10;  // (family, class, rows bucket) segments of the sorted task list
+constexpr int kShortInst = 4;                // DP queues for tasks below Ptrs::long_rows rows (each with its own streams, task list and direction arena)
+constexpr int kLongInst = 12;                // ... and for the long tasks
+constexpr int kQueues = kShortInst + kLongInst;   // queue ids: short 0 .. kShortInst - 1, long kShortInst .. kQueues - 1
 
 enum Stage : int {
     ST_FREE = 0, ST_DONE, ST_WALK, ST_WALKING, ST_ZOMBIE_WALKING, ST_NEED_SEARCH, ST_WAIT_SEARCH, ST_NEED_POLISH, ST_NEED_CONS, ST_WAIT_CONS, ST_NEED_DP, ST_WAIT_DP
@@ -68,16 +72,26 @@ struct Chain {                     // one k of one candidate: find_tandem_repeat
     int ring;                      // ring position of its candidate (absolute), for the cell accounting
     int aux_off;                   // CONSENSUS block (int32 offset into the aux pool of queue aux_q)
     int pending;                   // DP results this chain is still waiting for (the traceback kernels count it down)
-    int aux_q;                     // 0: the wave's queue, 1 + i: long queue i
+    int aux_q;                     // queue whose aux pool holds it
+    // Search DPs shared inside a candidate: different k (and the two walk directions) very often end in the SAME unit
+    // string, and the DP of the same window against the same unit is the same DP.  lead[d] >= 0: direction d takes its two
+    // results from chain lead[d] / 2, direction lead[d] % 2 of the same candidate instead of running them again.
+    int lead[2];
+    int wait_lead;                 // directions still waiting for their leader's results
+    int search_done;               // the four search results are final (they stay valid: the revise passes use slot kResRevise)
     int pad_[2];
 };
 
 struct Cand { int qs, qe, set, spec, min_k, n_k; long long cells; };   // set < 0: no k passed the maxFreq gate
 
+// A Read is a SLOT: it holds one read of the resident batch at a time and takes the next unstarted one (Counters::next_read)
+// as soon as its read has finished, so that every wave works on n_slots reads until the batch runs out.
+struct ReadDesc { long long word_off, pos_off; int L, pad; };   // one read of the resident batch (packed words, directional-index arrays)
+
 struct Read {
     long long word_off, pos_off;
     int L, cursor, head, n_ring;   // ring entries head .. head + n_ring - 1 (mod kRing), in candidate order
-    int phase, n_accepted, candidates, pad0;
+    int phase, n_accepted, candidates, id;   // phase 0: at work on read `id` of the batch, 1: free
     unsigned set_mask;             // chain sets in use
     unsigned zombie_mask;          // ... by dropped candidates whose walks have not finished yet
     long long cells_wasted;
@@ -99,46 +113,53 @@ struct Counters {
     int walks_running, walks_done; // chains a walk kernel is working on right now / has finished so far
     int unfinished, error, error_read, n_accepted;
     int deferred, msgs, waves, progress;
+    int next_read, pad1;           // reads of the batch handed to slots so far
+    unsigned long long shared_cells;   // cells of search DPs that were not run because a sibling chain ran the identical DP
     unsigned long long cells, slot_cells, spec_cells, jobs, candidates, tables, walks, table_positions, dir_bytes, tasks_total;
     // profile (clock64 ticks, thread 0 / lane 0 of the walking warps): table build, node list, walks per direction; walk steps; tasks per table layout
     unsigned long long prof_build, prof_list, prof_walk[2], prof_steps, prof_kind[3], prof_walk_tasks, prof_max_task;
     unsigned long long prof_probe_rounds, prof_memo_hits, prof_deep_steps, prof_fail_walks, prof_max_walk;
+    // estimated K3 work per (family, fill class), smoothed over the uses of all queues: the fill kernels of every queue map
+    // the classes to the SMs by these shares, so that concurrent launches agree on which SM runs which class
+    unsigned long long class_share[20];
+    unsigned long long prof_k3[10];   // K3 per family: fill ticks, traceback ticks, slot rows, slots, traceback rows (wdp.cu WdpTb)
 };
 
 // One queue of wrap-around DP tasks: the list as emitted, the list sorted by segment, the sort's work arrays, and the
-// per-use reservations (task slots, direction-matrix bytes, consensus-histogram ints).  The wave's own queue is filled,
-// run and drained inside one wave (the wave waits for it: rows < Ptrs::long_rows only).  Tasks with more rows go to one
-// of kLongInst long queues that run beside the waves on their own streams -- a 20 k-row DP takes milliseconds, and the
-// 500 other reads of the group must not wait for it; the chain that owns it simply stays in WAIT_* until its `pending`
-// count reaches zero.
+// per-use reservations (task slots, direction-matrix bytes, consensus-histogram ints).  No wave waits for a DP: a wave
+// (tick) emits the tasks of the chains that are ready into one free short queue (rows < Ptrs::long_rows) and one free
+// long queue, the K3 kernels of a queue run on its own streams beside the following waves, and the chain that owns a
+// task stays in WAIT_* until its `pending` count -- counted down by the warp that finishes a task's traceback -- reaches
+// zero.  A 20 k-row DP takes milliseconds; the thousands of other reads at work must not wait for it.
 struct QueueCtr { int n_tasks, deferred; unsigned long long dir_used, aux_used; };
 struct DpQueue {
     WdpTask *tasks_in, *tasks;     // as emitted / sorted by (family, rows descending, class)
     int task_cap;
     int *hist, *seg_task, *seg_slot, *bucket_cursor;   // [kSegs (+1)]
-    int *class_begin;              // [WDP_NCLASS + 1]: only the last entry (total number of tasks) is used
+    int *class_begin;              // [WDP_NCLASS + 1]: entries 0 .. 19: estimated work of fill class c of family f at 10 f + c (plan_tasks); last entry: total number of tasks
     int *slot_counter;             // [WDP_NCLASS] work-queue heads of the fill / traceback kernels
     int *aux;                      // consensus histograms
     long long aux_cap;             // in int32
     long long dir_cap;             // bytes of direction matrices
     QueueCtr *qc;
-    int id;                        // 0: the wave's queue, 1 + i: long queue i
+    int id;                        // index among the kQueues queues of the group
 };
 
 struct Ptrs {
     const uint32_t *packed;
-    Read *reads;
-    int n_reads;
+    Read *reads;                   // the slots
+    int n_reads;                   // number of slots
+    const ReadDesc *descs;         // the reads of the batch
+    int n_total;                   // ... and their number
     int *end, *w;                  // directional_index_end / _w of every read (Read::pos_off)
     Chain *chains;                 // [n_reads * kSets * kMaxK]
     unsigned char *units;          // [chain][4][kUnitStride]
     unsigned char *scores;         // [chain][3][kUnitStride]
-    mtr_wdp_result *results;       // [chain][4]: search: direction d, penalty set s at 2d + s; revise: slot 0
+    mtr_wdp_result *results;       // [chain][kResSlots]: search: direction d, penalty set s at 2d + s; revise: slot kResRevise
     int *polish_list;
     int *walk_ring;                // queue of chains in ST_WALK (Counters::walk_tail / walk_head, never reset)
     unsigned walk_ring_mask;
-    DpQueue q;                     // the wave's DP queue
-    int *aux_of[1 + kLongInst];    // aux pools by Chain::aux_q
+    int *aux_of[kQueues];          // aux pools by Chain::aux_q
     int long_rows;                 // tasks with at least this many rows go to a long queue
     Accepted *acc;
     int acc_cap;
@@ -151,6 +172,7 @@ struct Ptrs {
     int direct_max_k;              // largest k that gets a DIRECT table (7)
     float min_match_ratio;
     int speculate;
+    int share_search;              // identical search DPs of one candidate run once (MTR_ENGINE_SHARE=0: off)
     unsigned long long *stamps;    // MTR_TIMELINE: [wave][16] %globaltimer values written by the wave's kernels (nullptr: off)
     int stamp_waves;
 };
@@ -902,15 +924,42 @@ MTR_DEV bool chain_ready(const Ptrs &P, int chain)
 {
     const Chain &ch = P.chains[chain];
     const int st = ch.stage;
-    return (st == ST_WAIT_SEARCH || st == ST_WAIT_CONS || st == ST_WAIT_DP) && ldv(&ch.pending) == 0;
+    return (st == ST_WAIT_SEARCH || st == ST_WAIT_CONS || st == ST_WAIT_DP) && ldv(&ch.pending) == 0 && ldv(&ch.wait_lead) == 0;
 }
 MTR_DEV void advance_chain(const Ptrs &P, int chain)
 {
     Chain &ch = P.chains[chain];
     fence();                                                   // (pending reached zero: the results are behind the fence)
-    const mtr_wdp_result *res = P.results + (size_t)chain * 4;
+    const mtr_wdp_result *res = P.results + (size_t)chain * kResSlots;
     const int stage = ch.stage;
     if (stage == ST_WAIT_SEARCH) {
+        // a direction that shares the DPs of my own other direction
+        {
+            mtr_wdp_result *mine = P.results + (size_t)chain * kResSlots;
+            for (int d = 0; d < 2; d++)
+                if (ch.lead[d] <= -2) {
+                    const int d2 = -2 - ch.lead[d];
+                    ENG_LANE0(mine[2 * d] = mine[2 * d2]; mine[2 * d + 1] = mine[2 * d2 + 1]; ch.lead[d] = -1);
+                }
+            wsync();
+        }
+        // my four results are final: hand them to the sibling chains that wait for them (lane = sibling, direction)
+        {
+            const int set0 = chain - chain % kMaxK;
+            for (int q = lane(); q < 2 * kMaxK; q += NL) {
+                const int c2 = set0 + q / 2, d2 = q % 2;
+                Chain &o = P.chains[c2];
+                const int ld = c2 != chain && ldv(&o.stage) == (int)ST_WAIT_SEARCH ? ldv(&o.lead[d2]) : -1;
+                if (ld >= 0 && ld / 2 == chain) {
+                    mtr_wdp_result *dst = P.results + (size_t)c2 * kResSlots + 2 * d2;
+                    dst[0] = res[2 * (ld % 2)]; dst[1] = res[2 * (ld % 2) + 1];
+                    o.lead[d2] = -1;
+                    fence();
+                    atomic_add(&o.wait_lead, -1);
+                }
+            }
+            ENG_LANE0(ch.search_done = 1);
+        }
         // max_rr of search_De_Bruijn_graph starts cleared; wrap_around_DP (wrap_around_DP.c:357-429) keeps the strictly
         // better of the two penalty sets of a direction (NaN never wins); a cleared record never qualifies
         int best_d = -1, best_s = -1;
@@ -978,7 +1027,7 @@ MTR_DEV void advance_chain(const Ptrs &P, int chain)
     }
     if (stage == ST_WAIT_DP) {
         Rec t = ch.tmp;
-        apply_dp(t, ch.tmp.rep_start, res[0], kReviseParams[ch.pass][0], kReviseParams[ch.pass][1], kReviseParams[ch.pass][2]);
+        apply_dp(t, ch.tmp.rep_start, res[kResRevise], kReviseParams[ch.pass][0], kReviseParams[ch.pass][1], kReviseParams[ch.pass][2]);
         if (ch.ratio0 < rec_ratio(t)) {                         // ratio0 is never refreshed (Q10)
             copy_bytes(unit_ptr(P, chain, U_RR), unit_ptr(P, chain, U_TMP), t.period);
             ENG_LANE0(ch.rr = t);
@@ -1018,11 +1067,17 @@ MTR_DEV int row_bucket(int rows)
     return b < kRowBuckets - 1 ? b : kRowBuckets - 1;
 }
 
-// segment of a task: family-major, longest rows first, then class
+// segment of a task: family, then fill class, then longest rows first.  All tasks of a class are contiguous: the fill
+// kernels keep the warps of an SM on ONE class as long as it has work (the ten instantiations of a family are 200-270 KB
+// of code; an SM that runs several of them at once lives on instruction-cache misses)
 MTR_DEV int seg_of(int cls20, int rows)
 {
-    const int fam = cls20 >= 10 ? 1 : 0, c = cls20 - 10 * fam;
-    return (fam * kRowBuckets + (kRowBuckets - 1 - row_bucket(rows))) * 10 + c;
+    return cls20 * kRowBuckets + (kRowBuckets - 1 - row_bucket(rows));
+}
+MTR_DEV int bucket_rows(int b)                                 // a row count inside row bucket b
+{
+    if (b < 4) return b;
+    return (4 + (b & 3)) << ((b >> 2) - 2);
 }
 
 struct TaskSpec { int first, rows, ulen, uslot, n_param, mode, res_slot; const int *params; };
@@ -1072,7 +1127,7 @@ MTR_DEV bool emit_tasks(const Ptrs &P, const DpQueue &Q, int chain, const TaskSp
             t.aux_off = aoff; aoff += ((long long)(sp[i].ulen + 1) * 9 + 3) & ~3LL;
             ch.aux_off = (int)t.aux_off; ch.aux_q = Q.id;
         }
-        t.result_idx = chain * 4 + sp[i].res_slot;
+        t.result_idx = chain * kResSlots + sp[i].res_slot;
         t.n_param = (unsigned char)sp[i].n_param; t.mode = (unsigned char)sp[i].mode; t.pad_ = 0;
         for (int p = 0; p < 2; p++) {
             const int *q = sp[i].params + 3 * (p < sp[i].n_param ? p : 0);
@@ -1102,8 +1157,9 @@ MTR_DEV bool emit_tasks(const Ptrs &P, const DpQueue &Q, int chain, const TaskSp
     return true;
 }
 
-// QL: the long queue that takes this wave's long tasks (QL.tasks_in == nullptr: none is free, they wait for the next wave)
-MTR_DEV void emit_chain(const Ptrs &P, const DpQueue &QL, int chain)
+// QS / QL: the short and the long queue that take this wave's tasks (tasks_in == nullptr: none is free, the chain is
+// emitted again by a later wave)
+MTR_DEV void emit_chain(const Ptrs &P, const DpQueue &QS, const DpQueue &QL, int chain)
 {
     Chain &ch = P.chains[chain];
     const int stage = ldv(&ch.stage);
@@ -1111,16 +1167,52 @@ MTR_DEV void emit_chain(const Ptrs &P, const DpQueue &QL, int chain)
     fence();                                                   // (a walk may have published NEED_SEARCH a moment ago: read its data after the stage)
     TaskSpec sp[2];
     int n = 0;
+    int follow[2] = {-1, -1};                                  // direction d shares the results of chain follow[d] / 2, direction follow[d] % 2
     if (stage == ST_NEED_SEARCH) {
+        const int set0 = chain - chain % kMaxK;
         for (int d = 0; d < 2; d++) {
             if (!ch.dir_found[d]) continue;
+            // wrap_around_DP.c:260-263 (checked for every direction, shared or not: a leader that aborts hands nothing out)
+            if ((long long)(ch.dir_period[d] + 1) * (ch.qe - ch.qs + 1) + ch.dir_period[d] >= kWrapCap) {
+                ch.fatal = ERR_WRAPCAP; rec_clear(ch.rr); ch.stage = ST_DONE;
+                return;
+            }
+        }
+        for (int d = 0; d < 2; d++) {
+            if (!ch.dir_found[d]) continue;
+            // A sibling chain of the same candidate (or my own other direction) with the very same unit string runs, or
+            // has run, the very same two DPs.  Leaders are chains that own their results (lead < 0): siblings whose
+            // search tasks are out already (WAIT_SEARCH or later), or -- among those still to be emitted -- lower ones.
+            const int period = ch.dir_period[d];
+            const unsigned char *mine = unit_ptr(P, chain, U_DIR0 + d);
+            for (int q = 0; q < 2 * kMaxK && follow[d] < 0 && P.share_search; q++) {
+                const int c2 = set0 + q / 2, d2 = q % 2;
+                if (c2 == chain && d2 >= d) continue;
+                const Chain &o = P.chains[c2];
+                const int st2 = ldv(&o.stage);
+                const bool out = st2 == ST_WAIT_SEARCH || st2 == ST_NEED_POLISH || st2 == ST_NEED_CONS || st2 == ST_WAIT_CONS || st2 == ST_NEED_DP || st2 == ST_WAIT_DP ||
+                                 (st2 == ST_DONE && o.search_done);
+                if (!(out || (st2 == ST_NEED_SEARCH && c2 < chain) || c2 == chain)) continue;
+                fence();
+                if (o.read != ch.read || o.ring != ch.ring || o.qs != ch.qs || o.qe != ch.qe) continue;      // (a slot of an older candidate)
+                if (!o.dir_found[d2] || o.dir_period[d2] != period) continue;
+                // a sibling that is out must own these results (lead == -1) and must not wait for anybody itself: results
+                // are handed out when a chain advances, so following a chain that waits (perhaps, through others, for me)
+                // could close a circle; siblings still to be emitted are followed downwards only
+                if (c2 != chain && out && (ldv(&o.lead[d2]) != -1 || ldv(&o.wait_lead) != 0)) continue;
+                const unsigned char *other = unit_ptr(P, c2, U_DIR0 + d2);
+                bool same = true;
+                for (int x = 0; x < period && same; x++) same = other[x] == mine[x];
+                if (same) follow[d] = 2 * c2 + d2;
+            }
+            if (follow[d] >= 0) continue;
             sp[n].first = ch.qs; sp[n].rows = ch.qe - ch.qs + 1; sp[n].ulen = ch.dir_period[d]; sp[n].uslot = U_DIR0 + d;
             sp[n].n_param = 2; sp[n].mode = MTR_TB_COUNTS; sp[n].res_slot = 2 * d; sp[n].params = &kSearchParams[0][0];
             n++;
         }
     } else {
         sp[0].first = ch.tmp.rep_start; sp[0].rows = ch.tmp.rep_end - ch.tmp.rep_start + 1; sp[0].ulen = ch.tmp.period; sp[0].uslot = U_TMP;
-        sp[0].n_param = 1; sp[0].mode = stage == ST_NEED_CONS ? MTR_TB_CONSENSUS : MTR_TB_COUNTS; sp[0].res_slot = 0;
+        sp[0].n_param = 1; sp[0].mode = stage == ST_NEED_CONS ? MTR_TB_CONSENSUS : MTR_TB_COUNTS; sp[0].res_slot = kResRevise;
         sp[0].params = &kReviseParams[ch.pass][0];
         n = 1;
     }
@@ -1131,9 +1223,34 @@ MTR_DEV void emit_chain(const Ptrs &P, const DpQueue &QL, int chain)
             return;
         }
     }
-    const bool is_long = sp[0].rows >= P.long_rows;
-    if (is_long && !QL.tasks_in) { atomic_add(&P.ctr->deferred, 1); return; }
-    if (!emit_tasks(P, is_long ? QL : P.q, chain, sp, n)) return;
+    if (n > 0) {
+        const bool is_long = sp[0].rows >= P.long_rows;
+        const DpQueue &Q = is_long ? QL : QS;
+        if (!Q.tasks_in) { atomic_add(&P.ctr->deferred, 1); return; }
+        if (!emit_tasks(P, Q, chain, sp, n)) return;
+    }
+    if (stage == ST_NEED_SEARCH) {
+        // shared directions: results that exist already are copied now, the others arrive when the leader's do
+        int waits = 0;
+        for (int d = 0; d < 2; d++) {
+            if (follow[d] < 0) continue;
+            const int c2 = follow[d] / 2, d2 = follow[d] % 2;
+            const long long cells = 2LL * (ch.qe - ch.qs + 1) * ch.dir_period[d];
+            atomic_add(&P.ctr->shared_cells, (unsigned long long)cells);
+            if (c2 != chain && P.chains[c2].search_done) {
+                const mtr_wdp_result *src = P.results + (size_t)c2 * kResSlots + 2 * d2;
+                mtr_wdp_result *dst = P.results + (size_t)chain * kResSlots + 2 * d;
+                dst[0] = src[0]; dst[1] = src[1];
+            } else if (c2 == chain) {
+                ch.lead[d] = -2 - d2;                           // my own other direction: copied when my results are in
+            } else {
+                ch.lead[d] = follow[d];
+                waits++;
+            }
+        }
+        ch.wait_lead = waits;
+        fence();
+    }
     ch.stage = stage == ST_NEED_SEARCH ? ST_WAIT_SEARCH : (stage == ST_NEED_CONS ? ST_WAIT_CONS : ST_WAIT_DP);
 }
 
@@ -1142,30 +1259,45 @@ MTR_DEV void queue_reset(const DpQueue &Q)
 {
     Q.qc->n_tasks = 0; Q.qc->deferred = 0; Q.qc->dir_used = 0; Q.qc->aux_used = 0;
 }
-MTR_DEV void wave_begin(const Ptrs &P, const DpQueue &QL)
+MTR_DEV void wave_begin(const Ptrs &P, const DpQueue &QS, const DpQueue &QL)
 {
     Counters &c = *P.ctr;
     c.n_polish = 0; c.polish_head = 0; c.deferred = 0;
-    queue_reset(P.q);
+    if (QS.tasks_in) queue_reset(QS);
     if (QL.tasks_in) queue_reset(QL);
     c.waves++;
 }
 
 // one warp: prefix sums over the segments (tasks and warp slots), and the reset of the histogram for the next wave
 MTR_CONST int kClassJpw[10] = {8, 8, 8, 4, 4, 4, 2, 2, 1, 1};  // tasks per warp slot = 32 / G of the fill classes of wdp.cu
+MTR_CONST int kClassCols[10] = {4, 8, 12, 8, 12, 16, 12, 16, 12, 16};   // columns per lane
 MTR_DEV void plan_tasks(const Ptrs &P, const DpQueue &Q)
 {
     int at = 0, slots = 0;
-    for (int s0 = 0; s0 < kSegs; s0 += NL) {
+    for (int s0 = 0; s0 < kSegs; s0 += NL) {                    // (kRowBuckets is a multiple of NL or NL == 1: a step never straddles two classes)
         const int sg = s0 + lane();
         const int h = sg < kSegs ? Q.hist[sg] : 0;
-        const int jpw = kClassJpw[(sg < kSegs ? sg : 0) % 10];
+        const int cls = (sg < kSegs ? sg : 0) / kRowBuckets;    // 0 .. 19
+        const int jpw = kClassJpw[cls % 10];
         const int sl = (h + jpw - 1) / jpw;
         const int off = wscan_excl(h), soff = wscan_excl(sl);
         if (sg < kSegs) { Q.seg_task[sg] = at + off; Q.seg_slot[sg] = slots + soff; Q.hist[sg] = 0; Q.bucket_cursor[sg] = 0; }
+        // estimated work of the class: slot rows x columns per lane, in units of 1024 (saturating)
+        const int rows = bucket_rows(kRowBuckets - 1 - (sg < kSegs ? sg : 0) % kRowBuckets);
+        long long work = (long long)sl * rows * kClassCols[cls % 10];
+        work = wsum(work);
+        if (lane() == 0) {
+            const long long prev = (s0 % kRowBuckets) == 0 ? 0 : (long long)Q.class_begin[cls] * 1024;
+            const long long tot = prev + work;
+            Q.class_begin[cls] = (int)((tot + 1023) / 1024 < 0x7fffffffLL ? (tot + 1023) / 1024 : 0x7fffffffLL);
+        }
         at += wsum(h); slots += wsum(sl);
     }
     ENG_LANE0(Q.seg_task[kSegs] = at; Q.seg_slot[kSegs] = slots; Q.class_begin[WDP_NCLASS] = at; atomic_add(&P.ctr->tasks_total, (unsigned long long)at));
+    for (int q = lane(); q < 20; q += NL) {
+        const unsigned long long old = P.ctr->class_share[q];
+        P.ctr->class_share[q] = old - old / 16 + (unsigned long long)(unsigned)Q.class_begin[q];
+    }
     for (int q = lane(); q < WDP_NCLASS; q += NL) Q.slot_counter[q] = 0;
     wsync();
 }
@@ -1219,10 +1351,6 @@ MTR_DEV void drop_set(const Ptrs &P, Read &rs, int read, int set)
 MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, unsigned table_cap, int *sh)
 {
     Read &rs = P.reads[read];
-    if (rs.phase != 0) return;
-    const uint32_t *rd = P.packed + rs.word_off;
-    int *END = P.end + rs.pos_off, *WW = P.w + rs.pos_off;
-    const int L = rs.L;
     int started = 0;
     // chain sets of dropped candidates whose walks were still running: free them once the walks have let go
     for (unsigned zm = rs.zombie_mask; zm; zm &= zm - 1u) {
@@ -1235,6 +1363,22 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
         }
         if (!busy) { ENG_LANE0(rs.zombie_mask &= ~(1u << set)); free_set(P, rs, read, set); }
     }
+  next_read:
+    if (rs.phase != 0) {
+        // a free slot takes the next read of the batch -- once nothing of its previous read is in flight any more
+        if (rs.set_mask != 0u || started >= kSchedBudget) return;
+        int idx = P.n_total;
+        if (lane() == 0 && ldv(&P.ctr->next_read) < P.n_total) idx = atomic_add(&P.ctr->next_read, 1);
+        idx = bcast(idx, 0);
+        if (idx >= P.n_total) return;
+        const ReadDesc d = P.descs[idx];
+        ENG_LANE0(rs.word_off = d.word_off; rs.pos_off = d.pos_off; rs.L = d.L; rs.cursor = 0; rs.head = 0; rs.n_ring = 0;
+                  rs.n_accepted = 0; rs.candidates = 0; rs.id = idx; rs.zombie_mask = 0u; rs.cells_wasted = 0; rs.phase = 0);
+        wsync();
+    }
+    const uint32_t *rd = P.packed + rs.word_off;
+    int *END = P.end + rs.pos_off, *WW = P.w + rs.pos_off;
+    const int L = rs.L;
     for (;;) {
         // ---- commit finished candidates in candidate order
         while (rs.n_ring > 0) {
@@ -1257,7 +1401,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                 }
             }
             if (fatal) {
-                ENG_LANE0(if (atomic_max(&P.ctr->error, fatal) < fatal) P.ctr->error_read = read; rs.phase = 1; atomic_add(&P.ctr->unfinished, -1));
+                ENG_LANE0(if (atomic_max(&P.ctr->error, fatal) < fatal) P.ctr->error_read = rs.id; rs.phase = 1; atomic_add(&P.ctr->unfinished, -1));
                 wsync();
                 return;
             }
@@ -1280,7 +1424,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                     }
                     Accepted &a = P.acc[slot];
                     copy_bytes(a.unit, unit_ptr(P, chain, U_RR), pick.period < kUnitStride ? pick.period : kUnitStride);
-                    ENG_LANE0(a.read = read; a.seq = rs.n_accepted; a.rec = pick; rs.n_accepted++);
+                    ENG_LANE0(a.read = rs.id; a.seq = rs.n_accepted; a.rec = pick; rs.n_accepted++);
                     // remove_redundant_ranges_from_directional_index (:178-188)
                     const int hi = pick.rep_end < L ? pick.rep_end : L;
                     for (int i = pick.rep_start + lane(); i < hi; i += NL)
@@ -1331,6 +1475,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
             if (rs.n_ring == 0) {
                 ENG_LANE0(rs.phase = 1; atomic_add(&P.ctr->unfinished, -1); atomic_add(&P.ctr->candidates, (unsigned long long)rs.candidates));
                 wsync();
+                goto next_read;
             }
             return;
         }
@@ -1398,6 +1543,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                 ch.read = read; ch.qs = qs; ch.qe = qe;
                 ch.dir_found[0] = ch.dir_found[1] = 0; ch.dir_period[0] = ch.dir_period[1] = 0;
                 ch.fatal = 0; ch.msg = 0; ch.ring = pos; ch.aux_off = 0; ch.pending = 0; ch.aux_q = 0;
+                ch.lead[0] = ch.lead[1] = -1; ch.wait_lead = 0; ch.search_done = 0;
                 if (pass_mask & (1u << c)) {
                     // a walk kernel may be running right now and may hold a stale queue entry for this very chain (a
                     // cancelled walk of the set's previous owner): the fields first, then the stage

@@ -3,6 +3,7 @@
 // which are sized separately), so binding eng::Ptrs is pointer arithmetic on a base address -- device or host.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "eng_core.h"
@@ -10,7 +11,8 @@
 namespace eng {
 
 struct Config {
-    int n_reads = 0;
+    int n_reads = 0;             // read SLOTS: reads of the batch at work at the same time
+    int n_total = 0;             // reads of the batch
     long long total_bases = 0;
     int max_len = 0;
     int uf_ctas = 0;             // persistent ctas of the walk kernel (each owns a scratch slice and a WIDE table)
@@ -18,40 +20,41 @@ struct Config {
     int polish_ctas = 0;         // ... of the polish kernel (scratch slices behind the walk banks: it runs beside the walks)
     unsigned compact_cap = kCompactCap;
     int direct_max_k = 7;
-    int task_cap = 0;            // DP tasks per wave
+    int task_cap = 0;            // DP tasks per use of a short queue
     int acc_cap = 0;             // accepted repeats of the whole group
-    long long aux_cap = 0;       // int32 of consensus histograms per wave
-    long long dir_cap = 0;       // bytes of direction matrices per wave
-    int long_rows = 2048;        // DP tasks with at least this many rows run in a long queue, beside the waves
+    long long aux_cap = 0;       // its consensus pool (int32)
+    long long dir_cap = 0;       // its direction arena (bytes)
+    int long_rows = 2048;        // DP tasks with at least this many rows go to the long queues
     int long_task_cap = 0;       // tasks per use of a long queue
     long long long_dir_cap = 0, long_aux_cap = 0;   // its direction arena (bytes) and consensus pool (int32)
     int walk_cap = 0;
 };
 
 struct Layout {
-    size_t reads, chains, units, scores, results, polish_list, walk_ring, acc, ctr, zero_begin, total;
-    struct Q { size_t tasks_in, tasks, aux, hist, seg_task, seg_slot, bucket_cursor, class_begin, slot_counter, qc; } q[1 + kLongInst];
+    size_t reads, descs, chains, units, scores, results, polish_list, walk_ring, acc, ctr, zero_begin, total;
+    struct Q { size_t tasks_in, tasks, aux, hist, seg_task, seg_slot, bucket_cursor, class_begin, slot_counter, qc; } q[kQueues];
     int n_chains;
     unsigned table_cap;
     long long uf_stride;
 };
 
-inline Config default_config(int n_reads, long long total_bases, int max_len, int n_sm)
+inline Config default_config(int n_slots, int n_total, long long total_bases, int max_len, int n_sm)
 {
     Config c;
-    c.n_reads = n_reads; c.total_bases = total_bases; c.max_len = max_len;
+    const int n_reads = std::max(1, std::min(n_slots, n_total));
+    c.n_reads = n_reads; c.n_total = n_total; c.total_bases = total_bases; c.max_len = max_len;
     // every cta owns a WIDE table sized for the longest read: at most 1 GB of them per group
     unsigned cap = 64;
     while (cap < 2u * (unsigned)(max_len + 8)) cap <<= 1;
     c.uf_ctas = (int)std::max<long long>(4, std::min<long long>(n_sm / 2, (1LL << 28) / ((long long)cap * 8)));
-    c.polish_ctas = c.uf_ctas;
+    c.polish_ctas = std::max(c.uf_ctas, std::min(2 * n_sm, 4 * c.uf_ctas));   // polish runs inside the wave: as wide as the GPU
     const long long n_chains = (long long)n_reads * kSets * kMaxK;
-    c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains), 1 << 20);
-    c.acc_cap = (int)std::min<long long>((long long)n_reads * 32 + total_bases / 48 + 64, 1 << 24);
+    c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains / 2), 1 << 19);
+    c.acc_cap = (int)std::min<long long>((long long)n_total * 32 + total_bases / 48 + 64, 1 << 24);
     c.aux_cap = std::max<long long>((long long)c.task_cap / 8 * 512, 2 * 4500);
-    c.dir_cap = std::min<long long>(2LL << 30, std::max<long long>(256LL << 20, total_bases * 64));
+    c.dir_cap = std::min<long long>(2LL << 30, std::max<long long>(std::max<long long>(16LL << 20, 1024LL * max_len), total_bases * 32));
     c.long_task_cap = (int)std::min<long long>(std::max<long long>(1024, 8LL * n_reads), 1 << 18);
-    c.long_dir_cap = std::min<long long>(1LL << 30, std::max<long long>(256LL << 20, total_bases * 64));
+    c.long_dir_cap = std::min<long long>(3LL << 30, std::max<long long>(std::max<long long>(16LL << 20, 1024LL * max_len), total_bases * 32));
     c.long_aux_cap = std::max<long long>((long long)c.long_task_cap / 8 * 512, 2 * 4500);
     // walk queue: a power of two well above the chains that can be queued at once (entries of cancelled walks linger
     // until a walk kernel pops them)
@@ -67,23 +70,24 @@ inline Layout make_layout(const Config &c)
     auto take = [&](size_t bytes) { const size_t o = at; at += (bytes + 255) & ~(size_t)255; return o; };
     l.n_chains = c.n_reads * kSets * kMaxK;
     l.reads = take(sizeof(Read) * (size_t)std::max(c.n_reads, 1));
+    l.descs = take(sizeof(ReadDesc) * (size_t)std::max(c.n_total, 1));
     l.chains = take(sizeof(Chain) * (size_t)std::max(l.n_chains, 1));
     l.units = take((size_t)std::max(l.n_chains, 1) * 4 * kUnitStride);
     l.scores = take((size_t)std::max(l.n_chains, 1) * 3 * kUnitStride);
-    l.results = take(sizeof(mtr_wdp_result) * (size_t)std::max(l.n_chains, 1) * 4);
+    l.results = take(sizeof(mtr_wdp_result) * (size_t)std::max(l.n_chains, 1) * kResSlots);
     l.polish_list = take(4 * (size_t)std::max(l.n_chains, 1));
     l.walk_ring = take(4 * (size_t)c.walk_cap);
     l.acc = take(sizeof(Accepted) * (size_t)c.acc_cap);
-    for (int i = 0; i <= kLongInst; i++) {
-        const int cap = i == 0 ? c.task_cap : c.long_task_cap;
+    for (int i = 0; i < kQueues; i++) {
+        const int cap = i < kShortInst ? c.task_cap : c.long_task_cap;
         l.q[i].tasks_in = take(sizeof(WdpTask) * (size_t)cap);
         l.q[i].tasks = take(sizeof(WdpTask) * (size_t)cap);
-        l.q[i].aux = take(4 * (size_t)(i == 0 ? c.aux_cap : c.long_aux_cap));
+        l.q[i].aux = take(4 * (size_t)(i < kShortInst ? c.aux_cap : c.long_aux_cap));
     }
     // everything from here on starts as zero
     l.zero_begin = at;
     l.ctr = take(sizeof(Counters));
-    for (int i = 0; i <= kLongInst; i++) {
+    for (int i = 0; i < kQueues; i++) {
         l.q[i].hist = take(4 * (size_t)kSegs);
         l.q[i].seg_task = take(4 * (size_t)(kSegs + 1));
         l.q[i].seg_slot = take(4 * (size_t)(kSegs + 1));
@@ -105,12 +109,12 @@ inline DpQueue bind_queue(void *base, const Layout &l, const Config &c, int i)
     unsigned char *b = (unsigned char *)base;
     DpQueue q;
     q.tasks_in = (WdpTask *)(b + l.q[i].tasks_in); q.tasks = (WdpTask *)(b + l.q[i].tasks);
-    q.task_cap = i == 0 ? c.task_cap : c.long_task_cap;
+    q.task_cap = i < kShortInst ? c.task_cap : c.long_task_cap;
     q.hist = (int *)(b + l.q[i].hist); q.seg_task = (int *)(b + l.q[i].seg_task); q.seg_slot = (int *)(b + l.q[i].seg_slot);
     q.bucket_cursor = (int *)(b + l.q[i].bucket_cursor); q.class_begin = (int *)(b + l.q[i].class_begin);
     q.slot_counter = (int *)(b + l.q[i].slot_counter);
-    q.aux = (int *)(b + l.q[i].aux); q.aux_cap = i == 0 ? c.aux_cap : c.long_aux_cap;
-    q.dir_cap = i == 0 ? c.dir_cap : c.long_dir_cap;
+    q.aux = (int *)(b + l.q[i].aux); q.aux_cap = i < kShortInst ? c.aux_cap : c.long_aux_cap;
+    q.dir_cap = i < kShortInst ? c.dir_cap : c.long_dir_cap;
     q.qc = (QueueCtr *)(b + l.q[i].qc);
     q.id = i;
     return q;
@@ -123,32 +127,37 @@ inline Ptrs bind(void *base, const Layout &l, const Config &c)
     Ptrs P;
     memset(&P, 0, sizeof P);
     P.reads = (Read *)(b + l.reads); P.n_reads = c.n_reads;
+    P.descs = (const ReadDesc *)(b + l.descs); P.n_total = c.n_total;
     P.chains = (Chain *)(b + l.chains);
     P.units = b + l.units; P.scores = b + l.scores;
     P.results = (mtr_wdp_result *)(b + l.results);
     P.polish_list = (int *)(b + l.polish_list);
     P.walk_ring = (int *)(b + l.walk_ring); P.walk_ring_mask = (unsigned)c.walk_cap - 1u;
-    P.q = bind_queue(base, l, c, 0);
-    for (int i = 0; i <= kLongInst; i++) P.aux_of[i] = (int *)(b + l.q[i].aux);
+    for (int i = 0; i < kQueues; i++) P.aux_of[i] = (int *)(b + l.q[i].aux);
     P.long_rows = c.long_rows;
     P.acc = (Accepted *)(b + l.acc); P.acc_cap = c.acc_cap;
     P.ctr = (Counters *)(b + l.ctr);
     P.table_cap = l.table_cap; P.uf_stride = l.uf_stride;
+    P.share_search = getenv("MTR_ENGINE_SHARE") ? atoi(getenv("MTR_ENGINE_SHARE")) : 1;
     P.compact_cap = c.compact_cap; P.direct_max_k = c.direct_max_k;
     return P;
 }
 
-// initial per-read state (host side; copied into the group's buffer)
-inline void init_reads(std::vector<Read> &out, const int64_t *word_off, const int32_t *len, int n)
+// the reads of the batch (host side; copied into the group's buffer) and the initial state of the slots: all free
+inline void init_descs(std::vector<ReadDesc> &out, const int64_t *word_off, const int32_t *len, int n)
 {
-    out.assign((size_t)n, Read());
+    out.assign((size_t)n, ReadDesc());
     long long pos = 0;
     for (int r = 0; r < n; r++) {
-        Read &rs = out[r];
-        memset(&rs, 0, sizeof rs);
-        rs.word_off = word_off[r]; rs.pos_off = pos; rs.L = len[r];
+        ReadDesc &d = out[r];
+        d.word_off = word_off[r]; d.pos_off = pos; d.L = len[r]; d.pad = 0;
         pos += len[r];
     }
+}
+inline void init_slots(std::vector<Read> &out, int n_slots)
+{
+    out.assign((size_t)n_slots, Read());
+    for (Read &rs : out) { memset(&rs, 0, sizeof rs); rs.phase = 1; rs.id = -1; }
 }
 
 // converts the accepted list into the ABI records, ordered by (read, insertion order)
@@ -180,7 +189,7 @@ inline void export_stats(const Counters &c, mtr_engine_stats *s)
     if (!s) return;
     s->waves = c.waves; s->candidates = (int64_t)c.candidates; s->dp_jobs = (int64_t)c.jobs; s->dp_tasks = (int64_t)c.tasks_total;
     s->dp_cells = (int64_t)c.cells; s->dp_slot_cells = (int64_t)c.slot_cells; s->dp_dir_bytes = (int64_t)c.dir_bytes;
-    s->spec_cells = (int64_t)c.spec_cells; s->tables = (int64_t)c.tables; s->table_positions = (int64_t)c.table_positions;
+    s->spec_cells = (int64_t)c.spec_cells; s->shared_cells = (int64_t)c.shared_cells; s->tables = (int64_t)c.tables; s->table_positions = (int64_t)c.table_positions;
     s->walks = (int64_t)c.walks; s->repeats = c.n_accepted; s->wrapdp_messages = c.msgs;
 }
 

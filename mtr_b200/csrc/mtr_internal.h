@@ -80,6 +80,8 @@ struct WdpTask {
 };
 
 constexpr int WDP_NCLASS = 26;
+constexpr int kWdpOwnerShift = 3;     // engine: result slot r belongs to owner r >> kWdpOwnerShift (eight result slots per chain)
+constexpr int kWdpRowBuckets = 96;   // quarter-octave buckets of a task's row count in the engine's sorted task lists (eng_core.h kRowBuckets)
 struct WdpClass { int G, C, paired; };          // lanes per job, cells per lane, int16x2 pairing
 
 struct WdpState {
@@ -146,6 +148,7 @@ struct WdpDevLaunch {
     const int *seg_task, *seg_slot;   // prefix sums over the 2 * nseg_family segments (+1) of the sorted task list
     int nseg_family;
     int *counters;                // [WDP_NCLASS] slot-queue heads, zero at launch
+    const unsigned long long *class_share;   // [20] estimated work per (family, fill class): SM s starts with the class its share of the SMs covers
     const uint32_t *packed;
     const uint8_t *units;
     uint8_t *dirs;
@@ -154,7 +157,11 @@ struct WdpDevLaunch {
     char *pending0;               // &owner[0].pending; owner of result r is r / 4 (nullptr: nobody counts)
     int pending_stride;           // sizeof(owner)
     int *pending_total;
-    int blocks;                   // persistent grid of every kernel
+    int blocks;                   // persistent grid of every kernel ...
+    int blocks_i32, blocks_p16;   // ... unless the caller knows how many warp slots each fill family has (< 0: use `blocks`)
+    int fused;                    // tracebacks inside the fill kernels (no traceback kernel)
+    int fill_smem;                // dynamic shared memory asked for by the fill kernels (bounds their blocks per SM)
+    unsigned long long *prof;     // MTR_PROFILE: 10 counters (see WdpTb), nullptr = off
     cudaStream_t side[8];
     cudaEvent_t fork, join[8];
     int n_side;

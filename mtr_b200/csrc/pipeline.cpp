@@ -24,6 +24,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <sys/stat.h>
 #include <thread>
 #include <time.h>
 #include <unistd.h>
@@ -389,6 +390,23 @@ int parse_fasta_text(const char *text, int64_t len, int first, int count, int th
 }
 
 // ---------------------------------------------------------------- groups of reads on one engine context
+// A group is one engine run: its reads pass through the engine's read slots (MTR_ENGINE_SLOTS at a time, a slot takes the
+// next read as soon as its read has finished), so a group should be several times the slot count; two contexts per GPU
+// let the tail of one group (a few reads with long dependent chains) overlap with the bulk of the next.
+constexpr int kDefaultContexts = 2;
+constexpr int kDefaultGroupReads = 24576;
+constexpr long long kDefaultGroupBases = 320LL << 20;
+// bases per group when the amount of input is known (a file's size, a parsed text): the smallest multiple of the number
+// of contexts that keeps every group under the cap, so that the contexts finish together
+long long balanced_group_bases(long long total_bases, int contexts, long long cap)
+{
+    if (total_bases <= 0 || contexts <= 0) return cap;
+    const long long per_round = (long long)contexts * cap;
+    const long long rounds = (total_bases + per_round - 1) / per_round;
+    const long long groups = rounds * contexts;
+    return std::min(cap, (total_bases + groups - 1) / groups + (1LL << 16));
+}
+
 struct Resident {                      // what stays on the host for the reads resident in one context
     std::vector<int64_t> stale_off;    // indexed like the resident batch
     std::vector<uint16_t> stale;
@@ -536,7 +554,7 @@ void run_group(mtr_ctx *ctx, Group &g, int print_alignment, int manhattan, float
     g.ps.chain_ms = (now_s() - tc0) * 1e3;
     g.ps.candidates += es.candidates; g.ps.waves += es.waves; g.ps.jobs += es.dp_jobs; g.ps.dp_tasks += es.dp_tasks;
     g.ps.wdp_cells += es.dp_cells; g.ps.wdp_slot_cells += es.dp_slot_cells; g.ps.wdp_dir_bytes += es.dp_dir_bytes;
-    g.ps.spec_cells += es.spec_cells; g.ps.tables += es.tables; g.ps.table_positions += es.table_positions; g.ps.walks += es.walks;
+    g.ps.spec_cells += es.spec_cells; g.ps.shared_cells += es.shared_cells; g.ps.tables += es.tables; g.ps.table_positions += es.table_positions; g.ps.walks += es.walks;
     g.ps.repeats += es.repeats; g.ps.launches += es.launches;
     g.ps.dp_ms += es.dp_ms; g.ps.di_kernel_ms += es.di_ms; g.ps.uf_kernel_ms += es.uf_ms; g.ps.engine_wall_ms += es.wall_ms;
 }
@@ -545,7 +563,7 @@ void add_stats(mtr_pipeline_stats &t, const mtr_pipeline_stats &p)
 {
     t.reads += p.reads; t.bases += p.bases; t.candidates += p.candidates; t.waves += p.waves; t.groups += p.groups; t.jobs += p.jobs;
     t.dp_tasks += p.dp_tasks; t.wdp_cells += p.wdp_cells; t.wdp_slot_cells += p.wdp_slot_cells; t.wdp_dir_bytes += p.wdp_dir_bytes;
-    t.spec_cells += p.spec_cells; t.tables += p.tables; t.table_positions += p.table_positions; t.walks += p.walks; t.repeats += p.repeats;
+    t.spec_cells += p.spec_cells; t.shared_cells += p.shared_cells; t.tables += p.tables; t.table_positions += p.table_positions; t.walks += p.walks; t.repeats += p.repeats;
     t.h2d_bytes += p.h2d_bytes; t.d2h_bytes += p.d2h_bytes; t.launches += p.launches;
     t.dp_ms += p.dp_ms; t.di_kernel_ms += p.di_kernel_ms; t.uf_kernel_ms += p.uf_kernel_ms; t.engine_wall_ms += p.engine_wall_ms;
     t.pack_ms += p.pack_ms; t.chain_ms += p.chain_ms;
@@ -554,9 +572,9 @@ void add_stats(mtr_pipeline_stats &t, const mtr_pipeline_stats &p)
 // ---------------------------------------------------------------- process-wide state behind the C entry points
 struct Runtime {
     std::vector<mtr_ctx *> ctxs;       // groups_per_gpu engine contexts on each GPU, GPU-major
-    int n_gpu = 1, groups_per_gpu = 16;
-    int group_reads = 512;            // reads per group (MTR_GROUP_READS) ...
-    long long group_bases = 24LL << 20;   // ... or bases per group (MTR_GROUP_MBASES), whichever fills first
+    int n_gpu = 1, groups_per_gpu = kDefaultContexts;
+    int group_reads = kDefaultGroupReads;            // reads per group (MTR_GROUP_READS) ...
+    long long group_bases = kDefaultGroupBases;      // ... or bases per group (MTR_GROUP_MBASES), whichever fills first
     StaleTracker stale;
     std::vector<ReadInput> pending;    // handle_one_read: reads enqueued since the last flush
     int pending_print = 0, pending_manhattan = 1;
@@ -760,10 +778,15 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     Dispatcher disp(rt, print_alignment, Manhattan_Distance, min_match_ratio);
     int n_reads = 0;
     bool more = true;
+    long long group_bases = rt.group_bases;
+    {
+        struct stat st;
+        if (stat(inputFile, &st) == 0 && st.st_size > 0) group_bases = balanced_group_bases((long long)st.st_size, (int)rt.ctxs.size(), rt.group_bases);
+    }
     while (more) {
         std::unique_ptr<Group> g(new Group());
         long long bases = 0;
-        while ((int)g->reads.size() < rt.group_reads && bases < rt.group_bases) {
+        while ((int)g->reads.size() < rt.group_reads && bases < group_bases) {
             ReadInput in;
             if (!reader.next(in)) { more = false; break; }
             bases += in.len;
@@ -796,15 +819,15 @@ struct mtr_pipeline {
     std::string out;
     mtr_pipeline_stats ps = {};
     int threads = 1;
-    int group_reads = 512;
-    long long group_bases = 24LL << 20;
+    int group_reads = kDefaultGroupReads;
+    long long group_bases = kDefaultGroupBases;
 };
 
 extern "C" int mtr_pipeline_open(int device, int threads, mtr_pipeline **out)
 {
     if (!out) return MTR_EINVAL;
     *out = nullptr;
-    int k = 16;
+    int k = kDefaultContexts;
     if (const char *e = getenv("MTR_GROUPS_PER_GPU")) k = std::max(1, atoi(e));
     mtr_pipeline *p = new mtr_pipeline();
     for (int i = 0; i < k; i++) {
@@ -855,10 +878,13 @@ extern "C" int mtr_pipeline_load_fasta_shard(mtr_pipeline *p, const char *text, 
     const int n = (int)reads.size();
     // the same groups handle_one_file would cut (MTR_GROUP_READS / MTR_GROUP_MBASES), dealt round-robin to the contexts;
     // all groups of a context are uploaded as one resident batch
+    long long total_bases = 0;
+    for (const ReadInput &r : reads) total_bases += r.len;
+    const long long group_bases = balanced_group_bases(total_bases, (int)p->ctxs.size(), p->group_bases);
     for (size_t a = 0; a < reads.size();) {
         std::unique_ptr<Group> g(new Group());
         long long bases = 0;
-        while (a < reads.size() && (int)g->reads.size() < p->group_reads && bases < p->group_bases) {
+        while (a < reads.size() && (int)g->reads.size() < p->group_reads && bases < group_bases) {
             bases += reads[a].len;
             g->reads.push_back(std::move(reads[a++]));
         }

@@ -565,67 +565,6 @@ wdp_fill_p16(const WdpTask *__restrict__ tasks, int ntasks, const uint32_t *__re
     }
 }
 
-// ---------------------------------------------------------------- resident engine: task lists built on the device
-// The engine (eng_core.h) writes the sorted task array and the class boundaries in device memory; the host cannot know
-// the counts, so these kernels are launched with a fixed persistent grid and read their range from class_begin[].
-// Split traceback: the fill stores the argmax into results[], wdp_traceback_dev finishes the record in place.
-// One kernel per score family (int32 | paired int16x2) covers all ten fill classes: the task list is sorted by segment =
-// (family, rows bucket descending, class), a warp pulls the next slot of the family's queue, finds its segment by binary
-// search in the slot prefix sums and runs that class's fill.  Longest tasks first across ALL classes, two launches per
-// wave instead of twenty.
-struct WdpSegs { const int *task; const int *slot; int nseg_family; };   // prefix sums over 2 * nseg_family segments (+1)
-
-template <bool P16>
-__global__ void __launch_bounds__(64, 8)
-wdp_fill_family(const WdpTask *__restrict__ tasks, const WdpSegs sg, const uint32_t *__restrict__ packed,
-                const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counters)
-{
-    const int seg0 = P16 ? sg.nseg_family : 0;
-    const int slot0 = sg.slot[seg0], slot1 = sg.slot[seg0 + sg.nseg_family];
-    for (;;) {
-        int slot = 0;
-        if ((threadIdx.x & 31) == 0) slot = atomicAdd(counters + (P16 ? 1 : 0), 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0) + slot0;
-        if (slot >= slot1) break;
-        int lo = seg0, hi = seg0 + sg.nseg_family;          // largest segment with slot[seg] <= slot (empty segments share a value)
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (sg.slot[mid] <= slot) lo = mid; else hi = mid;
-        }
-        const WdpTask *ct = tasks + sg.task[lo];
-        const int cn = sg.task[lo + 1] - sg.task[lo];
-        const int ls = slot - sg.slot[lo];
-        const int cls = (lo - seg0) % 10;
-        if (P16) {
-            switch (cls) {
-            case 0: fill_slot_p16<4, 4, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 1: fill_slot_p16<4, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 2: fill_slot_p16<4, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 3: fill_slot_p16<8, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 4: fill_slot_p16<8, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 5: fill_slot_p16<8, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 6: fill_slot_p16<16, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 7: fill_slot_p16<16, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 8: fill_slot_p16<32, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            default: fill_slot_p16<32, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            }
-        } else {
-            switch (cls) {
-            case 0: fill_slot_i32<4, 4, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 1: fill_slot_i32<4, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 2: fill_slot_i32<4, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 3: fill_slot_i32<8, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 4: fill_slot_i32<8, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 5: fill_slot_i32<8, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 6: fill_slot_i32<16, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 7: fill_slot_i32<16, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            case 8: fill_slot_i32<32, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            default: fill_slot_i32<32, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
-            }
-        }
-    }
-}
-
 // Warp-cooperative traceback of one (task, penalty set): wrap_around_DP.c:288-333 (counts) and consensus.c:919-962
 // (histograms).  The walk itself is sequential, but one thread chasing it pays an L2 round trip per step (read base,
 // direction byte): here the 32 lanes fetch the next 32 rows at once -- lane q the read base of row i - q and 64 direction
@@ -701,6 +640,150 @@ __device__ __forceinline__ void traceback_warp(const WdpTask &t, const int p, co
     }
 }
 
+// ---------------------------------------------------------------- resident engine: task lists built on the device
+// The engine (eng_core.h) writes the sorted task array and the class boundaries in device memory; the host cannot know
+// the counts, so these kernels are launched with a fixed persistent grid and read their range from class_begin[].
+// Split traceback: the fill stores the argmax into results[], wdp_traceback_dev finishes the record in place.
+// One kernel per score family (int32 | paired int16x2) covers all ten fill classes: the task list is sorted by segment =
+// (family, rows bucket descending, class), a warp pulls the next slot of the family's queue, finds its segment by binary
+// search in the slot prefix sums and runs that class's fill.  Longest tasks first across ALL classes, two launches per
+// wave instead of twenty.
+struct WdpSegs { const int *task; const int *slot; const unsigned long long *class_work; int nseg_family; };   // prefix sums over the 2 * 10 * kWdpRowBuckets (family, class, rows bucket) segments (+1); estimated work per (family, class)
+
+// tb.fused: the warp that filled a slot also walks the tracebacks of its tasks (all 32 lanes on one task at a time) and
+// counts the owners' outstanding results down, so that every task is complete on its own -- nothing waits for the
+// longest fill of the launch.
+struct WdpTb { void *aux; char *pending0; int pending_stride; int *pending_total; int fused; unsigned long long *prof; };   // prof: [fill ticks, traceback ticks, slot rows, slots, traceback rows] per family (5 + 5), nullptr = off
+
+template <bool P16>
+__global__ void __launch_bounds__(64, 8)
+wdp_fill_family(const WdpTask *__restrict__ tasks, const WdpSegs sg, const uint32_t *__restrict__ packed,
+                const uint8_t *__restrict__ units, uint8_t *dirs, mtr_wdp_result *results, int *__restrict__ counters, const WdpTb tb)
+{
+    constexpr int RB = kWdpRowBuckets;
+    const int fam = P16 ? 1 : 0;
+    const int seg0 = fam * 10 * RB;
+    const int lane = threadIdx.x & 31;
+    // The class this SM starts with: the classes share the SMs in proportion to their estimated work (class_work, written
+    // by the engine's plan pass), so that the warps of one SM run one instantiation at a time.
+    int cls = 0;
+    {
+        unsigned smid, nsm;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        long long total = 0;
+        for (int c = 0; c < 10; c++) total += (long long)sg.class_work[fam * 10 + c];
+        const long long target = (total * (2 * (long long)smid + 1)) / (2 * (long long)(nsm ? nsm : 1));
+        long long acc = 0;
+        for (int c = 0; c < 10; c++) {
+            acc += (long long)sg.class_work[fam * 10 + c];
+            cls = c;
+            if (target < acc) break;
+        }
+    }
+    for (int tried = 0; tried < 10; tried++, cls = (cls + 1) % 10) {
+        const int sega = seg0 + cls * RB;
+        const int slot0 = sg.slot[sega], slot1 = sg.slot[sega + RB];
+        if (slot0 >= slot1) continue;
+        const int jpw = cls < 3 ? 8 : (cls < 6 ? 4 : (cls < 8 ? 2 : 1));
+        for (;;) {
+            int slot = 0;
+            if (lane == 0) slot = atomicAdd(counters + fam * 10 + cls, 1);
+            slot = __shfl_sync(0xffffffffu, slot, 0) + slot0;
+            if (slot >= slot1) break;
+            int lo = sega, hi = sega + RB;                      // largest segment with slot[seg] <= slot (empty segments share a value)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sg.slot[mid] <= slot) lo = mid; else hi = mid;
+            }
+            const WdpTask *ct = tasks + sg.task[lo];
+            const int cn = sg.task[lo + 1] - sg.task[lo];
+            const int ls = slot - sg.slot[lo];
+            const long long pt0 = tb.prof ? clock64() : 0;
+            if (P16) {
+                switch (cls) {
+                case 0: fill_slot_p16<4, 4, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 1: fill_slot_p16<4, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 2: fill_slot_p16<4, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 3: fill_slot_p16<8, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 4: fill_slot_p16<8, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 5: fill_slot_p16<8, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 6: fill_slot_p16<16, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 7: fill_slot_p16<16, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 8: fill_slot_p16<32, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                default: fill_slot_p16<32, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                }
+            } else {
+                switch (cls) {
+                case 0: fill_slot_i32<4, 4, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 1: fill_slot_i32<4, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 2: fill_slot_i32<4, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 3: fill_slot_i32<8, 8, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 4: fill_slot_i32<8, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 5: fill_slot_i32<8, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 6: fill_slot_i32<16, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 7: fill_slot_i32<16, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                case 8: fill_slot_i32<32, 12, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                default: fill_slot_i32<32, 16, false>(ct, cn, ls, packed, units, dirs, results, nullptr); break;
+                }
+            }
+            const long long pt1 = tb.prof ? clock64() : 0;
+            long long tb_rows = 0;
+            if (tb.fused) {
+                __syncwarp();                               // argmax records and direction rows written by the lanes of this warp
+                if (jpw >= 4) {
+                    // many short tasks in the slot: one lane per (task, penalty set), all of them at once
+                    constexpr int NP = P16 ? 2 : 1;
+                    const int g = lane / NP, p = lane % NP;
+                    const int tidx = ls * jpw + g;
+                    if (g < jpw && tidx < cn) {
+                        const WdpTask &t = ct[tidx];
+                        if (p < (int)t.n_param) {
+                            const mtr_wdp_result in = results[t.result_idx + p];
+                            traceback_one(t, p, in.best, in.max_i, in.max_j, packed, units, dirs, results + t.result_idx + p, tb.aux);
+                            tb_rows = t.rows;
+                            if (tb.pending0) {
+                                __threadfence();
+                                atomicSub(reinterpret_cast<int *>(tb.pending0 + (size_t)(t.result_idx >> kWdpOwnerShift) * tb.pending_stride), 1);
+                                atomicSub(tb.pending_total, 1);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (tb.prof) for (int off = 16; off >= 1; off >>= 1) tb_rows += __shfl_xor_sync(0xffffffffu, tb_rows, off);
+                } else {
+                    // one or two long tasks: the whole warp walks one traceback at a time
+                    for (int g = 0; g < jpw; g++) {
+                        const int tidx = ls * jpw + g;
+                        if (tidx >= cn) break;
+                        const WdpTask &t = ct[tidx];
+                        const int np = (int)t.n_param;
+                        tb_rows += (long long)t.rows * np;
+                        for (int p = 0; p < np; p++) {
+                            const mtr_wdp_result in = results[t.result_idx + p];
+                            __syncwarp();
+                            traceback_warp(t, p, in.best, in.max_i, in.max_j, packed, units, dirs, results + t.result_idx + p, tb.aux);
+                            __syncwarp();
+                        }
+                        // the owner of the results (an engine chain: four result slots each) counts its outstanding results down
+                        if (tb.pending0 && lane == 0) {
+                            __threadfence();
+                            atomicSub(reinterpret_cast<int *>(tb.pending0 + (size_t)(t.result_idx >> kWdpOwnerShift) * tb.pending_stride), np);
+                            atomicSub(tb.pending_total, np);
+                        }
+                    }
+                }
+            }
+            if (tb.prof && lane == 0) {
+                unsigned long long *pr = tb.prof + (P16 ? 5 : 0);
+                const long long pt2 = clock64();
+                atomicAdd(pr + 0, (unsigned long long)(pt1 - pt0)); atomicAdd(pr + 1, (unsigned long long)(pt2 - pt1));
+                atomicAdd(pr + 2, (unsigned long long)ct[ls * jpw].rows); atomicAdd(pr + 3, 1ull); atomicAdd(pr + 4, (unsigned long long)tb_rows);
+            }
+        }
+    }
+}
+
 // one warp per (task, penalty set), pulled from a queue in task order (longest tasks of every class first)
 __global__ void __launch_bounds__(128)
 wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ class_begin, const uint32_t *__restrict__ packed,
@@ -723,32 +806,38 @@ wdp_traceback_dev(const WdpTask *__restrict__ tasks, const int *__restrict__ cla
         // the owner of the result (an engine chain: four result slots each) counts its outstanding results down
         if (pending0 && (threadIdx.x & 31) == 0) {
             __threadfence();
-            atomicSub(reinterpret_cast<int *>(pending0 + (size_t)(t.result_idx >> 2) * pending_stride), 1);
+            atomicSub(reinterpret_cast<int *>(pending0 + (size_t)(t.result_idx >> kWdpOwnerShift) * pending_stride), 1);
             atomicSub(pending_total, 1);
         }
     }
 }
 
-// enqueues the two family fill kernels (the paired one on the side stream) and the traceback on `s`
+// enqueues the two family fill kernels (the paired one on the side stream); the traceback runs inside them (L.fused) or
+// as a kernel of its own behind both
 cudaError_t wdp_launch_dev(const WdpDevLaunch &L, cudaStream_t s)
 {
     cudaError_t e;
     WdpSegs sg;
-    sg.task = L.seg_task; sg.slot = L.seg_slot; sg.nseg_family = L.nseg_family;
-    cudaStream_t ps = L.n_side > 0 ? L.side[0] : s;
-    if (L.n_side > 0) {
+    sg.task = L.seg_task; sg.slot = L.seg_slot; sg.class_work = L.class_share; sg.nseg_family = L.nseg_family;
+    WdpTb tb;
+    tb.aux = L.aux; tb.pending0 = L.pending0; tb.pending_stride = L.pending_stride; tb.pending_total = L.pending_total; tb.fused = L.fused; tb.prof = L.prof;
+    const int b0 = L.blocks_i32 >= 0 ? L.blocks_i32 : L.blocks, b1 = L.blocks_p16 >= 0 ? L.blocks_p16 : L.blocks;
+    const bool fork = L.n_side > 0 && b0 > 0 && b1 > 0;
+    cudaStream_t ps = fork ? L.side[0] : s;
+    if (fork) {
         if ((e = cudaEventRecord(L.fork, s)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(ps, L.fork, 0)) != cudaSuccess) return e;
     }
-    wdp_fill_family<false><<<L.blocks, 64, 0, s>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
+    if (b0 > 0) wdp_fill_family<false><<<b0, 64, L.fill_smem, s>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters, tb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    wdp_fill_family<true><<<L.blocks, 64, 0, ps>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters);
+    if (b1 > 0) wdp_fill_family<true><<<b1, 64, L.fill_smem, ps>>>(L.tasks, sg, L.packed, L.units, L.dirs, L.results, L.counters, tb);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (L.n_side > 0) {
+    if (fork) {
         if ((e = cudaEventRecord(L.join[0], ps)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(s, L.join[0], 0)) != cudaSuccess) return e;
     }
-    wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 10, L.pending0, L.pending_stride, L.pending_total);
+    if (!L.fused)
+        wdp_traceback_dev<<<L.blocks, 128, 0, s>>>(L.tasks, L.class_begin, L.packed, L.units, L.dirs, L.results, L.aux, L.counters + 20, L.pending0, L.pending_stride, L.pending_total);
     return cudaGetLastError();
 }
 

@@ -62,7 +62,7 @@ static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, const DpQueue &Q, mtro_ctx
             d.best = r.best; d.max_i = r.max_i; d.max_j = r.max_j; d.end_i = r.end_i; d.end_j = r.end_j;
             d.n_match = r.n_match; d.n_mismatch = r.n_mismatch; d.n_ins = r.n_ins; d.n_del = r.n_del; d.n_scanned = r.n_scanned;
             d.path_len = r.path_len; d.flags = 0;
-            P.chains[t.result_idx >> 2].pending--;              // what wdp_traceback_dev does on the GPU
+            P.chains[t.result_idx >> kWdpOwnerShift].pending--;              // what wdp_traceback_dev does on the GPU
             P.ctr->dp_pending--;
         }
     }
@@ -100,7 +100,11 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     int rc = mtr_di_run_range(ctx, manhattan, stale, stale_off, pos_off.data(), nullptr, E.end.data(), E.w.data(), first, n);
     if (rc) return rc;
 
-    Config cfg = default_config(n, pos_off[first + n], max_len, 1);
+    // MTR_ENGINE_SLOTS: reads at work at the same time (a slot takes the next read of the batch when its read has finished)
+    int n_slots = n;
+    if (const char *e = getenv("MTR_ENGINE_SLOTS")) n_slots = std::max(1, atoi(e));
+    Config cfg = default_config(n_slots, n, pos_off[first + n], max_len, 1);
+    n_slots = cfg.n_reads;
     cfg.uf_ctas = 1;
     // MTR_SIM_COMPACT_CAP / MTR_SIM_DIRECT_K: shrink the shared-memory table layouts so that small test windows reach
     // the COMPACT and the WIDE (+ probe cache) paths too
@@ -131,9 +135,12 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     P.min_match_ratio = min_match_ratio;
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
-    std::vector<Read> reads;
-    init_reads(reads, ctx->word_off.data() + first, ctx->len.data() + first, n);
-    memcpy(P.reads, reads.data(), sizeof(Read) * (size_t)n);
+    std::vector<Read> slots;
+    std::vector<ReadDesc> descs;
+    init_slots(slots, n_slots);
+    init_descs(descs, ctx->word_off.data() + first, ctx->len.data() + first, n);
+    memcpy(P.reads, slots.data(), sizeof(Read) * (size_t)n_slots);
+    memcpy((void *)P.descs, descs.data(), sizeof(ReadDesc) * (size_t)n);
     P.ctr->unfinished = n;
     mtro_ctx *o = sim_oracle(ctx, manhattan);
     std::vector<unsigned long long> inline_tab(kInlineSlots);
@@ -141,20 +148,28 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     unsigned long long last_sig = ~0ull;
     int idle = 0;
     std::vector<unsigned> tails;
-    DpQueue QLs[kLongInst];
-    for (int i = 0; i < kLongInst; i++) QLs[i] = bind_queue(E.main_buf.data(), lay, cfg, 1 + i);
+    DpQueue Qs[kQueues];
+    for (int i = 0; i < kQueues; i++) Qs[i] = bind_queue(E.main_buf.data(), lay, cfg, i);
     const DpQueue none = no_queue();
-    int long_pending = -1, long_due = 0;                        // long queue in flight and the wave its results arrive
+    // K3 of a queue "runs" for every[k] waves: its results arrive that many waves after the emission (minus one), and the
+    // queue cannot be used again before
+    const int every[2] = {getenv("MTR_SIM_SHORT_EVERY") ? std::max(1, std::min(5, atoi(getenv("MTR_SIM_SHORT_EVERY")))) : 1, long_every};
+    int due[kQueues];
+    for (int i = 0; i < kQueues; i++) due[i] = -1;             // wave at which the queue's results arrive (-1: free)
     int wave = 0;
     while (P.ctr->unfinished > 0 && !P.ctr->error) {
         wave++;
-        if (long_pending >= 0 && wave >= long_due) { run_dp_tasks(ctx, P, QLs[long_pending], o); long_pending = -1; }
-        const int li = long_pending < 0 ? wave % kLongInst : -1;
-        const DpQueue &QL = li >= 0 ? QLs[li] : none;
-        wave_begin(P, QL);
+        for (int i = 0; i < kQueues; i++) if (due[i] >= 0 && wave >= due[i]) { run_dp_tasks(ctx, P, Qs[i], o); due[i] = -1; }
+        int qi[2] = {-1, -1};
+        for (int k = 0; k < kShortInst && qi[0] < 0; k++) { const int i = (wave + k) % kShortInst; if (due[i] < 0) qi[0] = i; }
+        for (int k = 0; k < kLongInst && qi[1] < 0; k++) { const int i = kShortInst + (wave + k) % kLongInst; if (due[i] < 0) qi[1] = i; }
+        if (every[0] > 1 && wave % 3 == 0) qi[0] = -1;          // now and then no queue is free at all
+        if (every[1] > 1 && wave % 4 == 0) qi[1] = -1;
+        const DpQueue &QS = qi[0] >= 0 ? Qs[qi[0]] : none, &QL = qi[1] >= 0 ? Qs[qi[1]] : none;
+        wave_begin(P, QS, QL);
         for (int c = 0; c < lay.n_chains; c++) if (chain_ready(P, c)) advance_chain(P, c);
         for (int i = 0; i < P.ctr->n_polish; i++) polish_chain(P, P.polish_list[i], S, cta, smem.data());
-        for (int r = 0; r < n; r++) sched_read(P, r, inline_tab.data(), kInlineSlots, sh);
+        for (int r = 0; r < n_slots; r++) sched_read(P, r, inline_tab.data(), kInlineSlots, sh);
         // the walk queue: with MTR_SIM_WALK_LAG = n the entries pushed by a scheduler pass are only walked n waves later,
         // like walks that are still running when the next passes start (dropped candidates then meet chains in ST_WALK)
         {
@@ -163,24 +178,32 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             const unsigned limit = (int)tails.size() > lag ? tails[tails.size() - 1 - (size_t)lag] : 0u;
             while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(P, P.walk_ring[P.ctr->walk_head++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
         }
-        for (int c = 0; c < lay.n_chains; c++) emit_chain(P, QL, c);
-        for (int qi = 0; qi < 2; qi++) {
-            const DpQueue &Q = qi == 0 ? P.q : QL;
-            if (!Q.tasks_in) continue;
+        // (one thread per chain on the GPU, in any order: MTR_SIM_EMIT_ORDER = 1 emits in descending, 2 in a scrambled order)
+        {
+            static const int order = getenv("MTR_SIM_EMIT_ORDER") ? atoi(getenv("MTR_SIM_EMIT_ORDER")) : 0;
+            const int nc = lay.n_chains;
+            if (order == 0) for (int c = 0; c < nc; c++) emit_chain(P, QS, QL, c);
+            else if (order == 1) for (int c = nc - 1; c >= 0; c--) emit_chain(P, QS, QL, c);
+            else {
+                long long step = 7919;
+                while (std::__gcd((long long)nc, step) != 1) step++;
+                for (long long i = 0, c = (wave * 31) % nc; i < nc; i++, c = (c + step) % nc) emit_chain(P, QS, QL, (int)c);
+            }
+        }
+        for (int k = 0; k < 2; k++) {
+            if (qi[k] < 0) continue;
+            const DpQueue &Q = Qs[qi[k]];
             plan_tasks(P, Q);
             const int nt = std::min(Q.qc->n_tasks, Q.task_cap);
             for (int i = 0; i < nt; i++) scatter_task(Q, i);
             const long long na = std::min<long long>((long long)Q.qc->aux_used, Q.aux_cap);
             for (long long i = 0; i < na; i++) Q.aux[i] = 0;
-        }
-        run_dp_tasks(ctx, P, P.q, o);
-        if (li >= 0) {
-            if (long_every <= 1) run_dp_tasks(ctx, P, QL, o);
-            else { long_pending = li; long_due = wave + long_every - 1; }
+            if (every[k] <= 1) run_dp_tasks(ctx, P, Q, o);
+            else due[qi[k]] = wave + every[k] - 1;
         }
         const unsigned long long sig = (unsigned long long)(unsigned)P.ctr->dp_pending * 7919ull + P.ctr->tasks_total * 1315423911ull + P.ctr->tables * 2654435761ull + (unsigned)P.ctr->progress * 97ull + (unsigned)P.ctr->unfinished;
         if (sig == last_sig) {
-            if (++idle > 8) { mtr_set_error(ctx, "hostsim engine_run: no progress (wave %d, %d tasks deferred)", P.ctr->waves, P.ctr->deferred); return MTR_ECUDA; }
+            if (++idle > 24) { mtr_set_error(ctx, "hostsim engine_run: no progress (wave %d, %d tasks deferred)", P.ctr->waves, P.ctr->deferred); return MTR_ECUDA; }
         } else idle = 0;
         last_sig = sig;
     }
@@ -199,7 +222,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     if (units) *units = E.units.data();
     export_stats(c, stats);
     if (stats) {                                                // what the real engine would move over PCIe
-        stats->h2d_bytes = (int64_t)sizeof(Read) * n + (int64_t)sizeof(Counters);
+        stats->h2d_bytes = (int64_t)sizeof(ReadDesc) * n + (int64_t)sizeof(Read) * n_slots + (int64_t)sizeof(Counters);
         stats->d2h_bytes = (int64_t)sizeof(Accepted) * c.n_accepted + (int64_t)sizeof(Counters);
     }
     return MTR_OK;

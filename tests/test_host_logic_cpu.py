@@ -67,12 +67,19 @@ def test_host_logic_on_synthetic_cases(sim, synthetic_dir, name):
 def test_grouping_contexts_and_budgets_do_not_change_the_output(sim, synthetic_dir):
     """Group boundaries (the stale state crosses them), the number of engine contexts, the two-device round-robin and
     the per-wave budgets of the engine (direction-matrix bytes, task slots: a chain that does not fit is emitted again
-    by the next wave) are scheduling only: not a byte may change."""
+    by the next wave) and the number of read slots (reads at work at the same time) are scheduling only: not a byte may
+    change."""
     path = os.path.join(synthetic_dir, "mixed.fa")
     ref = DIGESTS["synthetic"]["mixed"]["default"]["md5"]
     for env in ({"MTR_GROUP_READS": "1"}, {"MTR_GROUP_READS": "5", "MTR_GROUPS_PER_GPU": "1"}, {"MTR_GROUP_READS": "3", "MTR_GPUS": "2"},
                 {"MTR_GROUP_READS": "7", "MTR_GROUPS_PER_GPU": "3", "MTR_GPUS": "2"}, {"MTR_ENGINE_DIR_KB": "600"},
-                {"MTR_ENGINE_TASK_CAP": "6", "MTR_GROUP_READS": "4"}):
+                {"MTR_ENGINE_TASK_CAP": "6", "MTR_GROUP_READS": "4"},
+                # read slots: a slot takes the next read of the group when its read has finished
+                {"MTR_ENGINE_SLOTS": "1"}, {"MTR_ENGINE_SLOTS": "3", "MTR_GROUPS_PER_GPU": "2", "MTR_GROUP_READS": "11"},
+                {"MTR_ENGINE_SLOTS": "2", "MTR_ENGINE_LONG_ROWS": "40", "MTR_SIM_LONG_EVERY": "3", "MTR_SIM_WALK_LAG": "2"},
+                # DP queues whose results arrive waves later (and waves that find no free queue at all)
+                {"MTR_SIM_SHORT_EVERY": "3", "MTR_SIM_LONG_EVERY": "5", "MTR_ENGINE_LONG_ROWS": "60"},
+                {"MTR_SIM_SHORT_EVERY": "2", "MTR_SIM_WALK_LAG": "1", "MTR_ENGINE_SLOTS": "4", "MTR_SPECULATE": "3"}):
         assert hashlib.md5(run(sim, [], path, env)).hexdigest() == ref, env
 
 

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 while IFS= read -r line; do
   [ -z "$line" ] && continue
   echo "## $line" >> gpurun_out/${TAG}.log
-  env $line timeout 400 python bench.py --quick --steps $STEPS --warmup $WARM >> gpurun_out/${TAG}.log 2>> gpurun_out/${TAG}.err
+  env $line timeout 150 python bench.py --quick --steps $STEPS --warmup $WARM >> gpurun_out/${TAG}.log 2>> gpurun_out/${TAG}.err
   echo "rc=$?" >> gpurun_out/${TAG}.log
 done
 cat gpurun_out/${TAG}.log
