@@ -241,7 +241,7 @@ def main():
     if a.quick:
         if rank == 0:
             cells = acc["wdp_cells"] - acc["spec_cells"]
-            print(json.dumps({"quick": True, "reads_per_s": round(R * a.steps * world / t_res, 1), "ms_per_step": round(t_res / a.steps * 1e3, 1),
+            print(json.dumps({"quick": True, "cells_run": int(cells), "dir_bytes": int(acc["wdp_dir_bytes"]), "shared_cells_frac": round(acc["shared_cells"] / max(cells + acc["shared_cells"], 1), 3), "reads_per_s": round(R * a.steps * world / t_res, 1), "ms_per_step": round(t_res / a.steps * 1e3, 1),
                               "dp_busy_ms_per_step": round(dp_busy_ms / a.steps, 1), "gcups_busy": round(cells / max(dp_busy_ms, 1e-9) / 1e6, 1),
                               "gcups_wall": round(cells / t_res / 1e9, 1), "waves_per_group": round(acc["waves"] / max(acc["groups"], 1), 1),
                               "groups": acc["groups"], "md5": res_md5, "env": {k: v for k, v in os.environ.items() if k.startswith("MTR_")}}), flush=True)
@@ -279,23 +279,27 @@ def main():
     e2e_md5 = hashlib.md5(out_file).hexdigest()
     clk = clocks.stop()
 
-    # algorithmic cells = what the reference executes: cells spent on look-ahead candidates that were pruned after all
-    # (MTR_SPECULATE) are launched and timed but not counted
+    # cells: `run` = what the K3 kernels computed for candidates the reference visits too (cells of look-ahead candidates that
+    # were pruned after all are launched and timed but not counted); `reference` = what the reference executes for the
+    # same reads = run + the search DPs that were NOT launched because a sibling chain ran the identical DP
     cells = acc["wdp_cells"] - acc["spec_cells"]
+    cells_ref = cells + acc["shared_cells"]
     reads_all = sum_over_ranks(R * a.steps)
     cells_all = sum_over_ranks(cells)
     # K3 time of the timed region: the UNION of the intervals in which fill / traceback kernels of any engine context of this
-    # GPU were running (several groups share the GPU, their K3 phases overlap) -- never more than the wall clock
+    # GPU were running (several queues and contexts share the GPU, their K3 phases overlap) -- never more than the wall clock
     gcups_busy = cells / max(dp_busy_ms, 1e-9) / 1e6
     gcups_wall = cells / t_res / 1e9
     # ceiling: integer-ALU issue rate measured now / instructions per cell: 15 for the int32 kernels, 7.5
-    # for the paired int16x2 kernels (one VIADDMNMX.S16x2 serves both penalty sets); weighted by the cells of each family
+    # for the paired int16x2 kernels (one VIADDMNMX.S16x2 serves both penalty sets); harmonic mix by the cells of each family
     peak_i32 = alu["viaddmnmx_s32"] / I_CELL_INT32
-    peak_gcups = peak_i32
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
+    peak_p16 = alu["viaddmnmx_s16x2"] / (I_CELL_INT32 / 2)
+    f16 = acc["wdp_cells_p16"] / max(acc["wdp_cells"], 1)
+    peak_gcups = 1.0 / ((1.0 - f16) / peak_i32 + f16 / peak_p16)
+    traffic = None
+    try:                                                       # measured DRAM traffic of the fill kernels: profiles/r2_k3_traffic.json (ncu --set full)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_k3_traffic.json")))
+    except (OSError, ValueError):
         pass
 
     line = {
@@ -313,16 +317,18 @@ def main():
                 "output_md5": e2e_md5},
         "gpu_launches": int(acc["launches"]),
         "gcups": {"k3_busy": round(gcups_busy, 2), "whole_job_cells_per_s": round(cells_all / t_res / 1e9, 3),
-                  "algorithmic_cells_per_step": int(cells / a.steps), "speculative_cells_per_step": int(acc["spec_cells"] / a.steps)},
-        "roofline": {"kernel": "wdp_fill_family<int32 | int16x2> + wdp_traceback_dev (K3 wrap-around DP), all launches of the timed region",
+                  "cells_run_per_step": int(cells / a.steps), "cells_reference_per_step": int(cells_ref / a.steps),
+                  "cells_shared_per_step": int(acc["shared_cells"] / a.steps), "speculative_cells_per_step": int(acc["spec_cells"] / a.steps),
+                  "reference_cells_per_s": round(sum_over_ranks(cells_ref) / t_res / 1e9, 3), "int16x2_share_of_cells": round(f16, 3)},
+        "roofline": {"kernel": "wdp_fill_family<int32 | int16x2> (K3 wrap-around DP: fill + fused traceback), all launches of the timed region",
                      "bound": "int-alu", "achieved": round(gcups_busy, 2), "peak": round(peak_gcups, 1), "unit": "GCUPS",
                      "frac": round(gcups_busy / peak_gcups, 4),
-                     "how": "algorithmic cells / union of the K3 kernel intervals of all engine contexts (%.1f ms of %.1f ms wall per step)"
+                     "how": "cells run / union of the K3 kernel intervals of all queues and contexts (%.1f ms of %.1f ms wall per step)"
                             % (dp_busy_ms / a.steps, t_res / a.steps * 1e3),
                      "frac_by_wall": round(gcups_wall / peak_gcups, 4),
-                     "traffic": {"algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3)},
-                     "peak_how": "mtr_alu_probe: %.0f G lane-ops/s VIADDMNMX.RELU measured now / %.0f instr per cell (SURVEY.md 8(d))"
-                                 % (alu["viaddmnmx_s32"], I_CELL_INT32),
+                     "traffic": traffic, "algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3),
+                     "peak_how": "mtr_alu_probe now: %.0f G lane-ops/s VIADDMNMX.RELU / 15 instr per int32 cell = %.0f GCUPS, %.0f G VIADDMNMX.S16x2 / 7.5 per paired cell = %.0f GCUPS, "
+                                 "harmonic mix by the cells of each family (%.0f %% int16x2)" % (alu["viaddmnmx_s32"], peak_i32, alu["viaddmnmx_s16x2"], peak_p16, 100 * f16),
                      "alu_probe_gops": {k: round(v, 1) for k, v in alu.items()}},
         "breakdown_ms_per_step": {"k3_busy_union": round(dp_busy_ms / a.steps, 2),
                                   **{k: round(acc[k] / a.steps, 2) for k in ("dp_ms", "di_kernel_ms", "uf_kernel_ms", "engine_wall_ms", "pack_ms", "chain_ms")}},

@@ -191,6 +191,7 @@ typedef struct {
     int64_t dp_cells;          /* sum rows * ulen over every DP launched (both penalty sets) */
     int64_t dp_slot_cells, dp_dir_bytes;
     int64_t spec_cells;        /* part of dp_cells run for look-ahead candidates that were pruned after all */
+    int64_t dp_cells_p16;      /* part of dp_cells run by the paired int16x2 kernels */
     int64_t shared_cells;      /* cells of DPs the reference runs that were NOT launched: another k (or walk direction) of the same
                                   candidate had found the identical unit, and the identical DP was run once (not in dp_cells) */
     int64_t tables, table_positions, walks;   /* k-mer count tables built, positions counted, greedy walks run */
@@ -255,6 +256,7 @@ typedef struct {
     int64_t wdp_cells, wdp_slot_cells, wdp_dir_bytes;      /* cells = sum rows * ulen over every DP launched */
     int64_t spec_cells;                                    /* part of wdp_cells run for look-ahead candidates that were pruned
                                                               after all (MTR_SPECULATE, default 8): not algorithmic cells */
+    int64_t wdp_cells_p16;                                 /* part of wdp_cells run by the paired int16x2 kernels */
     int64_t shared_cells;                                  /* algorithmic cells NOT launched: identical search DPs of one candidate
                                                               (same window, same unit found for another k) run once */
     int64_t tables, table_positions, walks, repeats;

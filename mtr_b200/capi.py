@@ -57,13 +57,13 @@ class Stats(C.Structure):
 class PipelineStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "reads", "bases", "groups", "candidates", "waves", "jobs", "dp_tasks", "wdp_cells", "wdp_slot_cells", "wdp_dir_bytes",
-        "spec_cells", "shared_cells", "tables", "table_positions", "walks", "repeats", "h2d_bytes", "d2h_bytes", "launches")] + \
+        "spec_cells", "wdp_cells_p16", "shared_cells", "tables", "table_positions", "walks", "repeats", "h2d_bytes", "d2h_bytes", "launches")] + \
         [(n, C.c_double) for n in ("dp_ms", "di_kernel_ms", "uf_kernel_ms", "engine_wall_ms", "pack_ms", "chain_ms", "wall_ms")]
 
 
 class EngineStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
-        "waves", "candidates", "dp_jobs", "dp_tasks", "dp_cells", "dp_slot_cells", "dp_dir_bytes", "spec_cells", "shared_cells", "tables",
+        "waves", "candidates", "dp_jobs", "dp_tasks", "dp_cells", "dp_slot_cells", "dp_dir_bytes", "spec_cells", "dp_cells_p16", "shared_cells", "tables",
         "table_positions", "walks", "repeats", "wrapdp_messages", "launches", "h2d_bytes", "d2h_bytes")] + \
         [(n, C.c_double) for n in ("di_ms", "dp_ms", "uf_ms", "wall_ms")]
 

@@ -354,6 +354,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     if (const char *e = getenv("MTR_ENGINE_DIR_MB")) cfg.dir_cap = std::max(64LL, atoll(e)) << 20;
     if (const char *e = getenv("MTR_ENGINE_LONG_DIR_MB")) cfg.long_dir_cap = std::max(64LL, atoll(e)) << 20;
     if (const char *e = getenv("MTR_ENGINE_LONG_ROWS")) cfg.long_rows = std::max(1, atoi(e));
+    if (const char *e = getenv("MTR_ENGINE_COMPACT_CAP")) cfg.compact_cap = (unsigned)std::max(64, std::min((int)kCompactCap, atoi(e)));
     int n_short = kShortInst, n_long = kLongInst;            // queues in use (fewer: less memory, more deferred emissions)
     if (const char *e = getenv("MTR_ENGINE_SHORT_QUEUES")) n_short = std::max(1, std::min(kShortInst, atoi(e)));
     if (const char *e = getenv("MTR_ENGINE_LONG_QUEUES")) n_long = std::max(1, std::min(kLongInst, atoi(e)));

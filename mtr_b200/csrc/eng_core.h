@@ -114,6 +114,7 @@ struct Counters {
     int unfinished, error, error_read, n_accepted;
     int deferred, msgs, waves, progress;
     int next_read, pad1;           // reads of the batch handed to slots so far
+    unsigned long long cells_p16;      // part of `cells` run by the paired int16x2 kernels (both penalty sets in one register)
     unsigned long long shared_cells;   // cells of search DPs that were not run because a sibling chain ran the identical DP
     unsigned long long cells, slot_cells, spec_cells, jobs, candidates, tables, walks, table_positions, dir_bytes, tasks_total;
     // profile (clock64 ticks, thread 0 / lane 0 of the walking warps): table build, node list, walks per direction; walk steps; tasks per table layout
@@ -252,8 +253,8 @@ MTR_DEV int cta_bcast(const Cta &c, int v, int slot)           // value of threa
 //            probes into the by then frozen table, go through a direct-mapped (node -> count) CACHE in shared memory
 //            (an L2 round trip costs ~700 cycles, a shared-memory hit ~30)
 enum { TB_WIDE = 0, TB_COMPACT = 1, TB_DIRECT = 2 };
-constexpr int kUfSmemWords = 8192;                       // 32 KB of table / cache per unit-finder cta
-constexpr unsigned kCompactCap = 4096;                   // slots of a COMPACT table: 4096 * 6 B = 24 KB
+constexpr int kUfSmemWords = 24576;                      // 96 KB of table / cache per unit-finder cta
+constexpr unsigned kCompactCap = 16384;                  // slots of a COMPACT table: 16384 * 6 B = 96 KB (windows up to 12286 positions)
 constexpr unsigned kCacheSlots = 4096;                   // 64-bit entries of the probe cache
 struct Table {
     unsigned long long *slots;      // WIDE
@@ -1146,6 +1147,7 @@ MTR_DEV bool emit_tasks(const Ptrs &P, const DpQueue &Q, int chain, const TaskSp
         atomic_add(&Q.hist[seg_of(t.cls, t.rows)], 1);
         results += sp[i].n_param;
         cells += (long long)t.rows * t.ulen * sp[i].n_param;
+        if (paired[i]) atomic_add(&P.ctr->cells_p16, (unsigned long long)((long long)t.rows * t.ulen * 2));
         atomic_add(&P.ctr->slot_cells, (unsigned long long)((long long)t.rows * kClassCap[cls] * sp[i].n_param));
     }
     atomic_add(&P.ctr->cells, (unsigned long long)cells);

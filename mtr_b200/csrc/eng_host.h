@@ -189,7 +189,7 @@ inline void export_stats(const Counters &c, mtr_engine_stats *s)
     if (!s) return;
     s->waves = c.waves; s->candidates = (int64_t)c.candidates; s->dp_jobs = (int64_t)c.jobs; s->dp_tasks = (int64_t)c.tasks_total;
     s->dp_cells = (int64_t)c.cells; s->dp_slot_cells = (int64_t)c.slot_cells; s->dp_dir_bytes = (int64_t)c.dir_bytes;
-    s->spec_cells = (int64_t)c.spec_cells; s->shared_cells = (int64_t)c.shared_cells; s->tables = (int64_t)c.tables; s->table_positions = (int64_t)c.table_positions;
+    s->spec_cells = (int64_t)c.spec_cells; s->shared_cells = (int64_t)c.shared_cells; s->dp_cells_p16 = (int64_t)c.cells_p16; s->tables = (int64_t)c.tables; s->table_positions = (int64_t)c.table_positions;
     s->walks = (int64_t)c.walks; s->repeats = c.n_accepted; s->wrapdp_messages = c.msgs;
 }
 

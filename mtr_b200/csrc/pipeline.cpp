@@ -554,7 +554,7 @@ void run_group(mtr_ctx *ctx, Group &g, int print_alignment, int manhattan, float
     g.ps.chain_ms = (now_s() - tc0) * 1e3;
     g.ps.candidates += es.candidates; g.ps.waves += es.waves; g.ps.jobs += es.dp_jobs; g.ps.dp_tasks += es.dp_tasks;
     g.ps.wdp_cells += es.dp_cells; g.ps.wdp_slot_cells += es.dp_slot_cells; g.ps.wdp_dir_bytes += es.dp_dir_bytes;
-    g.ps.spec_cells += es.spec_cells; g.ps.shared_cells += es.shared_cells; g.ps.tables += es.tables; g.ps.table_positions += es.table_positions; g.ps.walks += es.walks;
+    g.ps.spec_cells += es.spec_cells; g.ps.shared_cells += es.shared_cells; g.ps.wdp_cells_p16 += es.dp_cells_p16; g.ps.tables += es.tables; g.ps.table_positions += es.table_positions; g.ps.walks += es.walks;
     g.ps.repeats += es.repeats; g.ps.launches += es.launches;
     g.ps.dp_ms += es.dp_ms; g.ps.di_kernel_ms += es.di_ms; g.ps.uf_kernel_ms += es.uf_ms; g.ps.engine_wall_ms += es.wall_ms;
 }
@@ -563,7 +563,7 @@ void add_stats(mtr_pipeline_stats &t, const mtr_pipeline_stats &p)
 {
     t.reads += p.reads; t.bases += p.bases; t.candidates += p.candidates; t.waves += p.waves; t.groups += p.groups; t.jobs += p.jobs;
     t.dp_tasks += p.dp_tasks; t.wdp_cells += p.wdp_cells; t.wdp_slot_cells += p.wdp_slot_cells; t.wdp_dir_bytes += p.wdp_dir_bytes;
-    t.spec_cells += p.spec_cells; t.shared_cells += p.shared_cells; t.tables += p.tables; t.table_positions += p.table_positions; t.walks += p.walks; t.repeats += p.repeats;
+    t.spec_cells += p.spec_cells; t.shared_cells += p.shared_cells; t.wdp_cells_p16 += p.wdp_cells_p16; t.tables += p.tables; t.table_positions += p.table_positions; t.walks += p.walks; t.repeats += p.repeats;
     t.h2d_bytes += p.h2d_bytes; t.d2h_bytes += p.d2h_bytes; t.launches += p.launches;
     t.dp_ms += p.dp_ms; t.di_kernel_ms += p.di_kernel_ms; t.uf_kernel_ms += p.uf_kernel_ms; t.engine_wall_ms += p.engine_wall_ms;
     t.pack_ms += p.pack_ms; t.chain_ms += p.chain_ms;
