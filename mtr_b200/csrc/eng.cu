@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(128) eng_advance(Ptrs P, int n_chains)
     const int nw = gridDim.x * (blockDim.x >> 5);
     for (int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < n_chains; base += nw * 32) {
         const int mine = base + lane();
+        if (mine < n_chains) take_shared(P, mine);
         unsigned m = wballot(mine < n_chains && chain_ready(P, mine));
         while (m) {
             const int c = base + ffs(m) - 1;
@@ -52,13 +53,13 @@ __global__ void __launch_bounds__(128) eng_advance(Ptrs P, int n_chains)
 // walk / polish kernels: one block (four warps) per task, persistent blocks pulling from a list; shared memory = 16 ints
 // of cta scratch + 32 KB for the count table (DIRECT / COMPACT) or for the probe cache of a WIDE table
 template <int WHICH>      // 0: walks (queue entries below the tail seen at the start), 1: polish
-__global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0)
+__global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0, int table_words, int big)
 {
     __shared__ int sh[16];
-    extern __shared__ __align__(16) unsigned char uf_dyn[];     // kUfDynSmem bytes: count table | near tie lists | walk memos
+    extern __shared__ __align__(16) unsigned char uf_dyn[];     // count table (table_words words) | near tie lists | walk memos
     unsigned *tab = (unsigned *)uf_dyn;
-    int *near = (int *)(uf_dyn + kUfSmemWords * 4);
-    MemoEntry *memos = (MemoEntry *)(uf_dyn + kUfSmemWords * 4 + 4 * kTiesNear * 4);   // zeroed once: epoch 0 is never current
+    int *near = (int *)(uf_dyn + (size_t)table_words * 4);
+    MemoEntry *memos = (MemoEntry *)(uf_dyn + (size_t)table_words * 4 + 4 * kTiesNear * 4);   // zeroed once: epoch 0 is never current
     if (WHICH == 0) { for (int i = threadIdx.x; i < 2 * kMemoSlots; i += blockDim.x) memos[i].epoch = 0u; __syncthreads(); }
     const Cta c = cta_of_block(sh);
     const Scratch S = scratch_of(P, slice0 + blockIdx.x);
@@ -75,14 +76,16 @@ __global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0)
         return;
     }
     // every entry below `limit` was written before this instance was launched (later ones belong to later instances)
-    const unsigned limit = *(volatile unsigned *)&P.ctr->walk_tail;
+    unsigned *tail = big ? &P.ctr->walk_tail_big : &P.ctr->walk_tail, *head = big ? &P.ctr->walk_head_big : &P.ctr->walk_head;
+    const int *ring = big ? P.walk_ring_big : P.walk_ring;
+    const unsigned limit = *(volatile unsigned *)tail;
     for (;;) {
         int chain = -1;
         if (c.tid == 0) {
-            unsigned h = *(volatile unsigned *)&P.ctr->walk_head;
+            unsigned h = *(volatile unsigned *)head;
             while ((int)(limit - h) > 0) {
-                const unsigned seen = atomicCAS(&P.ctr->walk_head, h, h + 1u);
-                if (seen == h) { chain = P.walk_ring[h & P.walk_ring_mask]; break; }
+                const unsigned seen = atomicCAS(head, h, h + 1u);
+                if (seen == h) { chain = ring[h & P.walk_ring_mask]; break; }
                 h = seen;
             }
         }
@@ -139,7 +142,7 @@ __global__ void eng_publish(Ptrs P, DpQueue QS, DpQueue QL, EngSnapshot *snap)
     const Counters &c = *P.ctr;
     snap->error = c.error; snap->error_read = c.error_read; snap->deferred = c.deferred; snap->waves = c.waves;
     snap->n_accepted = c.n_accepted;
-    snap->in_flight = (int)(c.walk_tail - c.walk_head) + c.walks_running + c.dp_pending;
+    snap->in_flight = (int)(c.walk_tail - c.walk_head) + (int)(c.walk_tail_big - c.walk_head_big) + c.walks_running + c.dp_pending;
     for (int i = 0; i < 2; i++) {
         const DpQueue &Q = i == 0 ? QS : QL;
         const bool on = Q.tasks_in != nullptr;
@@ -151,6 +154,12 @@ __global__ void eng_publish(Ptrs P, DpQueue QS, DpQueue QL, EngSnapshot *snap)
     snap->progress_sig = c.tables + (unsigned long long)(unsigned)c.progress + ((unsigned long long)(unsigned)c.walks_done << 32) + ((unsigned long long)(unsigned)c.next_read << 16);
     __threadfence_system();
     snap->unfinished = c.unfinished;
+}
+
+__global__ void __launch_bounds__(256) eng_unshare(Ptrs P, int n_chains)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_chains) unshare_chain(P, c);
 }
 
 // diagnostic for the "no progress" failure: the chains that are neither free nor done, and the candidates of their reads
@@ -182,7 +191,7 @@ struct EngState {
     Layout lay;
     Ptrs P;
     int speculate = 8;
-    cudaStream_t walk_stream[4] = {};      // walk kernel instances run here, beside everything else
+    cudaStream_t walk_stream[4] = {}, walk_stream_big[4] = {};      // walk kernel instances run here, beside everything else
     cudaEvent_t sched_done[4] = {};
     bool ready = false;
     std::vector<mtr_repeat> reps;
@@ -203,7 +212,7 @@ void eng_state_free(mtr_ctx *ctx)
     if (e->tick) cudaStreamDestroy(e->tick);
     if (e->tick_done) cudaEventDestroy(e->tick_done);
     e->h_snap.release(); e->h_acc.release(); e->h_ctr.release();
-    for (int i = 0; i < 4; i++) { if (e->walk_stream[i]) cudaStreamDestroy(e->walk_stream[i]); if (e->sched_done[i]) cudaEventDestroy(e->sched_done[i]); }
+    for (int i = 0; i < 4; i++) { if (e->walk_stream[i]) cudaStreamDestroy(e->walk_stream[i]); if (e->walk_stream_big[i]) cudaStreamDestroy(e->walk_stream_big[i]); if (e->sched_done[i]) cudaEventDestroy(e->sched_done[i]); }
     delete e;
     ctx->eng = nullptr;
 }
@@ -300,6 +309,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         }
         for (int i = 0; i < 4; i++) {
             MTR_CUDA(ctx, cudaStreamCreateWithPriority(&E.walk_stream[i], cudaStreamNonBlocking, mid));
+            MTR_CUDA(ctx, cudaStreamCreateWithPriority(&E.walk_stream_big[i], cudaStreamNonBlocking, mid));
             MTR_CUDA(ctx, cudaEventCreateWithFlags(&E.sched_done[i], cudaEventDisableTiming));
         }
         E.ready = true;
@@ -350,6 +360,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     n_slots = cfg.n_reads;
     if (const char *e = getenv("MTR_ENGINE_WALK_STREAMS")) cfg.walk_streams = std::max(1, std::min(4, atoi(e)));
     if (const char *e = getenv("MTR_ENGINE_WALK_CTAS")) cfg.uf_ctas = std::max(1, atoi(e));
+    if (const char *e = getenv("MTR_ENGINE_WALK_CTAS_BIG")) cfg.uf_ctas_big = std::max(1, atoi(e));
     if (const char *e = getenv("MTR_ENGINE_POLISH_CTAS")) cfg.polish_ctas = std::max(1, atoi(e));
     if (const char *e = getenv("MTR_ENGINE_DIR_MB")) cfg.dir_cap = std::max(64LL, atoll(e)) << 20;
     if (const char *e = getenv("MTR_ENGINE_LONG_DIR_MB")) cfg.long_dir_cap = std::max(64LL, atoll(e)) << 20;
@@ -360,7 +371,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     if (const char *e = getenv("MTR_ENGINE_LONG_QUEUES")) n_long = std::max(1, std::min(kLongInst, atoi(e)));
     Layout lay = make_layout(cfg);
     MTR_CUDA(ctx, E.d_main.reserve(lay.total));
-    const size_t n_slices = (size_t)cfg.uf_ctas * (size_t)cfg.walk_streams + (size_t)cfg.polish_ctas;
+    const size_t n_slices = (size_t)(cfg.uf_ctas + cfg.uf_ctas_big) * (size_t)cfg.walk_streams + (size_t)cfg.polish_ctas;
     MTR_CUDA(ctx, E.d_scratch.reserve((size_t)lay.uf_stride * n_slices));
     MTR_CUDA(ctx, E.d_wide.reserve((size_t)lay.table_cap * 8 * n_slices));
     for (int i = 0; i < kQueues; i++) {
@@ -388,6 +399,8 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         P.stamps = (unsigned long long *)E.d_stamps.p;
     }
     E.P = P;
+    Ptrs Psmall = P;                                         // the small-window walk kernel: 32 KB count tables
+    Psmall.compact_cap = std::min(P.compact_cap, kCompactCapSmall);
 
     // zero: chain stages (ST_FREE), lists, counters, histograms, the scratch epochs; then the slots and the reads
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.chains, 0, sizeof(Chain) * (size_t)lay.n_chains, s));
@@ -436,7 +449,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     MTR_CUDA(ctx, cudaFuncSetAttribute(eng_unitfinder<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUfDynSmem));
     cudaEvent_t base = busy_base(ctx->device);
     double dp_ms = 0;
-    long long launches = di_launches, k3_uses = 0, idle_ticks = 0;
+    long long launches = di_launches, k3_uses = 0, idle_ticks = 0, rescues = 0;
     int wave_no = 0, next_short = 0, next_long = 0, quiet = 0;
     unsigned long long last_tasks = ~0ull, last_sig = ~0ull;
     int last_accepted = -1, last_unfinished = -1;
@@ -468,14 +481,18 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         const DpQueue &QS = qi[0] >= 0 ? Qs[qi[0]] : none, &QL = qi[1] >= 0 ? Qs[qi[1]] : none;
         eng_begin<<<1, 32, 0, t>>>(P, QS, QL);
         eng_advance<<<ctx->n_sm * 4, 128, 0, t>>>(P, lay.n_chains);
-        eng_unitfinder<1><<<cfg.polish_ctas, 128, kUfDynSmem, t>>>(P, cfg.uf_ctas * cfg.walk_streams);
+        eng_unitfinder<1><<<cfg.polish_ctas, 128, kUfDynSmem, t>>>(P, (cfg.uf_ctas + cfg.uf_ctas_big) * cfg.walk_streams, kUfSmemWords, 0);
         eng_sched<<<n_slots, 32, 0, t>>>(P);
         {
-            // the walk kernel of this wave: on the next walk stream, behind the scheduler pass, beside everything else
+            // the walk kernels of this wave (small and big windows): on the next walk stream pair, behind the scheduler pass,
+            // beside everything else
             const int ws = wave_no++ % cfg.walk_streams;
             MTR_CUDA(ctx, cudaEventRecord(E.sched_done[ws], t));
             MTR_CUDA(ctx, cudaStreamWaitEvent(E.walk_stream[ws], E.sched_done[ws], 0));
-            eng_unitfinder<0><<<cfg.uf_ctas, 128, kUfDynSmem, E.walk_stream[ws]>>>(P, ws * cfg.uf_ctas);
+            MTR_CUDA(ctx, cudaStreamWaitEvent(E.walk_stream_big[ws], E.sched_done[ws], 0));
+            eng_unitfinder<0><<<cfg.uf_ctas, 128, kUfDynSmemSmall, E.walk_stream[ws]>>>(Psmall, ws * cfg.uf_ctas, kUfSmemWordsSmall, 0);
+            eng_unitfinder<0><<<cfg.uf_ctas_big, 128, kUfDynSmem, E.walk_stream_big[ws]>>>(P, cfg.uf_ctas * cfg.walk_streams + ws * cfg.uf_ctas_big, kUfSmemWords, 1);
+            launches++;
         }
         eng_emit<<<(lay.n_chains + 255) / 256, 256, 0, t>>>(P, QS, QL, lay.n_chains);
         for (int k = 0; k < 2; k++) {
@@ -533,6 +550,9 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         bool any_busy = false;
         for (int i = 0; i < kQueues; i++) any_busy = any_busy || E.q_busy[i];
         if (snap->in_flight == 0 && !any_busy) {
+            // nothing in flight and nothing moves: chains that wait for shared DP results run their own instead (should
+            // never be needed; Counters::unshared says how often it was)
+            if (quiet == 8 || quiet == 32) { eng_unshare<<<(lay.n_chains + 255) / 256, 256, 0, t>>>(P, lay.n_chains); rescues++; }
             if (++quiet > 64) {
                 mtr_set_error(ctx, "engine_run: no progress after wave %d (%d reads unfinished, %d tasks deferred)", snap->waves, snap->unfinished, snap->deferred);
                 if (getenv("MTR_ENGINE_DUMP")) { eng_dump_stuck<<<1, 1, 0, t>>>(P, lay.n_chains); cudaStreamSynchronize(t); }
@@ -554,7 +574,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             while (wall_ms() - w0 < 0.05) std::this_thread::yield();   // walks only: they publish through the chains' stages
         }
     }
-    for (int i = 0; i < cfg.walk_streams; i++) MTR_CUDA(ctx, cudaStreamSynchronize(E.walk_stream[i]));   // walks nobody waits for any more
+    for (int i = 0; i < cfg.walk_streams; i++) { MTR_CUDA(ctx, cudaStreamSynchronize(E.walk_stream[i])); MTR_CUDA(ctx, cudaStreamSynchronize(E.walk_stream_big[i])); }   // walks nobody waits for any more
     for (int i = 0; i < kQueues; i++) MTR_CUDA(ctx, reap(i, true));                                       // ... and DPs of dropped candidates
     s = t;
     Counters *hc = (Counters *)E.h_ctr.p;
@@ -571,6 +591,9 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             fprintf(stderr, "\n");
         }
     }
+    if (prof)
+        fprintf(stderr, "[mtr engine] ctx %p: rescue passes %lld, chains unshared %d\n", (void *)ctx, rescues, hc->unshared);
+    if (rescues > 0 && !prof) fprintf(stderr, "[mtr engine] note: %lld rescue pass(es), %d chain(s) re-ran shared DPs on their own\n", rescues, hc->unshared);
     if (prof)
         fprintf(stderr, "[mtr engine] ctx %p: host ms: launching waves %.1f, waiting for waves %.1f, launching K3 %.1f (%lld uses), idle waves %lld, whole call so far %.1f (di %.1f)\n", (void *)ctx, t_launch, t_wait, t_k3, k3_uses, idle_ticks, wall_ms() - t_wall0, di_ms);
     if (prof)

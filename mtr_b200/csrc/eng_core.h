@@ -79,7 +79,8 @@ struct Chain {                     // one k of one candidate: find_tandem_repeat
     int lead[2];
     int wait_lead;                 // directions still waiting for their leader's results
     int search_done;               // the four search results are final (they stay valid: the revise passes use slot kResRevise)
-    int pad_[2];
+    int no_share;                  // this chain runs its own search DPs (set by unshare_chain)
+    int pad_[1];
 };
 
 struct Cand { int qs, qe, set, spec, min_k, n_k; long long cells; };   // set < 0: no k passed the maxFreq gate
@@ -110,10 +111,12 @@ struct Counters {
     // not the group): sched_read pushes chains at walk_tail, the walk kernel instance launched after a scheduler pass pops
     // below the tail it saw at its start.  Both counters only grow.
     unsigned walk_tail, walk_head;
+    unsigned walk_tail_big, walk_head_big;   // the same for the windows that need the 96 KB count table (their kernel fits one cta per SM)
     int walks_running, walks_done; // chains a walk kernel is working on right now / has finished so far
     int unfinished, error, error_read, n_accepted;
     int deferred, msgs, waves, progress;
-    int next_read, pad1;           // reads of the batch handed to slots so far
+    int next_read;                 // reads of the batch handed to slots so far
+    int unshared;                  // chains taken out of the sharing by a rescue pass (should stay 0)
     unsigned long long cells_p16;      // part of `cells` run by the paired int16x2 kernels (both penalty sets in one register)
     unsigned long long shared_cells;   // cells of search DPs that were not run because a sibling chain ran the identical DP
     unsigned long long cells, slot_cells, spec_cells, jobs, candidates, tables, walks, table_positions, dir_bytes, tasks_total;
@@ -159,6 +162,7 @@ struct Ptrs {
     mtr_wdp_result *results;       // [chain][kResSlots]: search: direction d, penalty set s at 2d + s; revise: slot kResRevise
     int *polish_list;
     int *walk_ring;                // queue of chains in ST_WALK (Counters::walk_tail / walk_head, never reset)
+    int *walk_ring_big;            // ... whose windows need the big shared-memory count table (same size)
     unsigned walk_ring_mask;
     int *aux_of[kQueues];          // aux pools by Chain::aux_q
     int long_rows;                 // tasks with at least this many rows go to a long queue
@@ -254,6 +258,8 @@ MTR_DEV int cta_bcast(const Cta &c, int v, int slot)           // value of threa
 //            (an L2 round trip costs ~700 cycles, a shared-memory hit ~30)
 enum { TB_WIDE = 0, TB_COMPACT = 1, TB_DIRECT = 2 };
 constexpr int kUfSmemWords = 24576;                      // 96 KB of table / cache per unit-finder cta
+constexpr int kUfSmemWordsSmall = 8192;                  // ... of the walk kernel for small windows (32 KB)
+constexpr unsigned kCompactCapSmall = 4096;              // its COMPACT tables: 24 KB, windows up to 3070 positions
 constexpr unsigned kCompactCap = 16384;                  // slots of a COMPACT table: 16384 * 6 B = 96 KB (windows up to 12286 positions)
 constexpr unsigned kCacheSlots = 4096;                   // 64-bit entries of the probe cache
 struct Table {
@@ -511,6 +517,7 @@ MTR_DEV int score_byte(int count) { return count > 254 ? 254 : count; }
 constexpr int kTiesNear = 64;
 struct TieList { int *near, *far; };
 constexpr int kUfDynSmem = kUfSmemWords * 4 + 4 * kTiesNear * 4 + 2 * kMemoSlots * 16;   // dynamic shared memory of a unit-finder cta
+constexpr int kUfDynSmemSmall = kUfSmemWordsSmall * 4 + 4 * kTiesNear * 4 + 2 * kMemoSlots * 16;
 MTR_DEV int tie_get(const TieList &t, int i) { return i < kTiesNear ? t.near[i] : t.far[i]; }
 MTR_DEV void tie_put(const TieList &t, int i, int v) { if (i < kTiesNear) t.near[i] = v; else t.far[i] = v; }
 
@@ -927,6 +934,37 @@ MTR_DEV bool chain_ready(const Ptrs &P, int chain)
     const int st = ch.stage;
     return (st == ST_WAIT_SEARCH || st == ST_WAIT_CONS || st == ST_WAIT_DP) && ldv(&ch.pending) == 0 && ldv(&ch.wait_lead) == 0;
 }
+// one thread: a chain that waits for a leader whose results are final takes them itself (the leader hands them out when
+// it advances; a follower that registers around that moment must not depend on having been seen)
+MTR_DEV void take_shared(const Ptrs &P, int chain)
+{
+    Chain &ch = P.chains[chain];
+    if (ldv(&ch.stage) != (int)ST_WAIT_SEARCH || ldv(&ch.wait_lead) <= 0) return;
+    for (int d = 0; d < 2; d++) {
+        const int ld = ldv(&ch.lead[d]);
+        if (ld < 0) continue;
+        const Chain &o = P.chains[ld / 2];
+        if (!ldv(&o.search_done)) continue;
+        fence();
+        if (atomic_cas(&ch.lead[d], ld, -1) != ld) continue;
+        const mtr_wdp_result *src = P.results + (size_t)(ld / 2) * kResSlots + 2 * (ld % 2);
+        mtr_wdp_result *dst = P.results + (size_t)chain * kResSlots + 2 * d;
+        dst[0] = src[0]; dst[1] = src[1];
+        fence();
+        atomic_add(&ch.wait_lead, -1);
+    }
+}
+// one thread, only while nothing at all is in flight (the host's rescue pass): a chain still waiting for shared results
+// goes back to NEED_SEARCH and will run every one of its search DPs itself -- same results, the sharing is an optimisation
+MTR_DEV void unshare_chain(const Ptrs &P, int chain)
+{
+    Chain &ch = P.chains[chain];
+    if (ch.stage != ST_WAIT_SEARCH || ch.wait_lead <= 0 || ch.pending != 0) return;
+    ch.lead[0] = ch.lead[1] = -1; ch.wait_lead = 0; ch.no_share = 1;
+    ch.stage = ST_NEED_SEARCH;
+    atomic_add(&P.ctr->unshared, 1);
+}
+
 MTR_DEV void advance_chain(const Ptrs &P, int chain)
 {
     Chain &ch = P.chains[chain];
@@ -951,10 +989,10 @@ MTR_DEV void advance_chain(const Ptrs &P, int chain)
                 const int c2 = set0 + q / 2, d2 = q % 2;
                 Chain &o = P.chains[c2];
                 const int ld = c2 != chain && ldv(&o.stage) == (int)ST_WAIT_SEARCH ? ldv(&o.lead[d2]) : -1;
-                if (ld >= 0 && ld / 2 == chain) {
+                // (the follower may be taking the results itself at this moment, see take_shared: whoever clears `lead` delivers)
+                if (ld >= 0 && ld / 2 == chain && atomic_cas(&o.lead[d2], ld, -1) == ld) {
                     mtr_wdp_result *dst = P.results + (size_t)c2 * kResSlots + 2 * d2;
                     dst[0] = res[2 * (ld % 2)]; dst[1] = res[2 * (ld % 2) + 1];
-                    o.lead[d2] = -1;
                     fence();
                     atomic_add(&o.wait_lead, -1);
                 }
@@ -1187,7 +1225,7 @@ MTR_DEV void emit_chain(const Ptrs &P, const DpQueue &QS, const DpQueue &QL, int
             // search tasks are out already (WAIT_SEARCH or later), or -- among those still to be emitted -- lower ones.
             const int period = ch.dir_period[d];
             const unsigned char *mine = unit_ptr(P, chain, U_DIR0 + d);
-            for (int q = 0; q < 2 * kMaxK && follow[d] < 0 && P.share_search; q++) {
+            for (int q = 0; q < 2 * kMaxK && follow[d] < 0 && P.share_search && !ch.no_share; q++) {
                 const int c2 = set0 + q / 2, d2 = q % 2;
                 if (c2 == chain && d2 >= d) continue;
                 const Chain &o = P.chains[c2];
@@ -1545,13 +1583,18 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
                 ch.read = read; ch.qs = qs; ch.qe = qe;
                 ch.dir_found[0] = ch.dir_found[1] = 0; ch.dir_period[0] = ch.dir_period[1] = 0;
                 ch.fatal = 0; ch.msg = 0; ch.ring = pos; ch.aux_off = 0; ch.pending = 0; ch.aux_q = 0;
-                ch.lead[0] = ch.lead[1] = -1; ch.wait_lead = 0; ch.search_done = 0;
+                ch.lead[0] = ch.lead[1] = -1; ch.wait_lead = 0; ch.search_done = 0; ch.no_share = 0;
                 if (pass_mask & (1u << c)) {
                     // a walk kernel may be running right now and may hold a stale queue entry for this very chain (a
                     // cancelled walk of the set's previous owner): the fields first, then the stage
                     fence();
                     atomic_exch(&ch.stage, (int)ST_WALK);
-                    P.walk_ring[atomic_add(&P.ctr->walk_tail, 1u) & P.walk_ring_mask] = chain;
+                    // two walk kernels: 32 KB count tables (DIRECT k <= 7, COMPACT up to 3070 positions; several ctas per SM)
+                    // and 96 KB ones (COMPACT up to 12286 positions; one cta per SM)
+                    if (min_k + c > P.direct_max_k && width > compact_max_n(kCompactCapSmall))
+                        P.walk_ring_big[atomic_add(&P.ctr->walk_tail_big, 1u) & P.walk_ring_mask] = chain;
+                    else
+                        P.walk_ring[atomic_add(&P.ctr->walk_tail, 1u) & P.walk_ring_mask] = chain;
                 } else {
                     rec_clear(ch.rr);
                     ch.stage = ST_DONE;

@@ -15,7 +15,8 @@ struct Config {
     int n_total = 0;             // reads of the batch
     long long total_bases = 0;
     int max_len = 0;
-    int uf_ctas = 0;             // persistent ctas of the walk kernel (each owns a scratch slice and a WIDE table)
+    int uf_ctas = 0;             // persistent ctas of the small-window walk kernel (each owns a scratch slice and a WIDE table)
+    int uf_ctas_big = 0;         // ... of the big-window walk kernel
     int walk_streams = 4;        // walk kernel instances in flight (one scratch bank of uf_ctas slices each)
     int polish_ctas = 0;         // ... of the polish kernel (scratch slices behind the walk banks: it runs beside the walks)
     unsigned compact_cap = kCompactCap;
@@ -31,7 +32,7 @@ struct Config {
 };
 
 struct Layout {
-    size_t reads, descs, chains, units, scores, results, polish_list, walk_ring, acc, ctr, zero_begin, total;
+    size_t reads, descs, chains, units, scores, results, polish_list, walk_ring, walk_ring_big, acc, ctr, zero_begin, total;
     struct Q { size_t tasks_in, tasks, aux, hist, seg_task, seg_slot, bucket_cursor, class_begin, slot_counter, qc; } q[kQueues];
     int n_chains;
     unsigned table_cap;
@@ -47,6 +48,8 @@ inline Config default_config(int n_slots, int n_total, long long total_bases, in
     unsigned cap = 64;
     while (cap < 2u * (unsigned)(max_len + 8)) cap <<= 1;
     c.uf_ctas = (int)std::max<long long>(4, std::min<long long>(n_sm / 2, (1LL << 28) / ((long long)cap * 8)));
+    c.uf_ctas_big = c.uf_ctas;
+    c.uf_ctas = std::max(c.uf_ctas, std::min(2 * n_sm, 4 * c.uf_ctas));   // small windows: several ctas per SM
     c.polish_ctas = std::max(c.uf_ctas, std::min(2 * n_sm, 4 * c.uf_ctas));   // polish runs inside the wave: as wide as the GPU
     const long long n_chains = (long long)n_reads * kSets * kMaxK;
     c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains / 2), 1 << 19);
@@ -77,6 +80,7 @@ inline Layout make_layout(const Config &c)
     l.results = take(sizeof(mtr_wdp_result) * (size_t)std::max(l.n_chains, 1) * kResSlots);
     l.polish_list = take(4 * (size_t)std::max(l.n_chains, 1));
     l.walk_ring = take(4 * (size_t)c.walk_cap);
+    l.walk_ring_big = take(4 * (size_t)c.walk_cap);
     l.acc = take(sizeof(Accepted) * (size_t)c.acc_cap);
     for (int i = 0; i < kQueues; i++) {
         const int cap = i < kShortInst ? c.task_cap : c.long_task_cap;
@@ -132,7 +136,7 @@ inline Ptrs bind(void *base, const Layout &l, const Config &c)
     P.units = b + l.units; P.scores = b + l.scores;
     P.results = (mtr_wdp_result *)(b + l.results);
     P.polish_list = (int *)(b + l.polish_list);
-    P.walk_ring = (int *)(b + l.walk_ring); P.walk_ring_mask = (unsigned)c.walk_cap - 1u;
+    P.walk_ring = (int *)(b + l.walk_ring); P.walk_ring_big = (int *)(b + l.walk_ring_big); P.walk_ring_mask = (unsigned)c.walk_cap - 1u;
     for (int i = 0; i < kQueues; i++) P.aux_of[i] = (int *)(b + l.q[i].aux);
     P.long_rows = c.long_rows;
     P.acc = (Accepted *)(b + l.acc); P.acc_cap = c.acc_cap;

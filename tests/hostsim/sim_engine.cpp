@@ -135,6 +135,8 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     P.min_match_ratio = min_match_ratio;
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
+    Ptrs Psmall = P;
+    Psmall.compact_cap = std::min(P.compact_cap, kCompactCapSmall);
     std::vector<Read> slots;
     std::vector<ReadDesc> descs;
     init_slots(slots, n_slots);
@@ -147,7 +149,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     const Scratch S = scratch_of(P, 0);
     unsigned long long last_sig = ~0ull;
     int idle = 0;
-    std::vector<unsigned> tails;
+    std::vector<unsigned> tails, tails_big;
     DpQueue Qs[kQueues];
     for (int i = 0; i < kQueues; i++) Qs[i] = bind_queue(E.main_buf.data(), lay, cfg, i);
     const DpQueue none = no_queue();
@@ -167,7 +169,7 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
         if (every[1] > 1 && wave % 4 == 0) qi[1] = -1;
         const DpQueue &QS = qi[0] >= 0 ? Qs[qi[0]] : none, &QL = qi[1] >= 0 ? Qs[qi[1]] : none;
         wave_begin(P, QS, QL);
-        for (int c = 0; c < lay.n_chains; c++) if (chain_ready(P, c)) advance_chain(P, c);
+        for (int c = 0; c < lay.n_chains; c++) { take_shared(P, c); if (chain_ready(P, c)) advance_chain(P, c); }
         for (int i = 0; i < P.ctr->n_polish; i++) polish_chain(P, P.polish_list[i], S, cta, smem.data());
         for (int r = 0; r < n_slots; r++) sched_read(P, r, inline_tab.data(), kInlineSlots, sh);
         // the walk queue: with MTR_SIM_WALK_LAG = n the entries pushed by a scheduler pass are only walked n waves later,
@@ -176,7 +178,11 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             static const int lag = getenv("MTR_SIM_WALK_LAG") ? std::min(5, atoi(getenv("MTR_SIM_WALK_LAG"))) : 0;
             tails.push_back(P.ctr->walk_tail);
             const unsigned limit = (int)tails.size() > lag ? tails[tails.size() - 1 - (size_t)lag] : 0u;
-            while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(P, P.walk_ring[P.ctr->walk_head++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
+            while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(Psmall, P.walk_ring[P.ctr->walk_head++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
+            // (the windows that need the big shared-memory count table have a queue and a kernel of their own)
+            tails_big.push_back(P.ctr->walk_tail_big);
+            const unsigned limit_big = (int)tails_big.size() > lag ? tails_big[tails_big.size() - 1 - (size_t)lag] : 0u;
+            while ((int)(limit_big - P.ctr->walk_head_big) > 0) walk_chain(P, P.walk_ring_big[P.ctr->walk_head_big++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
         }
         // (one thread per chain on the GPU, in any order: MTR_SIM_EMIT_ORDER = 1 emits in descending, 2 in a scrambled order)
         {
