@@ -990,9 +990,31 @@ void mtro_freq_2mer(const int *unit, int len, int *f)               /* handle_on
     f[unit[len - 1] * 4 + unit[0]]++;
 }
 
-int mtro_trs_in_neighborhood(const int *a, const int *b, int unit_len_a)   /* k_means_clustering.c:169-180 */
+int mtro_trs_in_neighborhood(const int *a, const int *rep, int rep_period)   /* k_means_clustering.c:169-180 */
 {
+    /* +1 if aTR lies in the neighbourhood of the representative, -1 otherwise: sum_i |a[i] - rep[i]| over the 16 2-mer
+     * frequencies against MH_distance_threshold * repTR.actual_rep_period.  The reference never defines
+     * MH_distance_threshold (the file is dead code and does not compile); 0.3 is the value SURVEY.md App. A records. */
     int diff = 0;
-    for (int i = 0; i < 16; i++) diff += a[i] > b[i] ? a[i] - b[i] : b[i] - a[i];
-    return diff <= 0.3 * unit_len_a;
+    for (int i = 0; i < 16; i++) diff += a[i] > rep[i] ? a[i] - rep[i] : rep[i] - a[i];
+    return (0.3 * rep_period < diff) ? -1 : 1;
+}
+
+int mtro_cmp_tr(int period_a, const int *f2_a, int units_a, int rep_freq_a, int rep_id_a,
+                int period_b, const int *f2_b, int units_b, int rep_freq_b, int rep_id_b, int mode)   /* k_means_clustering.c:62-101 */
+{
+    if (mode == 0 || mode == 1) {
+        int diff = period_a - period_b;                        /* <actual_rep_period, freq_2mer [, Num_freq_unit]> */
+        if (diff != 0) return diff;
+        for (int i = 0; i < 16; i++) {
+            diff = f2_a[i] - f2_b[i];
+            if (diff != 0) return diff;
+        }
+        return mode == 1 ? units_a - units_b : 0;
+    }
+    if (mode == 2) {                                            /* <frequency descending, identifier> of the representatives */
+        const int diff = -(rep_freq_a - rep_freq_b);
+        return diff == 0 ? rep_id_a - rep_id_b : diff;
+    }
+    return 0;
 }

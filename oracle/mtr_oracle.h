@@ -96,7 +96,9 @@ int mtro_min_missing_raw(int i, int j, int k);
 
 /* TRs_in_neighborhood / cmp_TR of the dead k_means_clustering.c (:169-180, :62-101), restated for
  * completeness. */
-int mtro_trs_in_neighborhood(const int *freq2mer_a, const int *freq2mer_b, int unit_len_a);
+int mtro_trs_in_neighborhood(const int *freq2mer_a, const int *freq2mer_rep, int rep_period);   /* +1 / -1 */
+int mtro_cmp_tr(int period_a, const int *f2_a, int units_a, int rep_freq_a, int rep_id_a,
+                int period_b, const int *f2_b, int units_b, int rep_freq_b, int rep_id_b, int mode);
 void mtro_freq_2mer(const int *unit, int len, int *freq16);
 
 /* Counters for the roofline denominators. */

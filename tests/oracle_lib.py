@@ -71,6 +71,9 @@ def lib():
         L.mtro_set_output.argtypes = [C.c_void_p, C.c_void_p]
         L.mtro_trs_in_neighborhood.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.mtro_freq_2mer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.mtro_trs_in_neighborhood.restype = C.c_int
+        L.mtro_cmp_tr.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mtro_cmp_tr.restype = C.c_int
         _lib = L
     return _lib
 

@@ -176,3 +176,25 @@ def test_speculative_look_ahead_does_not_change_the_output(synthetic_dir, shippe
         for mode, flags in golden_cases.MODES.items():
             out = run(MTR, flags, path, {"MTR_SPECULATE": spec})
             assert hashlib.md5(out).hexdigest() == want[mode]["md5"], (path, mode, spec, explain(out, flags, path))
+
+
+REFMAIN = os.path.join(ROOT, "bin", "mTR_refmain")
+
+
+@pytest.mark.skipif(not os.path.exists(REFMAIN), reason="bin/mTR_refmain is built where the reference sources are (__graft_entry__.build)")
+def test_reference_main_linked_against_the_cuda_library(shipped_dir):
+    """The reference's own main.c (unmodified; compiled from /root/reference by __graft_entry__.build, -fcommon) linked
+    against libmtr_b200.so: same bytes as the reference in every mode, and its -c report (main.c:108-121) shows the
+    library's timers and query counter -- the globals main.c declares are the ones the library updates."""
+    for name in ("10_20.fasta", "worm_chrII_1.fasta"):
+        path = os.path.join(shipped_dir, name)
+        for mode, flags in golden_cases.MODES.items():
+            out = run(REFMAIN, flags, path)
+            assert hashlib.md5(out).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode, explain(out, flags, path))
+    p = subprocess.run([REFMAIN, "-c", os.path.join(shipped_dir, "10_20.fasta")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert p.returncode == 0
+    report = dict((l.split("\t")[-1], l.strip().split("\t")[0]) for l in p.stderr.decode().splitlines() if "\t" in l)
+    assert int(report["Count of queries"]) > 0, report
+    for key in ("all", "ranges", "Computing periods", "wrap around", "count table generation", "Initialize the input", "chaining"):
+        assert key in report, report
+    assert float(report["Computing periods"]) > 0 and float(report["wrap around"]) > 0 and float(report["ranges"]) > 0, report
