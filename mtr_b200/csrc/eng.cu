@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0, int ta
     }
     // every entry below `limit` was written before this instance was launched (later ones belong to later instances)
     unsigned *tail = big ? &P.ctr->walk_tail_big : &P.ctr->walk_tail, *head = big ? &P.ctr->walk_head_big : &P.ctr->walk_head;
-    const int *ring = big ? P.walk_ring_big : P.walk_ring;
+    int *ring = big ? P.walk_ring_big : P.walk_ring;
     const unsigned limit = *(volatile unsigned *)tail;
     for (;;) {
         int chain = -1;
@@ -85,7 +85,17 @@ __global__ void __launch_bounds__(128) eng_unitfinder(Ptrs P, int slice0, int ta
             unsigned h = *(volatile unsigned *)head;
             while ((int)(limit - h) > 0) {
                 const unsigned seen = atomicCAS(head, h, h + 1u);
-                if (seen == h) { chain = ring[h & P.walk_ring_mask]; break; }
+                if (seen == h) {
+                    // A pusher takes its place in the queue first (tail) and writes the entry second; this instance may
+                    // have started while a later scheduler pass was between the two.  Entries start as -1 and are set
+                    // back to -1 when taken, so "not written yet" is visible: wait the few cycles.
+                    volatile int *slot = (volatile int *)&ring[h & P.walk_ring_mask];
+                    int v;
+                    while ((v = *slot) < 0) { }
+                    *slot = -1;
+                    chain = v;
+                    break;
+                }
                 h = seen;
             }
         }
@@ -154,6 +164,19 @@ __global__ void eng_publish(Ptrs P, DpQueue QS, DpQueue QL, EngSnapshot *snap)
     snap->progress_sig = c.tables + (unsigned long long)(unsigned)c.progress + ((unsigned long long)(unsigned)c.walks_done << 32) + ((unsigned long long)(unsigned)c.next_read << 16);
     __threadfence_system();
     snap->unfinished = c.unfinished;
+}
+
+// expected work of a read: the summed widths of its candidate ranges (one warp per read)
+__global__ void __launch_bounds__(128) eng_read_weight(const int *__restrict__ end, const long long *__restrict__ pos_off, const int *__restrict__ len, int n, long long *out)
+{
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const int L = len[r];
+    const int *e = end + pos_off[r];
+    long long sum = 0;
+    for (int i = lane(); i < L; i += 32) { const int q = e[i]; if (q > -1 && q < L) sum += q - i + 1; }
+    sum = wsum(sum);
+    if (lane() == 0) out[r] = sum;
 }
 
 __global__ void __launch_bounds__(256) eng_unshare(Ptrs P, int n_chains)
@@ -406,10 +429,29 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.chains, 0, sizeof(Chain) * (size_t)lay.n_chains, s));
     MTR_CUDA(ctx, cudaMemsetAsync((char *)E.d_main.p + lay.zero_begin, 0, lay.total - lay.zero_begin, s));
     MTR_CUDA(ctx, cudaMemsetAsync(E.d_scratch.p, 0, (size_t)lay.uf_stride * n_slices, s));
+    MTR_CUDA(ctx, cudaMemsetAsync(P.walk_ring, 0xff, 4 * (size_t)cfg.walk_cap, s));            // walk queues: every entry "not written" (-1)
+    MTR_CUDA(ctx, cudaMemsetAsync(P.walk_ring_big, 0xff, 4 * (size_t)cfg.walk_cap, s));
     std::vector<Read> slots;
     std::vector<ReadDesc> descs;
     init_slots(slots, n_slots);
-    init_descs(descs, ctx->word_off.data() + first, ctx->len.data() + first, n);
+    // the slots take the reads heaviest first (summed widths of the candidate ranges): the reads with the longest chains
+    // of dependent DPs start early instead of making the group's tail
+    std::vector<int> order((size_t)n);
+    for (int r = 0; r < n; r++) order[r] = r;
+    if (n > n_slots / 2 && !getenv("MTR_ENGINE_INPUT_ORDER")) {
+        DevBuf d_w8, d_pos, d_len;
+        std::vector<long long> w8((size_t)n), pos_rel((size_t)n);
+        for (int r = 0; r < n; r++) pos_rel[r] = pos_off[first + r];
+        MTR_CUDA(ctx, d_w8.reserve(8 * (size_t)n)); MTR_CUDA(ctx, d_pos.reserve(8 * (size_t)n)); MTR_CUDA(ctx, d_len.reserve(4 * (size_t)n));
+        MTR_CUDA(ctx, cudaMemcpyAsync(d_pos.p, pos_rel.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, s));
+        MTR_CUDA(ctx, cudaMemcpyAsync(d_len.p, ctx->len.data() + first, 4 * (size_t)n, cudaMemcpyHostToDevice, s));
+        eng_read_weight<<<(n + 3) / 4, 128, 0, s>>>((const int *)E.d_end.p, (const long long *)d_pos.p, (const int *)d_len.p, n, (long long *)d_w8.p);
+        MTR_CUDA(ctx, cudaMemcpyAsync(w8.data(), d_w8.p, 8 * (size_t)n, cudaMemcpyDeviceToHost, s));
+        MTR_CUDA(ctx, mtr_sync(ctx));
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return w8[a] > w8[b]; });
+        d_w8.release(); d_pos.release(); d_len.release();
+    }
+    init_descs(descs, ctx->word_off.data() + first, ctx->len.data() + first, n, order.data());
     MTR_CUDA(ctx, cudaMemcpyAsync(P.reads, slots.data(), sizeof(Read) * (size_t)n_slots, cudaMemcpyHostToDevice, s));
     MTR_CUDA(ctx, cudaMemcpyAsync((void *)P.descs, descs.data(), sizeof(ReadDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
     {

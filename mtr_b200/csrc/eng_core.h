@@ -87,7 +87,7 @@ struct Cand { int qs, qe, set, spec, min_k, n_k; long long cells; };   // set < 
 
 // A Read is a SLOT: it holds one read of the resident batch at a time and takes the next unstarted one (Counters::next_read)
 // as soon as its read has finished, so that every wave works on n_slots reads until the batch runs out.
-struct ReadDesc { long long word_off, pos_off; int L, pad; };   // one read of the resident batch (packed words, directional-index arrays)
+struct ReadDesc { long long word_off, pos_off; int L, id; };   // one read of the resident batch (packed words, directional-index arrays, index in the batch); slots take them in array order
 
 struct Read {
     long long word_off, pos_off;
@@ -1413,7 +1413,7 @@ MTR_DEV void sched_read(const Ptrs &P, int read, unsigned long long *table_mem, 
         if (idx >= P.n_total) return;
         const ReadDesc d = P.descs[idx];
         ENG_LANE0(rs.word_off = d.word_off; rs.pos_off = d.pos_off; rs.L = d.L; rs.cursor = 0; rs.head = 0; rs.n_ring = 0;
-                  rs.n_accepted = 0; rs.candidates = 0; rs.id = idx; rs.zombie_mask = 0u; rs.cells_wasted = 0; rs.phase = 0);
+                  rs.n_accepted = 0; rs.candidates = 0; rs.id = d.id; rs.zombie_mask = 0u; rs.cells_wasted = 0; rs.phase = 0);
         wsync();
     }
     const uint32_t *rd = P.packed + rs.word_off;

@@ -148,14 +148,17 @@ inline Ptrs bind(void *base, const Layout &l, const Config &c)
 }
 
 // the reads of the batch (host side; copied into the group's buffer) and the initial state of the slots: all free
-inline void init_descs(std::vector<ReadDesc> &out, const int64_t *word_off, const int32_t *len, int n)
+inline void init_descs(std::vector<ReadDesc> &out, const int64_t *word_off, const int32_t *len, int n, const int *order = nullptr)
 {
+    // order: the sequence in which the slots take the reads (heaviest first keeps the tail of a group short); ids stay
+    // the reads' positions in the batch, so nothing downstream sees the order
+    std::vector<long long> pos((size_t)n + 1, 0);
+    for (int r = 0; r < n; r++) pos[r + 1] = pos[r] + len[r];
     out.assign((size_t)n, ReadDesc());
-    long long pos = 0;
-    for (int r = 0; r < n; r++) {
-        ReadDesc &d = out[r];
-        d.word_off = word_off[r]; d.pos_off = pos; d.L = len[r]; d.pad = 0;
-        pos += len[r];
+    for (int i = 0; i < n; i++) {
+        const int r = order ? order[i] : i;
+        ReadDesc &d = out[i];
+        d.word_off = word_off[r]; d.pos_off = pos[r]; d.L = len[r]; d.id = r;
     }
 }
 inline void init_slots(std::vector<Read> &out, int n_slots)

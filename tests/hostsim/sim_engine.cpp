@@ -43,6 +43,15 @@ extern "C" int mtr_engine_set_speculate(mtr_ctx *ctx, int depth)
 
 extern "C" double mtr_engine_dp_busy_ms(int, int) { return 0.0; }
 
+// walk-queue entries start as -1 and go back to -1 when taken (eng.cu: a taker waits for an entry that is still being written)
+static int take_entry(int *ring, unsigned at)
+{
+    const int v = ring[at];
+    if (v < 0) { fprintf(stderr, "hostsim: walk queue entry %u taken before it was written\n", at); abort(); }
+    ring[at] = -1;
+    return v;
+}
+
 static void run_dp_tasks(mtr_ctx *ctx, const Ptrs &P, const DpQueue &Q, mtro_ctx *o)
 {
     const int total = Q.class_begin[WDP_NCLASS];
@@ -135,12 +144,16 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     P.min_match_ratio = min_match_ratio;
     P.speculate = E.speculate;
     if (const char *e = getenv("MTR_SPECULATE")) P.speculate = std::max(0, atoi(e));
+    for (int i = 0; i < cfg.walk_cap; i++) { P.walk_ring[i] = -1; P.walk_ring_big[i] = -1; }
     Ptrs Psmall = P;
     Psmall.compact_cap = std::min(P.compact_cap, kCompactCapSmall);
     std::vector<Read> slots;
     std::vector<ReadDesc> descs;
     init_slots(slots, n_slots);
-    init_descs(descs, ctx->word_off.data() + first, ctx->len.data() + first, n);
+    // the order in which the slots take the reads is scheduling only (eng.cu: heaviest first); MTR_SIM_READ_ORDER = 1: last first
+    std::vector<int> order((size_t)n);
+    for (int r = 0; r < n; r++) order[r] = getenv("MTR_SIM_READ_ORDER") && atoi(getenv("MTR_SIM_READ_ORDER")) == 1 ? n - 1 - r : r;
+    init_descs(descs, ctx->word_off.data() + first, ctx->len.data() + first, n, order.data());
     memcpy(P.reads, slots.data(), sizeof(Read) * (size_t)n_slots);
     memcpy((void *)P.descs, descs.data(), sizeof(ReadDesc) * (size_t)n);
     P.ctr->unfinished = n;
@@ -178,11 +191,11 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             static const int lag = getenv("MTR_SIM_WALK_LAG") ? std::min(5, atoi(getenv("MTR_SIM_WALK_LAG"))) : 0;
             tails.push_back(P.ctr->walk_tail);
             const unsigned limit = (int)tails.size() > lag ? tails[tails.size() - 1 - (size_t)lag] : 0u;
-            while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(Psmall, P.walk_ring[P.ctr->walk_head++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
+            while ((int)(limit - P.ctr->walk_head) > 0) walk_chain(Psmall, take_entry(P.walk_ring, P.ctr->walk_head++ & P.walk_ring_mask), S, cta, smem.data(), near, memos.data());
             // (the windows that need the big shared-memory count table have a queue and a kernel of their own)
             tails_big.push_back(P.ctr->walk_tail_big);
             const unsigned limit_big = (int)tails_big.size() > lag ? tails_big[tails_big.size() - 1 - (size_t)lag] : 0u;
-            while ((int)(limit_big - P.ctr->walk_head_big) > 0) walk_chain(P, P.walk_ring_big[P.ctr->walk_head_big++ & P.walk_ring_mask], S, cta, smem.data(), near, memos.data());
+            while ((int)(limit_big - P.ctr->walk_head_big) > 0) walk_chain(P, take_entry(P.walk_ring_big, P.ctr->walk_head_big++ & P.walk_ring_mask), S, cta, smem.data(), near, memos.data());
         }
         // (one thread per chain on the GPU, in any order: MTR_SIM_EMIT_ORDER = 1 emits in descending, 2 in a scrambled order)
         {

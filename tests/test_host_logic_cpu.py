@@ -75,7 +75,7 @@ def test_grouping_contexts_and_budgets_do_not_change_the_output(sim, synthetic_d
                 {"MTR_GROUP_READS": "7", "MTR_GROUPS_PER_GPU": "3", "MTR_GPUS": "2"}, {"MTR_ENGINE_DIR_KB": "600"},
                 {"MTR_ENGINE_TASK_CAP": "6", "MTR_GROUP_READS": "4"},
                 # read slots: a slot takes the next read of the group when its read has finished
-                {"MTR_ENGINE_SLOTS": "1"}, {"MTR_ENGINE_SLOTS": "3", "MTR_GROUPS_PER_GPU": "2", "MTR_GROUP_READS": "11"},
+                {"MTR_ENGINE_SLOTS": "1"}, {"MTR_ENGINE_SLOTS": "2", "MTR_SIM_READ_ORDER": "1"}, {"MTR_ENGINE_SLOTS": "3", "MTR_GROUPS_PER_GPU": "2", "MTR_GROUP_READS": "11"},
                 {"MTR_ENGINE_SLOTS": "2", "MTR_ENGINE_LONG_ROWS": "40", "MTR_SIM_LONG_EVERY": "3", "MTR_SIM_WALK_LAG": "2"},
                 # DP queues whose results arrive waves later (and waves that find no free queue at all)
                 {"MTR_SIM_SHORT_EVERY": "3", "MTR_SIM_LONG_EVERY": "5", "MTR_ENGINE_LONG_ROWS": "60"},
