@@ -55,9 +55,10 @@ inline Config default_config(int n_slots, int n_total, long long total_bases, in
     c.task_cap = (int)std::min<long long>(std::max<long long>(4096, n_chains / 2), 1 << 19);
     c.acc_cap = (int)std::min<long long>((long long)n_total * 32 + total_bases / 48 + 64, 1 << 24);
     c.aux_cap = std::max<long long>((long long)c.task_cap / 8 * 512, 2 * 4500);
-    c.dir_cap = std::min<long long>(2LL << 30, std::max<long long>(std::max<long long>(16LL << 20, 1024LL * max_len), total_bases * 32));
+    // direction arenas: full size for a batch that fills the slots, scaled down for small batches (tests, short files)
+    c.dir_cap = std::min<long long>(2LL << 30, std::max<long long>(std::max<long long>(16LL << 20, 1024LL * max_len), total_bases * 64));
     c.long_task_cap = (int)std::min<long long>(std::max<long long>(1024, 8LL * n_reads), 1 << 18);
-    c.long_dir_cap = std::min<long long>(3LL << 30, std::max<long long>(std::max<long long>(16LL << 20, 1024LL * max_len), total_bases * 32));
+    c.long_dir_cap = std::min<long long>(3LL << 30, std::max<long long>(std::max<long long>(16LL << 20, 1024LL * max_len), total_bases * 64));
     c.long_aux_cap = std::max<long long>((long long)c.long_task_cap / 8 * 512, 2 * 4500);
     // walk queue: a power of two well above the chains that can be queued at once (entries of cancelled walks linger
     // until a walk kernel pops them)

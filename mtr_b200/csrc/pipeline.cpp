@@ -451,16 +451,36 @@ void upload_groups(mtr_ctx *ctx, const std::vector<Group *> &groups)
     }
     std::vector<uint32_t> packed((size_t)word_off[n], 0u);
     res->stale.assign((size_t)res->stale_off[n], 0);
+    // 2-bit packing, a contiguous share of the reads per thread (every read owns whole words)
+    std::vector<const ReadInput *> flat((size_t)n);
     r = 0;
     for (Group *g : groups)
-        for (const ReadInput &in : g->reads) {
-            uint32_t *dst = packed.data() + word_off[r];
-            const uint8_t *b = in.bases.data();
+        for (const ReadInput &in : g->reads) flat[r++] = &in;
+    auto pack_range = [&](int a, int b) {
+        for (int q = a; q < b; q++) {
+            const ReadInput &in = *flat[q];
+            uint32_t *dst = packed.data() + word_off[q];
+            const uint8_t *bs = in.bases.data();
             const int nb = in.len + 2;
-            for (int i = 0; i < nb; i++) dst[i >> 4] |= (uint32_t)b[i] << ((i & 15) * 2);
-            if (!in.stale.empty()) memcpy(res->stale.data() + res->stale_off[r], in.stale.data(), in.stale.size() * 2);
-            r++;
+            int i = 0;
+            for (; i + 16 <= nb; i += 16) {
+                uint32_t w = 0;
+                for (int t = 0; t < 16; t++) w |= (uint32_t)bs[i + t] << (2 * t);
+                dst[i >> 4] = w;
+            }
+            for (; i < nb; i++) dst[i >> 4] |= (uint32_t)bs[i] << ((i & 15) * 2);
+            if (!in.stale.empty()) memcpy(res->stale.data() + res->stale_off[q], in.stale.data(), in.stale.size() * 2);
         }
+    };
+    {
+        int nt = (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+        if (const char *e = getenv("MTR_PACK_THREADS")) nt = std::max(1, atoi(e));
+        if (n < 64) nt = 1;
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(pack_range, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
+        pack_range(0, (int)((long long)n / nt));
+        for (std::thread &x : th) x.join();
+    }
     const int rc = mtr_reads_upload(ctx, packed.data(), word_off.data(), lens.data(), n);
     if (rc) die(ctx, "mtr_reads_upload", rc);
     const double ms = (now_s() - t0) * 1e3;
