@@ -385,6 +385,11 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     if (const char *e = getenv("MTR_ENGINE_WALK_CTAS")) cfg.uf_ctas = std::max(1, atoi(e));
     if (const char *e = getenv("MTR_ENGINE_WALK_CTAS_BIG")) cfg.uf_ctas_big = std::max(1, atoi(e));
     if (const char *e = getenv("MTR_ENGINE_POLISH_CTAS")) cfg.polish_ctas = std::max(1, atoi(e));
+    // threads of a walk cta: every warp builds the count table, warps 0 and 1 walk (forward / backward); the registers of
+    // the idle warps are held as long as the walks last
+    int walk_threads = 128, walk_threads_big = 128;
+    if (const char *e = getenv("MTR_ENGINE_WALK_THREADS")) walk_threads = atoi(e) <= 32 ? 32 : (atoi(e) <= 64 ? 64 : 128);
+    if (const char *e = getenv("MTR_ENGINE_WALK_THREADS_BIG")) walk_threads_big = atoi(e) <= 32 ? 32 : (atoi(e) <= 64 ? 64 : 128);
     if (const char *e = getenv("MTR_ENGINE_DIR_MB")) cfg.dir_cap = std::max(64LL, atoll(e)) << 20;
     if (const char *e = getenv("MTR_ENGINE_LONG_DIR_MB")) cfg.long_dir_cap = std::max(64LL, atoll(e)) << 20;
     if (const char *e = getenv("MTR_ENGINE_LONG_ROWS")) cfg.long_rows = std::max(1, atoi(e));
@@ -397,11 +402,33 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
     const size_t n_slices = (size_t)(cfg.uf_ctas + cfg.uf_ctas_big) * (size_t)cfg.walk_streams + (size_t)cfg.polish_ctas;
     MTR_CUDA(ctx, E.d_scratch.reserve((size_t)lay.uf_stride * n_slices));
     MTR_CUDA(ctx, E.d_wide.reserve((size_t)lay.table_cap * 8 * n_slices));
-    for (int i = 0; i < kQueues; i++) {
-        const bool used = i < kShortInst ? i < n_short : i - kShortInst < n_long;
-        const size_t want = (size_t)(i < kShortInst ? cfg.dir_cap : cfg.long_dir_cap);
-        if (used && want > E.d_dirs_q[i].cap) MTR_CUDA(ctx, E.d_dirs_q[i].reserve_exact(want));
-        E.q_busy[i] = false;
+    {
+        // direction arenas: the caps are what a full group would like; a context takes what the device still has (several
+        // contexts share a GPU and allocate one after the other: a smaller arena only means more deferred emissions, the
+        // queue's own cap below follows the size it got).  One task of the longest read must fit, and kArenaHeadroom stays
+        // free for the buffers that grow later (accepted repeats, alignments).
+        static std::mutex arena_mu;
+        std::lock_guard<std::mutex> ga(arena_mu);
+        constexpr size_t kArenaHeadroom = 4ull << 30;
+        const size_t floor_b = std::max<size_t>(16u << 20, (size_t)1024 * (size_t)std::max(max_len, 1));
+        for (int i = 0; i < kQueues; i++) {
+            const bool used = i < kShortInst ? i < n_short : i - kShortInst < n_long;
+            size_t want = (size_t)(i < kShortInst ? cfg.dir_cap : cfg.long_dir_cap);
+            E.q_busy[i] = false;
+            if (!used || want <= E.d_dirs_q[i].cap) continue;
+            size_t free_b = 0, total_b = 0;
+            MTR_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+            const size_t room = free_b + E.d_dirs_q[i].cap > kArenaHeadroom ? free_b + E.d_dirs_q[i].cap - kArenaHeadroom : 0;
+            if (want > room) want = std::max(floor_b, room & ~(size_t)0xfffff);
+            if (want <= E.d_dirs_q[i].cap) continue;
+            cudaError_t e = E.d_dirs_q[i].reserve_exact(want);
+            while (e == cudaErrorMemoryAllocation && want / 2 >= floor_b) {     // (fragmentation, a racing allocation of another process)
+                cudaGetLastError();
+                want /= 2;
+                e = E.d_dirs_q[i].reserve_exact(want);
+            }
+            MTR_CUDA(ctx, e);
+        }
     }
     MTR_CUDA(ctx, E.h_snap.reserve(sizeof(EngSnapshot)));
     MTR_CUDA(ctx, E.h_ctr.reserve(sizeof(Counters)));
@@ -532,8 +559,8 @@ extern "C" int mtr_engine_run_range(mtr_ctx *ctx, int first, int count, int manh
             MTR_CUDA(ctx, cudaEventRecord(E.sched_done[ws], t));
             MTR_CUDA(ctx, cudaStreamWaitEvent(E.walk_stream[ws], E.sched_done[ws], 0));
             MTR_CUDA(ctx, cudaStreamWaitEvent(E.walk_stream_big[ws], E.sched_done[ws], 0));
-            eng_unitfinder<0><<<cfg.uf_ctas, 128, kUfDynSmemSmall, E.walk_stream[ws]>>>(Psmall, ws * cfg.uf_ctas, kUfSmemWordsSmall, 0);
-            eng_unitfinder<0><<<cfg.uf_ctas_big, 128, kUfDynSmem, E.walk_stream_big[ws]>>>(P, cfg.uf_ctas * cfg.walk_streams + ws * cfg.uf_ctas_big, kUfSmemWords, 1);
+            eng_unitfinder<0><<<cfg.uf_ctas, walk_threads, kUfDynSmemSmall, E.walk_stream[ws]>>>(Psmall, ws * cfg.uf_ctas, kUfSmemWordsSmall, 0);
+            eng_unitfinder<0><<<cfg.uf_ctas_big, walk_threads_big, kUfDynSmem, E.walk_stream_big[ws]>>>(P, cfg.uf_ctas * cfg.walk_streams + ws * cfg.uf_ctas_big, kUfSmemWords, 1);
             launches++;
         }
         eng_emit<<<(lay.n_chains + 255) / 256, 256, 0, t>>>(P, QS, QL, lay.n_chains);
