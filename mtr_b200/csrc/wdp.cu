@@ -178,11 +178,14 @@ __device__ __forceinline__ void fill_slot_i32(const WdpTask *__restrict__ tasks,
         const int rows = have ? tp->rows : 0;
         const int ulen = tp->ulen;
         const long long base0 = tp->base0;
-        const int g4 = 4 * tp->gain[0];
-        const int cD = -4 * tp->mis[0] + 3;        // diagonal (mismatch) candidate, tag 3
-        const int cL = -4 * tp->indel[0] + 2;      // left (deletion) candidate, tag 2
-        const int cU = -4 * tp->indel[0] + 1;      // up (insertion) candidate, tag 1
-        const int in4 = 4 * tp->indel[0];
+        // int32 scores are kept x16 (the paired kernels: x4): the low two bits carry the direction tag as described in the
+        // header, and the four low bits of an UNTAGGED score are free for the column tag of the argmax key, which then
+        // costs one VIADDMNMX per cell (key = max(key, W + (15 - c)))
+        const int g4 = 16 * tp->gain[0];
+        const int cD = -16 * tp->mis[0] + 3;       // diagonal (mismatch) candidate, tag 3
+        const int cL = -16 * tp->indel[0] + 2;     // left (deletion) candidate, tag 2
+        const int cU = -16 * tp->indel[0] + 1;     // up (insertion) candidate, tag 1
+        const int in4 = 16 * tp->indel[0];
         uint8_t *drow = dirs + tp->dir_off + (size_t)gl * (C / 4);
         const int dstride = tp->dir_stride;
 
@@ -276,7 +279,7 @@ __device__ __forceinline__ void fill_slot_i32(const WdpTask *__restrict__ tasks,
             for (int c = C - 1; c >= 0; c--) {
                 accR = accR * 4u + (unsigned)R[c];
                 accW = accW * 4u + (unsigned)Wd[c];
-                key = max(key, Wd[c] * 4 + (15 - c));
+                key = __viaddmax_s32(Wd[c], 15 - c, key);
             }
             unsigned bits = accR - accW;
             // traceback at j == 1 tests "deletion" against W[i][0] == W[i][U] before insertion
@@ -494,8 +497,12 @@ __device__ __forceinline__ void fill_slot_p16(const WdpTask *__restrict__ tasks,
             for (int c = C - 1; c >= 0; c--) {
                 const unsigned code2 = R[c] - Wd[c];
                 if (c >= 8) acc1 = acc1 * 4u + code2; else acc0 = acc0 * 4u + code2;
-                key0 = max(key0, (int)(Wd[c] & 0xffffu) * 4 + (15 - c));
-                key1 = max(key1, (int)(Wd[c] >> 16) * 4 + (15 - c));
+            }
+            // argmax keys, one 32-bit key per half: the score (x4) in bits 16..30, 15 - c below; two cells per 3-input max
+#pragma unroll
+            for (int c = C - 1; c >= 1; c -= 2) {
+                key0 = __vimax3_s32(key0, (int)(Wd[c] << 16) + (15 - c), (int)(Wd[c - 1] << 16) + (16 - c));
+                key1 = __vimax3_s32(key1, (int)((Wd[c] & 0xffff0000u) | (unsigned)(15 - c)), (int)((Wd[c - 1] & 0xffff0000u) | (unsigned)(16 - c)));
             }
             unsigned bits0 = (acc0 & 0xffffu) | (acc1 << 16);
             unsigned bits1 = (acc0 >> 16) | (acc1 & 0xffff0000u);
@@ -514,8 +521,8 @@ __device__ __forceinline__ void fill_slot_p16(const WdpTask *__restrict__ tasks,
                     p[0] = (uint8_t)bits0; p[1] = (uint8_t)(bits0 >> 8); p[2] = (uint8_t)(bits0 >> 16);
                     q[0] = (uint8_t)bits1; q[1] = (uint8_t)(bits1 >> 8); q[2] = (uint8_t)(bits1 >> 16);
                 } else { *(uint32_t *)p = bits0; *(uint32_t *)q = bits1; }
-                if ((key0 >> 4) > best_v[0]) { best_v[0] = key0 >> 4; best_i[0] = i; best_c[0] = 15 - (key0 & 15); }
-                if ((key1 >> 4) > best_v[1]) { best_v[1] = key1 >> 4; best_i[1] = i; best_c[1] = 15 - (key1 & 15); }
+                if ((key0 >> 18) > best_v[0]) { best_v[0] = key0 >> 18; best_i[0] = i; best_c[0] = 15 - (key0 & 15); }
+                if ((key1 >> 18) > best_v[1]) { best_v[1] = key1 >> 18; best_i[1] = i; best_c[1] = 15 - (key1 & 15); }
             }
             dgin = (gl == 0) ? wU : cin;
         };
@@ -609,26 +616,37 @@ __device__ __forceinline__ void traceback_warp(const WdpTask &t, const int p, co
         }
         while (i > 0 && run > 0 && i > top - 32) {
             const int q = top - i;
-            const int xi = __shfl_sync(FULL, xq, q);
-            const int uj = un[j - 1];
-            int op;
-            if (xi == uj) {
-                op = 0;
-            } else {
-                const int s = j - 1 - __shfl_sync(FULL, c0, q);
-                if (s < 0 || s >= 64) break;                   // the path left the fetched columns: fetch again from here
-                const int wi = s >> 4;
-                const unsigned mine = wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
-                const unsigned v = __shfl_sync(FULL, mine, q);
-                const int code = (int)((v >> ((s & 15) * 2)) & 3u);
-                if (code == 0) { flags |= 2; run = 0; break; }  // cannot happen: run > 0 means W[i][j] > 0
-                op = code == 3 ? 1 : (code == 2 ? 2 : 3);
+            // A run of matches is a run of diagonal steps that ask nothing of the direction matrix (:306 tests
+            // x_i == u_j first): lane q + k looks at the k-th cell down the diagonal from (i, j), one ballot finds
+            // the length of the run, and the whole run is taken at once -- every lane adds its own histogram entry.
+            // The running score loses G per step and the walk stops when it reaches zero: ceil(run / G) steps at most.
+            int jl = j - (lane - q);
+            if (jl < 1) jl = ulen - ((-jl) % ulen);
+            bool mt = false;
+            if (lane >= q && rq >= 1) mt = xq == (int)un[jl - 1];
+            const unsigned bal = __ballot_sync(FULL, mt) >> q;
+            int n = bal == FULL ? 32 : __ffs(~bal) - 1;
+            if (n > 0) {
+                if (G > 0) { const int kmax = (run + G - 1) / G; n = n < kmax ? n : kmax; }
+                if (cons && lane >= q && lane < q + n) atomicAdd(&cons[jl * 5 + xq], 1);
+                run -= n * G; i -= n; nm += n; steps += n;
+                j -= n;
+                if (j < 1) j = ulen - ((-j) % ulen);
+                continue;
             }
+            // one step that is not a match: the direction code of (i, j)
+            const int xi = __shfl_sync(FULL, xq, q);
+            const int s = j - 1 - __shfl_sync(FULL, c0, q);
+            if (s < 0 || s >= 64) break;                       // the path left the fetched columns: fetch again from here
+            const int wi = s >> 4;
+            const unsigned mine = wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3));
+            const unsigned v = __shfl_sync(FULL, mine, q);
+            const int code = (int)((v >> ((s & 15) * 2)) & 3u);
+            if (code == 0) { flags |= 2; run = 0; break; }      // cannot happen: run > 0 means W[i][j] > 0
             steps++;
-            if (op == 0)      { if (cons && lane == 0) atomicAdd(&cons[j * 5 + xi], 1); run -= G;  i--; j--; nm++; }
-            else if (op == 1) { if (cons && lane == 0) atomicAdd(&cons[j * 5 + xi], 1); run += MM; i--; j--; nx++; }
-            else if (op == 2) { if (cons && lane == 0) atomicAdd(&cons[j * 5 + 4], 1);  run += IN; j--;      nd++; }
-            else              { if (miss && lane == 0) atomicAdd(&miss[j * 4 + xi], 1); run += IN; i--;      ni++; }
+            if (code == 3)      { if (cons && lane == 0) atomicAdd(&cons[j * 5 + xi], 1); run += MM; i--; j--; nx++; }
+            else if (code == 2) { if (cons && lane == 0) atomicAdd(&cons[j * 5 + 4], 1);  run += IN; j--;      nd++; }
+            else                { if (miss && lane == 0) atomicAdd(&miss[j * 4 + xi], 1); run += IN; i--;      ni++; }
             if (j == 0) j = ulen;
         }
     }
