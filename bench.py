@@ -309,7 +309,7 @@ def main():
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": "C5 synthetic long reads 10-20 kb, unit 2-500 bp, 5-15% noise", "reads_per_step_per_gpu": R,
                    "mode": "default (Manhattan), -m 0.6", "engine_contexts_per_gpu": int(os.environ.get("MTR_GROUPS_PER_GPU", "2")),
-                   "read_slots_per_context": int(os.environ.get("MTR_ENGINE_SLOTS", "8192")),
+                   "read_slots_per_context": int(os.environ.get("MTR_ENGINE_SLOTS", "16384")),
                    "groups": "the resident reads are cut into equal groups, one or more per context (<= 320 Mbases each)",
                    "l2": "working set per step (direction matrices, %d MB) exceeds the 126 MB L2" % (acc["wdp_dir_bytes"] / a.steps / 2 ** 20)},
         "e2e": {"value": round(reads_all / t_e2e, 3), "unit": "reads/s", "h2d_bytes_per_step": int(h2d / a.steps),

@@ -48,7 +48,7 @@ constexpr int kDpClasses = 20;               // 10 int32 + 10 paired int16x2 fil
 constexpr int kRowBuckets = kWdpRowBuckets;  // quarter-octave buckets of a task's row count (longest first)
 constexpr int kSegs = 2 * kRowBuckets * 10;  // (family, class, rows bucket) segments of the sorted task list
 constexpr int kShortInst = 4;                // DP queues for tasks below Ptrs::long_rows rows (each with its own streams, task list and direction arena)
-constexpr int kLongInst = 12;                // ... and for the long tasks
+constexpr int kLongInst = 12;               // ... and for the long tasks
 constexpr int kQueues = kShortInst + kLongInst;   // queue ids: short 0 .. kShortInst - 1, long kShortInst .. kQueues - 1
 
 enum Stage : int {

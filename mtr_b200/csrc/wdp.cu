@@ -16,7 +16,8 @@
 //             (monotone fixpoint, at most G rounds, usually none or one)
 //   epilogue  W[i][U] is shuffled to lane 0 (wrap), direction codes are packed and stored, argmax updated.
 //
-// Scores are kept multiplied by 4 with the low two bits free, so that the candidate that wins the max
+// Scores are kept multiplied by 4 (paired int16x2 kernels) or 16 (int32 kernels: four free low bits in an untagged score
+// hold the column tag of the argmax key) with the low two bits free, so that the candidate that wins the max
 // carries its own traceback code: diag-MM is tagged 3, left-IN 2, up-IN 1, the zero floor 0.  A tie between
 // candidates is then resolved by the max itself in the reference's traceback priority (mismatch before
 // deletion before insertion, wrap_around_DP.c:306-323) and the 2-bit direction code is just (r & 3):
