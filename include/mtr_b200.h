@@ -291,6 +291,28 @@ void mtr_flush(void);
  * have processed since the previous call; resets them.  The reference has only the -c timers (mTR.h:142-143). */
 int  mtr_file_stats(mtr_pipeline_stats *out);
 
+/* ------------------------------------------------------------------ the reference's C <-> C++ bridge */
+/* mTR.h:146-175 / chaining.h:30-56: the interface between handle_one_read.c and chaining.cpp, for a caller that keeps
+ * its own per-read code above this library.  The library's own per-read loop runs on the device and never goes
+ * through these four symbols.
+ *   insert_an_alignment_into_set  chaining.cpp:203-241: adds one repeat of the current read to the set (the set is kept
+ *                                 in insertion order: the canonical order of the reference's pointer-ordered std::set)
+ *   chaining                      chaining.cpp:243-363: best chain over the set by the reference's own sweep, prints its
+ *                                 records to stdout (print_one_TR), print_alignment == 1: a blank line and
+ *                                 pretty_print_alignment after each; empties the set
+ *   pretty_print_alignment        wrap_around_DP.c:57-213: rows = orgInputString[rep_start..rep_end]; the DP and its
+ *                                 traceback run on the GPU (one K3 job, mode MTR_TB_PATH), the text is the reference's
+ *   print_freq                    consensus.c:1089-1131 (debugging aid): k-mer counts of the unit's rotations in the
+ *                                 window, one digit per position                                                   */
+void insert_an_alignment_into_set(char *readID, int inputLen, int rep_start, int rep_end, int repeat_len, int rep_period,
+                                  int Num_freq_unit, int Num_matches, int Num_mismatches, int Num_insertions,
+                                  int Num_deletions, int Kmer, int match_gain, int mismatch_penalty, int indel_penalty,
+                                  char *string, int *string_score);
+void chaining(int print_alignment);
+void pretty_print_alignment(char *unit_string, int unit_len, int rep_start, int rep_end, int match_gain,
+                            int mismatch_penalty, int indel_penalty);
+void print_freq(int rep_start, int rep_end, int rep_period, char *string, int inputLen, int k);
+
 extern int   Manhattan_Distance;      /* mTR.h:61, set by main.c:56,77 */
 extern float min_match_ratio;         /* mTR.h:62, set by main.c:54,68 */
 extern int  *orgInputString;          /* mTR.h:65 */

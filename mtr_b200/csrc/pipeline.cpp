@@ -831,6 +831,140 @@ extern "C" int mtr_file_stats(mtr_pipeline_stats *out)
     return MTR_OK;
 }
 
+// ================================================================ the reference's C <-> C++ bridge (mTR.h:146-175, chaining.h:30-56)
+// insert_an_alignment_into_set / chaining are chaining.cpp's interface towards handle_one_read.c; pretty_print_alignment
+// and print_freq are the two C functions chaining.cpp calls back.  The product's own per-read loop lives on the device and
+// never goes through these symbols (run_group chains and prints a whole group); they are exported so that a caller
+// that keeps the reference's handle_one_read.c -- or its own per-read code -- above this library finds every symbol of
+// the reference's interface, with the reference's semantics: the set is taken in insertion order, the read
+// is orgInputString (mTR.h:65), output goes to stdout.
+namespace {
+std::vector<ChainItem> g_set;              // set_of_alignments, chaining.cpp:201
+std::vector<std::string> g_set_ids;
+mtr_ctx *g_bridge_ctx = nullptr;           // pretty_print_alignment runs its DP on the GPU (one PATH job of K3)
+
+int base_of_char(char c, const char *who)
+{
+    switch (c) {
+    case 'A': return 0;
+    case 'C': return 1;
+    case 'G': return 2;
+    case 'T': return 3;
+    default: fprintf(stderr, "%s: fatal input char %c\n", who, c); exit(EXIT_FAILURE);
+    }
+}
+}   // namespace
+
+extern "C" void insert_an_alignment_into_set(char *readID, int inputLen, int rep_start, int rep_end, int repeat_len, int rep_period,
+                                             int Num_freq_unit, int Num_matches, int Num_mismatches, int Num_insertions,
+                                             int Num_deletions, int Kmer, int match_gain, int mismatch_penalty, int indel_penalty,
+                                             char *string, int *string_score)
+{
+    (void)string_score;                    // kept by the reference's Alignment, read by nothing that prints
+    ChainItem it;
+    it.rec.inputLen = inputLen; it.rec.rep_start = rep_start; it.rec.rep_end = rep_end; it.rec.repeat_len = repeat_len;
+    it.rec.period = rep_period; it.rec.units = Num_freq_unit; it.rec.nm = Num_matches; it.rec.nx = Num_mismatches;
+    it.rec.ni = Num_insertions; it.rec.nd = Num_deletions; it.rec.kmer = Kmer; it.rec.gain = match_gain;
+    it.rec.mis = mismatch_penalty; it.rec.indel = indel_penalty;
+    // print_one_TR prints the string with %s (chaining.cpp:127): what follows its first NUL is not part of the unit
+    for (int i = 0; string && string[i] && i < rep_period; i++) it.rec.unit.push_back((uint8_t)base_of_char(string[i], "insert_an_alignment_into_set"));
+    it.start = rep_start; it.end = rep_end; it.score = Num_matches; it.pred = nullptr;
+    g_set.push_back(std::move(it));
+    g_set_ids.push_back(readID ? readID : "");
+}
+
+extern "C" void pretty_print_alignment(char *unit_string, int unit_len, int rep_start, int rep_end, int match_gain,
+                                       int mismatch_penalty, int indel_penalty)
+{
+    const int rows = rep_end - rep_start + 1;
+    if (!orgInputString || !unit_string || unit_len <= 0 || rows <= 0) return;
+    if (!g_bridge_ctx) {
+        int dev = 0;
+        if (const char *e = getenv("MTR_DEVICE")) dev = atoi(e);
+        const int rc = mtr_cuda_init(dev, &g_bridge_ctx);
+        if (rc) die(nullptr, "mtr_cuda_init", rc);
+    }
+    mtr_ctx *ctx = g_bridge_ctx;
+    // the rows of the DP are orgInputString[rep_start .. rep_end] (wrap_around_DP.c:86-88): a one-read batch of that window
+    // plus the two bases behind it, job rows 1..rows = positions 0..rows-1 of the batch (first = -1)
+    std::vector<uint8_t> win((size_t)rows + 3, 0);             // win[i] = row i, as append_alignment indexes it
+    for (int i = 1; i <= rows + 2; i++) win[i] = (uint8_t)(orgInputString[rep_start + i - 1] & 3);
+    const int64_t words = (rows + 2 + 15) / 16;
+    const int64_t word_off[2] = {0, ((words + 3) / 4) * 4};
+    std::vector<uint32_t> packed((size_t)word_off[1], 0u);
+    for (int i = 0; i < rows + 2; i++) packed[i >> 4] |= (uint32_t)win[i + 1] << ((i & 15) * 2);
+    const int32_t len = rows;
+    int rc = mtr_reads_upload(ctx, packed.data(), word_off, &len, 1);
+    if (rc) die(ctx, "mtr_reads_upload", rc);
+    Rec r;
+    r.rep_start = 1; r.rep_end = rows; r.period = unit_len; r.gain = match_gain; r.mis = mismatch_penalty; r.indel = indel_penalty;
+    for (int i = 0; i < unit_len; i++) r.unit.push_back((uint8_t)base_of_char(unit_string[i], "pretty_print_alignment"));
+    mtr_wdp_job j;
+    memset(&j, 0, sizeof j);
+    j.read = 0; j.first = -1; j.rows = rows; j.ulen = unit_len; j.unit_off = 0;
+    j.gain[0] = (int8_t)match_gain; j.mis[0] = (int8_t)mismatch_penalty; j.indel[0] = (int8_t)indel_penalty;
+    j.n_param = 1; j.mode = MTR_TB_PATH;
+    j.aux_off = 0; j.aux_cap = (int64_t)6 * rows + 64;
+    std::vector<uint8_t> aux((size_t)j.aux_cap);
+    mtr_wdp_result res[2];
+    rc = mtr_wdp_run(ctx, &j, 1, r.unit.data(), (int64_t)r.unit.size(), res, aux.data(), j.aux_cap);
+    if (rc) { fflush(stdout); die(ctx, "mtr_wdp_run", rc); }
+    std::string out;
+    append_alignment(out, r, win.data(), res[0], aux.data());
+    fwrite(out.data() + 1, 1, out.size() - 1, stdout);         // (the blank line before "match gain" is print_one_TR's, chaining.cpp:165)
+}
+
+extern "C" void chaining(int print_alignment)
+{
+    if (g_set.empty()) return;                                  // chaining.cpp:244
+    const std::vector<const Rec *> chain = best_chain(g_set);
+    for (const Rec *p : chain) {
+        size_t at = 0;
+        while (at < g_set.size() && &g_set[at].rec != p) at++;
+        std::string out;
+        append_record(out, g_set_ids[at], *p);
+        fwrite(out.data(), 1, out.size(), stdout);
+        if (print_alignment == 1) {
+            printf("\n");
+            std::string unit;
+            for (uint8_t b : p->unit) unit += "ACGT"[b];
+            pretty_print_alignment(&unit[0], p->period, p->rep_start, p->rep_end, p->gain, p->mis, p->indel);
+        }
+        fflush(stdout);
+    }
+    g_set.clear();
+    g_set_ids.clear();
+}
+
+// consensus.c:1089-1131 (debugging aid of chaining.cpp, DEBUG_unit_score): one digit per unit position, the number of
+// times the k-mer that starts there occurs in orgInputString[rep_start .. rep_end] ('*' from 10 on).  The window is
+// coded as init_inputString does (consensus.c:37-57): k-mer codes below min(rep_end, inputLen - k + 1), raw bases above.
+extern "C" void print_freq(int rep_start, int rep_end, int rep_period, char *string, int inputLen, int k)
+{
+    if (!orgInputString || !string || k < 1 || k > 15) return;
+    std::map<unsigned, int> count;
+    const int coded_end = std::min(rep_end, inputLen - k + 1);
+    for (int i = rep_start; i <= rep_end; i++) {
+        unsigned code = 0;
+        if (i < coded_end) for (int t = 0; t < k; t++) code = 4u * code + (unsigned)(orgInputString[i + t] & 3);
+        else if (i < inputLen && (k > 1 || i < rep_end)) code = (unsigned)(orgInputString[i] & 3);   // (k == 1: init_inputString never writes position rep_end -- 0 in a fresh process)
+        count[code]++;
+    }
+    std::vector<int> unit((size_t)std::max(rep_period, 0));
+    for (int i = 0; i < rep_period; i++) unit[i] = base_of_char(string[i], "print_freq");
+    const unsigned keep = 1u << (2 * (k - 1));                  // pow4[k-1]
+    unsigned tmp = 0;
+    for (int i = 0; i < k - 1; i++) tmp = 4u * tmp + (unsigned)unit[i % std::max(rep_period, 1)];   // (k - 1 > rep_period: the reference reads uninitialised stack here)
+    for (int i = 0; i < rep_period; i++) {
+        const unsigned node = 4u * tmp + (unsigned)unit[(i + k - 1) % rep_period];
+        tmp = node % keep;
+        const std::map<unsigned, int>::const_iterator f = count.find(node);
+        const int freq = f == count.end() ? 0 : f->second;
+        if (freq < 10) printf("%i", freq); else printf("*");
+    }
+    printf("\n");
+}
+
 // ================================================================ batch-level pipeline ABI (bench, tests, embedding)
 struct mtr_pipeline {
     std::vector<mtr_ctx *> ctxs;
