@@ -291,6 +291,22 @@ void mtr_flush(void);
  * have processed since the previous call; resets them.  The reference has only the -c timers (mTR.h:142-143). */
 int  mtr_file_stats(mtr_pipeline_stats *out);
 
+/* ------------------------------------------------------------------ optional post-pass: cross-read clustering */
+/* the reference's k_means_clustering.c:136-355 restated over the emitted TSV records (that file is dead
+ * code in the reference -- not built, does not compile -- so this has no binary to be compared with; cluster.cpp states what
+ * is restated and which choices the source leaves open).  tsv: records as bin/mTR prints them (other lines are skipped).
+ * Output (malloc'ed, free with mtr_cluster_free): one line per qualified record, "<id of the representative>\t<record>" with
+ * the representative's unit length and unit string in place of the record's own, clusters by falling size.
+ * params == NULL: min_match_ratio 0.6 (MIN_MATCH_RATIO, mTR.h:32), mh_distance_threshold 0.3, min_rep_len 0, min_num_rep 1. */
+typedef struct {
+    double min_match_ratio;        /* MIN_MATCH_RATIO < matches / repeat_len */
+    double mh_distance_threshold;  /* sum |d 2-mer| <= threshold * unit length of the representative (TRs_in_neighborhood) */
+    int    min_rep_len;            /* MIN_REP_LEN < unit length * number of units */
+    int    min_num_rep;            /* MIN_NUM_repTR; only 1 is defined by the source */
+} mtr_cluster_params;
+int  mtr_cluster_records(const char *tsv, int64_t len, const mtr_cluster_params *params, char **out_text, int64_t *out_len);
+void mtr_cluster_free(char *text);
+
 /* ------------------------------------------------------------------ the reference's C <-> C++ bridge */
 /* mTR.h:146-175 / chaining.h:30-56: the interface between handle_one_read.c and chaining.cpp, for a caller that keeps
  * its own per-read code above this library.  The library's own per-read loop runs on the device and never goes

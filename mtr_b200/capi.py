@@ -21,7 +21,7 @@ ABI_FUNCTIONS = [
     "mtr_cuda_init", "mtr_cuda_shutdown", "mtr_last_error", "mtr_device_count", "mtr_set_blocking_sync", "mtr_set_priority", "mtr_reads_upload", "mtr_reads_share",
     "mtr_wdp_run", "mtr_wdp_upload", "mtr_wdp_launch", "mtr_wdp_download", "mtr_wdp_set_fused_traceback", "mtr_di_run", "mtr_di_run_range", "mtr_get_stats",
     "mtr_alu_probe", "mtr_uf_run", "mtr_pipeline_open", "mtr_pipeline_close", "mtr_pipeline_load_fasta", "mtr_pipeline_load_fasta_shard",
-    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_ctx", "mtr_engine_run", "mtr_engine_run_range", "mtr_engine_set_speculate", "mtr_engine_dp_busy_ms", "handle_one_file", "handle_one_read", "mtr_flush", "mtr_file_stats",
+    "mtr_pipeline_run", "mtr_pipeline_get_stats", "mtr_pipeline_ctx", "mtr_engine_run", "mtr_engine_run_range", "mtr_engine_set_speculate", "mtr_engine_dp_busy_ms", "handle_one_file", "handle_one_read", "mtr_flush", "mtr_file_stats", "mtr_cluster_records", "mtr_cluster_free",
     "insert_an_alignment_into_set", "chaining", "pretty_print_alignment", "print_freq",      # the reference's C <-> C++ bridge (mTR.h:146-175)
 ]
 ABI_GLOBALS = [
