@@ -159,8 +159,10 @@ struct ReadInput {
 {
     if (rc == MTR_ERANGE) fprintf(stderr, "%s\n", mtr_last_error(ctx));        // the reference's own abort messages
     else fprintf(stderr, "mTR (B200): %s failed (%d): %s\n", what, rc, mtr_last_error(ctx));
-    fflush(stdout);
-    exit(EXIT_FAILURE);
+    // other workers are still launching and the writer may be printing: leave without running exit handlers and static
+    // destructors under their feet (the streams are flushed here)
+    fflush(NULL);
+    _exit(EXIT_FAILURE);
 }
 
 // ---------------------------------------------------------------- cross-read stale state
@@ -271,6 +273,9 @@ struct FastaReader {
     FILE *fp = nullptr;
     std::string next_id;
     bool started = false, eof = false;
+    std::string fatal;                 // the reference's abort message when the input ends the run (the caller prints it and exits
+                                       // AFTER the reads in front of the bad one are done: the reference parses a read only when
+                                       // the one before it has been printed, handle_one_file.c:277-289)
     std::vector<char> buf;
     explicit FastaReader(const char *path) : buf(1 << 20)
     {
@@ -305,14 +310,15 @@ struct FastaReader {
             uint8_t *dst = out.bases.data() + old;
             for (size_t i = 0; i < lim; i++) {
                 const int8_t b = lut.v[(unsigned char)s[i]];
-                if (b < 0) { fprintf(stderr, "Invalid character: %c \n", s[i]); exit(EXIT_FAILURE); }
+                if (b < 0) { char m[64]; snprintf(m, sizeof m, "Invalid character: %c \n", s[i]); fatal = m; eof = true; return false; }
                 dst[i] = (uint8_t)b;
             }
             if (kMaxLen <= (int)out.bases.size()) {
-                fprintf(stderr, "fatal error: The length %d is tentatively at most %i.\nread ID = %s\nSet MAX_INPUT_LENGTH to a larger value",
-                        (int)out.bases.size(), kMaxLen, out.id.c_str());
-                fprintf(stderr, "cannot allocate space for one of global variables in the heap.\n");
-                exit(EXIT_FAILURE);
+                char m[2304];
+                snprintf(m, sizeof m, "fatal error: The length %d is tentatively at most %i.\nread ID = %.2000s\nSet MAX_INPUT_LENGTH to a larger value"
+                         "cannot allocate space for one of global variables in the heap.\n", (int)out.bases.size(), kMaxLen, out.id.c_str());
+                fatal = m; eof = true;
+                return false;
             }
         }
         eof = true;
@@ -818,6 +824,12 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
         disp.submit(std::move(g));
     }
     disp.finish();
+    if (!reader.fatal.empty()) {                        // every read in front of the bad one has been printed, as in the reference
+        fflush(stdout);
+        fputs(reader.fatal.c_str(), stderr);
+        fflush(stderr);
+        exit(EXIT_FAILURE);
+    }
     return n_reads;
 }
 

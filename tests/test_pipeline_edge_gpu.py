@@ -79,6 +79,16 @@ def test_abort_behaviour(tmp_path):
     p = write(tmp_path, "bad.fa", b">x\nACGTNACGT\n")
     a = subprocess.run([MTR, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert a.returncode == 1 and a.stderr.startswith(b"Invalid character: N") and a.stdout == b""
+    # a bad read in the middle of the file: the reference has printed the reads in front of it when it aborts
+    # (handle_one_file.c:277-289 parses a read only after the one before it is done); also across group boundaries
+    rd = synth.rand_seq_reads(5, 30, 0.0, 0.03, 0.03, 40, 40, 4, seed=9)[0]
+    t = [">%d\n%s\n" % (i, synth.to_text(r)) for i, r in enumerate(rd)]
+    p = write(tmp_path, "bad_mid.fa", (t[0] + t[1] + t[2] + ">bad\nACGTNACGT\n" + t[3]).encode())
+    b = subprocess.run([ORACLE_BIN, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert b.returncode == 1 and b.stdout.count(b"\n") >= 3
+    for env in ({}, {"MTR_GROUP_READS": "2"}, {"MTR_GROUP_READS": "1", "MTR_GROUPS_PER_GPU": "1"}):
+        a = subprocess.run([MTR, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **env))
+        assert a.returncode == 1 and a.stderr.startswith(b"Invalid character: N") and a.stdout == b.stdout, env
     a = subprocess.run([MTR, os.path.join(str(tmp_path), "missing.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert a.returncode == 1 and b"fatal error: cannot open" in a.stderr
 
