@@ -277,7 +277,9 @@ struct FastaReader {
                                        // AFTER the reads in front of the bad one are done: the reference parses a read only when
                                        // the one before it has been printed, handle_one_file.c:277-289)
     std::vector<char> buf;
-    explicit FastaReader(const char *path) : buf(1 << 20)
+    // lines are read in pieces of BLK - 1 = 4095 characters exactly as the reference's fgets(s, BLK, fp) does (handle_one_file.c:208):
+    // what follows the first piece of a longer header line is read as bases there, and here
+    explicit FastaReader(const char *path) : buf(4096)
     {
         fp = fopen(path, "r");
         if (!fp) { fprintf(stderr, "fatal error: cannot open %s\n", path); fflush(stderr); exit(EXIT_FAILURE); }
@@ -360,6 +362,7 @@ int parse_fasta_text(const char *text, int64_t len, int first, int count, int th
                 q++;                                               // past '>'
                 const char *nl = (const char *)memchr(q, '\n', (size_t)(end - q));
                 hend = nl ? nl : end;
+                if (hend - (q - 1) > 4095) hend = q - 1 + 4095;     // (the reference reads a header line in pieces of BLK - 1 characters: the rest is bases)
                 const char *idend = hend;
                 for (const char *c = q; c < hend; c++) if (*c == '\r') { idend = c; break; }
                 in.id.assign(q, idend);

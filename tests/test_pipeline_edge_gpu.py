@@ -89,6 +89,12 @@ def test_abort_behaviour(tmp_path):
     for env in ({}, {"MTR_GROUP_READS": "2"}, {"MTR_GROUP_READS": "1", "MTR_GROUPS_PER_GPU": "1"}):
         a = subprocess.run([MTR, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **env))
         assert a.returncode == 1 and a.stderr.startswith(b"Invalid character: N") and a.stdout == b.stdout, env
+    # a header line of more than BLK - 1 = 4095 characters: the reference's fgets(s, BLK, fp) reads it in pieces and takes the
+    # rest for bases (handle_one_file.c:208)
+    p = write(tmp_path, "long_header.fa", (">" + "x" * 5000 + "\n" + synth.to_text(rd[0]) + "\n").encode())
+    a = subprocess.run([MTR, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    b = subprocess.run([ORACLE_BIN, p], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert a.returncode == 1 and b.returncode == 1 and a.stderr.startswith(b"Invalid character: x") and b.stderr.startswith(b"Invalid character: x") and a.stdout == b""
     a = subprocess.run([MTR, os.path.join(str(tmp_path), "missing.fa")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert a.returncode == 1 and b"fatal error: cannot open" in a.stderr
 
