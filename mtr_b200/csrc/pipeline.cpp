@@ -153,6 +153,8 @@ struct ReadInput {
     std::vector<uint8_t> bases;        // len + 2 (the two stale bases of H4a at the end)
     std::vector<uint16_t> stale;       // inputString_w_rand beyond len + 4r (H3)
     int len = 0;
+    int8_t bad = 0;                    // parse_records: 1 = a character that is not a base (bad_char), 2 = MAX_INPUT_LENGTH reached
+    char bad_char = 0;
 };
 
 [[noreturn]] void die(mtr_ctx *ctx, const char *what, int rc)
@@ -331,10 +333,14 @@ struct FastaReader {
     }
 };
 
-// The same parser for FASTA text that is already in memory (mtr_pipeline_load_fasta*): records are cut at every '>' that
-// starts a line and parsed in parallel.  Bases in front of the first header join the first read, like in FastaReader
-// (and in return_one_read, handle_one_file.c:201-269).  Keeps records [0, first + count) (count < 0: all).
-int parse_fasta_text(const char *text, int64_t len, int first, int count, int threads, std::vector<ReadInput> &reads)
+// The same parser for FASTA text that is in memory (a block of a file in handle_one_file, the whole text in
+// mtr_pipeline_load_fasta*): records are cut at every '>' that starts a line and parsed in parallel, line by line with the
+// reference's rules (handle_one_file.c:201-269): a line ends at its first '\r' or '\n' (what follows a '\r' in the same line is
+// dropped), a header line is read in pieces of BLK - 1 characters (the rest of a longer one is bases), anything but
+// A/C/G/T in either case is fatal, a read of MAX_INPUT_LENGTH bases or more is fatal.  Bases in front of the first header
+// join the first read (only where `leading` is set: the start of the input).  A bad record is marked (ReadInput::bad) and
+// parsing goes on: the caller decides what happens to the records in front of it.
+void parse_records(const char *text, int64_t len, bool leading, int max_records, int threads, std::vector<ReadInput> &reads)
 {
     reads.clear();
     std::vector<int64_t> starts;
@@ -346,13 +352,13 @@ int parse_fasta_text(const char *text, int64_t len, int first, int count, int th
     }
     const int64_t prefix_end = starts.empty() ? len : starts[0];      // headerless bases in front
     int nrec = (int)starts.size();
-    const bool headerless_only = nrec == 0 && prefix_end > 0;
+    const bool headerless_only = nrec == 0 && prefix_end > 0 && leading;
     if (headerless_only) { starts.push_back(0); nrec = 1; }
-    if (count >= 0) nrec = std::min(nrec, first + count);
+    if (max_records >= 0) nrec = std::min(nrec, max_records);
     starts.push_back(nrec < (int)starts.size() ? starts[nrec] : len);
     reads.resize((size_t)nrec);
-    static const struct Lut { int8_t v[256]; Lut() { memset(v, -1, sizeof v); v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; v['\n'] = v['\r'] = -2; } } lut;
-    std::atomic<int> next{0}, bad{0};
+    static const struct Lut { int8_t v[256]; Lut() { memset(v, -1, sizeof v); v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3; } } lut;
+    std::atomic<int> next{0};
     auto parse = [&] {
         for (int i; (i = next.fetch_add(1)) < nrec;) {
             ReadInput &in = reads[(size_t)i];
@@ -367,36 +373,119 @@ int parse_fasta_text(const char *text, int64_t len, int first, int count, int th
                 for (const char *c = q; c < hend; c++) if (*c == '\r') { idend = c; break; }
                 in.id.assign(q, idend);
             }
-            const int64_t pre = (i == 0 && !headerless_only) ? prefix_end : 0;
-            in.bases.resize((size_t)(end - hend) + (size_t)pre + 2);
-            uint8_t *dst = in.bases.data();
-            auto take = [&](const char *a, const char *b) {
-                for (const char *c = a; c < b; c++) {
-                    const int8_t v = lut.v[(unsigned char)*c];
-                    if (v >= 0) *dst++ = (uint8_t)v;
-                    else if (v == -1) { bad.store(1); return; }
+            const int64_t pre = (i == 0 && leading && !headerless_only) ? prefix_end : 0;
+            in.bases.resize((size_t)std::min<int64_t>((end - hend) + pre, kMaxLen) + 2);
+            uint8_t *dst = in.bases.data(), *cap = dst + kMaxLen;
+            auto take = [&](const char *a, const char *b) {       // the lines of [a, b)
+                while (a < b && !in.bad) {
+                    const char *nl = (const char *)memchr(a, '\n', (size_t)(b - a));
+                    const char *le = nl ? nl : b;
+                    for (const char *c = a; c < le && *c != '\r'; c++) {
+                        const int8_t v = lut.v[(unsigned char)*c];
+                        if (v < 0) { in.bad = 1; in.bad_char = *c; break; }
+                        if (dst < cap) *dst++ = (uint8_t)v;
+                        if (dst == cap) { in.bad = 2; break; }     // MAX_INPUT_LENGTH reached (handle_one_file.c:190-197)
+                    }
+                    a = nl ? nl + 1 : b;
                 }
             };
             if (pre > 0) take(text, text + pre);
             take(hend, end);
             in.len = (int)(dst - in.bases.data());
             in.bases.resize((size_t)in.len + 2);
-            if (in.len >= kMaxLen) bad.store(2);
         }
     };
-    {
-        const int T = std::max(1, std::min(threads, nrec / 16));
-        std::vector<std::thread> th;
-        for (int t = 1; t < T; t++) th.emplace_back(parse);
-        parse();
-        for (auto &x : th) x.join();
+    const int T = std::max(1, std::min(threads, nrec / 16));
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(parse);
+    parse();
+    for (auto &x : th) x.join();
+}
+
+// Keeps records [0, first + count) (count < 0: all); MTR_EINVAL / MTR_ERANGE where the reference aborts
+int parse_fasta_text(const char *text, int64_t len, int first, int count, int threads, std::vector<ReadInput> &reads)
+{
+    parse_records(text, len, true, count >= 0 ? first + count : -1, threads, reads);
+    for (size_t i = 0; i < reads.size(); i++) {
+        if (reads[i].bad == 1) return MTR_EINVAL;           // the reference aborts: "Invalid character"
+        if (reads[i].bad == 2) return MTR_ERANGE;
+        if (reads[i].len == 0) { reads.resize(i); break; }   // a zero-length read ends the run (handle_one_file.c:283)
     }
-    if (bad.load() == 1) return MTR_EINVAL;                 // the reference aborts: "Invalid character"
-    if (bad.load() == 2) return MTR_ERANGE;
-    for (int i = 0; i < nrec; i++)
-        if (reads[(size_t)i].len == 0) { reads.resize((size_t)i); break; }   // a zero-length read ends the run (handle_one_file.c:283)
     return MTR_OK;
 }
+
+// ---------------------------------------------------------------- block reader of handle_one_file
+// The file is read in blocks (MTR_READ_BLOCK_MB, default 64), every block is cut at its last record boundary and its
+// records are parsed in parallel by parse_records; what is left over joins the next block.  Same results as FastaReader
+// (the reference's own line-by-line loop, kept for MTR_SERIAL_READER=1), and the same order of events: the reads in front
+// of a bad record are handed out before `fatal` is reported, a zero-length read ends the run.
+struct BlockReader {
+    FILE *fp = nullptr;
+    std::vector<char> buf;
+    size_t have = 0, block = 64u << 20;
+    bool eof = false, leading = true, done = false;
+    int threads = 4;
+    std::string fatal, last_id;
+    explicit BlockReader(const char *path)
+    {
+        fp = fopen(path, "r");
+        if (!fp) { fprintf(stderr, "fatal error: cannot open %s\n", path); fflush(stderr); exit(EXIT_FAILURE); }
+        if (const char *e = getenv("MTR_READ_BLOCK_MB")) block = (size_t)std::max(1, atoi(e)) << 20;
+        if (const char *e = getenv("MTR_READ_BLOCK_BYTES")) block = (size_t)std::max(16, atoi(e));      // (tests: boundaries everywhere)
+        threads = (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 4));
+        if (const char *e = getenv("MTR_PARSE_THREADS")) threads = std::max(1, atoi(e));
+    }
+    ~BlockReader() { if (fp) fclose(fp); }
+    // the next reads of the file, in order; false: nothing more (see `fatal`)
+    bool next(std::vector<ReadInput> &out)
+    {
+        out.clear();
+        while (!done && out.empty()) {
+            if (!eof) {
+                if (buf.size() < have + block) buf.resize(have + block);
+                const size_t got = fread(buf.data() + have, 1, block, fp);
+                have += got;
+                if (got < block) eof = true;
+            }
+            size_t cut = have;
+            if (!eof) {
+                // up to the last '>' that starts a line -- behind the first one, whose record must be whole (at the start of
+                // the input the bases in front of the first header belong to it)
+                size_t first = have;
+                for (size_t p = 0; p < have; p++)
+                    if (buf[p] == '>' && (p == 0 || buf[p - 1] == '\n')) { first = p; break; }
+                    else if (!leading) break;                      // (later blocks begin with a header)
+                cut = 0;
+                for (size_t p = have; p-- > first + 1;)
+                    if (buf[p] == '>' && buf[p - 1] == '\n') { cut = p; break; }
+                if (cut == 0) continue;                            // no whole record yet: read on
+            }
+            if (cut == 0) { done = true; break; }
+            parse_records(buf.data(), (int64_t)cut, leading, -1, threads, out);
+            leading = false;
+            memmove(buf.data(), buf.data() + cut, have - cut);
+            have -= cut;
+            if (eof && have == 0) done = true;
+            for (size_t i = 0; i < out.size(); i++) {
+                const ReadInput &r = out[i];
+                if (r.bad == 1) {
+                    char m[64];
+                    snprintf(m, sizeof m, "Invalid character: %c \n", r.bad_char);
+                    fatal = m;
+                } else if (r.bad == 2) {
+                    // (handle_one_file.c:244-248 prints currentRead->ID, which still holds the read before)
+                    char m[2304];
+                    snprintf(m, sizeof m, "fatal error: The length %d is tentatively at most %i.\nread ID = %.2000s\nSet MAX_INPUT_LENGTH to a larger value"
+                             "cannot allocate space for one of global variables in the heap.\n", kMaxLen, kMaxLen, i ? out[i - 1].id.c_str() : last_id.c_str());
+                    fatal = m;
+                }
+                if (r.bad || r.len == 0) { out.resize(i); done = true; break; }   // a zero-length read ends the run (handle_one_file.c:283)
+            }
+            if (!out.empty()) last_id = out.back().id;
+        }
+        return !out.empty();
+    }
+};
 
 // ---------------------------------------------------------------- groups of reads on one engine context
 // A group is one engine run: its reads pass through the engine's read slots (MTR_ENGINE_SLOTS at a time, a slot takes the
@@ -803,33 +892,45 @@ extern "C" int handle_one_file(char *inputFile, int print_alignment)
     Runtime &rt = runtime();
     mtr_flush();
     rt.stale.reset();                                   // the reference allocates its buffers anew for every file (handle_one_file.c:71-136)
-    FastaReader reader(inputFile);
+    const bool serial = getenv("MTR_SERIAL_READER") != nullptr && atoi(getenv("MTR_SERIAL_READER")) != 0;
+    std::unique_ptr<FastaReader> reader(serial ? new FastaReader(inputFile) : nullptr);
+    std::unique_ptr<BlockReader> blocks(serial ? nullptr : new BlockReader(inputFile));
     Dispatcher disp(rt, print_alignment, Manhattan_Distance, min_match_ratio);
     int n_reads = 0;
-    bool more = true;
     long long group_bases = rt.group_bases;
     {
         struct stat st;
         if (stat(inputFile, &st) == 0 && st.st_size > 0) group_bases = balanced_group_bases((long long)st.st_size, (int)rt.ctxs.size(), rt.group_bases);
     }
-    while (more) {
-        std::unique_ptr<Group> g(new Group());
-        long long bases = 0;
-        while ((int)g->reads.size() < rt.group_reads && bases < group_bases) {
-            ReadInput in;
-            if (!reader.next(in)) { more = false; break; }
-            bases += in.len;
-            g->reads.push_back(std::move(in));
-            n_reads++;
-        }
-        if (g->reads.empty()) break;
+    std::unique_ptr<Group> g(new Group());
+    long long bases = 0;
+    auto add = [&](ReadInput &&in) {                    // reads join the current group; a full group is sent off
+        bases += in.len;
+        g->reads.push_back(std::move(in));
+        n_reads++;
+        if ((int)g->reads.size() < rt.group_reads && bases < group_bases) return;
+        rt.stale.visit_batch(g->reads, 0, g->reads.size(), 4, nullptr);
+        disp.submit(std::move(g));
+        g.reset(new Group());
+        bases = 0;
+    };
+    if (serial) {
+        ReadInput in;
+        while (reader->next(in)) { add(std::move(in)); in = ReadInput(); }
+    } else {
+        std::vector<ReadInput> batch;
+        while (blocks->next(batch))
+            for (ReadInput &in : batch) add(std::move(in));
+    }
+    if (!g->reads.empty()) {
         rt.stale.visit_batch(g->reads, 0, g->reads.size(), 4, nullptr);
         disp.submit(std::move(g));
     }
     disp.finish();
-    if (!reader.fatal.empty()) {                        // every read in front of the bad one has been printed, as in the reference
+    const std::string &fatal = serial ? reader->fatal : blocks->fatal;
+    if (!fatal.empty()) {                               // every read in front of the bad one has been printed, as in the reference
         fflush(stdout);
-        fputs(reader.fatal.c_str(), stderr);
+        fputs(fatal.c_str(), stderr);
         fflush(stderr);
         exit(EXIT_FAILURE);
     }

@@ -79,7 +79,11 @@ def test_grouping_contexts_and_budgets_do_not_change_the_output(sim, synthetic_d
                 {"MTR_ENGINE_SLOTS": "2", "MTR_ENGINE_LONG_ROWS": "40", "MTR_SIM_LONG_EVERY": "3", "MTR_SIM_WALK_LAG": "2"},
                 # DP queues whose results arrive waves later (and waves that find no free queue at all)
                 {"MTR_SIM_SHORT_EVERY": "3", "MTR_SIM_LONG_EVERY": "5", "MTR_ENGINE_LONG_ROWS": "60"},
-                {"MTR_SIM_SHORT_EVERY": "2", "MTR_SIM_WALK_LAG": "1", "MTR_ENGINE_SLOTS": "4", "MTR_SPECULATE": "3"}):
+                {"MTR_SIM_SHORT_EVERY": "2", "MTR_SIM_WALK_LAG": "1", "MTR_ENGINE_SLOTS": "4", "MTR_SPECULATE": "3"},
+                # the file reader: blocks of any size cut at record boundaries and parsed in parallel / the reference's own
+                # line-by-line loop
+                {"MTR_READ_BLOCK_BYTES": "64", "MTR_GROUP_READS": "3"}, {"MTR_READ_BLOCK_BYTES": "1000", "MTR_PARSE_THREADS": "3"},
+                {"MTR_READ_BLOCK_BYTES": "70000"}, {"MTR_SERIAL_READER": "1", "MTR_GROUP_READS": "4"}):
         assert hashlib.md5(run(sim, [], path, env)).hexdigest() == ref, env
 
 
