@@ -297,10 +297,12 @@ def main():
     peak_p16 = alu["viaddmnmx_s16x2"] / (I_CELL_INT32 / 2)
     f16 = acc["wdp_cells_p16"] / max(acc["wdp_cells"], 1)
     peak_gcups = 1.0 / ((1.0 - f16) / peak_i32 + f16 / peak_p16)
-    traffic = None
-    try:                                                       # measured DRAM traffic of the fill kernels: profiles/r2_k3_traffic.json (ncu --set full)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_k3_traffic.json")))
-    except (OSError, ValueError):
+    traffic = traffic_detail = None
+    try:                                                       # measured DRAM traffic of the fill kernels: profiles/r2_k3_traffic.json (ncu, all K3 launches of a run)
+        traffic_detail = json.load(open(os.path.join(ROOT, "profiles", "r2_k3_traffic.json")))
+        # per launch, like the contract asks: dram__bytes_read.sum + dram__bytes_write.sum averaged over the profiled K3 launches
+        traffic = round((traffic_detail["dram_bytes_read"] + traffic_detail["dram_bytes_write"]) / max(traffic_detail["k3_launches"], 1))
+    except (OSError, ValueError, KeyError, TypeError):
         pass
 
     line = {
@@ -327,7 +329,7 @@ def main():
                      "how": "cells run / union of the K3 kernel intervals of all queues and contexts (%.1f ms of %.1f ms wall per step)"
                             % (dp_busy_ms / a.steps, t_res / a.steps * 1e3),
                      "frac_by_wall": round(gcups_wall / peak_gcups, 4),
-                     "traffic": traffic, "algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3),
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per K3 launch (ncu)", "traffic_detail": traffic_detail, "algorithmic_dir_bytes_per_cell": round(acc["wdp_dir_bytes"] / max(acc["wdp_cells"], 1), 3),
                      "peak_how": "mtr_alu_probe now: %.0f G lane-ops/s VIADDMNMX.RELU / 15 instr per int32 cell = %.0f GCUPS, %.0f G VIADDMNMX.S16x2 / 7.5 per paired cell = %.0f GCUPS, "
                                  "harmonic mix by the cells of each family (%.0f %% int16x2)" % (alu["viaddmnmx_s32"], peak_i32, alu["viaddmnmx_s16x2"], peak_p16, 100 * f16),
                      "alu_probe_gops": {k: round(v, 1) for k, v in alu.items()}},

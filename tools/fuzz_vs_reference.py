@@ -4,7 +4,7 @@
 knobs through the product's host sources + engine device code on the simulated device (tests/hostsim) and through the
 reference binary built from the reference's sources (oracle/_ref/mTR_ref_det, canonical set order); the bytes must be equal.
 
-    python tools/fuzz_vs_reference.py <first seed> <seconds>          # differing inputs are kept as /tmp/fuzz/BAD_<seed>.fa
+    python tools/fuzz_vs_reference.py <first seed> <seconds> [long]   # differing inputs are kept as /tmp/fuzz/BAD_<seed>.fa
 
 Round 2: 13 130 files, no difference; on 4 of them (-p) the reference itself dies with SIGSEGV in the middle of the file
 (state left behind by earlier reads: every read of those files passes alone) -- its output up to there is a prefix of the
@@ -14,6 +14,7 @@ import numpy as np
 sys.path.insert(0,'/root/repo')
 ref='/root/repo/oracle/_ref/mTR_ref_det'; sim='/root/repo/tests/hostsim/_build/mTR_hostsim'
 seed0=int(sys.argv[1]); budget=float(sys.argv[2])
+big=len(sys.argv)>3 and sys.argv[3]=='long'          # long: reads of several kb (units up to 500, flanks up to 3 kb)
 os.makedirs('/tmp/fuzz', exist_ok=True)
 t0=time.time(); n=0; bad=0
 while time.time()-t0<budget:
@@ -25,9 +26,9 @@ while time.time()-t0<budget:
         parts=[]
         for seg in range(int(rng.integers(1,4))):
             if rng.random()<0.7:
-                ul=int(rng.choice([1,2,3,4,5,7,10,13,20,33,50,80,120,200,300]))
+                ul=int(rng.choice([1,2,3,4,5,7,10,13,20,33,50,80,120,200,300]+([400,500] if big else [])))
                 unit=rng.integers(0,4,ul)
-                copies=int(rng.integers(2,max(3,min(60,1500//ul))))
+                copies=int(rng.integers(2,max(3,min(200 if big else 60,(9000 if big else 1500)//ul))))
                 rep=np.tile(unit,copies)
                 rate=float(rng.choice([0,0.02,0.05,0.1,0.15]))
                 out=[]
@@ -38,7 +39,7 @@ while time.time()-t0<budget:
                     out.append(int(rng.integers(0,4)) if rng.random()<rate/3 else int(b))
                 parts.append(np.array(out,dtype=np.int64))
             else:
-                parts.append(rng.integers(0,4,int(rng.integers(0,400))))
+                parts.append(rng.integers(0,4,int(rng.integers(0,3000 if big else 400))))
         seq=np.concatenate(parts) if parts else np.zeros(0,dtype=np.int64)
         if len(seq)==0: seq=rng.integers(0,4,5)
         s="".join("ACGT"[int(x)] for x in seq)
