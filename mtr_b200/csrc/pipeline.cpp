@@ -45,6 +45,15 @@ namespace {
 
 constexpr int kMaxLen = 1000000;      // MAX_INPUT_LENGTH, mTR.h:31
 
+// host cores this process may count on: the machine's, divided by the ranks a launcher has put on it (torchrun exports
+// LOCAL_WORLD_SIZE; one process per GPU share the host)
+int host_cores()
+{
+    int n = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) n = std::max(1, n / std::max(1, atoi(e)));
+    return n;
+}
+
 double now_s()
 {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -432,7 +441,7 @@ struct BlockReader {
         if (!fp) { fprintf(stderr, "fatal error: cannot open %s\n", path); fflush(stderr); exit(EXIT_FAILURE); }
         if (const char *e = getenv("MTR_READ_BLOCK_MB")) block = (size_t)std::max(1, atoi(e)) << 20;
         if (const char *e = getenv("MTR_READ_BLOCK_BYTES")) block = (size_t)std::max(16, atoi(e));      // (tests: boundaries everywhere)
-        threads = (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 4));
+        threads = std::min(8, std::max(1, host_cores() / 4));
         if (const char *e = getenv("MTR_PARSE_THREADS")) threads = std::max(1, atoi(e));
     }
     ~BlockReader() { if (fp) fclose(fp); }
@@ -571,7 +580,7 @@ void upload_groups(mtr_ctx *ctx, const std::vector<Group *> &groups)
         }
     };
     {
-        int nt = (int)std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2));
+        int nt = std::min(8, std::max(1, host_cores() / 2));
         if (const char *e = getenv("MTR_PACK_THREADS")) nt = std::max(1, atoi(e));
         if (n < 64) nt = 1;
         std::vector<std::thread> th;
@@ -1107,7 +1116,7 @@ extern "C" int mtr_pipeline_open(int device, int threads, mtr_pipeline **out)
         mtr_set_blocking_sync(c, 1);
         p->ctxs.push_back(c);
     }
-    p->threads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    p->threads = threads > 0 ? threads : host_cores();
     if (const char *e = getenv("MTR_GROUP_READS")) p->group_reads = std::max(1, atoi(e));
     if (const char *e = getenv("MTR_GROUP_MBASES")) p->group_bases = std::max(1LL, atoll(e)) << 20;
     p->stale = new StaleTracker();
