@@ -16,7 +16,7 @@ ref='/root/repo/oracle/_ref/mTR_ref_det'; sim='/root/repo/tests/hostsim/_build/m
 seed0=int(sys.argv[1]); budget=float(sys.argv[2])
 big=len(sys.argv)>3 and sys.argv[3]=='long'          # long: reads of several kb (units up to 500, flanks up to 3 kb)
 os.makedirs('/tmp/fuzz', exist_ok=True)
-t0=time.time(); n=0; bad=0
+t0=time.time(); n=0; bad=0; crashed=0
 while time.time()-t0<budget:
     seed=seed0+n; n+=1
     rng=np.random.default_rng(seed)
@@ -54,9 +54,12 @@ while time.time()-t0<budget:
     if rng.random()<0.5: env.update({'MTR_GROUP_READS':str(int(rng.integers(1,4))),'MTR_ENGINE_SLOTS':str(int(rng.integers(1,5))),'MTR_READ_BLOCK_BYTES':str(int(rng.integers(16,3000)))})
     a=subprocess.run([ref]+flags+[path],stdout=subprocess.PIPE,stderr=subprocess.PIPE)
     b=subprocess.run([sim]+flags+[path],stdout=subprocess.PIPE,stderr=subprocess.PIPE,env=env,timeout=600)
-    if a.returncode!=b.returncode or a.stdout!=b.stdout:
+    if a.returncode<0 and b.returncode==0 and b.stdout.startswith(a.stdout):
+        crashed+=1          # the reference itself died on a signal (seen with -p only); what it had printed is a prefix of the product's output
+        print('REFERENCE CRASHED seed',seed,flags,'signal',-a.returncode,flush=True)
+    elif a.returncode!=b.returncode or a.stdout!=b.stdout:
         bad+=1
         keep='/tmp/fuzz/BAD_%d.fa'%seed
         os.rename(path,keep)
         print('DIFF seed',seed,flags,{k:v for k,v in env.items() if k.startswith('MTR_')},'rc',a.returncode,b.returncode,'lines',a.stdout.count(b'\n'),b.stdout.count(b'\n'),b.stderr[:100],flush=True)
-print('done seed0',seed0,'cases',n,'bad',bad,flush=True)
+print('done seed0',seed0,'cases',n,'reference_crashes',crashed,'bad',bad,flush=True)
