@@ -9,6 +9,7 @@ import subprocess
 import pytest
 
 import golden_cases
+import multi_run
 
 pytestmark = pytest.mark.gpu
 
@@ -50,20 +51,60 @@ def synthetic_dir(tmp_path_factory, oracle_so):
     return str(d)
 
 
-@pytest.mark.parametrize("name", sorted(DIGESTS["shipped"]))
-def test_shipped_multiple_TRs(shipped_dir, name):
-    path = os.path.join(shipped_dir, name)
+LIB = os.path.join(ROOT, "mtr_b200", "lib", "libmtr_b200.so")
+_MANY = {}
+
+
+def outputs_in_one_process(shipped_dir, synthetic_dir, env=None, only=None):
+    """Every (file, mode) of the digest table through handle_one_file() of the library in ONE process (tests/multi_run.py):
+    one CUDA start-up for the whole table, and consecutive files in one process must not influence each other."""
+    key = (LIB, shipped_dir, synthetic_dir, tuple(sorted((env or {}).items())), only)
+    if key not in _MANY:
+        jobs, names = [], []
+        for kind, d, suffix in (("shipped", shipped_dir, ""), ("synthetic", synthetic_dir, ".fa")):
+            for name in sorted(DIGESTS[kind]):
+                if only is not None and name not in only:
+                    continue
+                for mode, flags in golden_cases.MODES.items():
+                    jobs.append((os.path.join(d, name + suffix), flags))
+                    names.append((kind, name, mode))
+        outs = multi_run.run_many(LIB, jobs, env)
+        _MANY[key] = dict(zip(names, outs))
+    return _MANY[key]
+
+
+def check_digests(outs, kind, name, directory, suffix=""):
+    """The digest of every mode: from the one-process run where it agrees, else from the command line itself (a file that
+    only goes wrong behind other files in the same process fails test_consecutive_files_in_one_process, not this test)."""
     for mode, flags in golden_cases.MODES.items():
-        out = run(MTR, flags, path)
-        assert hashlib.md5(out).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode, explain(out, flags, path))
+        out = outs[(kind, name, mode)]
+        if hashlib.md5(out).hexdigest() != DIGESTS[kind][name][mode]["md5"]:
+            out = run(MTR, flags, os.path.join(directory, name + suffix))
+        assert hashlib.md5(out).hexdigest() == DIGESTS[kind][name][mode]["md5"], (name, mode, explain(out, flags, os.path.join(directory, name + suffix)))
+
+
+@pytest.mark.parametrize("name", sorted(DIGESTS["shipped"]))
+def test_shipped_multiple_TRs(shipped_dir, synthetic_dir, name):
+    check_digests(outputs_in_one_process(shipped_dir, synthetic_dir), "shipped", name, shipped_dir)
+    if name == "10_20.fasta":                               # ... and the command line itself, once
+        for mode, flags in golden_cases.MODES.items():
+            assert hashlib.md5(run(MTR, flags, os.path.join(shipped_dir, name))).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode)
 
 
 @pytest.mark.parametrize("name", sorted(DIGESTS["synthetic"]))
-def test_synthetic_cases(synthetic_dir, name):
-    path = os.path.join(synthetic_dir, name + ".fa")
-    for mode, flags in golden_cases.MODES.items():
-        out = run(MTR, flags, path)
-        assert hashlib.md5(out).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode, explain(out, flags, path))
+def test_synthetic_cases(shipped_dir, synthetic_dir, name):
+    check_digests(outputs_in_one_process(shipped_dir, synthetic_dir), "synthetic", name, synthetic_dir, ".fa")
+    if name == "mixed":
+        for mode, flags in golden_cases.MODES.items():
+            assert hashlib.md5(run(MTR, flags, os.path.join(synthetic_dir, name + ".fa"))).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
+
+
+def test_consecutive_files_in_one_process(shipped_dir, synthetic_dir):
+    """81 handle_one_file() calls in one process (every file, every mode, one after the other on the same engine contexts):
+    each prints what it prints alone."""
+    outs = outputs_in_one_process(shipped_dir, synthetic_dir)
+    bad = [k for k, out in outs.items() if hashlib.md5(out).hexdigest() != DIGESTS[k[0]][k[1]][k[2]]["md5"]]
+    assert len(outs) == 81 and not bad, bad
 
 
 def test_small_groups_give_identical_output(synthetic_dir):
@@ -171,11 +212,13 @@ print(json.dumps({"n": n, "md5": hashlib.md5(out).hexdigest(), "reads": st["read
 @pytest.mark.parametrize("spec", ["0", "24"])
 def test_speculative_look_ahead_does_not_change_the_output(synthetic_dir, shipped_dir, spec):
     """MTR_SPECULATE (default 8): any depth of speculative candidate look-ahead, incl. none, prints the same bytes."""
-    cases = [(os.path.join(synthetic_dir, "mixed.fa"), DIGESTS["synthetic"]["mixed"]), (os.path.join(shipped_dir, "worm_chrII_1.fasta"), DIGESTS["shipped"]["worm_chrII_1.fasta"])]
-    for path, want in cases:
-        for mode, flags in golden_cases.MODES.items():
-            out = run(MTR, flags, path, {"MTR_SPECULATE": spec})
-            assert hashlib.md5(out).hexdigest() == want[mode]["md5"], (path, mode, spec, explain(out, flags, path))
+    only = ("mixed", "long4", "pacbio_200_200", "worm_chrII_1.fasta", "2_5_10_20_50_100_200_set.fasta")
+    outs = outputs_in_one_process(shipped_dir, synthetic_dir, {"MTR_SPECULATE": spec}, only)
+    for kind, name, mode in outs:
+        out = outs[(kind, name, mode)]
+        if hashlib.md5(out).hexdigest() != DIGESTS[kind][name][mode]["md5"]:      # (see check_digests)
+            out = run(MTR, golden_cases.MODES[mode], os.path.join(shipped_dir, name) if kind == "shipped" else os.path.join(synthetic_dir, name + ".fa"), {"MTR_SPECULATE": spec})
+        assert hashlib.md5(out).hexdigest() == DIGESTS[kind][name][mode]["md5"], (name, mode, spec)
 
 
 REFMAIN = os.path.join(ROOT, "bin", "mTR_refmain")
