@@ -9,6 +9,7 @@ import pytest
 
 import golden_cases
 import test_pipeline_gpu as gpu
+import test_zz_one_process_gpu as last
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIMDIR = os.path.join(ROOT, "tests", "hostsim")
@@ -37,7 +38,7 @@ def synthetic_dir(tmp_path_factory):
 
 
 def test_every_digest_in_one_process(shipped_dir, synthetic_dir):
-    gpu.test_consecutive_files_in_one_process(shipped_dir, synthetic_dir)
+    last.test_consecutive_files_in_one_process(shipped_dir, synthetic_dir)
     for name in sorted(gpu.DIGESTS["shipped"]):
         gpu.test_shipped_multiple_TRs(shipped_dir, synthetic_dir, name)
     for name in sorted(gpu.DIGESTS["synthetic"]):

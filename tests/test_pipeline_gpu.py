@@ -58,7 +58,7 @@ _MANY = {}
 def outputs_in_one_process(shipped_dir, synthetic_dir, env=None, only=None):
     """Every (file, mode) of the digest table through handle_one_file() of the library in ONE process (tests/multi_run.py):
     one CUDA start-up for the whole table, and consecutive files in one process must not influence each other."""
-    key = (LIB, shipped_dir, synthetic_dir, tuple(sorted((env or {}).items())), only)
+    key = (LIB, tuple(sorted((env or {}).items())), only)      # (the directories hold the same files whoever made them)
     if key not in _MANY:
         jobs, names = [], []
         for kind, d, suffix in (("shipped", shipped_dir, ""), ("synthetic", synthetic_dir, ".fa")):
@@ -75,7 +75,7 @@ def outputs_in_one_process(shipped_dir, synthetic_dir, env=None, only=None):
 
 def check_digests(outs, kind, name, directory, suffix=""):
     """The digest of every mode: from the one-process run where it agrees, else from the command line itself (a file that
-    only goes wrong behind other files in the same process fails test_consecutive_files_in_one_process, not this test)."""
+    only goes wrong behind other files in the same process fails tests/test_zz_one_process_gpu.py, not this test)."""
     for mode, flags in golden_cases.MODES.items():
         out = outs[(kind, name, mode)]
         if hashlib.md5(out).hexdigest() != DIGESTS[kind][name][mode]["md5"]:
@@ -97,14 +97,6 @@ def test_synthetic_cases(shipped_dir, synthetic_dir, name):
     if name == "mixed":
         for mode, flags in golden_cases.MODES.items():
             assert hashlib.md5(run(MTR, flags, os.path.join(synthetic_dir, name + ".fa"))).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
-
-
-def test_consecutive_files_in_one_process(shipped_dir, synthetic_dir):
-    """81 handle_one_file() calls in one process (every file, every mode, one after the other on the same engine contexts):
-    each prints what it prints alone."""
-    outs = outputs_in_one_process(shipped_dir, synthetic_dir)
-    bad = [k for k, out in outs.items() if hashlib.md5(out).hexdigest() != DIGESTS[k[0]][k[1]][k[2]]["md5"]]
-    assert len(outs) == 81 and not bad, bad
 
 
 def test_small_groups_give_identical_output(synthetic_dir):
