@@ -53,6 +53,7 @@ def synthetic_dir(tmp_path_factory, oracle_so):
 
 LIB = os.path.join(ROOT, "mtr_b200", "lib", "libmtr_b200.so")
 _MANY = {}
+_MANY_ERRORS = []
 
 
 def outputs_in_one_process(shipped_dir, synthetic_dir, env=None, only=None):
@@ -68,7 +69,11 @@ def outputs_in_one_process(shipped_dir, synthetic_dir, env=None, only=None):
                 for mode, flags in golden_cases.MODES.items():
                     jobs.append((os.path.join(d, name + suffix), flags))
                     names.append((kind, name, mode))
-        outs = multi_run.run_many(LIB, jobs, env)
+        try:
+            outs = multi_run.run_many(LIB, jobs, env)
+        except Exception as e:      # noqa: BLE001 -- the digest tests then run the command line per file; the last GPU test reports this
+            _MANY_ERRORS.append("%s: %s" % (type(e).__name__, e))
+            outs = [b"<the one-process run failed>"] * len(jobs)
         _MANY[key] = dict(zip(names, outs))
     return _MANY[key]
 

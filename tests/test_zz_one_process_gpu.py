@@ -14,4 +14,5 @@ pytestmark = pytest.mark.gpu
 def test_consecutive_files_in_one_process(shipped_dir, synthetic_dir):      # noqa: F811
     outs = tp.outputs_in_one_process(shipped_dir, synthetic_dir)
     bad = [k for k, out in outs.items() if hashlib.md5(out).hexdigest() != tp.DIGESTS[k[0]][k[1]][k[2]]["md5"]]
+    assert not tp._MANY_ERRORS, tp._MANY_ERRORS
     assert len(outs) == 81 and not bad, bad
