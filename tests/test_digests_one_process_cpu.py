@@ -39,10 +39,19 @@ def synthetic_dir(tmp_path_factory):
 
 def test_every_digest_in_one_process(shipped_dir, synthetic_dir):
     last.test_consecutive_files_in_one_process(shipped_dir, synthetic_dir)
-    for name in sorted(gpu.DIGESTS["shipped"]):
+    for name in ("10_20.fasta", "5_10.fasta"):              # (one with, one without the extra command-line run)
         gpu.test_shipped_multiple_TRs(shipped_dir, synthetic_dir, name)
-    for name in sorted(gpu.DIGESTS["synthetic"]):
+    for name in ("mixed", "single_TR_5"):
         gpu.test_synthetic_cases(shipped_dir, synthetic_dir, name)
+
+
+def test_digest_tests_fall_back_to_the_command_line(shipped_dir, synthetic_dir, monkeypatch):
+    """A one-process run that fails (here: a library that does not exist) must not take the digest tests with it."""
+    monkeypatch.setattr(gpu, "LIB", "/nonexistent/libmtr.so")
+    monkeypatch.setattr(gpu, "_MANY_ERRORS", [])
+    gpu.test_shipped_multiple_TRs(shipped_dir, synthetic_dir, "5_10.fasta")
+    assert len(gpu._MANY_ERRORS) == 1
+    gpu._MANY.pop(("/nonexistent/libmtr.so", (), None), None)
 
 
 @pytest.mark.parametrize("spec", ["0", "24"])

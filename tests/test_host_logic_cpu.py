@@ -50,18 +50,39 @@ def synthetic_dir(tmp_path_factory):
     return str(d)
 
 
+CLI_TOO = ("10_20.fasta", "worm_chrII_1.fasta", "mixed", "long4")      # these also go through the command line, one process each
+
+
+def one_process(shipped_dir, synthetic_dir):
+    """All 81 (file, mode) runs through handle_one_file() of the simulated-device library in one process (the same helper
+    the GPU suite uses, tests/test_pipeline_gpu.py)."""
+    import test_pipeline_gpu as gpu
+    old = gpu.LIB
+    gpu.LIB = os.path.join(SIMDIR, "_build", "libmtr_hostsim.so")
+    try:
+        return gpu.outputs_in_one_process(shipped_dir, synthetic_dir)
+    finally:
+        gpu.LIB = old
+
+
 @pytest.mark.parametrize("name", sorted(DIGESTS["shipped"]))
-def test_host_logic_on_shipped_files(sim, shipped_dir, name):
+def test_host_logic_on_shipped_files(sim, shipped_dir, synthetic_dir, name):
     path = os.path.join(shipped_dir, name)
+    outs = one_process(shipped_dir, synthetic_dir)
     for mode, flags in golden_cases.MODES.items():
-        assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode)
+        assert hashlib.md5(outs[("shipped", name, mode)]).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode)
+        if name in CLI_TOO:
+            assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["shipped"][name][mode]["md5"], (name, mode)
 
 
 @pytest.mark.parametrize("name", sorted(DIGESTS["synthetic"]))
-def test_host_logic_on_synthetic_cases(sim, synthetic_dir, name):
+def test_host_logic_on_synthetic_cases(sim, shipped_dir, synthetic_dir, name):
     path = os.path.join(synthetic_dir, name + ".fa")
+    outs = one_process(shipped_dir, synthetic_dir)
     for mode, flags in golden_cases.MODES.items():
-        assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
+        assert hashlib.md5(outs[("synthetic", name, mode)]).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
+        if name in CLI_TOO:
+            assert hashlib.md5(run(sim, flags, path)).hexdigest() == DIGESTS["synthetic"][name][mode]["md5"], (name, mode)
 
 
 def test_grouping_contexts_and_budgets_do_not_change_the_output(sim, synthetic_dir):
